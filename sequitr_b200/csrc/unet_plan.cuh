@@ -1,0 +1,53 @@
+// The device-side image of the reference UNet object (networks/unet.py:53-342).
+#pragma once
+#include "sq_common.cuh"
+
+struct SqHostTensor {
+    std::vector<float> data;
+    std::vector<int64_t> shape;
+};
+
+// one conv-like layer of the graph in execution order
+struct SqLayer {
+    enum Kind { CONV = 0, POOL = 1, UPCONV = 2, ELTWISE = 3, HEAD = 4 } kind;
+    std::string scope;            // TF variable scope, e.g. "UNet/down0/conv1"
+    int level = 0;                // resolution level (0 = full resolution)
+    int cin0 = 0, cin1 = 0;       // channels of the first / second (skip) input
+    int cout = 0;
+    int ksize = 3;
+    double flops_per_px = 0;      // algorithmic FLOPs per pixel of this layer's OUTPUT grid
+    // fp32-exact device weights
+    float *w = nullptr, *scale = nullptr, *shift = nullptr;
+    // tensor-core device weights (bf16, re-laid-out; see unet_tc.cu)
+    void *w_tc = nullptr;
+};
+
+struct SqLayerTimer {
+    std::vector<cudaEvent_t> ev;          // ev[i], ev[i+1] bracket layer i
+    std::vector<const char *> names;
+    std::vector<double> flops;
+    bool enabled = false;
+};
+
+struct sq_unet_s {
+    sq_handle_s *h = nullptr;
+    int ndim = 2, cin = 1, nout = 2, nlev = 5, bridge = SQ_BRIDGE_CONCAT, mode = SQ_MODE_FP32_EXACT;
+    std::vector<int> filters;
+    std::map<std::string, SqHostTensor> host;   // as loaded (TF names / layouts)
+    std::vector<SqLayer> layers;                // CONV / UPCONV / HEAD layers with weights
+    bool finalized = false;
+    int last_launches = 0;
+    std::vector<void *> dev_allocs;             // freed in sq_unet_destroy
+    void *tc_state = nullptr;                   // owned by unet_tc.cu
+    SqLayerTimer timer;
+};
+
+// ---- tensor-core path (unet_tc.cu)
+int sq_tc_finalize(sq_unet_s *u);
+int sq_tc_destroy(sq_unet_s *u);
+int sq_tc_workspace_bytes(sq_unet_s *u, int n, int d, int hgt, int wid, size_t *bytes);
+int sq_tc_forward(sq_unet_s *u, const float *in, int n, int d, int hgt, int wid, float *probs,
+                  uint8_t *mask, float *logits, void *ws, size_t ws_bytes, cudaStream_t st);
+
+// timer helpers (unet.cu)
+void sq_timer_mark(sq_unet_s *u, cudaStream_t st, const char *name, double flops);

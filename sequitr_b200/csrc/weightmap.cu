@@ -1,0 +1,431 @@
+// Per-pixel loss-weight maps on the GPU.
+//
+//   W1  sq_weightmap_edt   <- pipeline.ImageWeightMap.pipe (reference pipeline.py:475-479)
+//         d = EDT(1 - m);  w = w0*(1-m)*exp(-d*d/(2 sigma^2 + 1e-99)) + m + 1
+//   W3  sq_weightmap_unet  <- north-star formula on instance labels
+//         w = wc[m] + w0*(1-m)*exp(-(d1+d2)^2/(2 sigma^2 + 1e-99))
+//
+// Distance transform: EXACT separable Euclidean transform on integer squared
+// distances (so it is bit-identical to SciPy's distance_transform_edt, which a
+// jump-flooding pass is not):
+//   phase 1 (rows)    horizontal distance to the nearest seed in the same row --
+//                     a segmented prefix/suffix scan per row, uint16 per pixel;
+//   phase 2 (columns) d2(x,y) = min_dy dy^2 + g(x,y+dy)^2, scanned outwards from
+//                     the pixel and stopped as soon as dy^2 >= best (exact), or
+//                     at a cut-off radius beyond which w0*exp(..) is below half
+//                     an ulp of the class term -- the stored result is still the
+//                     one the exact transform would give after rounding.
+// W3 carries the two nearest DISTINCT instance labels through both phases.
+// Both kernels are HBM/L2-bound integer work: 1 B (W1) or 4 B (W3) in and one
+// float out per pixel; the uint16 / 12-byte intermediates stay L2-resident.
+#include "sq_common.cuh"
+#include <cmath>
+
+namespace {
+
+constexpr unsigned short INF16 = 0xFFFF;
+constexpr unsigned INF32 = 0xFFFFFFFFu;
+constexpr int ROW_THREADS = 256;
+
+// ------------------------------------------------------------------ W1 phase 1
+// grid (hgt, n), block 256, dyn smem: wid * 2 bytes
+__global__ void edt_rows(const uint8_t *__restrict__ mask, unsigned short *__restrict__ g,
+                         int *__restrict__ anyfg, int hgt, int wid)
+{
+    extern __shared__ unsigned short srow[];
+    __shared__ int lastp[ROW_THREADS], firstp[ROW_THREADS];
+    const int t = threadIdx.x;
+    const long long ro = ((long long)blockIdx.y * hgt + blockIdx.x) * wid;
+    const uint8_t *mk = mask + ro;
+    const int seg = (wid + ROW_THREADS - 1) / ROW_THREADS;
+    const int x0 = min(t * seg, wid), x1 = min(x0 + seg, wid);
+    int lp = -1, fp = 0x3fffffff;
+    for (int x = x0; x < x1; ++x)
+        if (mk[x]) { lp = x; if (fp == 0x3fffffff) fp = x; }
+    if (lp >= 0) anyfg[blockIdx.y] = 1;
+    lastp[t] = lp;
+    firstp[t] = fp;
+    __syncthreads();
+    // inclusive prefix-max of lastp, inclusive suffix-min of firstp (Hillis-Steele)
+    for (int o = 1; o < ROW_THREADS; o <<= 1) {
+        const int a = (t >= o) ? lastp[t - o] : -1;
+        const int b = (t + o < ROW_THREADS) ? firstp[t + o] : 0x3fffffff;
+        __syncthreads();
+        lastp[t] = max(lastp[t], a);
+        firstp[t] = min(firstp[t], b);
+        __syncthreads();
+    }
+    int last = (t > 0) ? lastp[t - 1] : -1;
+    for (int x = x0; x < x1; ++x) {
+        if (mk[x]) last = x;
+        srow[x] = (last >= 0) ? (unsigned short)min(x - last, 0xFFFE) : INF16;
+    }
+    int next = (t + 1 < ROW_THREADS) ? firstp[t + 1] : 0x3fffffff;
+    for (int x = x1 - 1; x >= x0; --x) {
+        if (mk[x]) next = x;
+        if (next != 0x3fffffff) srow[x] = min(srow[x], (unsigned short)min(next - x, 0xFFFE));
+    }
+    __syncthreads();
+    for (int x = t; x < wid; x += ROW_THREADS) g[ro + x] = srow[x];
+}
+
+// ------------------------------------------------------------------ W1 phase 2
+// grid (ceil(W/32), ceil(H/8), n), block (32,8)
+template <typename OutT>
+__global__ void edt_cols_weight(const uint8_t *__restrict__ mask,
+                                const unsigned short *__restrict__ g,
+                                const int *__restrict__ anyfg, OutT *__restrict__ out,
+                                int *__restrict__ d2_out, int hgt, int wid, int rmax,
+                                double w0e, double denom)
+{
+    const int x = blockIdx.x * 32 + threadIdx.x;
+    const int y = blockIdx.y * 8 + threadIdx.y;
+    if (x >= wid || y >= hgt) return;
+    const long long fo = (long long)blockIdx.z * hgt * wid;
+    const long long idx = fo + (long long)y * wid + x;
+    if (mask[idx]) {
+        out[idx] = (OutT)2.0;                       // w0*(1-1)*exp(0) + 1 + 1
+        if (d2_out) d2_out[idx] = 0;
+        return;
+    }
+    unsigned best;
+    if (!anyfg[blockIdx.z]) {
+        // SciPy's distance_transform_edt with no seed: virtual seed at (-1, 0)
+        best = (unsigned)(y + 1) * (unsigned)(y + 1) + (unsigned)x * (unsigned)x;
+    } else {
+        const unsigned short g0 = g[idx];
+        best = (g0 == INF16) ? INF32 : (unsigned)g0 * g0;
+        const int lim = min(rmax, max(y, hgt - 1 - y));
+        for (int dy = 1; dy <= lim; ++dy) {
+            const unsigned dy2 = (unsigned)dy * dy;
+            if (dy2 >= best) break;
+            if (y - dy >= 0) {
+                const unsigned short gv = g[idx - (long long)dy * wid];
+                if (gv != INF16) best = min(best, dy2 + (unsigned)gv * gv);
+            }
+            if (y + dy < hgt) {
+                const unsigned short gv = g[idx + (long long)dy * wid];
+                if (gv != INF16) best = min(best, dy2 + (unsigned)gv * gv);
+            }
+        }
+    }
+    if (d2_out) d2_out[idx] = (best == INF32) ? 0x7fffffff : (int)best;
+    double w = 1.0;
+    if (best != INF32) {
+        const double d = sqrt((double)best);        // SciPy returns sqrt(d2) ...
+        w = w0e * exp(-(d * d) / denom) + 0.0 + 1.0;  // ... and pipeline.py:477 squares it again
+    }
+    out[idx] = (OutT)w;
+}
+
+// ------------------------------------------------------------------ W3 phase 1
+struct Two {                 // two most recent distinct labels and their x positions
+    int l1, p1, l2, p2;      // label 0 = none
+};
+
+__device__ __forceinline__ Two two_push(Two s, int l, int p)
+{
+    if (l == s.l1) { s.p1 = p; return s; }
+    s.l2 = s.l1; s.p2 = s.p1;
+    s.l1 = l;    s.p1 = p;
+    return s;
+}
+
+// older A followed by newer B
+__device__ __forceinline__ Two two_combine(const Two &A, const Two &B)
+{
+    if (B.l1 == 0) return A;
+    Two r = B;
+    if (r.l2 == 0) {
+        if (A.l1 != 0 && A.l1 != r.l1) { r.l2 = A.l1; r.p2 = A.p1; }
+        else if (A.l2 != 0 && A.l2 != r.l1) { r.l2 = A.l2; r.p2 = A.p2; }
+    }
+    return r;
+}
+
+struct Best2 {               // two nearest distinct labels with (squared or plain) distances
+    int la, lb;
+    unsigned da, db;         // da <= db
+};
+
+__device__ __forceinline__ void best2_insert(Best2 &b, int l, unsigned d)
+{
+    if (l == 0) return;
+    if (l == b.la) { b.da = min(b.da, d); return; }
+    if (l == b.lb) {
+        b.db = min(b.db, d);
+        if (b.db < b.da) { int tl = b.la; unsigned td = b.da; b.la = b.lb; b.da = b.db; b.lb = tl; b.db = td; }
+        return;
+    }
+    if (d < b.da) { b.lb = b.la; b.db = b.da; b.la = l; b.da = d; }
+    else if (d < b.db) { b.lb = l; b.db = d; }
+}
+
+// grid (hgt, n), block 256
+__global__ void inst_rows(const int *__restrict__ labels, int *__restrict__ la,
+                          int *__restrict__ lb, unsigned short *__restrict__ da,
+                          unsigned short *__restrict__ db, int hgt, int wid)
+{
+    __shared__ Two sc[ROW_THREADS];
+    const int t = threadIdx.x;
+    const long long ro = ((long long)blockIdx.y * hgt + blockIdx.x) * wid;
+    const int *lr = labels + ro;
+    const int seg = (wid + ROW_THREADS - 1) / ROW_THREADS;
+    const int x0 = min(t * seg, wid), x1 = min(x0 + seg, wid);
+    const Two empty = {0, 0, 0, 0};
+
+    // ---- left-to-right
+    Two s = empty;
+    for (int x = x0; x < x1; ++x) { const int l = lr[x]; if (l > 0) s = two_push(s, l, x); }
+    sc[t] = s;
+    __syncthreads();
+    for (int o = 1; o < ROW_THREADS; o <<= 1) {
+        Two a = empty;
+        if (t >= o) a = sc[t - o];
+        __syncthreads();
+        if (t >= o) sc[t] = two_combine(a, sc[t]);
+        __syncthreads();
+    }
+    s = (t > 0) ? sc[t - 1] : empty;
+    for (int x = x0; x < x1; ++x) {
+        const int l = lr[x];
+        if (l > 0) s = two_push(s, l, x);
+        Best2 b = {0, 0, INF32, INF32};
+        if (s.l1) best2_insert(b, s.l1, (unsigned)(x - s.p1));
+        if (s.l2) best2_insert(b, s.l2, (unsigned)(x - s.p2));
+        la[ro + x] = b.la; lb[ro + x] = b.lb;
+        da[ro + x] = (unsigned short)min(b.da, 0xFFFEu + (b.la == 0));
+        db[ro + x] = (unsigned short)min(b.db, 0xFFFEu + (b.lb == 0));
+    }
+    __syncthreads();
+
+    // ---- right-to-left ("newer" = smaller x)
+    s = empty;
+    for (int x = x1 - 1; x >= x0; --x) { const int l = lr[x]; if (l > 0) s = two_push(s, l, x); }
+    sc[t] = s;
+    __syncthreads();
+    for (int o = 1; o < ROW_THREADS; o <<= 1) {
+        Two a = empty;
+        if (t + o < ROW_THREADS) a = sc[t + o];
+        __syncthreads();
+        if (t + o < ROW_THREADS) sc[t] = two_combine(a, sc[t]);
+        __syncthreads();
+    }
+    s = (t + 1 < ROW_THREADS) ? sc[t + 1] : empty;
+    for (int x = x1 - 1; x >= x0; --x) {
+        const int l = lr[x];
+        if (l > 0) s = two_push(s, l, x);
+        Best2 b;
+        b.la = la[ro + x]; b.lb = lb[ro + x];
+        b.da = b.la ? da[ro + x] : INF32;
+        b.db = b.lb ? db[ro + x] : INF32;
+        if (s.l1) best2_insert(b, s.l1, (unsigned)(s.p1 - x));
+        if (s.l2) best2_insert(b, s.l2, (unsigned)(s.p2 - x));
+        la[ro + x] = b.la; lb[ro + x] = b.lb;
+        da[ro + x] = b.la ? (unsigned short)min(b.da, 0xFFFEu) : INF16;
+        db[ro + x] = b.lb ? (unsigned short)min(b.db, 0xFFFEu) : INF16;
+    }
+}
+
+// ------------------------------------------------------------------ W3 phase 2
+template <typename OutT>
+__global__ void inst_cols_weight(const int *__restrict__ labels, const int *__restrict__ la,
+                                 const int *__restrict__ lb, const unsigned short *__restrict__ da,
+                                 const unsigned short *__restrict__ db, OutT *__restrict__ out,
+                                 int hgt, int wid, int rmax, double w0, double denom,
+                                 double wc0, double wc1)
+{
+    const int x = blockIdx.x * 32 + threadIdx.x;
+    const int y = blockIdx.y * 8 + threadIdx.y;
+    if (x >= wid || y >= hgt) return;
+    const long long fo = (long long)blockIdx.z * hgt * wid;
+    const long long idx = fo + (long long)y * wid + x;
+    if (labels[idx] > 0) { out[idx] = (OutT)wc1; return; }
+    Best2 b = {0, 0, INF32, INF32};
+    {
+        const int l1 = la[idx], l2 = lb[idx];
+        if (l1) { const unsigned d = da[idx]; best2_insert(b, l1, d * d); }
+        if (l2) { const unsigned d = db[idx]; best2_insert(b, l2, d * d); }
+    }
+    const int lim = min(rmax, max(y, hgt - 1 - y));
+    for (int dy = 1; dy <= lim; ++dy) {
+        const unsigned dy2 = (unsigned)dy * dy;
+        if (dy2 >= b.db) break;
+#pragma unroll
+        for (int sgn = -1; sgn <= 1; sgn += 2) {
+            const int yy = y + sgn * dy;
+            if (yy < 0 || yy >= hgt) continue;
+            const long long j = idx + (long long)sgn * dy * wid;
+            const int l1 = la[j];
+            if (l1) {
+                const unsigned d = da[j];
+                best2_insert(b, l1, dy2 + d * d);
+                const int l2 = lb[j];
+                if (l2) { const unsigned e = db[j]; best2_insert(b, l2, dy2 + e * e); }
+            }
+        }
+    }
+    double w = wc0;
+    if (b.lb != 0) {
+        const double s = sqrt((double)b.da) + sqrt((double)b.db);
+        w = wc0 + w0 * exp(-(s * s) / denom);
+    }
+    out[idx] = (OutT)w;
+}
+
+// Radius beyond which |w0|*exp(-r^2/denom) is < 2^-bits * scale, i.e. cannot change
+// the rounded result (scale = magnitude of the class term it is added to).
+int cutoff_radius(double w0, double denom, double scale, int out_dtype, int maxdim)
+{
+    const double aw = std::fabs(w0);
+    if (aw == 0.0) return 1;
+    if (!(scale > 0.0) || !std::isfinite(aw) || !std::isfinite(denom)) return maxdim;
+    const double bits = (out_dtype == SQ_F32) ? 27.0 : 56.0;
+    const double t = std::log(aw / scale) + bits * 0.6931471805599453;
+    if (t <= 0.0) return 1;
+    const double r = std::ceil(std::sqrt(denom * t)) + 1.0;
+    if (!(r < (double)maxdim)) return maxdim;
+    return (int)(r < 1.0 ? 1.0 : r);
+}
+
+int check_common(sq_handle_t h, int n, int hgt, int wid, int out_dtype)
+{
+    SQ_REQUIRE(h, SQ_EINVAL, "weightmap: null handle");
+    SQ_REQUIRE(n >= 1 && hgt >= 1 && wid >= 1, SQ_EINVAL, "weightmap: bad shape (%d,%d,%d)", n, hgt, wid);
+    SQ_REQUIRE(wid <= 32768 && hgt <= 32768, SQ_EINVAL, "weightmap: image side > 32768");
+    SQ_REQUIRE(n <= 65535, SQ_EINVAL, "weightmap: more than 65535 frames per call");
+    SQ_REQUIRE(out_dtype == SQ_F32 || out_dtype == SQ_F64, SQ_EINVAL, "weightmap: bad out_dtype");
+    return SQ_OK;
+}
+
+}  // namespace
+
+extern "C" int sq_weightmap_workspace_bytes(sq_handle_t h, int n, int hgt, int wid,
+                                            int instance_mode, size_t *bytes)
+{
+    SQ_REQUIRE(bytes, SQ_EINVAL, "weightmap: null pointer");
+    SQ_TRY(check_common(h, n, hgt, wid, SQ_F32));
+    const size_t px = (size_t)n * hgt * wid;
+    SqArena a(nullptr, 0);
+    if (instance_mode) {
+        a.take<int>(px); a.take<int>(px);
+        a.take<unsigned short>(px); a.take<unsigned short>(px);
+    } else {
+        a.take<unsigned short>(px);
+        a.take<int>(n);
+    }
+    *bytes = a.off;
+    return SQ_OK;
+}
+
+extern "C" int sq_weightmap_edt(sq_handle_t h, const uint8_t *mask, int n, int hgt, int wid,
+                                double w0, double sigma, int out_dtype, void *out, int32_t *d2,
+                                void *ws, size_t ws_bytes, void *stream_)
+{
+    SQ_TRY(check_common(h, n, hgt, wid, out_dtype));
+    SQ_REQUIRE(mask && out && ws, SQ_EINVAL, "weightmap_edt: null pointer");
+    const size_t px = (size_t)n * hgt * wid;
+    SqArena a(ws, ws_bytes);
+    unsigned short *g = a.take<unsigned short>(px);
+    int *anyfg = a.take<int>(n);
+    SQ_REQUIRE(a.ok(), SQ_ENOMEM, "weightmap_edt: workspace %zu < %zu bytes", ws_bytes, a.off);
+    cudaStream_t st = (cudaStream_t)stream_;
+    const double denom = 2.0 * sigma * sigma + 1e-99;          // pipeline.py:478
+    const double w0e = (double)(float)w0;   // w0*(1.-image) is float32 arithmetic (image is float32)
+    const int maxdim = hgt > wid ? hgt : wid;
+    const int rmax = d2 ? maxdim : cutoff_radius(w0e, denom, 1.0, out_dtype, maxdim);
+
+    SQ_CUDA(cudaMemsetAsync(anyfg, 0, n * sizeof(int), st));
+    edt_rows<<<dim3(hgt, n), ROW_THREADS, (size_t)wid * sizeof(unsigned short), st>>>(
+        mask, g, anyfg, hgt, wid);
+    const dim3 grid(sq_div_up(wid, 32), sq_div_up(hgt, 8), n), blk(32, 8);
+    if (out_dtype == SQ_F32)
+        edt_cols_weight<float><<<grid, blk, 0, st>>>(mask, g, anyfg, (float *)out, d2, hgt, wid,
+                                                    rmax, w0e, denom);
+    else
+        edt_cols_weight<double><<<grid, blk, 0, st>>>(mask, g, anyfg, (double *)out, d2, hgt,
+                                                     wid, rmax, w0e, denom);
+    SQ_CHECK_LAUNCH();
+    return SQ_OK;
+}
+
+extern "C" int sq_weightmap_unet(sq_handle_t h, const int32_t *labels, int n, int hgt, int wid,
+                                 double w0, double sigma, const double *wc, int out_dtype,
+                                 void *out, void *ws, size_t ws_bytes, void *stream_)
+{
+    SQ_TRY(check_common(h, n, hgt, wid, out_dtype));
+    SQ_REQUIRE(labels && out && ws, SQ_EINVAL, "weightmap_unet: null pointer");
+    const size_t px = (size_t)n * hgt * wid;
+    SqArena a(ws, ws_bytes);
+    int *la = a.take<int>(px), *lb = a.take<int>(px);
+    unsigned short *da = a.take<unsigned short>(px), *db = a.take<unsigned short>(px);
+    SQ_REQUIRE(a.ok(), SQ_ENOMEM, "weightmap_unet: workspace %zu < %zu bytes", ws_bytes, a.off);
+    cudaStream_t st = (cudaStream_t)stream_;
+    const double denom = 2.0 * sigma * sigma + 1e-99;
+    const double wc0 = wc ? wc[0] : 1.0, wc1 = wc ? wc[1] : 2.0;
+    const int maxdim = hgt > wid ? hgt : wid;
+    // d1 + d2 >= d2 >= dy: once dy passes the cut-off the gap term cannot matter
+    const int rmax = cutoff_radius(w0, denom, std::fabs(wc0), out_dtype, maxdim);
+
+    inst_rows<<<dim3(hgt, n), ROW_THREADS, 0, st>>>(labels, la, lb, da, db, hgt, wid);
+    const dim3 grid(sq_div_up(wid, 32), sq_div_up(hgt, 8), n), blk(32, 8);
+    if (out_dtype == SQ_F32)
+        inst_cols_weight<float><<<grid, blk, 0, st>>>(labels, la, lb, da, db, (float *)out, hgt,
+                                                     wid, rmax, w0, denom, wc0, wc1);
+    else
+        inst_cols_weight<double><<<grid, blk, 0, st>>>(labels, la, lb, da, db, (double *)out, hgt,
+                                                      wid, rmax, w0, denom, wc0, wc1);
+    SQ_CHECK_LAUNCH();
+    return SQ_OK;
+}
+
+extern "C" int sq_weightmap_edt_host(sq_handle_t h, const uint8_t *mask_host, int n, int hgt,
+                                     int wid, double w0, double sigma, int out_dtype,
+                                     void *out_host, int32_t *d2_host)
+{
+    SQ_TRY(check_common(h, n, hgt, wid, out_dtype));
+    SQ_REQUIRE(mask_host && out_host, SQ_EINVAL, "weightmap_edt_host: null pointer");
+    SQ_CUDA(cudaSetDevice(h->device));
+    const size_t px = (size_t)n * hgt * wid;
+    const size_t esz = out_dtype == SQ_F32 ? 4 : 8;
+    size_t ws_bytes = 0;
+    SQ_TRY(sq_weightmap_workspace_bytes(h, n, hgt, wid, 0, &ws_bytes));
+    SQ_TRY(sq_reserve_device(h, sq_align_up(px) + sq_align_up(px * esz) + sq_align_up(px * 4) +
+                                    ws_bytes + 1024));
+    SqArena a(h->dev_arena, h->dev_arena_bytes);
+    uint8_t *mask = a.take<uint8_t>(px);
+    char *out = a.take<char>(px * esz);
+    int32_t *d2 = d2_host ? a.take<int32_t>(px) : nullptr;
+    void *ws = a.take<char>(ws_bytes);
+    cudaStream_t st = h->stream;
+    SQ_CUDA(cudaMemcpyAsync(mask, mask_host, px, cudaMemcpyHostToDevice, st));
+    SQ_TRY(sq_weightmap_edt(h, mask, n, hgt, wid, w0, sigma, out_dtype, out, d2, ws, ws_bytes, st));
+    SQ_CUDA(cudaMemcpyAsync(out_host, out, px * esz, cudaMemcpyDeviceToHost, st));
+    if (d2_host) SQ_CUDA(cudaMemcpyAsync(d2_host, d2, px * 4, cudaMemcpyDeviceToHost, st));
+    SQ_CUDA(cudaStreamSynchronize(st));
+    return SQ_OK;
+}
+
+extern "C" int sq_weightmap_unet_host(sq_handle_t h, const int32_t *labels_host, int n, int hgt,
+                                      int wid, double w0, double sigma, const double *wc,
+                                      int out_dtype, void *out_host)
+{
+    SQ_TRY(check_common(h, n, hgt, wid, out_dtype));
+    SQ_REQUIRE(labels_host && out_host, SQ_EINVAL, "weightmap_unet_host: null pointer");
+    SQ_CUDA(cudaSetDevice(h->device));
+    const size_t px = (size_t)n * hgt * wid;
+    const size_t esz = out_dtype == SQ_F32 ? 4 : 8;
+    size_t ws_bytes = 0;
+    SQ_TRY(sq_weightmap_workspace_bytes(h, n, hgt, wid, 1, &ws_bytes));
+    SQ_TRY(sq_reserve_device(h, sq_align_up(px * 4) + sq_align_up(px * esz) + ws_bytes + 1024));
+    SqArena a(h->dev_arena, h->dev_arena_bytes);
+    int32_t *labels = a.take<int32_t>(px);
+    char *out = a.take<char>(px * esz);
+    void *ws = a.take<char>(ws_bytes);
+    cudaStream_t st = h->stream;
+    SQ_CUDA(cudaMemcpyAsync(labels, labels_host, px * 4, cudaMemcpyHostToDevice, st));
+    SQ_TRY(sq_weightmap_unet(h, labels, n, hgt, wid, w0, sigma, wc, out_dtype, out, ws, ws_bytes, st));
+    SQ_CUDA(cudaMemcpyAsync(out_host, out, px * esz, cudaMemcpyDeviceToHost, st));
+    SQ_CUDA(cudaStreamSynchronize(st));
+    return SQ_OK;
+}

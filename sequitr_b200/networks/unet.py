@@ -1,0 +1,442 @@
+"""Drop-in for the reference ``sequitr/networks/unet.py`` (``UNet`` base class,
+:53-342) plus the concrete ``UNet2D`` / ``UNet3D`` the reference names (:56) but does
+not ship.  TensorFlow is replaced by a CUDA plan behind the C ABI
+(``sq_unet_create / load_weights / finalize / forward``).
+
+Same constructor (``params`` dict keys ``name, filters, dropout, num_inputs,
+num_outputs, shape, bridge, kernel`` with the reference defaults, :132-139), same
+topology walk (``build`` :224-262, ``conv_block`` :265-277, ``down_layer`` :282-296,
+``up_layer`` :299-322), same subclass hooks (``conv_layer``, ``conv_layer_1x1``,
+``conv_transpose_layer``, ``max_pool_layer``, ``reshape_input``), same errors
+(``ValueError('Bridge type not recognized')`` :186-187, ``NotImplementedError`` from
+the abstract primitives :326-342).  Where TF builds a symbolic graph and runs it
+in a session, ``build(features)`` here traces the same hooks symbolically (to check
+the topology the plan implements) and then executes the plan, returning the logits.
+
+Layer definitions (the reference leaves them abstract; see include/sequitr_b200.h):
+3x3 SAME conv + bias (+ folded-BN affine) + ReLU; 2x2 max-pool; 2x2 stride-2
+transposed conv + bias; 1x1 conv head.  Extra ``params`` key ``compute``:
+``'bf16'`` (tcgen05 tensor cores, default) or ``'fp32'`` (bit-exact verification mode).
+"""
+import contextlib
+import ctypes
+import logging
+
+import numpy as np
+
+from .. import _lib, ops, synth
+
+DEFAULT_FILTERS = (16, 32, 64, 128, 256)
+DEFAULT_DROPOUT = 0.4
+BRIDGE_TYPES = ('eltwise_add', 'eltwise_mul', 'eltwise_sub', 'concat', None)
+
+logger = logging.getLogger('worker_process')
+
+
+class ModeKeys(object):
+    """tf.estimator.ModeKeys values (reference networks/unet.py:172)."""
+    TRAIN = 'train'
+    EVAL = 'eval'
+    PREDICT = 'infer'
+
+
+class _Sym(object):
+    """Symbolic channels-last tensor used while tracing the topology."""
+
+    def __init__(self, shape, op=None, scope=None, inputs=()):
+        self.shape = tuple(shape)
+        self.op, self.scope, self.inputs = op, scope, inputs
+
+    @property
+    def channels(self):
+        return self.shape[-1]
+
+
+class UNet(object):
+    """ UNet
+
+    ** This is the Base Class, use the sublasses UNet2D or UNet3D **
+    (reference networks/unet.py:53-124 for the full description.)
+    """
+
+    def __init__(self, params, mode=ModeKeys.PREDICT):
+        self._mode = mode
+        self.name = params.get('name', 'UNet2d_test')
+        self.filters = tuple(params.get('filters', DEFAULT_FILTERS))
+        self.dropout = params.get('dropout', DEFAULT_DROPOUT)
+        self.n_inputs = params.get('num_inputs', 1)
+        self.n_outputs = params.get('num_outputs', 2)
+        self.shape = tuple(params.get('shape', (1024, 1024)))
+        self.bridge_type = params.get('bridge', 'eltwise_mul')
+        self.kernel = tuple(params.get('kernel', (3, 3)))
+        self.compute = params.get('compute', 'bf16')
+        if self.compute not in ('bf16', 'fp32'):
+            raise ValueError("compute must be 'bf16' or 'fp32'")
+        self._activation = 'relu'
+        self._initializer = 'variance_scaling'
+        self._net = None
+        self._scopes = []
+        self._trace = []
+        self._weights = None
+        self._plan = None
+        self._ws = ops.Workspace()
+
+    # ------------------------------------------------------------ properties
+    @property
+    def width(self):
+        """ width of the image volume """
+        return self.shape[0]
+
+    @property
+    def height(self):
+        """ height of the image volume """
+        return self.shape[1]
+
+    @property
+    def slices(self):
+        """ depth (number of slices) of the image volume """
+        if self.ndim < 3:
+            return 0
+        return self.shape[2]
+
+    @property
+    def ndim(self):
+        """ number of dimensions of image volume """
+        return len(self.shape)
+
+    @property
+    def training(self):
+        """ training mode flag """
+        return self._mode == ModeKeys.TRAIN
+
+    @property
+    def btype(self):
+        """ DEPRECATED: bridge type  """
+        raise DeprecationWarning("Use @bridge_type")
+
+    @property
+    def bridge_type(self):
+        return self._bridge_type
+
+    @bridge_type.setter
+    def bridge_type(self, bridge):
+        """ Set the bridge type """
+        if bridge not in BRIDGE_TYPES:
+            raise ValueError('Bridge type not recognized')
+        if bridge == 'concat':
+            self.bridge = lambda x, y: _Sym(x.shape[:-1] + (x.channels + y.channels,), 'concat',
+                                            self._scope(), (x, y))
+        elif bridge is None:
+            logger.warning('Bridge function in UNet not recognized')
+            self.bridge = lambda x, y: x
+        else:
+            self.bridge = lambda x, y: _Sym(x.shape, bridge, self._scope(), (x, y))
+        self._bridge_type = bridge
+        self._drop_plan()
+
+    # ------------------------------------------------------------ graph walk
+    @contextlib.contextmanager
+    def variable_scope(self, name):
+        self._scopes.append(name)
+        try:
+            yield
+        finally:
+            self._scopes.pop()
+
+    def _scope(self):
+        return '/'.join(self._scopes)
+
+    def reshape_input(self, features):
+        """ Reshape the input layer from the dataset features:
+        (batch, depth (aka slices), height, width, channels) """
+        full_shape = [-1, self.slices, self.width, self.height, self.n_inputs]
+        input_shape = [d for d in full_shape if d != 0]
+        return features.reshape(input_shape)
+
+    def logits(self):
+        """ return the un-normalized logits (i.e. last) layer of the network """
+        return self._net[-1]
+
+    def build(self, features):
+        """ build
+
+        Build the network using the given parameters and the features and run it.
+        Returns the final output layer (logits, channels-last, float32); a numpy
+        array for numpy features, a cuda tensor for cuda-tensor features.
+        """
+        logger.info('Building UNet ({0:s})...'.format(self.__class__.__name__))
+        self._trace = []
+        with self.variable_scope('UNet'):
+            input_layer = self.reshape_input(features)
+            x = _Sym(tuple(input_layer.shape), 'input', self._scope())
+
+            # BUILD THE NET!
+            self._net = [self.down_layer(x, self.filters[0], name=0)]
+
+            # do the down layers
+            for i, f in enumerate(self.filters[1:]):
+                prev_layer = self.max_pool_layer(self._net[-1])
+                self._net.append(self.down_layer(prev_layer, f, name=i + 1))
+
+            # now add the up layers
+            for i, f in reversed(list(enumerate(self.filters[:-1]))):
+                prev_layer = self._net[-1]  # layer below
+                bridge = self._net[i]       # bridge information
+                self._net.append(self.up_layer(prev_layer, f, bridge, name=i))
+
+            # make an output layer with a 1x1 convolution
+            with self.variable_scope('to_image'):
+                logits_sym = self.conv_layer_1x1(self._net[-1], self.n_outputs)
+
+        logger.info('Output layer -> shape {0:s}'.format(str(logits_sym.shape)))
+        self._check_trace()
+        logits = self._execute(input_layer, want=('logits',))['logits']
+        # append this layer for completeness
+        self._net.append(logits)
+        logger.info('...Done')
+        return logits
+
+    def conv_block(self, x, filters):
+        """ convolutional block """
+        with self.variable_scope('conv1'):
+            conv1 = self.conv_layer(x, filters)
+        with self.variable_scope('conv2'):
+            conv2 = self.conv_layer(conv1, filters)
+        # Dropout (tf.layers.dropout, networks/unet.py:274-276) is the identity unless training
+        if self.training:
+            raise NotImplementedError('the CUDA plan implements inference only (dropout off)')
+        return conv2
+
+    def down_layer(self, x, filters, name=None):
+        """ down_layer: 2x [3x3 convolution, ReLu]; tensor shape NHWC """
+        logger.info('Down layer -> shape {0:s}'.format(str(x.shape)))
+        with self.variable_scope('down{0:d}'.format(name)):
+            out = self.conv_block(x, filters)
+        return out
+
+    def up_layer(self, x, filters, bridge, name=None):
+        """ up_layer: transpose convolution, bridge, conv block """
+        logger.info('Up layer -> shape {0:s} (bridge: {1:s})'.format(str(x.shape),
+                                                                      str(self.bridge_type)))
+        with self.variable_scope('up{0:d}'.format(name)):
+            # scale up the image
+            with self.variable_scope('upscale'):
+                upscale = self.conv_transpose_layer(x, filters)
+            # now we need to incorporate the filters using the bridge
+            with self.variable_scope('bridge'):
+                bridge = self.bridge(upscale, bridge)
+            out = self.conv_block(bridge, filters)
+        return out
+
+    def conv_layer(self, x, filters):
+        """ Convolution layer, conv-relu with padding """
+        raise NotImplementedError
+
+    def conv_layer_1x1(self, x, filters):
+        """ Return a 1x1 convolution layer """
+        raise NotImplementedError
+
+    def conv_transpose_layer(self, x, filters):
+        """ Transpose convolution (aka deconvolution) layer """
+        raise NotImplementedError
+
+    def max_pool_layer(self, x):
+        """ Max pool operation """
+        raise NotImplementedError
+
+    # the reference declares it under this name (:340) but calls max_pool_layer (:242)
+    pool_layer = max_pool_layer
+
+    # ------------------------------------------------------------ weights
+    def load_weights(self, weights):
+        """weights: dict TF-scope name -> float32 ndarray (see synth.unet_weights)."""
+        self._weights = {k: np.ascontiguousarray(v, dtype=np.float32) for k, v in weights.items()}
+        self._drop_plan()
+
+    def _drop_plan(self):
+        plan = getattr(self, '_plan', None)
+        if plan is not None:
+            _lib.load().sq_unet_destroy(plan)
+        self._plan = None
+
+    def __del__(self):
+        try:
+            self._drop_plan()
+        except Exception:
+            pass
+
+    def _ensure_plan(self):
+        if self._plan is not None:
+            return self._plan
+        if any(k != 3 for k in self.kernel):
+            raise NotImplementedError('only 3x3(x3) kernels are implemented')
+        if self._weights is None:
+            # the reference initialises variables with variance_scaling (networks/unet.py:143)
+            self._weights = synth.unet_weights(self.filters, self.n_inputs, self.n_outputs,
+                                               ndim=self.ndim, bridge=self.bridge_type)
+        lib = _lib.load()
+        filt = (ctypes.c_int * len(self.filters))(*self.filters)
+        plan = ctypes.c_void_p()
+        mode = _lib.MODE_BF16_TC if self.compute == 'bf16' else _lib.MODE_FP32_EXACT
+        _lib.check(lib.sq_unet_create(_lib.handle(), self.ndim, self.n_inputs, self.n_outputs, filt,
+                                      len(self.filters), _lib.BRIDGE_CODES[self.bridge_type], mode,
+                                      ctypes.byref(plan)))
+        try:
+            for name, arr in self._weights.items():
+                shape = (ctypes.c_int64 * arr.ndim)(*arr.shape)
+                _lib.check(lib.sq_unet_load_weights(plan, name.encode(), arr.ctypes.data, shape,
+                                                    arr.ndim))
+            _lib.check(lib.sq_unet_finalize(plan))
+        except Exception:
+            lib.sq_unet_destroy(plan)
+            raise
+        self._plan = plan
+        return plan
+
+    def _expected_trace(self):
+        ops_ = []
+        cin = self.n_inputs
+        for i, f in enumerate(self.filters):
+            if i > 0:
+                ops_.append(('pool', 'UNet', cin, cin))
+            ops_.append(('conv', 'UNet/down%d/conv1' % i, cin, f))
+            ops_.append(('conv', 'UNet/down%d/conv2' % i, f, f))
+            cin = f
+        for i in reversed(range(len(self.filters) - 1)):
+            f = self.filters[i]
+            ops_.append(('upconv', 'UNet/up%d/upscale' % i, cin, f))
+            merged = 2 * f if self.bridge_type == 'concat' else f
+            ops_.append(('conv', 'UNet/up%d/conv1' % i, merged, f))
+            ops_.append(('conv', 'UNet/up%d/conv2' % i, f, f))
+            cin = f
+        ops_.append(('conv1x1', 'UNet/to_image', cin, self.n_outputs))
+        return ops_
+
+    def _check_trace(self):
+        if self._trace != self._expected_trace():
+            raise NotImplementedError('the traced topology differs from the one the CUDA plan '
+                                      'implements (reference networks/unet.py:224-262)')
+
+    # ------------------------------------------------------------ execution
+    def _execute(self, input_layer, want=('logits', 'probs', 'mask')):
+        import torch
+        plan = self._ensure_plan()
+        lib = _lib.load()
+        is_numpy = isinstance(input_layer, np.ndarray)
+        if is_numpy:
+            x = torch.from_numpy(np.ascontiguousarray(input_layer, dtype=np.float32)).cuda()
+        else:
+            x = input_layer.contiguous().float()
+            if not x.is_cuda:
+                raise ValueError('features must be a numpy array or a cuda tensor')
+        if x.dim() != self.ndim + 2 or x.shape[-1] != self.n_inputs:
+            raise ValueError('features have shape %s, expected (N,%s%d)' %
+                             (tuple(x.shape), 'D,H,W,' if self.ndim == 3 else 'H,W,', self.n_inputs))
+        n = x.shape[0]
+        d, h, w = (1,) + tuple(x.shape[1:3]) if self.ndim == 2 else tuple(x.shape[1:4])
+        need = ctypes.c_size_t()
+        _lib.check(lib.sq_unet_workspace_bytes(plan, n, d, h, w, ctypes.byref(need)))
+        ws = self._ws.get(need.value)
+        sp = tuple(x.shape[:-1])
+        out = {}
+        if 'logits' in want:
+            out['logits'] = torch.empty(sp + (self.n_outputs,), dtype=torch.float32, device=x.device)
+        if 'probs' in want:
+            out['probs'] = torch.empty(sp + (self.n_outputs,), dtype=torch.float32, device=x.device)
+        if 'mask' in want:
+            out['mask'] = torch.empty(sp, dtype=torch.uint8, device=x.device)
+        _lib.check(lib.sq_unet_forward(plan, x.data_ptr(), n, d, h, w, _lib.ptr(out.get('probs')),
+                                       _lib.ptr(out.get('mask')), _lib.ptr(out.get('logits')),
+                                       ws.data_ptr(), ws.numel(), _lib.stream_ptr()))
+        if is_numpy:
+            out = {k: v.cpu().numpy() for k, v in out.items()}
+        return out
+
+    def _as_input(self, features):
+        """Channels-last batches pass through; anything else goes through reshape_input."""
+        if features.ndim == self.ndim + 2 and features.shape[-1] == self.n_inputs:
+            return features
+        return self.reshape_input(features)
+
+    def predict(self, features, want=('logits', 'probs', 'mask')):
+        """Logits + softmax probabilities + argmax mask (uint8, first max wins) -- the
+        head the consumer ``utils.CentroidWriter`` implies (reference utils.py:492)."""
+        return self._execute(self._as_input(features), want)
+
+    def segment(self, features):
+        """uint8 class mask (N,[D,]H,W)."""
+        return self.predict(features, want=('mask',))['mask']
+
+    def segment_and_localise(self, frames, frame0=0, max_rows=4096, return_mask=False):
+        """The whole hot path on HOST frames (2-D): H2D -> UNet -> argmax -> label-and-
+        localise -> D2H.  frames float32 (N,H,W,Cin).  Returns the list of per-frame
+        (n_i,5) float32 centroid tables (rows as utils.CentroidWriter writes them)."""
+        plan = self._ensure_plan()
+        lib = _lib.load()
+        frames = np.ascontiguousarray(self._as_input(np.asarray(frames)), dtype=np.float32)
+        n, h, w = frames.shape[:3]
+        mask = np.empty((n, h, w), dtype=np.uint8) if return_mask else None
+        while True:
+            table = np.empty((n, max_rows, 5), dtype=np.float32)
+            counts = np.empty((n,), dtype=np.int32)
+            st = lib.sq_segment_localise_host(plan, frames.ctypes.data, n, h, w, frame0,
+                                              table.ctypes.data, counts.ctypes.data, max_rows,
+                                              _lib.ptr(mask))
+            if st == _lib.SQ_EOVERFLOW:
+                max_rows = int(counts.max())
+                continue
+            _lib.check(st)
+            break
+        tables = [table[i, :counts[i]].copy() for i in range(n)]
+        return (tables, mask) if return_mask else tables
+
+
+class _ConcreteUNet(UNet):
+    """Shared primitive definitions of UNet2D / UNet3D (symbolic tracing side)."""
+
+    def _record(self, kind, cin, cout):
+        self._trace.append((kind, self._scope() if kind != 'pool' else 'UNet', cin, cout))
+
+    def conv_layer(self, x, filters):
+        """ Convolution layer, conv-relu with SAME padding """
+        self._record('conv', x.channels, filters)
+        return _Sym(x.shape[:-1] + (filters,), 'conv', self._scope(), (x,))
+
+    def conv_layer_1x1(self, x, filters):
+        """ 1x1 convolution layer (logits, no activation) """
+        self._record('conv1x1', x.channels, filters)
+        return _Sym(x.shape[:-1] + (filters,), 'conv1x1', self._scope(), (x,))
+
+    def conv_transpose_layer(self, x, filters):
+        """ 2x2 stride-2 transpose convolution: doubles the spatial size """
+        self._record('upconv', x.channels, filters)
+        sp = tuple(2 * s if s and s > 0 else s for s in x.shape[1:-1])
+        return _Sym((x.shape[0],) + sp + (filters,), 'upconv', self._scope(), (x,))
+
+    def max_pool_layer(self, x):
+        """ 2x2 max pool, stride 2 """
+        self._record('pool', x.channels, x.channels)
+        sp = tuple(s // 2 if s and s > 0 else s for s in x.shape[1:-1])
+        return _Sym((x.shape[0],) + sp + (x.channels,), 'pool', self._scope(), (x,))
+
+    pool_layer = max_pool_layer
+
+
+class UNet2D(_ConcreteUNet):
+    """ 2-D UNet: features (N,H,W,Cin) NHWC (or anything reshape_input accepts). """
+
+    def __init__(self, params, mode=ModeKeys.PREDICT):
+        _ConcreteUNet.__init__(self, params, mode)
+        if self.ndim != 2:
+            raise ValueError('UNet2D needs a 2-D shape')
+
+
+class UNet3D(_ConcreteUNet):
+    """ 3-D UNet: params['shape'] = (width, height, slices); features (N,D,H,W,Cin). """
+
+    def __init__(self, params, mode=ModeKeys.PREDICT):
+        p = dict(params)
+        p.setdefault('kernel', (3, 3, 3))
+        _ConcreteUNet.__init__(self, p, mode)
+        if self.ndim != 3:
+            raise ValueError('UNet3D needs a 3-D shape (width, height, slices)')

@@ -1,0 +1,174 @@
+"""Device-level wrappers over the C ABI (torch tensors own the memory).
+
+These are the calls ``bench.py`` times with inputs resident in HBM; the
+reference-facing classes in ``utils`` / ``pipeline`` / ``networks.unet`` use the
+``*_host`` entry points (host buffers in, host buffers out).
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+
+
+def _torch():
+    import torch
+    return torch
+
+
+class Workspace(object):
+    """Grow-only device scratch buffer (allocated through torch)."""
+
+    def __init__(self, device=None):
+        self.buf = None
+        self.device = device
+
+    def get(self, nbytes):
+        torch = _torch()
+        if self.buf is None or self.buf.numel() < nbytes:
+            self.buf = None
+            self.buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8,
+                                   device=self.device or 'cuda')
+        return self.buf
+
+
+_default_ws = {}
+
+
+def _ws(key):
+    if key not in _default_ws:
+        _default_ws[key] = Workspace()
+    return _default_ws[key]
+
+
+def label_centroids(mask, max_rows=4096, frame0=0, want_labels=False, workspace=None):
+    """mask: uint8 cuda tensor (N,H,W) or (N,D,H,W) (already in utils.py:519's swapped
+    order for volumes).  Returns (table (N,max_rows,5) f32, counts (N) i32[, labels i32])."""
+    torch = _torch()
+    lib = _lib.load()
+    assert mask.is_cuda and mask.dtype == torch.uint8 and mask.is_contiguous()
+    if mask.dim() == 3:
+        n, (d, h, w) = mask.shape[0], (1,) + tuple(mask.shape[1:])
+    elif mask.dim() == 4:
+        n, d, h, w = mask.shape
+    else:
+        raise ValueError("Incorrect image data shape.")
+    hd = _lib.handle(mask.device.index)
+    need = ctypes.c_size_t()
+    _lib.check(lib.sq_label_workspace_bytes(hd, n, d, h, w, max_rows, ctypes.byref(need)))
+    ws = (workspace or _ws(('label', mask.device.index))).get(need.value)
+    table = torch.empty((n, max_rows, 5), dtype=torch.float32, device=mask.device)
+    counts = torch.empty((n,), dtype=torch.int32, device=mask.device)
+    labels = torch.empty(mask.shape, dtype=torch.int32, device=mask.device) if want_labels else None
+    _lib.check(lib.sq_label_centroids(hd, mask.data_ptr(), n, d, h, w, frame0, _lib.ptr(labels),
+                                      table.data_ptr(), counts.data_ptr(), max_rows,
+                                      ws.data_ptr(), ws.numel(), _lib.stream_ptr()))
+    return (table, counts, labels) if want_labels else (table, counts)
+
+
+def weightmap_edt(mask, w0=10., sigma=5., out_dtype='float32', want_d2=False, workspace=None):
+    """W1 on a uint8 cuda tensor (N,H,W) -> weights (N,H,W) [, exact squared distances int32]."""
+    torch = _torch()
+    lib = _lib.load()
+    assert mask.is_cuda and mask.dtype == torch.uint8 and mask.is_contiguous() and mask.dim() == 3
+    n, h, w = mask.shape
+    hd = _lib.handle(mask.device.index)
+    need = ctypes.c_size_t()
+    _lib.check(lib.sq_weightmap_workspace_bytes(hd, n, h, w, 0, ctypes.byref(need)))
+    ws = (workspace or _ws(('wm', mask.device.index))).get(need.value)
+    tdt = torch.float32 if out_dtype == 'float32' else torch.float64
+    out = torch.empty((n, h, w), dtype=tdt, device=mask.device)
+    d2 = torch.empty((n, h, w), dtype=torch.int32, device=mask.device) if want_d2 else None
+    _lib.check(lib.sq_weightmap_edt(hd, mask.data_ptr(), n, h, w, float(w0), float(sigma),
+                                    _lib.F32 if out_dtype == 'float32' else _lib.F64,
+                                    out.data_ptr(), _lib.ptr(d2), ws.data_ptr(), ws.numel(),
+                                    _lib.stream_ptr()))
+    return (out, d2) if want_d2 else out
+
+
+def weightmap_unet(labels, w0=10., sigma=5., wc=None, out_dtype='float32', workspace=None):
+    """W3 on an int32 cuda tensor of instance labels (N,H,W) -> weights (N,H,W)."""
+    torch = _torch()
+    lib = _lib.load()
+    assert labels.is_cuda and labels.dtype == torch.int32 and labels.is_contiguous() and labels.dim() == 3
+    n, h, w = labels.shape
+    hd = _lib.handle(labels.device.index)
+    need = ctypes.c_size_t()
+    _lib.check(lib.sq_weightmap_workspace_bytes(hd, n, h, w, 1, ctypes.byref(need)))
+    ws = (workspace or _ws(('wm', labels.device.index))).get(need.value)
+    tdt = torch.float32 if out_dtype == 'float32' else torch.float64
+    out = torch.empty((n, h, w), dtype=tdt, device=labels.device)
+    wc_arr = None if wc is None else (ctypes.c_double * 2)(float(wc[0]), float(wc[1]))
+    _lib.check(lib.sq_weightmap_unet(hd, labels.data_ptr(), n, h, w, float(w0), float(sigma),
+                                     None if wc_arr is None else ctypes.cast(wc_arr, ctypes.c_void_p),
+                                     _lib.F32 if out_dtype == 'float32' else _lib.F64,
+                                     out.data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream_ptr()))
+    return out
+
+
+# ------------------------------------------------------------- host-buffer calls
+
+def label_centroids_host(mask, max_rows=4096, frame0=0, want_labels=False, device=None):
+    """mask: uint8 ndarray (N,H,W) / (N,D,H,W).  Returns list of per-frame (n_i,5) float32
+    tables [, labels int32 ndarray].  Retries with a larger table on overflow."""
+    lib = _lib.load()
+    mask = np.ascontiguousarray(mask, dtype=np.uint8)
+    if mask.ndim == 3:
+        n, (d, h, w) = mask.shape[0], (1,) + mask.shape[1:]
+    elif mask.ndim == 4:
+        n, d, h, w = mask.shape
+    else:
+        raise ValueError("Incorrect image data shape.")
+    hd = _lib.handle(device)
+    labels = np.empty(mask.shape, dtype=np.int32) if want_labels else None
+    while True:
+        table = np.empty((n, max_rows, 5), dtype=np.float32)
+        counts = np.empty((n,), dtype=np.int32)
+        st = lib.sq_label_centroids_host(hd, mask.ctypes.data, n, d, h, w, frame0,
+                                         _lib.ptr(labels), table.ctypes.data, counts.ctypes.data,
+                                         max_rows)
+        if st == _lib.SQ_EOVERFLOW:
+            max_rows = int(counts.max())
+            continue
+        _lib.check(st)
+        break
+    tables = [table[i, :counts[i]].copy() for i in range(n)]
+    return (tables, labels) if want_labels else tables
+
+
+def weightmap_edt_host(mask, w0=10., sigma=5., out_dtype='float64', want_d2=False, device=None):
+    lib = _lib.load()
+    mask = np.ascontiguousarray(mask)
+    if mask.dtype != np.uint8:
+        mask = (mask != 0).astype(np.uint8)
+    squeeze = mask.ndim == 2
+    if squeeze:
+        mask = mask[None]
+    n, h, w = mask.shape
+    out = np.empty((n, h, w), dtype=np.float32 if out_dtype == 'float32' else np.float64)
+    d2 = np.empty((n, h, w), dtype=np.int32) if want_d2 else None
+    _lib.check(lib.sq_weightmap_edt_host(_lib.handle(device), mask.ctypes.data, n, h, w,
+                                         float(w0), float(sigma),
+                                         _lib.F32 if out_dtype == 'float32' else _lib.F64,
+                                         out.ctypes.data, _lib.ptr(d2)))
+    if squeeze:
+        out = out[0]
+        d2 = d2[0] if want_d2 else None
+    return (out, d2) if want_d2 else out
+
+
+def weightmap_unet_host(labels, w0=10., sigma=5., wc=None, out_dtype='float64', device=None):
+    lib = _lib.load()
+    labels = np.ascontiguousarray(labels, dtype=np.int32)
+    squeeze = labels.ndim == 2
+    if squeeze:
+        labels = labels[None]
+    n, h, w = labels.shape
+    out = np.empty((n, h, w), dtype=np.float32 if out_dtype == 'float32' else np.float64)
+    wc_arr = None if wc is None else (ctypes.c_double * 2)(float(wc[0]), float(wc[1]))
+    _lib.check(lib.sq_weightmap_unet_host(_lib.handle(device), labels.ctypes.data, n, h, w,
+                                          float(w0), float(sigma),
+                                          None if wc_arr is None else ctypes.cast(wc_arr, ctypes.c_void_p),
+                                          _lib.F32 if out_dtype == 'float32' else _lib.F64,
+                                          out.ctypes.data))
+    return out[0] if squeeze else out

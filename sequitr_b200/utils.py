@@ -1,0 +1,141 @@
+"""Drop-in for the hot-path parts of the reference ``sequitr/utils.py``:
+``CentroidWriter`` (utils.py:479-578), ``HDF5FileHandler`` (:431-474) and the
+size-legality helpers (:230-240).  The per-frame / per-class SciPy loop is
+replaced by one call into the CUDA library (``sq_label_centroids_host``).
+"""
+import logging
+import os
+
+import numpy as np
+
+from . import ops
+
+logger = logging.getLogger('worker_process')
+
+try:                                    # h5py is optional in this image
+    import h5py
+except ImportError:                     # pragma: no cover - depends on the image
+    h5py = None
+
+
+def power_of_two(number):
+    """ Return a bool testing whether number is power of two or not (utils.py:230-232) """
+    return int(bin(number & (number - 1)), 2) == 0
+
+
+def divisible_by_two_n_times(x, n):
+    """ Check whether a number is divisible by two, n times (utils.py:234-240) """
+    for i in range(n):
+        x = x / 2.0
+    return x % 1 == 0
+
+
+class _NpzGroup(object):
+    """Minimal stand-in for an h5py group when h5py is absent: datasets are kept
+    in memory under their HDF5 path and written as one ``.npz`` on close()."""
+
+    def __init__(self, store, prefix):
+        self._store, self._prefix = store, prefix
+
+    def create_group(self, name):
+        return _NpzGroup(self._store, self._prefix + name + '/')
+
+    def __getitem__(self, name):
+        return _NpzGroup(self._store, self._prefix + name + '/')
+
+    def create_dataset(self, name, data=None, dtype=None):
+        arr = np.asarray(data, dtype=dtype)
+        self._store[self._prefix + name] = arr
+        return arr
+
+
+class HDF5FileHandler(object):
+    """ Base class for handling HDF files (utils.py:431-474).
+
+    With h5py installed this writes real HDF5; otherwise the same
+    ``frames/frame_<i>/coords`` datasets go to ``<name>.hdf5.npz``.
+    """
+
+    def __init__(self, filename=None, read_only=False):
+        if not isinstance(filename, str):
+            raise TypeError('Filename must be specified as a string')
+        pth, f = os.path.split(filename)
+        if not os.path.exists(pth):
+            raise IOError('Destination path {0:s} doesn\'t exist'.format(pth))
+        f_noext, f_ext = os.path.splitext(f)
+        if f_ext != '.hdf5':
+            # (the reference drops the directory here, utils.py:446-448; we keep it)
+            filename = os.path.join(pth, f_noext + '.hdf5')
+        self.filename = filename
+        self.read_only = read_only
+        logger.info('Opening HDF file: {0:s}'.format(filename))
+        if h5py is not None:
+            self._hdf = h5py.File(filename, 'r+' if read_only else 'w')
+            self._store = None
+        else:
+            self._store = {}
+            self._hdf = _NpzGroup(self._store, '')
+
+    @property
+    def hdf(self):
+        return self._hdf
+
+    def __del__(self):
+        if getattr(self, '_hdf', None) is not None:
+            self.close()
+
+    def close(self):
+        """ Manually close the HDF5 file, to prevent HDF5 corruption """
+        if self._hdf is None:
+            return
+        logger.info('Closing HDF file.')
+        if self._store is None:
+            self._hdf.close()
+        else:
+            np.savez(self.filename + '.npz', **self._store)
+        self._hdf = None
+
+
+class CentroidWriter(HDF5FileHandler):
+    """ CentroidWriter (utils.py:479-578)
+
+    Using the segmentation output, find the centre of mass of each object and
+    write these to the HDF file, grouped by the frame in which they were found.
+    Works with both images (N,H,W) and volumes (N,Z,X,Y).
+    """
+
+    def __init__(self, filename=None, max_rows=4096):
+        HDF5FileHandler.__init__(self, filename)
+        self._hdf.create_group('frames')
+        self.max_rows = max_rows
+
+    @staticmethod
+    def centroids(segmented, max_rows=4096, frame0=0):
+        """The arithmetic of ``write`` without the file: list of per-frame (n_i,5)
+        float32 tables with rows ``[frame, x, y, z, class]`` (utils.py:559-564)."""
+        segmented = np.asarray(segmented)
+        if segmented.ndim == 4:
+            # volumetric: default input is N,Z,X,Y (utils.py:518-519)
+            segmented = np.swapaxes(segmented, 1, -1)
+        elif segmented.ndim != 3:
+            logger.error("Incorrect image data shape.")
+            raise ValueError("Incorrect image data shape.")
+        if segmented.dtype != np.uint8:
+            if segmented.size and (segmented.min() < 0 or segmented.max() > 255):
+                raise ValueError("segmentation classes must fit in uint8")
+            segmented = segmented.astype(np.uint8)
+        return ops.label_centroids_host(np.ascontiguousarray(segmented), max_rows=max_rows,
+                                        frame0=frame0)
+
+    def write(self, segmented):
+        """ Take a (large!) numpy array and output dataset """
+        im_type = "Volumetric" if np.ndim(segmented) == 4 else "Image"
+        n = np.shape(segmented)[0]
+        chunk = 64
+        for start in range(0, n, chunk):
+            if start % 100 < chunk:
+                logger.info('Written out {0:d} of {1:d} frames ({2:s})...'.format(start, n, im_type))
+            tables = self.centroids(segmented[start:start + chunk], self.max_rows, frame0=start)
+            for j, this_frame in enumerate(tables):
+                grp = self._hdf['frames'].create_group('frame_' + str(start + j))
+                grp.create_dataset('coords', data=this_frame, dtype='float32')

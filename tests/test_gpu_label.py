@@ -1,0 +1,122 @@
+"""Parity of the CUDA label-and-localise path with the SciPy oracle (bit-exact)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import centroid_oracle as co
+from sequitr_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(ops, stack, swapped_for_gpu=None, max_rows=4096):
+    want = co.centroid_tables(stack)
+    gpu_in = stack if swapped_for_gpu is None else swapped_for_gpu
+    got = ops.label_centroids_host(gpu_in, max_rows=max_rows)
+    assert len(got) == len(want)
+    for i, (a, b) in enumerate(zip(got, want)):
+        assert a.dtype == np.float32 and a.shape == b.shape, (i, a.shape, b.shape)
+        np.testing.assert_array_equal(a, b)
+
+
+def test_golden_fixtures(sq, golden_dir):
+    from sequitr_b200 import ops, utils
+    g = np.load(os.path.join(golden_dir, 'centroid_scipy.npz'))
+    for name in ('discs2c', 'noise', 'empty', 'ushape', 'vol'):
+        st = g['in_' + name]
+        tabs = utils.CentroidWriter.centroids(st)        # the reference-facing entry point
+        counts = np.array([len(t) for t in tabs], np.int32)
+        np.testing.assert_array_equal(counts, g['counts_' + name])
+        flat = np.concatenate(tabs, 0) if counts.sum() else np.zeros((0, 5), np.float32)
+        np.testing.assert_array_equal(flat, g['table_' + name])
+
+
+@pytest.mark.parametrize('shape,density,classes', [((3, 37, 53), 0.5, 1), ((2, 64, 96), 0.6, 3),
+                                                   ((1, 130, 70), 0.35, 5), ((2, 33, 31), 0.9, 2)])
+def test_random_masks(sq, shape, density, classes):
+    from sequitr_b200 import ops
+    rng = np.random.default_rng(sum(shape))
+    m = (rng.random(shape) < density).astype(np.uint8) * rng.integers(1, classes + 1, shape).astype(np.uint8)
+    _check(ops, m, max_rows=8192)
+
+
+def test_label_matrix_matches_scipy_numbering(sq):
+    from sequitr_b200 import ops
+    m = synth.class_mask(200, 264, 40, n_classes=3, seed=8, rmin=4, rmax=10)[None]
+    m[0, 50, :] = 2                                   # a long thin bar crossing everything
+    tabs, labels = ops.label_centroids_host(m, want_labels=True)
+    np.testing.assert_array_equal(labels[0], co.label_matrix(m[0]))
+    np.testing.assert_array_equal(tabs[0], co.centroid_tables(m)[0])
+
+
+def test_edge_cases(sq):
+    from sequitr_b200 import ops
+    _check(ops, np.zeros((2, 16, 16), np.uint8))                       # empty frames
+    _check(ops, np.full((1, 40, 72), 7, np.uint8))                     # one frame-filling object
+    cb = (np.indices((1, 32, 32)).sum(0) % 2).astype(np.uint8)         # checkerboard: 512 singletons
+    _check(ops, cb)
+    tabs = ops.label_centroids_host(cb, max_rows=16)                   # overflow -> retried larger
+    assert len(tabs[0]) == 512
+    sp = np.zeros((1, 64, 64), np.uint8)                               # spiral / nested U shapes
+    for k in range(2, 30, 4):
+        sp[0, k, k:64 - k] = 1
+        sp[0, k:64 - k, 64 - k - 1] = 1
+        sp[0, 64 - k - 1, k:64 - k] = 1
+        sp[0, k + 4:64 - k, k] = 1
+    _check(ops, sp)
+    one = np.zeros((1, 1, 1), np.uint8)
+    one[0, 0, 0] = 255
+    _check(ops, one)
+    with pytest.raises(ValueError):
+        ops.label_centroids_host(np.zeros((4, 4), np.uint8))
+
+
+def test_volumetric_6_connectivity(sq):
+    from sequitr_b200 import ops, utils
+    rng = np.random.default_rng(5)
+    vol = (rng.random((2, 9, 20, 24)) > 0.6).astype(np.uint8) * rng.integers(1, 3, (2, 9, 20, 24)).astype(np.uint8)
+    want = co.centroid_tables(vol)                       # oracle swaps (N,Z,X,Y) -> (N,Y,X,Z)
+    got = utils.CentroidWriter.centroids(vol)
+    for a, b in zip(got, want):
+        np.testing.assert_array_equal(a, b)
+
+
+def test_full_size_frame_2048(sq):
+    from sequitr_b200 import ops
+    m = np.stack([synth.class_mask(2048, 2048, 600, n_classes=3, seed=s) for s in (1, 2)])
+    _check(ops, m)
+    # size-independent property: translating the frame translates every centroid
+    sh = np.zeros_like(m)
+    sh[:, 3:, 5:] = m[:, :-3, :-5]
+    a = ops.label_centroids_host(m[:, :-3, :-5].copy())
+    b = ops.label_centroids_host(sh)
+    for x, y in zip(a, b):
+        np.testing.assert_array_equal(x[:, 1] + 3, y[:, 1])
+        np.testing.assert_array_equal(x[:, 2] + 5, y[:, 2])
+
+
+def test_device_api_equals_host_api(sq):
+    import torch
+    from sequitr_b200 import ops
+    m = synth.class_mask(256, 320, 50, n_classes=2, seed=3, rmin=4, rmax=10)[None].repeat(3, 0)
+    m[1] = np.roll(m[1], 17, axis=1)
+    host = ops.label_centroids_host(m, frame0=10)
+    table, counts = ops.label_centroids(torch.from_numpy(m).cuda(), max_rows=256, frame0=10)
+    torch.cuda.synchronize()
+    for i in range(3):
+        np.testing.assert_array_equal(table[i, :int(counts[i])].cpu().numpy(), host[i])
+        assert host[i][0, 0] == 10 + i
+
+
+def test_centroid_writer_file(sq, tmp_path):
+    from sequitr_b200 import utils
+    m = synth.class_mask(96, 96, 8, n_classes=2, seed=1, rmin=4, rmax=8)[None].repeat(2, 0)
+    w = utils.CentroidWriter(str(tmp_path / 'cells.hdf5'))
+    w.write(m)
+    w.close()
+    want = co.centroid_tables(m)
+    if utils.h5py is None:
+        data = np.load(str(tmp_path / 'cells.hdf5.npz'))
+        for i in range(2):
+            np.testing.assert_array_equal(data['frames/frame_%d/coords' % i], want[i])

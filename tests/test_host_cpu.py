@@ -1,0 +1,175 @@
+"""Host-side logic and the C-ABI surface, runnable without a GPU."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import sequitr_b200
+from sequitr_b200 import _lib, ops, pipeline, utils, weightmap, synth
+from sequitr_b200.networks import unet as U
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    lib = _lib.load()
+    declared = _lib.declared_symbols()
+    assert len(declared) >= 22
+    for name in declared:
+        assert hasattr(lib, name), 'missing export %s' % name
+        assert name in _lib._SIGNATURES, 'no ctypes signature for %s' % name
+    assert b'sm_100a' in lib.sq_version()
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    with pytest.raises(_lib.SequitrError):
+        ops.weightmap_edt_host(np.zeros((8, 8), np.uint8))
+    with pytest.raises(_lib.SequitrError):
+        pipeline.ImageWeightMap()(np.zeros((8, 8), bool))
+    with pytest.raises(_lib.SequitrError):
+        utils.CentroidWriter.centroids(np.zeros((1, 8, 8), np.uint8))
+    h = ctypes.c_void_p()
+    st = _lib.load().sq_create(0, ctypes.byref(h))
+    assert st != 0 and len(_lib.load().sq_last_error()) > 0
+
+
+def test_product_never_imports_the_oracle():
+    root = os.path.dirname(os.path.abspath(sequitr_b200.__file__))
+    for dirpath, _, files in os.walk(root):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh', '.h')):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r'^\s*(from|import)\s+oracle', text, re.M), f
+                assert 'oracle/_build' not in text and 'libsqref' not in text, f
+
+
+def test_unet_constructor_defaults_and_errors():
+    net = U.UNet({}, U.ModeKeys.PREDICT)
+    assert net.filters == (16, 32, 64, 128, 256) and net.dropout == 0.4
+    assert net.n_inputs == 1 and net.n_outputs == 2 and net.shape == (1024, 1024)
+    assert net.bridge_type == 'eltwise_mul' and net.kernel == (3, 3)
+    assert net.width == 1024 and net.height == 1024 and net.slices == 0 and net.ndim == 2
+    assert not net.training and U.UNet({}, U.ModeKeys.TRAIN).training
+    with pytest.raises(ValueError, match='Bridge type not recognized'):
+        U.UNet({'bridge': 'bogus'})
+    with pytest.raises(DeprecationWarning):
+        net.btype
+    x = U._Sym((1, 8, 8, 1))
+    for fn, args in ((net.conv_layer, (x, 4)), (net.conv_layer_1x1, (x, 2)),
+                     (net.conv_transpose_layer, (x, 4)), (net.max_pool_layer, (x,))):
+        with pytest.raises(NotImplementedError):
+            fn(*args)
+    with pytest.raises(ValueError):
+        U.UNet2D({'shape': (8, 8, 8)})
+    with pytest.raises(ValueError):
+        U.UNet3D({'shape': (8, 8)})
+
+
+@pytest.mark.parametrize('bridge', U.BRIDGE_TYPES)
+def test_unet_topology_trace_matches_reference_walk(bridge, monkeypatch):
+    net = U.UNet2D({'filters': (4, 8, 16), 'shape': (16, 24), 'bridge': bridge, 'num_inputs': 3,
+                    'num_outputs': 3})
+    seen = {}
+
+    def fake_execute(self, input_layer, want=('logits',)):
+        seen['shape'] = tuple(input_layer.shape)
+        return {'logits': np.zeros(input_layer.shape[:-1] + (3,), np.float32)}
+    monkeypatch.setattr(U.UNet, '_execute', fake_execute)
+    feats = np.zeros((2, 16 * 24 * 3), np.float32)
+    logits = net.build(feats)
+    assert seen['shape'] == (2, 16, 24, 3) and logits.shape == (2, 16, 24, 3)
+    assert net.logits() is logits
+    scopes = [t[1] for t in net._trace if t[0] != 'pool']
+    assert scopes == synth.unet_layer_names((4, 8, 16))
+    merged = [t for t in net._trace if t[1] == 'UNet/up0/conv1'][0]
+    assert merged[2] == (8 if bridge == 'concat' else 4)
+    assert len(net._net) == 3 + 2 + 1      # down layers, up layers, logits
+
+
+def test_unet3d_reshape_and_trace(monkeypatch):
+    net = U.UNet3D({'filters': (4, 8), 'shape': (16, 12, 8), 'bridge': 'concat'})
+    assert net.slices == 8 and net.kernel == (3, 3, 3)
+    monkeypatch.setattr(U.UNet, '_execute',
+                        lambda self, x, want=('logits',): {'logits': np.zeros(x.shape[:-1] + (2,))})
+    out = net.build(np.zeros((1, 8 * 16 * 12), np.float32))
+    assert out.shape == (1, 8, 16, 12, 2)
+
+
+def test_image_pipe_contract():
+    class Double(pipeline.ImagePipe):
+        def pipe(self, image):
+            return image * 2
+    out = Double()(np.ones((4, 5)))
+    assert out.shape == (4, 5, 1) and out.dtype == np.float32
+    with pytest.raises(NotImplementedError):
+        pipeline.ImagePipe()(np.ones((2, 2)))
+    with pytest.raises(TypeError):
+        pipeline.ImagePipeline([Double(), 3])
+    p = pipeline.ImagePipeline([Double(), Double()])
+    assert len(p) == 1 and p(np.ones((2, 2))).max() == 4
+    d = Double()
+    d.update()
+    assert d.iter == 0
+    with pytest.raises(ValueError):
+        pipeline._binary_plane(np.full((4, 4, 1), 0.5, np.float32), 'x')
+
+
+def test_weightmap2_host_pipe_matches_reference_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, 'weightmap_ref.npz'))
+    got = pipeline.ImageWeightMap2(10., 5.)(g['in_discs64'])
+    np.testing.assert_allclose(got, g['w2_discs64_w0-10_s-5'], atol=1e-12)
+
+
+def test_create_weightmaps_files_and_names(tmp_path):
+    import cv2
+    lab_dir = tmp_path / 'setA' / 'label'
+    lab_dir.mkdir(parents=True)
+    mask = (synth.instance_labels(64, 64, 6, seed=1, rmin=4, rmax=8) > 0).astype(np.uint8) * 255
+    cv2.imwrite(str(lab_dir / 'pos1_GFP_0001.tif'), mask)
+    (lab_dir / 'notes.txt').write_text('x')
+    out = weightmap.create_weightmaps(str(tmp_path), ['setA'], w0=10., sigma=5., method='delaunay')
+    assert out == [str(tmp_path / 'setA' / 'weights_w0-10.00_sigma-5.00' / 'pos1_GFP_weights.tif')]
+    w = cv2.imread(out[0], cv2.IMREAD_UNCHANGED)
+    assert w.dtype == np.float32 and w.shape == (64, 64)
+    want = pipeline.ImageWeightMap2(10., 5.)(mask > 0)[..., 0].astype(np.float32)
+    np.testing.assert_array_equal(w, want)
+    with pytest.raises(ValueError):
+        weightmap.create_weightmaps(str(tmp_path), ['setA'], method='nope')
+
+
+def test_image_labels():
+    raw = np.zeros((3, 8, 8), np.uint8)
+    raw[0, :4] = 5
+    raw[2, 2:6] = 1
+    il = weightmap.ImageLabels(raw)
+    assert il.outputs == 4 and il.labels().dtype == np.uint8 and il.labels()[3, 0] == 3
+    assert weightmap.ImageLabels(np.eye(4)).outputs == 2
+    with pytest.raises(ValueError):
+        weightmap.ImageLabels(np.zeros((5, 4, 4)))
+
+
+def test_utils_helpers(tmp_path):
+    assert utils.power_of_two(1024) and not utils.power_of_two(1200)
+    assert utils.divisible_by_two_n_times(1200, 4) and not utils.divisible_by_two_n_times(1200, 5)
+    with pytest.raises(IOError):
+        utils.HDF5FileHandler('/nonexistent_dir_xyz/out.hdf5')
+    with pytest.raises(TypeError):
+        utils.HDF5FileHandler(None)
+    h = utils.HDF5FileHandler(str(tmp_path / 'out.h5'))
+    assert h.filename == str(tmp_path / 'out.hdf5')
+    h.close()
+
+
+def test_synthetic_generators_are_seeded():
+    a = synth.frames(2, 64, 64, 1, seed=5, n_objects=4)
+    b = synth.frames(2, 64, 64, 1, seed=5, n_objects=4)
+    assert a.dtype == np.float32 and a.shape == (2, 64, 64, 1) and np.array_equal(a, b)
+    lab = synth.instance_labels(128, 128, 12, seed=2, rmin=4, rmax=8)
+    assert lab.max() >= 8
+    from scipy.ndimage import label
+    assert label(lab > 0)[1] == lab.max()          # >= 2 px gaps: binary and instance views agree
+    w = synth.blob_detector_weights((8, 16), 1, 2)
+    assert set(k.rsplit('/', 1)[0] for k in w) == set(synth.unet_layer_names((8, 16)))
