@@ -92,8 +92,10 @@ def test_full_size_frame_2048(sq):
     a = ops.label_centroids_host(m[:, :-3, :-5].copy())
     b = ops.label_centroids_host(sh)
     for x, y in zip(a, b):
-        np.testing.assert_array_equal(x[:, 1] + 3, y[:, 1])
-        np.testing.assert_array_equal(x[:, 2] + 5, y[:, 2])
+        # (rows are float32: the shifted centroid may round differently by one ulp)
+        np.testing.assert_allclose(x[:, 1].astype(np.float64) + 3, y[:, 1], rtol=1.2e-7)
+        np.testing.assert_allclose(x[:, 2].astype(np.float64) + 5, y[:, 2], rtol=1.2e-7)
+        np.testing.assert_array_equal(x[:, 4], y[:, 4])
 
 
 def test_device_api_equals_host_api(sq):

@@ -73,9 +73,9 @@ def test_unet3d_bit_exact(sq):
 def test_errors(sq):
     from sequitr_b200.networks import UNet2D
     filters = (8, 16, 32)
-    net = _net(UNet2D, filters, (20, 24), 'concat')
-    with pytest.raises(ValueError):                      # 20 is not divisible by 4
-        net.predict(np.zeros((1, 20, 24, 1), np.float32))
+    net = _net(UNet2D, filters, (18, 24), 'concat')
+    with pytest.raises(ValueError):                      # 18 is not divisible by 4
+        net.predict(np.zeros((1, 18, 24, 1), np.float32))
     bad = synth.unet_weights(filters, 1, 2)
     bad['UNet/down0/conv1/kernel'] = np.zeros((3, 3, 2, 8), np.float32)
     net2 = _net(UNet2D, filters, (16, 16), 'concat', weights=bad)
