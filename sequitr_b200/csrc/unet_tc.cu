@@ -1,6 +1,649 @@
-// placeholder until the tcgen05 path lands
+// SQ_MODE_BF16_TC: the UNet on 5th-generation tensor cores (tcgen05 + TMEM + TMA).
+//
+// Data layout in HBM: activations are bf16, channel-blocked "NC/8HW8":
+//     act[n][c/8][y][x][c%8]
+// so that (a) a pixel's 8-channel slice is one 16-byte core-matrix row, (b) a TMA
+// box (8*PW, PH, 2 blocks, 1 image) lands in shared memory as [2][PH][PW][8] --
+// already a canonical K-major, no-swizzle UMMA operand whose rows are pixels -- and
+// (c) shifting the descriptor start address by (ky*PW + kx)*16 bytes selects the
+// 3x3 tap (ky,kx).  Each halo patch is therefore read from L2/HBM ONCE per 16 input
+// channels and multiplied 9 times from shared memory; SAME zero padding is TMA's
+// out-of-bounds fill; the skip-concat is just a second tensor map (k-steps
+// ks0..ks0+ks1 read the skip tensor), no concatenated tensor ever exists.
+//
+// One persistent, warp-specialised kernel template does every dense layer:
+//   warp 0      TMA producer   (patch via cp.async.bulk.tensor.4d, weights via cp.async.bulk)
+//   warp 1      MMA issuer     (tcgen05.mma kind::f16, M=128 pixels x N=Cout, K=16 per step)
+//   warps 2-5   epilogue       (tcgen05.ld -> scale/shift/ReLU -> bf16 -> 16-byte stores)
+// with an smem ring (full/empty mbarriers) and double-buffered TMEM accumulators
+// (tmem_full/tmem_empty) so the epilogue of tile i overlaps the MMAs of tile i+1.
+//   conv 3x3 : tile = 8 x (16*S) pixels, 9 taps accumulate into one accumulator
+//   up-conv  : 2x2 stride-2 transposed conv = 4 independent 1x1 GEMMs (one per
+//              output sub-position), 4 accumulators, scattered 2x upsampled store
+// The first conv (Cin = 1 or 3: K = 9..27, not tensor-core material), the 2x2 max
+// pool, the element-wise bridges and the 1x1 head + softmax + argmax are
+// bandwidth-bound CUDA-core kernels on the same layout.
+//
+// Numeric contract (oracle/unet_c.py contract='bf16'): inputs, weights and every
+// stored activation are bf16 (RNE); accumulation and the scale/shift epilogue are fp32.
 #include "unet_plan.cuh"
-int sq_tc_finalize(sq_unet_s *) { sq_set_error("bf16 tensor-core mode not built yet"); return SQ_EUNSUPPORTED; }
-int sq_tc_destroy(sq_unet_s *) { return SQ_OK; }
-int sq_tc_workspace_bytes(sq_unet_s *, int, int, int, int, size_t *) { return SQ_EUNSUPPORTED; }
-int sq_tc_forward(sq_unet_s *, const float *, int, int, int, int, float *, uint8_t *, float *, void *, size_t, cudaStream_t) { return SQ_EUNSUPPORTED; }
+#include "tc_common.cuh"
+#include <algorithm>
+
+namespace {
+
+typedef __nv_bfloat16 bf16;
+
+// ------------------------------------------------------------ tile configuration
+template <int COUT, int S, bool UP>
+struct Cfg {
+    static constexpr int TH = 16 * S;                    // tile height (pixels)
+    static constexpr int PW = UP ? 8 : 10;               // patch width incl. halo
+    static constexpr int PH = UP ? TH : TH + 2;
+    static constexpr int NT = UP ? 4 : 9;                // taps per k-step
+    static constexpr int NQ = UP ? 4 : 1;                // accumulators per sub-tile
+    static constexpr int A_BYTES = 2 * PH * PW * 16;     // 16 input channels of the patch
+    static constexpr int B_BYTES = NT * 2 * COUT * 16;   // 16 input channels of the weights
+    static constexpr int STAGE_BYTES = (A_BYTES + B_BYTES + 127) / 128 * 128;
+    static constexpr int ACC_COLS = S * NQ * COUT;
+    static constexpr uint32_t LBO_A = PH * PW * 16, SBO_A = PW * 16;
+    static constexpr uint32_t LBO_B = COUT * 16, SBO_B = 128;
+    static_assert(A_BYTES % 128 == 0, "TMA destination alignment");
+};
+
+constexpr int MAX_STAGES = 8;
+constexpr int TC_THREADS = 192;
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b)
+{
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t *>(&h);
+}
+
+template <int COUT, int S, bool UP, int NBUF>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
+               int ks0, int ks1, const bf16 *__restrict__ wts, const float *__restrict__ scale,
+               const float *__restrict__ shift, bf16 *__restrict__ out, int nimg, int H, int W,
+               int relu, int nstages)
+{
+    using C = Cfg<COUT, S, UP>;
+    constexpr int TMEM_COLS = (NBUF * C::ACC_COLS <= 32) ? 32 : (NBUF * C::ACC_COLS <= 64) ? 64
+                            : (NBUF * C::ACC_COLS <= 128) ? 128 : (NBUF * C::ACC_COLS <= 256) ? 256 : 512;
+    static_assert(NBUF * C::ACC_COLS <= 512, "TMEM overflow");
+    extern __shared__ uint8_t smem_raw[];
+    // the runtime only guarantees 16-byte alignment of dynamic shared memory: align by hand
+    uint8_t *smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+    __shared__ uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], tfull_bar[2], tempty_bar[2];
+    __shared__ uint32_t tmem_base_sh;
+    __shared__ float s_scale[COUT], s_shift[COUT];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_x = (W + 7) >> 3, tiles_y = (H + C::TH - 1) / C::TH;
+    const int ntiles = nimg * tiles_x * tiles_y;
+    const int ksteps = ks0 + ks1;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < nstages; ++i) { tc::mbar_init(&full_bar[i], 1); tc::mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < 2; ++i) { tc::mbar_init(&tfull_bar[i], 1); tc::mbar_init(&tempty_bar[i], 4); }
+        tc::fence_barrier_init();
+        tc::tma_prefetch_desc(&mapA0);
+        tc::tma_prefetch_desc(&mapA1);
+    }
+    if (warp == 1) { tc::tmem_alloc(&tmem_base_sh, TMEM_COLS); tc::tmem_relinquish(); }
+    for (int i = threadIdx.x; i < COUT; i += TC_THREADS) { s_scale[i] = scale[i]; s_shift[i] = shift[i]; }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = tmem_base_sh;
+
+    if (warp == 0) {
+        // ===================================================== TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+                const int tx = t % tiles_x, ty = (t / tiles_x) % tiles_y, n = t / (tiles_x * tiles_y);
+                const int x0 = tx * 8 - (UP ? 0 : 1), y0 = ty * C::TH - (UP ? 0 : 1);
+                for (int ks = 0; ks < ksteps; ++ks) {
+                    tc::mbar_wait(&empty_bar[stage], phase ^ 1);
+                    tc::mbar_arrive_expect_tx(&full_bar[stage], C::A_BYTES + C::B_BYTES);
+                    uint8_t *sA = smem + (size_t)stage * C::STAGE_BYTES;
+                    if (ks < ks0) tc::tma_load_4d(sA, &mapA0, &full_bar[stage], x0 * 8, y0, ks * 2, n);
+                    else          tc::tma_load_4d(sA, &mapA1, &full_bar[stage], x0 * 8, y0, (ks - ks0) * 2, n);
+                    tc::bulk_load(sA + C::A_BYTES, wts + (size_t)ks * (C::B_BYTES / 2), C::B_BYTES,
+                                  &full_bar[stage]);
+                    if (++stage == nstages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ======================================================= MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = tc::instr_desc_bf16(128, COUT);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+                const int buf = it % NBUF;
+                tc::mbar_wait(&tempty_bar[buf], ((it / NBUF) & 1) ^ 1);
+                tc::tc_fence_after();
+                for (int ks = 0; ks < ksteps; ++ks) {
+                    tc::mbar_wait(&full_bar[stage], phase);
+                    tc::tc_fence_after();
+                    const uint32_t a_base = tc::smem_u32(smem + (size_t)stage * C::STAGE_BYTES);
+                    const uint32_t b_base = a_base + C::A_BYTES;
+#pragma unroll
+                    for (int j = 0; j < S; ++j) {
+#pragma unroll
+                        for (int tp = 0; tp < C::NT; ++tp) {
+                            const uint32_t a_off = UP ? (uint32_t)(j * 16 * C::PW) * 16
+                                                      : (uint32_t)((j * 16 + tp / 3) * C::PW + tp % 3) * 16;
+                            const int q = UP ? tp : 0;
+                            const uint32_t d = tmem_base + buf * C::ACC_COLS + (j * C::NQ + q) * COUT;
+                            const uint32_t acc = UP ? (ks > 0) : (ks > 0 || tp > 0);
+                            tc::umma_bf16(d, tc::smem_desc(a_base + a_off, C::LBO_A, C::SBO_A),
+                                          tc::smem_desc(b_base + tp * 2 * COUT * 16, C::LBO_B, C::SBO_B),
+                                          idesc, acc);
+                        }
+                    }
+                    tc::umma_commit(&empty_bar[stage]);      // smem slot reusable once these MMAs retire
+                    if (++stage == nstages) { stage = 0; phase ^= 1; }
+                }
+                tc::umma_commit(&tfull_bar[buf]);            // accumulators of this tile complete
+            }
+        }
+    } else {
+        // ========================================================= epilogue
+        const int q4 = warp & 3;                            // TMEM lane quarter this warp may read
+        const int r = q4 * 32 + lane;                       // accumulator row = pixel of the sub-tile
+        const int ph = r >> 3, pw = r & 7;
+        const uint32_t lane_addr = (uint32_t)(q4 * 32) << 16;
+        const int CBo = COUT / 8;
+        int it = 0;
+        for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+            const int buf = it % NBUF;
+            const int tx = t % tiles_x, ty = (t / tiles_x) % tiles_y, n = t / (tiles_x * tiles_y);
+            tc::mbar_wait(&tfull_bar[buf], (it / NBUF) & 1);
+            tc::tc_fence_after();
+#pragma unroll 1
+            for (int j = 0; j < S; ++j) {
+                const int y = ty * C::TH + j * 16 + ph, x = tx * 8 + pw;
+                const bool valid = (y < H) && (x < W);
+                if (!UP) {
+#pragma unroll 1
+                    for (int c16 = 0; c16 < COUT / 16; ++c16) {
+                        uint32_t v[16];
+                        tc::tmem_ld16(tmem_base + lane_addr + buf * C::ACC_COLS + j * COUT + c16 * 16, v);
+                        tc::tmem_ld_wait();
+                        uint32_t o[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const int c = c16 * 16 + 2 * e;
+                            float a = fmaf(__uint_as_float(v[2 * e]), s_scale[c], s_shift[c]);
+                            float b = fmaf(__uint_as_float(v[2 * e + 1]), s_scale[c + 1], s_shift[c + 1]);
+                            if (relu) { a = a > 0.0f ? a : 0.0f; b = b > 0.0f ? b : 0.0f; }
+                            o[e] = pack_bf16(a, b);
+                        }
+                        if (valid) {
+                            bf16 *p = out + ((((size_t)n * CBo + c16 * 2) * H + y) * W + x) * 8;
+                            *reinterpret_cast<uint4 *>(p) = make_uint4(o[0], o[1], o[2], o[3]);
+                            *reinterpret_cast<uint4 *>(p + (size_t)H * W * 8) = make_uint4(o[4], o[5], o[6], o[7]);
+                        }
+                    }
+                } else {
+                    const int Ho = 2 * H, Wo = 2 * W;
+#pragma unroll 1
+                    for (int ky = 0; ky < 2; ++ky) {
+#pragma unroll 1
+                        for (int c8 = 0; c8 < COUT / 8; ++c8) {
+                            uint32_t v0[8], v1[8];
+                            const uint32_t col = tmem_base + lane_addr + buf * C::ACC_COLS +
+                                                 (j * 4 + ky * 2) * COUT + c8 * 8;
+                            tc::tmem_ld8(col, v0);
+                            tc::tmem_ld8(col + COUT, v1);
+                            tc::tmem_ld_wait();
+                            uint32_t o0[4], o1[4];
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const int c = c8 * 8 + 2 * e;
+                                o0[e] = pack_bf16(__uint_as_float(v0[2 * e]) + s_shift[c],
+                                                  __uint_as_float(v0[2 * e + 1]) + s_shift[c + 1]);
+                                o1[e] = pack_bf16(__uint_as_float(v1[2 * e]) + s_shift[c],
+                                                  __uint_as_float(v1[2 * e + 1]) + s_shift[c + 1]);
+                            }
+                            if (valid) {
+                                bf16 *p = out + ((((size_t)n * CBo + c8) * Ho + 2 * y + ky) * Wo + 2 * x) * 8;
+                                *reinterpret_cast<uint4 *>(p) = make_uint4(o0[0], o0[1], o0[2], o0[3]);
+                                *reinterpret_cast<uint4 *>(p + 8) = make_uint4(o1[0], o1[1], o1[2], o1[3]);
+                            }
+                        }
+                    }
+                }
+            }
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&tempty_bar[buf]);
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tc::tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------- bandwidth-bound kernels
+// First conv: fp32 NHWC input with few channels -> bf16 blocked.  wf: [9*CIN][COUT] fp32
+// holding bf16-rounded weights.  One thread per pixel, 8 output channels at a time.
+template <int CIN>
+__global__ void first_conv_kernel(const float *__restrict__ in, const float *__restrict__ wf,
+                                  const float *__restrict__ scale, const float *__restrict__ shift,
+                                  bf16 *__restrict__ out, int nimg, int H, int W, int COUT)
+{
+    extern __shared__ float sw[];                       // [9*CIN][COUT] + scale + shift
+    for (int i = threadIdx.x; i < 9 * CIN * COUT; i += blockDim.x) sw[i] = wf[i];
+    float *ssc = sw + 9 * CIN * COUT, *ssh = ssc + COUT;
+    for (int i = threadIdx.x; i < COUT; i += blockDim.x) { ssc[i] = scale[i]; ssh[i] = shift[i]; }
+    __syncthreads();
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= (long long)nimg * H * W) return;
+    const int x = (int)(p % W), y = (int)((p / W) % H);
+    const long long n = p / ((long long)W * H);
+    float v[9 * CIN];
+#pragma unroll
+    for (int tp = 0; tp < 9; ++tp) {
+        const int yy = y + tp / 3 - 1, xx = x + tp % 3 - 1;
+        const bool ok = yy >= 0 && yy < H && xx >= 0 && xx < W;
+#pragma unroll
+        for (int c = 0; c < CIN; ++c)
+            v[tp * CIN + c] = ok ? __bfloat162float(__float2bfloat16_rn(
+                                       in[((n * H + yy) * W + xx) * CIN + c])) : 0.0f;
+    }
+    for (int cb = 0; cb < COUT / 8; ++cb) {
+        float acc[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 9 * CIN; ++k) {
+            const float *wr = sw + k * COUT + cb * 8;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[e] = fmaf(v[k], wr[e], acc[e]);
+        }
+        uint32_t o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int c = cb * 8 + 2 * e;
+            float a = fmaf(acc[2 * e], ssc[c], ssh[c]);
+            float b = fmaf(acc[2 * e + 1], ssc[c + 1], ssh[c + 1]);
+            a = a > 0.0f ? a : 0.0f;
+            b = b > 0.0f ? b : 0.0f;
+            o[e] = pack_bf16(a, b);
+        }
+        *reinterpret_cast<uint4 *>(out + ((((size_t)n * (COUT / 8) + cb) * H + y) * W + x) * 8) =
+            make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+__device__ __forceinline__ uint32_t bf162_max(uint32_t a, uint32_t b)
+{
+    __nv_bfloat162 x = *reinterpret_cast<__nv_bfloat162 *>(&a), y = *reinterpret_cast<__nv_bfloat162 *>(&b);
+    __nv_bfloat162 m = __hmax2(x, y);
+    return *reinterpret_cast<uint32_t *>(&m);
+}
+
+// 2x2 max pool on the blocked layout: one thread per output 16-byte vector.
+__global__ void maxpool_bf16_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ out,
+                                    long long nvec, int Ho, int Wo)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nvec) return;
+    const int x = (int)(i % Wo);
+    const int y = (int)((i / Wo) % Ho);
+    const long long plane = i / ((long long)Wo * Ho);          // n*CB + cb
+    const uint4 *p = in + (plane * (2 * Ho) + 2 * y) * (2 * Wo) + 2 * x;
+    const uint4 a = p[0], b = p[1], c = p[2 * Wo], d = p[2 * Wo + 1];
+    uint4 m;
+    m.x = bf162_max(bf162_max(a.x, b.x), bf162_max(c.x, d.x));
+    m.y = bf162_max(bf162_max(a.y, b.y), bf162_max(c.y, d.y));
+    m.z = bf162_max(bf162_max(a.z, b.z), bf162_max(c.z, d.z));
+    m.w = bf162_max(bf162_max(a.w, b.w), bf162_max(c.w, d.w));
+    out[i] = m;
+}
+
+__global__ void eltwise_bf16_kernel(const uint32_t *__restrict__ a, const uint32_t *__restrict__ b,
+                                    long long n2, int op, uint32_t *__restrict__ out)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n2) return;
+    const uint32_t ua = a[i], ub = b[i];
+    const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&ua));
+    const float2 y = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&ub));
+    float r0, r1;
+    if (op == SQ_BRIDGE_ADD) { r0 = x.x + y.x; r1 = x.y + y.y; }
+    else if (op == SQ_BRIDGE_MUL) { r0 = x.x * y.x; r1 = x.y * y.y; }
+    else { r0 = x.x - y.x; r1 = x.y - y.y; }
+    out[i] = pack_bf16(r0, r1);
+}
+
+// 1x1 conv head + softmax + argmax.  wf: [C][K] fp32 (bf16-rounded values).
+__global__ void head_bf16_kernel(const bf16 *__restrict__ in, const float *__restrict__ wf,
+                                 const float *__restrict__ bias, int C, int K, long long npix_img,
+                                 int nimg, float *__restrict__ logits, float *__restrict__ probs,
+                                 uint8_t *__restrict__ mask)
+{
+    extern __shared__ float sw[];                       // [C][K] + bias[K]
+    for (int i = threadIdx.x; i < C * K + K; i += blockDim.x) sw[i] = i < C * K ? wf[i] : bias[i - C * K];
+    __syncthreads();
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npix_img * nimg) return;
+    const long long n = p / npix_img, q = p % npix_img;
+    float l[16];
+    for (int k = 0; k < K; ++k) l[k] = 0.0f;
+    for (int cb = 0; cb < C / 8; ++cb) {
+        const uint4 u = *reinterpret_cast<const uint4 *>(in + (((size_t)n * (C / 8) + cb) * npix_img + q) * 8);
+        const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&w4[e]));
+            const float *w0 = sw + (cb * 8 + 2 * e) * K;
+            for (int k = 0; k < K; ++k) l[k] = fmaf(f.y, w0[K + k], fmaf(f.x, w0[k], l[k]));
+        }
+    }
+    int best = 0;
+    float m = -INFINITY;
+    for (int k = 0; k < K; ++k) {
+        l[k] += sw[C * K + k];
+        if (l[k] > m) { m = l[k]; best = k; }
+    }
+    if (logits) for (int k = 0; k < K; ++k) logits[p * K + k] = l[k];
+    if (mask) mask[p] = (uint8_t)best;
+    if (probs) {
+        float s = 0.0f;
+        for (int k = 0; k < K; ++k) { l[k] = expf(l[k] - m); s += l[k]; }
+        for (int k = 0; k < K; ++k) probs[p * K + k] = l[k] / s;
+    }
+}
+
+// ------------------------------------------------------------------ host side
+uint16_t host_bf16(float f)
+{
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
+    u += 0x7fffu + ((u >> 16) & 1u);
+    return (uint16_t)(u >> 16);
+}
+float host_bf16_round(float f)
+{
+    uint32_t u = (uint32_t)host_bf16(f) << 16;
+    float r;
+    memcpy(&r, &u, 4);
+    return r;
+}
+
+struct TcState {
+    int sm_count = 148;
+};
+
+int dev_upload(sq_unet_s *u, const void *src, size_t bytes, void **dst)
+{
+    SQ_CUDA(cudaMalloc(dst, std::max<size_t>(bytes, 16)));
+    u->dev_allocs.push_back(*dst);
+    SQ_CUDA(cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice));
+    return SQ_OK;
+}
+
+int make_map(CUtensorMap *m, const bf16 *ptr, int nimg, int CB, int H, int W, int PW, int PH)
+{
+    sq_encode_tiled_fn enc = sq_get_encode_tiled();
+    SQ_REQUIRE(enc, SQ_ECUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[4] = {(cuuint64_t)W * 8, (cuuint64_t)H, (cuuint64_t)CB, (cuuint64_t)nimg};
+    cuuint64_t strides[3] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)CB * H * W * 16};
+    cuuint32_t box[4] = {(cuuint32_t)PW * 8, (cuuint32_t)PH, 2, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void *)ptr, dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    SQ_REQUIRE(r == CUDA_SUCCESS, SQ_ECUDA, "cuTensorMapEncodeTiled failed (%d) for (%d,%d,%d,%d)",
+               (int)r, nimg, CB, H, W);
+    return SQ_OK;
+}
+
+template <int COUT, int S, bool UP, int NBUF>
+int launch_tc(sq_unet_s *u, const SqLayer &L, const bf16 *in0, int cb0, const bf16 *in1, int cb1,
+              bf16 *out, int nimg, int H, int W, int relu, cudaStream_t st)
+{
+    using C = Cfg<COUT, S, UP>;
+    CUtensorMap m0, m1;
+    SQ_TRY(make_map(&m0, in0, nimg, cb0, H, W, C::PW, C::PH));
+    if (in1) SQ_TRY(make_map(&m1, in1, nimg, cb1, H, W, C::PW, C::PH));
+    else m1 = m0;
+    int nstages = std::min(MAX_STAGES, (200 * 1024) / C::STAGE_BYTES);
+    nstages = std::max(nstages, 2);
+    const size_t smem = (size_t)nstages * C::STAGE_BYTES + 1024;
+    auto kern = conv_tc_kernel<COUT, S, UP, NBUF>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        SQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    const int tiles = nimg * ((W + 7) / 8) * ((H + C::TH - 1) / C::TH);
+    const int grid = std::min(tiles, u->h->sm_count);
+    kern<<<grid, TC_THREADS, smem, st>>>(m0, m1, cb0 / 2, in1 ? cb1 / 2 : 0, (const bf16 *)L.w_tc, L.scale,
+                                         L.shift, out, nimg, H, W, relu, nstages);
+    ++u->last_launches;
+    SQ_CHECK_LAUNCH();
+    return SQ_OK;
+}
+
+int conv3x3_tc(sq_unet_s *u, const SqLayer &L, const bf16 *in0, int c0, const bf16 *in1, int c1,
+               bf16 *out, int nimg, int H, int W, cudaStream_t st)
+{
+    switch (L.cout) {
+    case 16:  return launch_tc<16, 4, false, 2>(u, L, in0, c0 / 8, in1, c1 / 8, out, nimg, H, W, 1, st);
+    case 32:  return launch_tc<32, 4, false, 2>(u, L, in0, c0 / 8, in1, c1 / 8, out, nimg, H, W, 1, st);
+    case 64:  return launch_tc<64, 4, false, 2>(u, L, in0, c0 / 8, in1, c1 / 8, out, nimg, H, W, 1, st);
+    case 128: return launch_tc<128, 2, false, 2>(u, L, in0, c0 / 8, in1, c1 / 8, out, nimg, H, W, 1, st);
+    case 256: return launch_tc<256, 1, false, 2>(u, L, in0, c0 / 8, in1, c1 / 8, out, nimg, H, W, 1, st);
+    }
+    SQ_REQUIRE(false, SQ_EUNSUPPORTED, "bf16 mode: unsupported filter count %d", L.cout);
+}
+
+int upconv_tc(sq_unet_s *u, const SqLayer &L, const bf16 *in, bf16 *out, int nimg, int H, int W,
+              cudaStream_t st)
+{
+    switch (L.cout) {
+    case 16:  return launch_tc<16, 2, true, 2>(u, L, in, L.cin0 / 8, nullptr, 0, out, nimg, H, W, 0, st);
+    case 32:  return launch_tc<32, 1, true, 2>(u, L, in, L.cin0 / 8, nullptr, 0, out, nimg, H, W, 0, st);
+    case 64:  return launch_tc<64, 1, true, 2>(u, L, in, L.cin0 / 8, nullptr, 0, out, nimg, H, W, 0, st);
+    case 128: return launch_tc<128, 1, true, 1>(u, L, in, L.cin0 / 8, nullptr, 0, out, nimg, H, W, 0, st);
+    }
+    SQ_REQUIRE(false, SQ_EUNSUPPORTED, "bf16 mode: unsupported up-conv filter count %d", L.cout);
+}
+
+SqLayer *layer_by_scope(sq_unet_s *u, const std::string &scope)
+{
+    for (SqLayer &l : u->layers)
+        if (l.scope == scope) return &l;
+    return nullptr;
+}
+
+}  // namespace
+
+int sq_tc_destroy(sq_unet_s *u)
+{
+    delete (TcState *)u->tc_state;
+    u->tc_state = nullptr;
+    return SQ_OK;
+}
+
+// Re-lay-out the weights for the tensor-core kernels (called from sq_unet_finalize after the
+// fp32 upload, so L.scale / L.shift already hold the folded epilogue).
+int sq_tc_finalize(sq_unet_s *u)
+{
+    SQ_REQUIRE(u->ndim == 2, SQ_EUNSUPPORTED,
+               "bf16 tensor-core mode implements UNet2D; use compute='fp32' for UNet3D");
+    SQ_REQUIRE(u->cin <= 4, SQ_EUNSUPPORTED, "bf16 mode: num_inputs must be <= 4 (got %d)", u->cin);
+    for (int f : u->filters)
+        SQ_REQUIRE(f == 16 || f == 32 || f == 64 || f == 128 || f == 256, SQ_EUNSUPPORTED,
+                   "bf16 mode: filters must be in {16,32,64,128,256} (got %d)", f);
+    for (SqLayer &L : u->layers) {
+        const std::vector<float> &k = u->host[L.scope + "/kernel"].data;
+        const int C = L.cin0 + L.cin1, CO = L.cout;
+        if (L.kind == SqLayer::CONV && C % 16 == 0) {
+            // [ks][tap][kb][co][8]  <-  HWIO kernel[tap][ci][co]
+            std::vector<uint16_t> w((size_t)9 * C * CO);
+            for (int ks = 0; ks < C / 16; ++ks)
+                for (int tp = 0; tp < 9; ++tp)
+                    for (int kb = 0; kb < 2; ++kb)
+                        for (int co = 0; co < CO; ++co)
+                            for (int e = 0; e < 8; ++e) {
+                                const int ci = ks * 16 + kb * 8 + e;
+                                w[((((size_t)ks * 9 + tp) * 2 + kb) * CO + co) * 8 + e] =
+                                    host_bf16(k[((size_t)tp * C + ci) * CO + co]);
+                            }
+            SQ_TRY(dev_upload(u, w.data(), w.size() * 2, &L.w_tc));
+        } else if (L.kind == SqLayer::UPCONV) {
+            // [ks][tap][kb][co][8]  <-  TF conv_transpose kernel[tap][co][ci]
+            std::vector<uint16_t> w((size_t)4 * C * CO);
+            for (int ks = 0; ks < C / 16; ++ks)
+                for (int tp = 0; tp < 4; ++tp)
+                    for (int kb = 0; kb < 2; ++kb)
+                        for (int co = 0; co < CO; ++co)
+                            for (int e = 0; e < 8; ++e) {
+                                const int ci = ks * 16 + kb * 8 + e;
+                                w[((((size_t)ks * 4 + tp) * 2 + kb) * CO + co) * 8 + e] =
+                                    host_bf16(k[((size_t)tp * CO + co) * C + ci]);
+                            }
+            SQ_TRY(dev_upload(u, w.data(), w.size() * 2, &L.w_tc));
+        } else {
+            // first conv / head: CUDA-core kernels read fp32 copies of the bf16-rounded weights
+            std::vector<float> w(k.size());
+            for (size_t i = 0; i < k.size(); ++i) w[i] = host_bf16_round(k[i]);
+            SQ_TRY(dev_upload(u, w.data(), w.size() * 4, &L.w_tc));
+        }
+    }
+    TcState *s = new TcState();
+    s->sm_count = u->h->sm_count;
+    u->tc_state = s;
+    return SQ_OK;
+}
+
+namespace {
+
+int tc_run(sq_unet_s *u, bool dry, const float *in, int n, int hgt, int wid, float *probs,
+           uint8_t *mask, float *logits, void *ws, size_t ws_bytes, cudaStream_t st, size_t *need)
+{
+    SqArena a(dry ? nullptr : ws, dry ? 0 : ws_bytes);
+    const int nl = u->nlev;
+    std::vector<bf16 *> t1(nl), skip(nl), pooled(nl, nullptr), up(nl, nullptr), merged(nl, nullptr),
+        ut(nl, nullptr), uo(nl, nullptr);
+    for (int l = 0; l < nl; ++l) {
+        const size_t px = (size_t)n * (hgt >> l) * (wid >> l);
+        const size_t f = u->filters[l];
+        t1[l] = a.take<bf16>(px * f);
+        skip[l] = a.take<bf16>(px * f);
+        if (l > 0) pooled[l] = a.take<bf16>(px * u->filters[l - 1]);
+        if (l < nl - 1) {
+            up[l] = a.take<bf16>(px * f);
+            if (u->bridge >= SQ_BRIDGE_ADD && u->bridge <= SQ_BRIDGE_SUB) merged[l] = a.take<bf16>(px * f);
+            ut[l] = a.take<bf16>(px * f);
+            uo[l] = a.take<bf16>(px * f);
+        }
+    }
+    if (need) *need = a.off;
+    if (dry) return SQ_OK;
+    SQ_REQUIRE(a.ok(), SQ_ENOMEM, "unet(bf16): workspace %zu < %zu bytes", ws_bytes, a.off);
+
+    u->last_launches = 0;
+    sq_timer_mark(u, st, nullptr, 0);
+    const int threads = 256;
+    char scope[64];
+    for (int l = 0; l < nl; ++l) {
+        const int H = hgt >> l, W = wid >> l;
+        const long long px = (long long)n * H * W;
+        snprintf(scope, sizeof scope, "UNet/down%d/conv1", l);
+        SqLayer *c1 = layer_by_scope(u, scope);
+        snprintf(scope, sizeof scope, "UNet/down%d/conv2", l);
+        SqLayer *c2 = layer_by_scope(u, scope);
+        if (l == 0) {
+            const size_t sm = (size_t)(9 * u->cin * c1->cout + 2 * c1->cout) * sizeof(float);
+            const unsigned gx = (unsigned)((px + 127) / 128);
+            switch (u->cin) {
+            case 1: first_conv_kernel<1><<<gx, 128, sm, st>>>(in, (const float *)c1->w_tc, c1->scale, c1->shift, t1[0], n, H, W, c1->cout); break;
+            case 2: first_conv_kernel<2><<<gx, 128, sm, st>>>(in, (const float *)c1->w_tc, c1->scale, c1->shift, t1[0], n, H, W, c1->cout); break;
+            case 3: first_conv_kernel<3><<<gx, 128, sm, st>>>(in, (const float *)c1->w_tc, c1->scale, c1->shift, t1[0], n, H, W, c1->cout); break;
+            default: first_conv_kernel<4><<<gx, 128, sm, st>>>(in, (const float *)c1->w_tc, c1->scale, c1->shift, t1[0], n, H, W, c1->cout); break;
+            }
+            ++u->last_launches;
+            SQ_CHECK_LAUNCH();
+        } else {
+            const long long nvec = px * (u->filters[l - 1] / 8);
+            maxpool_bf16_kernel<<<(unsigned)((nvec + threads - 1) / threads), threads, 0, st>>>(
+                (const uint4 *)skip[l - 1], (uint4 *)pooled[l], nvec, H, W);
+            ++u->last_launches;
+            SQ_CHECK_LAUNCH();
+            sq_timer_mark(u, st, "maxpool", 0);
+            SQ_TRY(conv3x3_tc(u, *c1, pooled[l], c1->cin0, nullptr, 0, t1[l], n, H, W, st));
+        }
+        sq_timer_mark(u, st, c1->scope.c_str(), c1->flops_per_px * px);
+        SQ_TRY(conv3x3_tc(u, *c2, t1[l], c2->cin0, nullptr, 0, skip[l], n, H, W, st));
+        sq_timer_mark(u, st, c2->scope.c_str(), c2->flops_per_px * px);
+    }
+    const bf16 *cur = skip[nl - 1];
+    for (int l = nl - 2; l >= 0; --l) {
+        const int H = hgt >> l, W = wid >> l;
+        const long long px = (long long)n * H * W;
+        snprintf(scope, sizeof scope, "UNet/up%d/upscale", l);
+        SqLayer *us = layer_by_scope(u, scope);
+        snprintf(scope, sizeof scope, "UNet/up%d/conv1", l);
+        SqLayer *c1 = layer_by_scope(u, scope);
+        snprintf(scope, sizeof scope, "UNet/up%d/conv2", l);
+        SqLayer *c2 = layer_by_scope(u, scope);
+        SQ_TRY(upconv_tc(u, *us, cur, up[l], n, H / 2, W / 2, st));
+        sq_timer_mark(u, st, us->scope.c_str(), us->flops_per_px * px);
+        const bf16 *in0 = up[l], *in1 = nullptr;
+        if (u->bridge == SQ_BRIDGE_CONCAT) {
+            in1 = skip[l];
+        } else if (u->bridge != SQ_BRIDGE_NONE) {
+            const long long n2 = px * us->cout / 2;
+            eltwise_bf16_kernel<<<(unsigned)((n2 + threads - 1) / threads), threads, 0, st>>>(
+                (const uint32_t *)up[l], (const uint32_t *)skip[l], n2, u->bridge, (uint32_t *)merged[l]);
+            ++u->last_launches;
+            SQ_CHECK_LAUNCH();
+            sq_timer_mark(u, st, "bridge", 0);
+            in0 = merged[l];
+        }
+        SQ_TRY(conv3x3_tc(u, *c1, in0, c1->cin0, in1, c1->cin1, ut[l], n, H, W, st));
+        sq_timer_mark(u, st, c1->scope.c_str(), c1->flops_per_px * px);
+        SQ_TRY(conv3x3_tc(u, *c2, ut[l], c2->cin0, nullptr, 0, uo[l], n, H, W, st));
+        sq_timer_mark(u, st, c2->scope.c_str(), c2->flops_per_px * px);
+        cur = uo[l];
+    }
+    SqLayer *head = layer_by_scope(u, "UNet/to_image");
+    const long long px0 = (long long)hgt * wid;
+    const size_t sm = (size_t)(head->cin0 * head->cout + head->cout) * sizeof(float);
+    head_bf16_kernel<<<(unsigned)((px0 * n + 127) / 128), 128, sm, st>>>(
+        cur, (const float *)head->w_tc, head->shift, head->cin0, head->cout, px0, n, logits, probs, mask);
+    ++u->last_launches;
+    SQ_CHECK_LAUNCH();
+    sq_timer_mark(u, st, head->scope.c_str(), head->flops_per_px * px0 * n);
+    return SQ_OK;
+}
+
+}  // namespace
+
+int sq_tc_workspace_bytes(sq_unet_s *u, int n, int d, int hgt, int wid, size_t *bytes)
+{
+    (void)d;
+    return tc_run(u, true, nullptr, n, hgt, wid, nullptr, nullptr, nullptr, nullptr, 0, nullptr, bytes);
+}
+
+int sq_tc_forward(sq_unet_s *u, const float *in, int n, int d, int hgt, int wid, float *probs,
+                  uint8_t *mask, float *logits, void *ws, size_t ws_bytes, cudaStream_t st)
+{
+    (void)d;
+    return tc_run(u, false, in, n, hgt, wid, probs, mask, logits, ws, ws_bytes, st, nullptr);
+}

@@ -363,6 +363,32 @@ class UNet(object):
         head the consumer ``utils.CentroidWriter`` implies (reference utils.py:492)."""
         return self._execute(self._as_input(features), want)
 
+    def profile(self, features):
+        """Per-layer device times of one instrumented forward pass:
+        list of (scope, milliseconds, algorithmic FLOPs).  ``features`` must be a cuda tensor."""
+        plan = self._ensure_plan()
+        lib = _lib.load()
+        x = self._as_input(features).contiguous().float()
+        n = x.shape[0]
+        d, h, w = (1,) + tuple(x.shape[1:3]) if self.ndim == 2 else tuple(x.shape[1:4])
+        need = ctypes.c_size_t()
+        _lib.check(lib.sq_unet_workspace_bytes(plan, n, d, h, w, ctypes.byref(need)))
+        ws = self._ws.get(need.value)
+        cap = 64
+        names = (ctypes.c_char_p * cap)()
+        ms = (ctypes.c_float * cap)()
+        flops = (ctypes.c_double * cap)()
+        nl = ctypes.c_int()
+        _lib.check(lib.sq_unet_profile(plan, x.data_ptr(), n, d, h, w, ws.data_ptr(), ws.numel(),
+                                       _lib.stream_ptr(), names, ms, flops, cap, ctypes.byref(nl)))
+        return [(names[i].decode(), float(ms[i]), float(flops[i])) for i in range(min(nl.value, cap))]
+
+    def launches(self):
+        """Kernel launches issued by the last forward pass."""
+        n = ctypes.c_int()
+        _lib.check(_lib.load().sq_unet_last_launches(self._ensure_plan(), ctypes.byref(n)))
+        return n.value
+
     def segment(self, features):
         """uint8 class mask (N,[D,]H,W)."""
         return self.predict(features, want=('mask',))['mask']
