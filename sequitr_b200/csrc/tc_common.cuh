@@ -141,6 +141,22 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
         "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// Same, descriptors given as (lo, hi) 32-bit halves: per-MMA descriptor math is then a single
+// 32-bit add on the start-address field (the issuing thread is the throughput limiter for
+// small-N MMAs, so every instruction on this path counts).
+__device__ __forceinline__ void umma_bf16_parts(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi,
+                                                uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                                uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // arrive on an mbarrier when all previously issued MMAs of this thread have completed
 __device__ __forceinline__ void umma_commit(uint64_t *bar)
 {

@@ -60,12 +60,31 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b)
     return *reinterpret_cast<uint32_t *>(&h);
 }
 
-template <int COUT, int S, bool UP, int NBUF>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__device__ __forceinline__ uint32_t bf162_max(uint32_t a, uint32_t b)
+{
+    __nv_bfloat162 x = *reinterpret_cast<__nv_bfloat162 *>(&a), y = *reinterpret_cast<__nv_bfloat162 *>(&b);
+    __nv_bfloat162 m = __hmax2(x, y);
+    return *reinterpret_cast<uint32_t *>(&m);
+}
+
+// Epilogue variants of the 3x3 conv kernel
+constexpr int EPI_STORE = 0;   // activation -> bf16 blocked tensor
+constexpr int EPI_POOL = 1;    // same + the 2x2 max-pooled tensor (fused max_pool_layer)
+constexpr int EPI_HEAD = 2;    // fused 1x1 head + softmax + argmax; the activation is never stored
+
+struct HeadArgs {
+    const float *w;            // [COUT][K] then bias[K] (bf16-rounded weights, fp32 bias)
+    int K;
+    float *logits, *probs;     // optional, (n,H,W,K) fp32
+    uint8_t *mask;             // optional, (n,H,W)
+};
+
+template <int COUT, int S, bool UP, int NBUF, int MINB, int EPI, int HK>
+__global__ void __launch_bounds__(TC_THREADS, MINB)
 conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                int ks0, int ks1, const bf16 *__restrict__ wts, const float *__restrict__ scale,
-               const float *__restrict__ shift, bf16 *__restrict__ out, int nimg, int H, int W,
-               int relu, int nstages)
+               const float *__restrict__ shift, bf16 *__restrict__ out, bf16 *__restrict__ out_pool,
+               HeadArgs head, int nimg, int H, int W, int relu, int nstages)
 {
     using C = Cfg<COUT, S, UP>;
     constexpr int TMEM_COLS = (NBUF * C::ACC_COLS <= 32) ? 32 : (NBUF * C::ACC_COLS <= 64) ? 64
@@ -77,6 +96,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     __shared__ uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], tfull_bar[2], tempty_bar[2];
     __shared__ uint32_t tmem_base_sh;
     __shared__ float s_scale[COUT], s_shift[COUT];
+    __shared__ __align__(16) float s_head[EPI == EPI_HEAD ? COUT * HK + HK : 4];   // [k][c] then bias[k]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_x = (W + 7) >> 3, tiles_y = (H + C::TH - 1) / C::TH;
@@ -92,6 +112,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     }
     if (warp == 1) { tc::tmem_alloc(&tmem_base_sh, TMEM_COLS); tc::tmem_relinquish(); }
     for (int i = threadIdx.x; i < COUT; i += TC_THREADS) { s_scale[i] = scale[i]; s_shift[i] = shift[i]; }
+    if (EPI == EPI_HEAD) {
+        // global layout is [c][k] (+ bias); keep it transposed so one class is 16 contiguous floats
+        for (int i = threadIdx.x; i < COUT * HK; i += TC_THREADS) s_head[(i % HK) * COUT + i / HK] = head.w[i];
+        for (int i = threadIdx.x; i < HK; i += TC_THREADS) s_head[COUT * HK + i] = head.w[COUT * HK + i];
+    }
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
@@ -119,39 +144,47 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         }
     } else if (warp == 1) {
         // ======================================================= MMA issuer
-        if (lane == 0) {
-            const uint32_t idesc = tc::instr_desc_bf16(128, COUT);
-            int stage = 0;
-            uint32_t phase = 0;
-            int it = 0;
-            for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
-                const int buf = it % NBUF;
-                tc::mbar_wait(&tempty_bar[buf], ((it / NBUF) & 1) ^ 1);
+        // The whole warp walks the loop converged (all lanes poll the barriers); one elected
+        // lane issues.  Descriptors = per-stage base + compile-time offset (one add each).
+        const uint32_t idesc = tc::instr_desc_bf16(128, COUT);
+        const uint32_t a_hi = ((C::SBO_A >> 4) & 0x3FFFu) | (1u << 14);
+        const uint32_t b_hi = ((C::SBO_B >> 4) & 0x3FFFu) | (1u << 14);
+        int stage = 0;
+        uint32_t phase = 0;
+        int it = 0;
+        for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+            const int buf = it % NBUF;
+            tc::mbar_wait(&tempty_bar[buf], ((it / NBUF) & 1) ^ 1);
+            tc::tc_fence_after();
+            for (int ks = 0; ks < ksteps; ++ks) {
+                tc::mbar_wait(&full_bar[stage], phase);
                 tc::tc_fence_after();
-                for (int ks = 0; ks < ksteps; ++ks) {
-                    tc::mbar_wait(&full_bar[stage], phase);
-                    tc::tc_fence_after();
+                if (tc::elect_one()) {
                     const uint32_t a_base = tc::smem_u32(smem + (size_t)stage * C::STAGE_BYTES);
-                    const uint32_t b_base = a_base + C::A_BYTES;
+                    const uint32_t a_lo = ((a_base >> 4) & 0x3FFFu) | (((C::LBO_A >> 4) & 0x3FFFu) << 16);
+                    const uint32_t b_lo = (((a_base + C::A_BYTES) >> 4) & 0x3FFFu) |
+                                          (((C::LBO_B >> 4) & 0x3FFFu) << 16);
+                    const uint32_t d0 = tmem_base + buf * C::ACC_COLS;
+                    const uint32_t first = (ks > 0) ? 1u : 0u;
 #pragma unroll
                     for (int j = 0; j < S; ++j) {
 #pragma unroll
                         for (int tp = 0; tp < C::NT; ++tp) {
-                            const uint32_t a_off = UP ? (uint32_t)(j * 16 * C::PW) * 16
-                                                      : (uint32_t)((j * 16 + tp / 3) * C::PW + tp % 3) * 16;
+                            const uint32_t a_off = UP ? (uint32_t)(j * 16 * C::PW)
+                                                      : (uint32_t)((j * 16 + tp / 3) * C::PW + tp % 3);
                             const int q = UP ? tp : 0;
-                            const uint32_t d = tmem_base + buf * C::ACC_COLS + (j * C::NQ + q) * COUT;
-                            const uint32_t acc = UP ? (ks > 0) : (ks > 0 || tp > 0);
-                            tc::umma_bf16(d, tc::smem_desc(a_base + a_off, C::LBO_A, C::SBO_A),
-                                          tc::smem_desc(b_base + tp * 2 * COUT * 16, C::LBO_B, C::SBO_B),
-                                          idesc, acc);
+                            tc::umma_bf16_parts(d0 + (j * C::NQ + q) * COUT, a_lo + a_off, a_hi,
+                                                b_lo + tp * 2 * COUT, b_hi, idesc,
+                                                (UP || tp == 0) ? first : 1u);
                         }
                     }
                     tc::umma_commit(&empty_bar[stage]);      // smem slot reusable once these MMAs retire
-                    if (++stage == nstages) { stage = 0; phase ^= 1; }
                 }
-                tc::umma_commit(&tfull_bar[buf]);            // accumulators of this tile complete
+                __syncwarp();
+                if (++stage == nstages) { stage = 0; phase ^= 1; }
             }
+            if (tc::elect_one()) tc::umma_commit(&tfull_bar[buf]);   // accumulators of this tile complete
+            __syncwarp();
         }
     } else {
         // ========================================================= epilogue
@@ -171,6 +204,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 const int y = ty * C::TH + j * 16 + ph, x = tx * 8 + pw;
                 const bool valid = (y < H) && (x < W);
                 if (!UP) {
+                    float hl[HK > 0 ? HK : 1];                     // fused head: running logits
+#pragma unroll
+                    for (int k = 0; k < HK; ++k) hl[k] = 0.0f;
 #pragma unroll 1
                     for (int c16 = 0; c16 < COUT / 16; ++c16) {
                         uint32_t v[16];
@@ -185,10 +221,83 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                             if (relu) { a = a > 0.0f ? a : 0.0f; b = b > 0.0f ? b : 0.0f; }
                             o[e] = pack_bf16(a, b);
                         }
-                        if (valid) {
-                            bf16 *p = out + ((((size_t)n * CBo + c16 * 2) * H + y) * W + x) * 8;
-                            *reinterpret_cast<uint4 *>(p) = make_uint4(o[0], o[1], o[2], o[3]);
-                            *reinterpret_cast<uint4 *>(p + (size_t)H * W * 8) = make_uint4(o[4], o[5], o[6], o[7]);
+                        if (EPI == EPI_HEAD) {
+                            // the head consumes the activation as it would have been stored (bf16)
+                            float f[16];
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) {
+                                const float2 t2 = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162 *>(&o[e]));
+                                f[2 * e] = t2.x;
+                                f[2 * e + 1] = t2.y;
+                            }
+#pragma unroll
+                            for (int k = 0; k < HK; ++k) {
+                                const float4 *wk = reinterpret_cast<const float4 *>(s_head + k * COUT + c16 * 16);
+#pragma unroll
+                                for (int g = 0; g < 4; ++g) {
+                                    const float4 w4 = wk[g];
+                                    hl[k] = fmaf(f[4 * g], w4.x, hl[k]);
+                                    hl[k] = fmaf(f[4 * g + 1], w4.y, hl[k]);
+                                    hl[k] = fmaf(f[4 * g + 2], w4.z, hl[k]);
+                                    hl[k] = fmaf(f[4 * g + 3], w4.w, hl[k]);
+                                }
+                            }
+                        } else {
+                            if (valid) {
+                                bf16 *p = out + ((((size_t)n * CBo + c16 * 2) * H + y) * W + x) * 8;
+                                *reinterpret_cast<uint4 *>(p) = make_uint4(o[0], o[1], o[2], o[3]);
+                                *reinterpret_cast<uint4 *>(p + (size_t)H * W * 8) = make_uint4(o[4], o[5], o[6], o[7]);
+                            }
+                            if (EPI == EPI_POOL) {
+                                // 2x2 max pool inside the warp: partner pixels are lane^1 (x) and lane^8 (y)
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) {
+                                    uint32_t m = bf162_max(o[e], __shfl_xor_sync(0xffffffffu, o[e], 1));
+                                    o[e] = bf162_max(m, __shfl_xor_sync(0xffffffffu, m, 8));
+                                }
+                                if (valid && (lane & 9) == 0) {
+                                    const int Hp = H >> 1, Wp = W >> 1;
+                                    bf16 *p = out_pool + ((((size_t)n * CBo + c16 * 2) * Hp + (y >> 1)) * Wp + (x >> 1)) * 8;
+                                    *reinterpret_cast<uint4 *>(p) = make_uint4(o[0], o[1], o[2], o[3]);
+                                    *reinterpret_cast<uint4 *>(p + (size_t)Hp * Wp * 8) = make_uint4(o[4], o[5], o[6], o[7]);
+                                }
+                            }
+                        }
+                    }
+                    if (EPI == EPI_HEAD) {
+                        const size_t p = ((size_t)n * H + y) * W + x;
+                        int best = 0;
+                        float m = -INFINITY;
+#pragma unroll
+                        for (int k = 0; k < HK; ++k) {
+                            hl[k] += s_head[COUT * HK + k];
+                            if (hl[k] > m) { m = hl[k]; best = k; }
+                        }
+                        if (head.mask) {
+                            // 8 pixels of one image row sit in 8 consecutive lanes: gather their class
+                            // bytes so that one lane writes 8 contiguous bytes
+                            uint32_t lo = (uint32_t)best << (8 * (lane & 3));
+                            lo |= __shfl_xor_sync(0xffffffffu, lo, 1);
+                            lo |= __shfl_xor_sync(0xffffffffu, lo, 2);
+                            const uint32_t hi = __shfl_down_sync(0xffffffffu, lo, 4);
+                            if (valid && (lane & 7) == 0) {
+                                if (x + 8 <= W && (W & 7) == 0)
+                                    *reinterpret_cast<uint2 *>(head.mask + p) = make_uint2(lo, hi);
+                                else
+                                    for (int i = 0; i < 8 && x + i < W; ++i)
+                                        head.mask[p + i] = (uint8_t)((i < 4 ? lo >> (8 * i) : hi >> (8 * (i - 4))) & 0xff);
+                            }
+                        }
+                        if (valid && head.logits) {
+#pragma unroll
+                            for (int k = 0; k < HK; ++k) head.logits[p * HK + k] = hl[k];
+                        }
+                        if (valid && head.probs) {
+                            float sum = 0.0f;
+#pragma unroll
+                            for (int k = 0; k < HK; ++k) { hl[k] = expf(hl[k] - m); sum += hl[k]; }
+#pragma unroll
+                            for (int k = 0; k < HK; ++k) head.probs[p * HK + k] = hl[k] / sum;
                         }
                     }
                 } else {
@@ -235,62 +344,76 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
 }
 
 // ------------------------------------------------------- bandwidth-bound kernels
-// First conv: fp32 NHWC input with few channels -> bf16 blocked.  wf: [9*CIN][COUT] fp32
-// holding bf16-rounded weights.  One thread per pixel, 8 output channels at a time.
+// First conv: fp32 NHWC input with few channels (K = 9*CIN, not tensor-core material) -> bf16
+// blocked.  wf: [9*CIN][COUT] fp32 holding bf16-rounded weights.  A warp owns one image row
+// segment of 128 pixels; each thread computes 4 pixels (x, x+32, x+64, x+96 -> every store
+// instruction is a fully coalesced 512-byte row) x 8 output channels at a time, so each pair
+// of LDS.128 weight reads feeds 32 FMAs.  HBM-bound: 4*CIN B in, 2*COUT B out per pixel.
 template <int CIN>
-__global__ void first_conv_kernel(const float *__restrict__ in, const float *__restrict__ wf,
-                                  const float *__restrict__ scale, const float *__restrict__ shift,
-                                  bf16 *__restrict__ out, int nimg, int H, int W, int COUT)
+__global__ void __launch_bounds__(128)
+first_conv_kernel(const float *__restrict__ in, const float *__restrict__ wf,
+                  const float *__restrict__ scale, const float *__restrict__ shift,
+                  bf16 *__restrict__ out, int nimg, int H, int W, int COUT)
 {
-    extern __shared__ float sw[];                       // [9*CIN][COUT] + scale + shift
+    extern __shared__ float4 sw4[];                      // [9*CIN][COUT] + scale + shift
+    float *sw = reinterpret_cast<float *>(sw4);
     for (int i = threadIdx.x; i < 9 * CIN * COUT; i += blockDim.x) sw[i] = wf[i];
     float *ssc = sw + 9 * CIN * COUT, *ssh = ssc + COUT;
     for (int i = threadIdx.x; i < COUT; i += blockDim.x) { ssc[i] = scale[i]; ssh[i] = shift[i]; }
     __syncthreads();
-    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= (long long)nimg * H * W) return;
-    const int x = (int)(p % W), y = (int)((p / W) % H);
-    const long long n = p / ((long long)W * H);
-    float v[9 * CIN];
+    const int lane = threadIdx.x & 31;
+    const int y = blockIdx.y * 4 + (threadIdx.x >> 5);
+    const int n = blockIdx.z;
+    if (y >= H) return;
+    const int xb = blockIdx.x * 128 + lane;
+    float v[4][9 * CIN];
 #pragma unroll
-    for (int tp = 0; tp < 9; ++tp) {
-        const int yy = y + tp / 3 - 1, xx = x + tp % 3 - 1;
-        const bool ok = yy >= 0 && yy < H && xx >= 0 && xx < W;
+    for (int j = 0; j < 4; ++j) {
+        const int x = xb + 32 * j;
 #pragma unroll
-        for (int c = 0; c < CIN; ++c)
-            v[tp * CIN + c] = ok ? __bfloat162float(__float2bfloat16_rn(
-                                       in[((n * H + yy) * W + xx) * CIN + c])) : 0.0f;
+        for (int tp = 0; tp < 9; ++tp) {
+            const int yy = y + tp / 3 - 1, xx = x + tp % 3 - 1;
+            const bool ok = yy >= 0 && yy < H && xx >= 0 && xx < W;
+#pragma unroll
+            for (int c = 0; c < CIN; ++c)
+                v[j][tp * CIN + c] = ok ? __bfloat162float(__float2bfloat16_rn(
+                                              in[(((size_t)n * H + yy) * W + xx) * CIN + c])) : 0.0f;
+        }
     }
     for (int cb = 0; cb < COUT / 8; ++cb) {
-        float acc[8];
+        float acc[4][8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) acc[e] = 0.0f;
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[j][e] = 0.0f;
 #pragma unroll
         for (int k = 0; k < 9 * CIN; ++k) {
-            const float *wr = sw + k * COUT + cb * 8;
+            const float4 w0 = *reinterpret_cast<const float4 *>(sw + k * COUT + cb * 8);
+            const float4 w1 = *reinterpret_cast<const float4 *>(sw + k * COUT + cb * 8 + 4);
+            const float wr[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
-            for (int e = 0; e < 8; ++e) acc[e] = fmaf(v[k], wr[e], acc[e]);
-        }
-        uint32_t o[4];
+            for (int j = 0; j < 4; ++j)
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const int c = cb * 8 + 2 * e;
-            float a = fmaf(acc[2 * e], ssc[c], ssh[c]);
-            float b = fmaf(acc[2 * e + 1], ssc[c + 1], ssh[c + 1]);
-            a = a > 0.0f ? a : 0.0f;
-            b = b > 0.0f ? b : 0.0f;
-            o[e] = pack_bf16(a, b);
+                for (int e = 0; e < 8; ++e) acc[j][e] = fmaf(v[j][k], wr[e], acc[j][e]);
         }
-        *reinterpret_cast<uint4 *>(out + ((((size_t)n * (COUT / 8) + cb) * H + y) * W + x) * 8) =
-            make_uint4(o[0], o[1], o[2], o[3]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int x = xb + 32 * j;
+            uint32_t o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int c = cb * 8 + 2 * e;
+                float a = fmaf(acc[j][2 * e], ssc[c], ssh[c]);
+                float b = fmaf(acc[j][2 * e + 1], ssc[c + 1], ssh[c + 1]);
+                a = a > 0.0f ? a : 0.0f;
+                b = b > 0.0f ? b : 0.0f;
+                o[e] = pack_bf16(a, b);
+            }
+            if (x < W)
+                *reinterpret_cast<uint4 *>(out + ((((size_t)n * (COUT / 8) + cb) * H + y) * W + x) * 8) =
+                    make_uint4(o[0], o[1], o[2], o[3]);
+        }
     }
-}
-
-__device__ __forceinline__ uint32_t bf162_max(uint32_t a, uint32_t b)
-{
-    __nv_bfloat162 x = *reinterpret_cast<__nv_bfloat162 *>(&a), y = *reinterpret_cast<__nv_bfloat162 *>(&b);
-    __nv_bfloat162 m = __hmax2(x, y);
-    return *reinterpret_cast<uint32_t *>(&m);
 }
 
 // 2x2 max pool on the blocked layout: one thread per output 16-byte vector.
@@ -411,42 +534,71 @@ int make_map(CUtensorMap *m, const bf16 *ptr, int nimg, int CB, int H, int W, in
     return SQ_OK;
 }
 
-template <int COUT, int S, bool UP, int NBUF>
+template <int COUT, int S, bool UP, int NBUF, int MINB, int EPI, int HK = 0>
 int launch_tc(sq_unet_s *u, const SqLayer &L, const bf16 *in0, int cb0, const bf16 *in1, int cb1,
-              bf16 *out, int nimg, int H, int W, int relu, cudaStream_t st)
+              bf16 *out, bf16 *out_pool, const HeadArgs &head, int nimg, int H, int W, int relu,
+              cudaStream_t st)
 {
     using C = Cfg<COUT, S, UP>;
     CUtensorMap m0, m1;
     SQ_TRY(make_map(&m0, in0, nimg, cb0, H, W, C::PW, C::PH));
     if (in1) SQ_TRY(make_map(&m1, in1, nimg, cb1, H, W, C::PW, C::PH));
     else m1 = m0;
-    int nstages = std::min(MAX_STAGES, (200 * 1024) / C::STAGE_BYTES);
+    static_assert(MINB * NBUF * C::ACC_COLS <= 512, "co-resident CTAs must fit in TMEM");
+    int nstages = std::min(MAX_STAGES, ((MINB == 2 ? 108 : 200) * 1024) / C::STAGE_BYTES);
     nstages = std::max(nstages, 2);
     const size_t smem = (size_t)nstages * C::STAGE_BYTES + 1024;
-    auto kern = conv_tc_kernel<COUT, S, UP, NBUF>;
+    auto kern = conv_tc_kernel<COUT, S, UP, NBUF, MINB, EPI, HK>;
     static bool attr_set = false;
     if (!attr_set) {
         SQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
     const int tiles = nimg * ((W + 7) / 8) * ((H + C::TH - 1) / C::TH);
-    const int grid = std::min(tiles, u->h->sm_count);
+    const int grid = std::min(tiles, MINB * u->h->sm_count);
     kern<<<grid, TC_THREADS, smem, st>>>(m0, m1, cb0 / 2, in1 ? cb1 / 2 : 0, (const bf16 *)L.w_tc, L.scale,
-                                         L.shift, out, nimg, H, W, relu, nstages);
+                                         L.shift, out, out_pool, head, nimg, H, W, relu, nstages);
     ++u->last_launches;
     SQ_CHECK_LAUNCH();
     return SQ_OK;
 }
 
+template <int COUT, int S, int MINB>
+int conv3x3_epi(sq_unet_s *u, const SqLayer &L, const bf16 *in0, int c0, const bf16 *in1, int c1,
+                bf16 *out, bf16 *out_pool, const HeadArgs *head, int nimg, int H, int W, cudaStream_t st)
+{
+    const HeadArgs none = {nullptr, 0, nullptr, nullptr, nullptr};
+    if (head) {
+        if constexpr (COUT <= 32) {
+            switch (head->K) {
+            case 2: return launch_tc<COUT, S, false, 2, MINB, EPI_HEAD, 2>(u, L, in0, c0 / 8, in1, c1 / 8, out, nullptr, *head, nimg, H, W, 1, st);
+            case 3: return launch_tc<COUT, S, false, 2, MINB, EPI_HEAD, 3>(u, L, in0, c0 / 8, in1, c1 / 8, out, nullptr, *head, nimg, H, W, 1, st);
+            case 4: return launch_tc<COUT, S, false, 2, MINB, EPI_HEAD, 4>(u, L, in0, c0 / 8, in1, c1 / 8, out, nullptr, *head, nimg, H, W, 1, st);
+            }
+        }
+        SQ_REQUIRE(false, SQ_EUNSUPPORTED, "fused head supports filters[0] <= 32 and 2..4 classes");
+    }
+    if (out_pool) {
+        if constexpr (COUT <= 128)
+            return launch_tc<COUT, S, false, 2, MINB, EPI_POOL>(u, L, in0, c0 / 8, in1, c1 / 8, out, out_pool,
+                                                                none, nimg, H, W, 1, st);
+        else
+            SQ_REQUIRE(false, SQ_EUNSUPPORTED, "fused pool needs filters <= 128");
+    }
+    return launch_tc<COUT, S, false, 2, MINB, EPI_STORE>(u, L, in0, c0 / 8, in1, c1 / 8, out, nullptr, none,
+                                                         nimg, H, W, 1, st);
+}
+
+// out_pool != NULL: also write the 2x2 max-pooled tensor; head != NULL: fused 1x1 head, no `out`.
 int conv3x3_tc(sq_unet_s *u, const SqLayer &L, const bf16 *in0, int c0, const bf16 *in1, int c1,
-               bf16 *out, int nimg, int H, int W, cudaStream_t st)
+               bf16 *out, bf16 *out_pool, const HeadArgs *head, int nimg, int H, int W, cudaStream_t st)
 {
     switch (L.cout) {
-    case 16:  return launch_tc<16, 4, false, 2>(u, L, in0, c0 / 8, in1, c1 / 8, out, nimg, H, W, 1, st);
-    case 32:  return launch_tc<32, 4, false, 2>(u, L, in0, c0 / 8, in1, c1 / 8, out, nimg, H, W, 1, st);
-    case 64:  return launch_tc<64, 4, false, 2>(u, L, in0, c0 / 8, in1, c1 / 8, out, nimg, H, W, 1, st);
-    case 128: return launch_tc<128, 2, false, 2>(u, L, in0, c0 / 8, in1, c1 / 8, out, nimg, H, W, 1, st);
-    case 256: return launch_tc<256, 1, false, 2>(u, L, in0, c0 / 8, in1, c1 / 8, out, nimg, H, W, 1, st);
+    case 16:  return conv3x3_epi<16, 4, 2>(u, L, in0, c0, in1, c1, out, out_pool, head, nimg, H, W, st);
+    case 32:  return conv3x3_epi<32, 4, 2>(u, L, in0, c0, in1, c1, out, out_pool, head, nimg, H, W, st);
+    case 64:  return conv3x3_epi<64, 2, 2>(u, L, in0, c0, in1, c1, out, out_pool, head, nimg, H, W, st);
+    case 128: return conv3x3_epi<128, 2, 1>(u, L, in0, c0, in1, c1, out, out_pool, head, nimg, H, W, st);
+    case 256: return conv3x3_epi<256, 1, 1>(u, L, in0, c0, in1, c1, out, out_pool, head, nimg, H, W, st);
     }
     SQ_REQUIRE(false, SQ_EUNSUPPORTED, "bf16 mode: unsupported filter count %d", L.cout);
 }
@@ -454,11 +606,12 @@ int conv3x3_tc(sq_unet_s *u, const SqLayer &L, const bf16 *in0, int c0, const bf
 int upconv_tc(sq_unet_s *u, const SqLayer &L, const bf16 *in, bf16 *out, int nimg, int H, int W,
               cudaStream_t st)
 {
+    const HeadArgs none = {nullptr, 0, nullptr, nullptr, nullptr};
     switch (L.cout) {
-    case 16:  return launch_tc<16, 2, true, 2>(u, L, in, L.cin0 / 8, nullptr, 0, out, nimg, H, W, 0, st);
-    case 32:  return launch_tc<32, 1, true, 2>(u, L, in, L.cin0 / 8, nullptr, 0, out, nimg, H, W, 0, st);
-    case 64:  return launch_tc<64, 1, true, 2>(u, L, in, L.cin0 / 8, nullptr, 0, out, nimg, H, W, 0, st);
-    case 128: return launch_tc<128, 1, true, 1>(u, L, in, L.cin0 / 8, nullptr, 0, out, nimg, H, W, 0, st);
+    case 16:  return launch_tc<16, 2, true, 2, 2, EPI_STORE>(u, L, in, L.cin0 / 8, nullptr, 0, out, nullptr, none, nimg, H, W, 0, st);
+    case 32:  return launch_tc<32, 1, true, 2, 2, EPI_STORE>(u, L, in, L.cin0 / 8, nullptr, 0, out, nullptr, none, nimg, H, W, 0, st);
+    case 64:  return launch_tc<64, 1, true, 2, 1, EPI_STORE>(u, L, in, L.cin0 / 8, nullptr, 0, out, nullptr, none, nimg, H, W, 0, st);
+    case 128: return launch_tc<128, 1, true, 1, 1, EPI_STORE>(u, L, in, L.cin0 / 8, nullptr, 0, out, nullptr, none, nimg, H, W, 0, st);
     }
     SQ_REQUIRE(false, SQ_EUNSUPPORTED, "bf16 mode: unsupported up-conv filter count %d", L.cout);
 }
@@ -522,6 +675,10 @@ int sq_tc_finalize(sq_unet_s *u)
             // first conv / head: CUDA-core kernels read fp32 copies of the bf16-rounded weights
             std::vector<float> w(k.size());
             for (size_t i = 0; i < k.size(); ++i) w[i] = host_bf16_round(k[i]);
+            if (L.kind == SqLayer::HEAD) {              // fused head reads [C][K] weights then bias[K]
+                const std::vector<float> &b = u->host[L.scope + "/bias"].data;
+                w.insert(w.end(), b.begin(), b.end());
+            }
             SQ_TRY(dev_upload(u, w.data(), w.size() * 4, &L.w_tc));
         }
     }
@@ -561,6 +718,7 @@ int tc_run(sq_unet_s *u, bool dry, const float *in, int n, int hgt, int wid, flo
     sq_timer_mark(u, st, nullptr, 0);
     const int threads = 256;
     char scope[64];
+    std::vector<char> pool_fused(nl + 1, 0);
     for (int l = 0; l < nl; ++l) {
         const int H = hgt >> l, W = wid >> l;
         const long long px = (long long)n * H * W;
@@ -570,28 +728,36 @@ int tc_run(sq_unet_s *u, bool dry, const float *in, int n, int hgt, int wid, flo
         SqLayer *c2 = layer_by_scope(u, scope);
         if (l == 0) {
             const size_t sm = (size_t)(9 * u->cin * c1->cout + 2 * c1->cout) * sizeof(float);
-            const unsigned gx = (unsigned)((px + 127) / 128);
+            const dim3 grid((W + 127) / 128, (H + 3) / 4, n);
             switch (u->cin) {
-            case 1: first_conv_kernel<1><<<gx, 128, sm, st>>>(in, (const float *)c1->w_tc, c1->scale, c1->shift, t1[0], n, H, W, c1->cout); break;
-            case 2: first_conv_kernel<2><<<gx, 128, sm, st>>>(in, (const float *)c1->w_tc, c1->scale, c1->shift, t1[0], n, H, W, c1->cout); break;
-            case 3: first_conv_kernel<3><<<gx, 128, sm, st>>>(in, (const float *)c1->w_tc, c1->scale, c1->shift, t1[0], n, H, W, c1->cout); break;
-            default: first_conv_kernel<4><<<gx, 128, sm, st>>>(in, (const float *)c1->w_tc, c1->scale, c1->shift, t1[0], n, H, W, c1->cout); break;
+            case 1: first_conv_kernel<1><<<grid, 128, sm, st>>>(in, (const float *)c1->w_tc, c1->scale, c1->shift, t1[0], n, H, W, c1->cout); break;
+            case 2: first_conv_kernel<2><<<grid, 128, sm, st>>>(in, (const float *)c1->w_tc, c1->scale, c1->shift, t1[0], n, H, W, c1->cout); break;
+            case 3: first_conv_kernel<3><<<grid, 128, sm, st>>>(in, (const float *)c1->w_tc, c1->scale, c1->shift, t1[0], n, H, W, c1->cout); break;
+            default: first_conv_kernel<4><<<grid, 128, sm, st>>>(in, (const float *)c1->w_tc, c1->scale, c1->shift, t1[0], n, H, W, c1->cout); break;
             }
             ++u->last_launches;
             SQ_CHECK_LAUNCH();
         } else {
-            const long long nvec = px * (u->filters[l - 1] / 8);
-            maxpool_bf16_kernel<<<(unsigned)((nvec + threads - 1) / threads), threads, 0, st>>>(
-                (const uint4 *)skip[l - 1], (uint4 *)pooled[l], nvec, H, W);
-            ++u->last_launches;
-            SQ_CHECK_LAUNCH();
-            sq_timer_mark(u, st, "maxpool", 0);
-            SQ_TRY(conv3x3_tc(u, *c1, pooled[l], c1->cin0, nullptr, 0, t1[l], n, H, W, st));
+            if (!pool_fused[l]) {
+                const long long nvec = px * (u->filters[l - 1] / 8);
+                maxpool_bf16_kernel<<<(unsigned)((nvec + threads - 1) / threads), threads, 0, st>>>(
+                    (const uint4 *)skip[l - 1], (uint4 *)pooled[l], nvec, H, W);
+                ++u->last_launches;
+                SQ_CHECK_LAUNCH();
+                sq_timer_mark(u, st, "maxpool", 0);
+            }
+            SQ_TRY(conv3x3_tc(u, *c1, pooled[l], c1->cin0, nullptr, 0, t1[l], nullptr, nullptr, n, H, W, st));
         }
         sq_timer_mark(u, st, c1->scope.c_str(), c1->flops_per_px * px);
-        SQ_TRY(conv3x3_tc(u, *c2, t1[l], c2->cin0, nullptr, 0, skip[l], n, H, W, st));
+        // the level's second conv also emits the pooled tensor the next level starts from
+        const bool fuse_pool = (l < nl - 1) && c2->cout <= 128;
+        if (l < nl - 1) pool_fused[l + 1] = fuse_pool;
+        SQ_TRY(conv3x3_tc(u, *c2, t1[l], c2->cin0, nullptr, 0, skip[l], fuse_pool ? pooled[l + 1] : nullptr,
+                          nullptr, n, H, W, st));
         sq_timer_mark(u, st, c2->scope.c_str(), c2->flops_per_px * px);
     }
+    SqLayer *head = layer_by_scope(u, "UNet/to_image");
+    const bool head_fused = nl >= 2 && head->cout >= 2 && head->cout <= 4 && u->filters[0] <= 32;
     const bf16 *cur = skip[nl - 1];
     for (int l = nl - 2; l >= 0; --l) {
         const int H = hgt >> l, W = wid >> l;
@@ -616,13 +782,19 @@ int tc_run(sq_unet_s *u, bool dry, const float *in, int n, int hgt, int wid, flo
             sq_timer_mark(u, st, "bridge", 0);
             in0 = merged[l];
         }
-        SQ_TRY(conv3x3_tc(u, *c1, in0, c1->cin0, in1, c1->cin1, ut[l], n, H, W, st));
+        SQ_TRY(conv3x3_tc(u, *c1, in0, c1->cin0, in1, c1->cin1, ut[l], nullptr, nullptr, n, H, W, st));
         sq_timer_mark(u, st, c1->scope.c_str(), c1->flops_per_px * px);
-        SQ_TRY(conv3x3_tc(u, *c2, ut[l], c2->cin0, nullptr, 0, uo[l], n, H, W, st));
+        if (l == 0 && head_fused) {
+            // last conv of the net: 1x1 head + softmax + argmax run in its epilogue
+            const HeadArgs ha = {(const float *)head->w_tc, head->cout, logits, probs, mask};
+            SQ_TRY(conv3x3_tc(u, *c2, ut[l], c2->cin0, nullptr, 0, nullptr, nullptr, &ha, n, H, W, st));
+            sq_timer_mark(u, st, c2->scope.c_str(), (c2->flops_per_px + head->flops_per_px) * px);
+            return SQ_OK;
+        }
+        SQ_TRY(conv3x3_tc(u, *c2, ut[l], c2->cin0, nullptr, 0, uo[l], nullptr, nullptr, n, H, W, st));
         sq_timer_mark(u, st, c2->scope.c_str(), c2->flops_per_px * px);
         cur = uo[l];
     }
-    SqLayer *head = layer_by_scope(u, "UNet/to_image");
     const long long px0 = (long long)hgt * wid;
     const size_t sm = (size_t)(head->cin0 * head->cout + head->cout) * sizeof(float);
     head_bf16_kernel<<<(unsigned)((px0 * n + 127) / 128), 128, sm, st>>>(

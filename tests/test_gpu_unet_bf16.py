@@ -65,6 +65,15 @@ def test_default_filters(sq, shape, cin, k):
     np.testing.assert_array_equal(out['logits'][1:2], one['logits'])
 
 
+def test_many_classes_uses_standalone_head(sq):
+    """K > 8 classes: the 1x1 head runs as its own kernel instead of in the last conv's epilogue."""
+    filters = (16, 32)
+    w = synth.unet_weights(filters, 1, 10, seed=11)
+    x = synth.frames(1, 64, 64, 1, seed=3, n_objects=3)
+    out = _net(filters, (64, 64), 'concat', 1, 10, w).predict(x)
+    _compare(out, unet_c.unet_forward(x, w, filters, 'concat', contract='bf16'), 'K=10')
+
+
 def test_layer_by_layer_first_level(sq):
     """Single-level net: first conv (CUDA cores) -> one tcgen05 conv -> head."""
     filters = (16,)
