@@ -36,6 +36,10 @@ extern "C" int sq_create(int device, sq_handle_t *out)
     h->total_mem = prop.totalGlobalMem;
     SQ_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     SQ_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        SQ_CUDA(cudaEventCreateWithFlags(&h->ev_h2d[i], cudaEventDisableTiming));
+        SQ_CUDA(cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
+    }
     *out = h;
     return SQ_OK;
 }
@@ -48,6 +52,10 @@ extern "C" int sq_destroy(sq_handle_t h)
     if (h->dev_arena) cudaFree(h->dev_arena);
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    for (int i = 0; i < 2; ++i) {
+        if (h->ev_h2d[i]) cudaEventDestroy(h->ev_h2d[i]);
+        if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
+    }
     delete h;
     return SQ_OK;
 }

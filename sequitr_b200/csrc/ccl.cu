@@ -79,7 +79,7 @@ __global__ void ccl_init(const uint8_t *__restrict__ mask, int *__restrict__ L, 
     const unsigned m = ~bits & ((2u << lane) - 1u);
     const int s = 31 - __clz(m);
     const int idx = (z * dm.H + y) * dm.W + x;
-    L[g] = v ? (idx - (lane - s)) : -1;
+    if (v) L[g] = idx - (lane - s);            // background entries of L are never read
 }
 
 __global__ void ccl_merge(const uint8_t *__restrict__ mask, int *__restrict__ L, Dims dm)
@@ -125,22 +125,22 @@ __device__ __forceinline__ int block_sum_256(int v, int *sh)
 }
 
 // grid (nchunks, n), block 256
-__global__ void ccl_compress(int *__restrict__ L, int *__restrict__ chunk_count, Dims dm)
+__global__ void ccl_compress(const uint8_t *__restrict__ mask, int *__restrict__ L,
+                             int *__restrict__ chunk_count, Dims dm)
 {
     __shared__ int sh[8];
     int *Lf = L + (long long)blockIdx.y * dm.vox;
+    const uint8_t *mk = mask + (long long)blockIdx.y * dm.vox;
     const int base = blockIdx.x * CHUNK;
     int cnt = 0;
 #pragma unroll
     for (int k = 0; k < CHUNK / CHUNK_THREADS; ++k) {
         const int i = base + k * CHUNK_THREADS + threadIdx.x;
-        if (i < dm.vox) {
+        if (i < dm.vox && mk[i]) {
             const int l = Lf[i];
-            if (l >= 0) {
-                const int r = find_root(Lf, i);
-                if (r != l) Lf[i] = r;
-                cnt += (r == i);
-            }
+            const int r = find_root(Lf, i);
+            if (r != l) Lf[i] = r;
+            cnt += (r == i);
         }
     }
     const int tot = block_sum_256(cnt, sh);
@@ -187,20 +187,21 @@ __global__ void ccl_scan(const int *__restrict__ chunk_count, int *__restrict__ 
 }
 
 // grid (nchunks, n), block 256: thread t owns 8 consecutive voxels (keeps raster order)
-__global__ void ccl_emit(const int *__restrict__ L, const int *__restrict__ chunk_count,
-                         const int *__restrict__ chunk_off, int *__restrict__ rootlist,
-                         Dims dm, int max_rows)
+__global__ void ccl_emit(const uint8_t *__restrict__ mask, const int *__restrict__ L,
+                         const int *__restrict__ chunk_count, const int *__restrict__ chunk_off,
+                         int *__restrict__ rootlist, Dims dm, int max_rows)
 {
     __shared__ int warp_sums[8];
     const int f = blockIdx.y;
     if (chunk_count[f * dm.nchunks + blockIdx.x] == 0) return;
     const int *Lf = L + (long long)f * dm.vox;
+    const uint8_t *mk = mask + (long long)f * dm.vox;
     const int base = blockIdx.x * CHUNK + threadIdx.x * 8;
     int flags = 0, cnt = 0;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         const int i = base + k;
-        if (i < dm.vox && Lf[i] == i) { flags |= 1 << k; ++cnt; }
+        if (i < dm.vox && mk[i] && Lf[i] == i) { flags |= 1 << k; ++cnt; }
     }
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     int s = cnt;
@@ -222,13 +223,19 @@ __global__ void ccl_emit(const int *__restrict__ L, const int *__restrict__ chun
 }
 
 // grid (n), block 256: stable counting sort of the frame's roots by class value.
-// Thread c owns class value c.  Writes L[root] = -2 - row, sorted_root, class_base.
+// Writes L[root] = -2 - row, sorted_root, class_base.  The class histogram uses shared-memory
+// atomics; the stable rank of root j is base[class] + #(i < j with the same class).  For up to
+// ORDER_PAR roots every thread counts its predecessors in parallel (O(n^2/256), a few
+// microseconds for the hundreds of cells of a real frame); beyond that thread c walks the
+// raster-ordered list for class c.
+constexpr int ORDER_PAR = 4096;
+
 __global__ void ccl_order(const uint8_t *__restrict__ mask, int *__restrict__ L,
                           const int *__restrict__ rootlist, const int *__restrict__ totals,
                           int *__restrict__ sorted_root, int *__restrict__ class_base,
                           Dims dm, int max_rows)
 {
-    __shared__ uint8_t cls[1024];
+    __shared__ uint8_t cls[ORDER_PAR];
     __shared__ int cnt_sh[256];
     const int f = blockIdx.x;
     const int c = threadIdx.x;
@@ -238,39 +245,38 @@ __global__ void ccl_order(const uint8_t *__restrict__ mask, int *__restrict__ L,
     const int *rl = rootlist + (long long)f * max_rows;
     int *sr = sorted_root + (long long)f * max_rows;
 
-    int cnt = 0;
-    for (int start = 0; start < n; start += 1024) {
-        const int m = min(1024, n - start);
-        for (int j = threadIdx.x; j < m; j += 256) cls[j] = mk[rl[start + j]];
-        __syncthreads();
-        for (int j = 0; j < m; ++j) cnt += (cls[j] == c);
-        __syncthreads();
+    cnt_sh[c] = 0;
+    __syncthreads();
+    for (int j = c; j < n; j += 256) {
+        const uint8_t v = mk[rl[j]];
+        if (j < ORDER_PAR) cls[j] = v;
+        atomicAdd(&cnt_sh[v], 1);
     }
-    cnt_sh[c] = cnt;
+    __syncthreads();
+    const int mine = cnt_sh[c];
     __syncthreads();
     if (c == 0) {
         int run = 0;
         for (int k = 0; k < 256; ++k) { int t = cnt_sh[k]; cnt_sh[k] = run; run += t; }
     }
     __syncthreads();
-    int k = cnt_sh[c];
-    class_base[f * 256 + c] = k;
-    if (cnt == 0) {
-        // still has to take part in the barriers below
-    }
-    for (int start = 0; start < n; start += 1024) {
-        const int m = min(1024, n - start);
-        for (int j = threadIdx.x; j < m; j += 256) cls[j] = mk[rl[start + j]];
-        __syncthreads();
-        if (cnt > 0)
-            for (int j = 0; j < m; ++j)
-                if (cls[j] == c) {
-                    const int r = rl[start + j];
-                    Lf[r] = -2 - k;
-                    sr[k] = r;
-                    ++k;
-                }
-        __syncthreads();
+    class_base[f * 256 + c] = cnt_sh[c];
+    if (n <= ORDER_PAR) {
+        for (int j = c; j < n; j += 256) {
+            const uint8_t v = cls[j];
+            int rank = 0;
+            for (int i = 0; i < j; ++i) rank += (cls[i] == v);
+            const int row = cnt_sh[v] + rank;
+            const int r = rl[j];
+            Lf[r] = -2 - row;
+            sr[row] = r;
+        }
+    } else if (mine > 0) {
+        int k = cnt_sh[c];
+        for (int j = 0; j < n; ++j) {
+            const int r = rl[j];
+            if (mk[r] == c) { Lf[r] = -2 - k; sr[k] = r; ++k; }
+        }
     }
 }
 
@@ -424,9 +430,9 @@ extern "C" int sq_label_centroids(sq_handle_t h, const uint8_t *mask, int n, int
         ccl_merge<<<grid, blk, 0, st>>>(mask + off, w.L + off, sub);
     }
     SQ_CHECK_LAUNCH();
-    ccl_compress<<<dim3(dm.nchunks, n), CHUNK_THREADS, 0, st>>>(w.L, w.chunk_count, dm);
+    ccl_compress<<<dim3(dm.nchunks, n), CHUNK_THREADS, 0, st>>>(mask, w.L, w.chunk_count, dm);
     ccl_scan<<<n, 1024, 0, st>>>(w.chunk_count, w.chunk_off, w.totals, dm);
-    ccl_emit<<<dim3(dm.nchunks, n), CHUNK_THREADS, 0, st>>>(w.L, w.chunk_count, w.chunk_off,
+    ccl_emit<<<dim3(dm.nchunks, n), CHUNK_THREADS, 0, st>>>(mask, w.L, w.chunk_count, w.chunk_off,
                                                            w.rootlist, dm, max_rows);
     ccl_order<<<n, 256, 0, st>>>(mask, w.L, w.rootlist, w.totals, w.sorted_root, w.class_base,
                                  dm, max_rows);

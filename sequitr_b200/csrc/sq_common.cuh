@@ -54,6 +54,7 @@ struct sq_handle_s {
     size_t dev_arena_bytes = 0;
     cudaStream_t stream = nullptr;      // library-owned stream for *_host calls
     cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
 };
 
 int sq_reserve_pinned(sq_handle_s *h, size_t bytes);

@@ -534,26 +534,42 @@ extern "C" int sq_segment_localise_host(sq_unet_t u, const float *frames_host, i
     SQ_REQUIRE(frames_host && table_host && counts_host, SQ_EINVAL, "segment_localise_host: null pointer");
     sq_handle_s *h = u->h;
     SQ_CUDA(cudaSetDevice(h->device));
-    const size_t px = (size_t)n * hgt * wid;
+    // Frames stream through in chunks: the H2D copy of chunk c+1 (copy stream, double-buffered
+    // input) overlaps the UNet of chunk c (compute stream); label-and-localise then runs once
+    // over the whole batch of masks and only the small centroid tables travel back.
+    const size_t px1 = (size_t)hgt * wid, px = (size_t)n * px1;
+    const int ch = n >= 8 ? 4 : (n >= 2 ? n / 2 : 1);
+    const int nchunks = (n + ch - 1) / ch;
     size_t unet_ws = 0, lab_ws = 0;
-    SQ_TRY(sq_unet_workspace_bytes(u, n, 1, hgt, wid, &unet_ws));
+    SQ_TRY(sq_unet_workspace_bytes(u, ch, 1, hgt, wid, &unet_ws));
     SQ_TRY(sq_label_workspace_bytes(h, n, 1, hgt, wid, max_rows, &lab_ws));
     SqArena probe(nullptr, 0);
-    probe.take<float>(px * u->cin);
+    probe.take<float>(2 * ch * px1 * u->cin);
     probe.take<uint8_t>(px);
     probe.take<float>((size_t)n * max_rows * 5);
     probe.take<int32_t>(n);
     SQ_TRY(sq_reserve_device(h, probe.off + sq_align_up(unet_ws) + sq_align_up(lab_ws) + 1024));
     SqArena a(h->dev_arena, h->dev_arena_bytes);
-    float *frames = a.take<float>(px * u->cin);
+    float *frames = a.take<float>(2 * ch * px1 * u->cin);
     uint8_t *mask = a.take<uint8_t>(px);
     float *table = a.take<float>((size_t)n * max_rows * 5);
     int32_t *counts = a.take<int32_t>(n);
     void *w1 = a.take<char>(unet_ws);
     void *w2 = a.take<char>(lab_ws);
-    cudaStream_t st = h->stream;
-    SQ_CUDA(cudaMemcpyAsync(frames, frames_host, px * u->cin * sizeof(float), cudaMemcpyHostToDevice, st));
-    SQ_TRY(sq_unet_forward(u, frames, n, 1, hgt, wid, nullptr, mask, nullptr, w1, unet_ws, st));
+    cudaStream_t st = h->stream, cs = h->copy_stream;
+    for (int c = 0; c < nchunks; ++c) {
+        const int b = c & 1;
+        const int f0 = c * ch, nc = (n - f0 < ch) ? n - f0 : ch;
+        float *buf = frames + (size_t)b * ch * px1 * u->cin;
+        if (c >= 2) SQ_CUDA(cudaStreamWaitEvent(cs, h->ev_done[b], 0));     // buffer b is free again
+        SQ_CUDA(cudaMemcpyAsync(buf, frames_host + (size_t)f0 * px1 * u->cin,
+                                (size_t)nc * px1 * u->cin * sizeof(float), cudaMemcpyHostToDevice, cs));
+        SQ_CUDA(cudaEventRecord(h->ev_h2d[b], cs));
+        SQ_CUDA(cudaStreamWaitEvent(st, h->ev_h2d[b], 0));
+        SQ_TRY(sq_unet_forward(u, buf, nc, 1, hgt, wid, nullptr, mask + (size_t)f0 * px1, nullptr, w1,
+                               unet_ws, st));
+        SQ_CUDA(cudaEventRecord(h->ev_done[b], st));
+    }
     SQ_TRY(sq_label_centroids(h, mask, n, 1, hgt, wid, frame0, nullptr, table, counts, max_rows, w2,
                               lab_ws, st));
     SQ_CUDA(cudaMemcpyAsync(counts_host, counts, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));

@@ -95,7 +95,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     uint8_t *smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
     __shared__ uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], tfull_bar[2], tempty_bar[2];
     __shared__ uint32_t tmem_base_sh;
-    __shared__ float s_scale[COUT], s_shift[COUT];
+    __shared__ __align__(16) float s_scale[COUT], s_shift[COUT];
     __shared__ __align__(16) float s_head[EPI == EPI_HEAD ? COUT * HK + HK : 4];   // [k][c] then bias[k]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -214,12 +214,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                         tc::tmem_ld_wait();
                         uint32_t o[8];
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            const int c = c16 * 16 + 2 * e;
-                            float a = fmaf(__uint_as_float(v[2 * e]), s_scale[c], s_shift[c]);
-                            float b = fmaf(__uint_as_float(v[2 * e + 1]), s_scale[c + 1], s_shift[c + 1]);
-                            if (relu) { a = a > 0.0f ? a : 0.0f; b = b > 0.0f ? b : 0.0f; }
-                            o[e] = pack_bf16(a, b);
+                        for (int g = 0; g < 4; ++g) {
+                            const float4 sc = *reinterpret_cast<const float4 *>(s_scale + c16 * 16 + 4 * g);
+                            const float4 sh = *reinterpret_cast<const float4 *>(s_shift + c16 * 16 + 4 * g);
+                            float a = fmaf(__uint_as_float(v[4 * g]), sc.x, sh.x);
+                            float b = fmaf(__uint_as_float(v[4 * g + 1]), sc.y, sh.y);
+                            float c = fmaf(__uint_as_float(v[4 * g + 2]), sc.z, sh.z);
+                            float d = fmaf(__uint_as_float(v[4 * g + 3]), sc.w, sh.w);
+                            if (relu) { a = fmaxf(a, 0.0f); b = fmaxf(b, 0.0f); c = fmaxf(c, 0.0f); d = fmaxf(d, 0.0f); }
+                            o[2 * g] = pack_bf16(a, b);
+                            o[2 * g + 1] = pack_bf16(c, d);
                         }
                         if (EPI == EPI_HEAD) {
                             // the head consumes the activation as it would have been stored (bf16)
@@ -314,12 +318,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                             tc::tmem_ld_wait();
                             uint32_t o0[4], o1[4];
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const int c = c8 * 8 + 2 * e;
-                                o0[e] = pack_bf16(__uint_as_float(v0[2 * e]) + s_shift[c],
-                                                  __uint_as_float(v0[2 * e + 1]) + s_shift[c + 1]);
-                                o1[e] = pack_bf16(__uint_as_float(v1[2 * e]) + s_shift[c],
-                                                  __uint_as_float(v1[2 * e + 1]) + s_shift[c + 1]);
+                            for (int g = 0; g < 2; ++g) {
+                                const float4 sh = *reinterpret_cast<const float4 *>(s_shift + c8 * 8 + 4 * g);
+                                o0[2 * g] = pack_bf16(__uint_as_float(v0[4 * g]) + sh.x, __uint_as_float(v0[4 * g + 1]) + sh.y);
+                                o0[2 * g + 1] = pack_bf16(__uint_as_float(v0[4 * g + 2]) + sh.z, __uint_as_float(v0[4 * g + 3]) + sh.w);
+                                o1[2 * g] = pack_bf16(__uint_as_float(v1[4 * g]) + sh.x, __uint_as_float(v1[4 * g + 1]) + sh.y);
+                                o1[2 * g + 1] = pack_bf16(__uint_as_float(v1[4 * g + 2]) + sh.z, __uint_as_float(v1[4 * g + 3]) + sh.w);
                             }
                             if (valid) {
                                 bf16 *p = out + ((((size_t)n * CBo + c8) * Ho + 2 * y + ky) * Wo + 2 * x) * 8;
@@ -344,75 +348,111 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
 }
 
 // ------------------------------------------------------- bandwidth-bound kernels
-// First conv: fp32 NHWC input with few channels (K = 9*CIN, not tensor-core material) -> bf16
-// blocked.  wf: [9*CIN][COUT] fp32 holding bf16-rounded weights.  A warp owns one image row
-// segment of 128 pixels; each thread computes 4 pixels (x, x+32, x+64, x+96 -> every store
-// instruction is a fully coalesced 512-byte row) x 8 output channels at a time, so each pair
-// of LDS.128 weight reads feeds 32 FMAs.  HBM-bound: 4*CIN B in, 2*COUT B out per pixel.
-template <int CIN>
-__global__ void __launch_bounds__(128)
+// First conv: fp32 NHWC input with few channels -> bf16 blocked.  K = 9*CIN (9 or 27) is far
+// too small for a tcgen05 tile, and on CUDA cores the layer is instruction-bound (144 FMA per
+// pixel at Cout=16) instead of HBM-bound.  A warp-level mma.sync (m16n8k16, bf16 x bf16 -> fp32)
+// does the 16-pixel x 16-tap x 8-channel product in one instruction from registers: the A
+// fragment is the im2col of 16 consecutive pixels (k = tap*CIN + c, zero beyond 9*CIN), built
+// straight from the (L1-cached) input; B fragments (weights) live in registers.
+// wf: [9*CIN][COUT] fp32 holding bf16-rounded weights.  HBM-bound: 4*CIN B in, 2*COUT B out per px.
+__device__ __forceinline__ void mma_m16n8k16_bf16(float *c, const uint32_t *a, uint32_t b0, uint32_t b1)
+{
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+        "{%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+constexpr int FIRST_ROWS = 8;              // rows per block (one warp per row)
+constexpr int FIRST_TW = 128;              // pixels per block row
+
+template <int CIN, int COUT>
+__global__ void __launch_bounds__(256)
 first_conv_kernel(const float *__restrict__ in, const float *__restrict__ wf,
                   const float *__restrict__ scale, const float *__restrict__ shift,
-                  bf16 *__restrict__ out, int nimg, int H, int W, int COUT)
+                  bf16 *__restrict__ out, int nimg, int H, int W)
 {
-    extern __shared__ float4 sw4[];                      // [9*CIN][COUT] + scale + shift
-    float *sw = reinterpret_cast<float *>(sw4);
-    for (int i = threadIdx.x; i < 9 * CIN * COUT; i += blockDim.x) sw[i] = wf[i];
-    float *ssc = sw + 9 * CIN * COUT, *ssh = ssc + COUT;
-    for (int i = threadIdx.x; i < COUT; i += blockDim.x) { ssc[i] = scale[i]; ssh[i] = shift[i]; }
-    __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const int y = blockIdx.y * 4 + (threadIdx.x >> 5);
-    const int n = blockIdx.z;
-    if (y >= H) return;
-    const int xb = blockIdx.x * 128 + lane;
-    float v[4][9 * CIN];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int x = xb + 32 * j;
-#pragma unroll
-        for (int tp = 0; tp < 9; ++tp) {
-            const int yy = y + tp / 3 - 1, xx = x + tp % 3 - 1;
-            const bool ok = yy >= 0 && yy < H && xx >= 0 && xx < W;
-#pragma unroll
-            for (int c = 0; c < CIN; ++c)
-                v[j][tp * CIN + c] = ok ? __bfloat162float(__float2bfloat16_rn(
-                                              in[(((size_t)n * H + yy) * W + xx) * CIN + c])) : 0.0f;
-        }
+    constexpr int KTOT = 9 * CIN, KS = (KTOT + 15) / 16, NT = COUT / 8;
+    constexpr int SROW = (FIRST_TW + 2) * CIN + 2;            // staged row pitch (floats)
+    __shared__ float tile[(FIRST_ROWS + 2) * SROW];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int n = blockIdx.z, x0 = blockIdx.x * FIRST_TW, y0 = blockIdx.y * FIRST_ROWS;
+
+    // stage the (ROWS+2) x (TW+2) input halo tile once (zero outside the image = SAME padding)
+    const float *img = in + (size_t)n * H * W * CIN;
+    for (int i = threadIdx.x; i < (FIRST_ROWS + 2) * (FIRST_TW + 2) * CIN; i += 256) {
+        const int ry = i / ((FIRST_TW + 2) * CIN), rx = i % ((FIRST_TW + 2) * CIN);
+        const int yy = y0 + ry - 1, e = (x0 - 1) * CIN + rx;
+        float v = 0.0f;
+        if (yy >= 0 && yy < H && e >= 0 && e < W * CIN) v = __ldg(img + (size_t)yy * W * CIN + e);
+        tile[ry * SROW + rx] = v;
     }
-    for (int cb = 0; cb < COUT / 8; ++cb) {
-        float acc[4][8];
+    // B fragments: b0 = (k = 2t, 2t+1 ; n = g), b1 = (k = 2t+8, 2t+9 ; n = g); zero beyond 9*CIN
+    uint32_t bw[KS][NT][2];
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+    for (int ks = 0; ks < KS; ++ks)
 #pragma unroll
-            for (int e = 0; e < 8; ++e) acc[j][e] = 0.0f;
+        for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
-        for (int k = 0; k < 9 * CIN; ++k) {
-            const float4 w0 = *reinterpret_cast<const float4 *>(sw + k * COUT + cb * 8);
-            const float4 w1 = *reinterpret_cast<const float4 *>(sw + k * COUT + cb * 8 + 4);
-            const float wr[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+            for (int h = 0; h < 2; ++h) {
+                const int k0 = ks * 16 + 2 * t + 8 * h;
+                const float w0 = k0 < KTOT ? wf[k0 * COUT + nt * 8 + g] : 0.0f;
+                const float w1 = k0 + 1 < KTOT ? wf[(k0 + 1) * COUT + nt * 8 + g] : 0.0f;
+                bw[ks][nt][h] = pack_bf16(w0, w1);
+            }
+    float sc[NT][2], sh[NT][2];
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
+    for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
-                for (int e = 0; e < 8; ++e) acc[j][e] = fmaf(v[j][k], wr[e], acc[j][e]);
-        }
+        for (int e = 0; e < 2; ++e) { sc[nt][e] = scale[nt * 8 + 2 * t + e]; sh[nt][e] = shift[nt * 8 + 2 * t + e]; }
+    // this thread's A-fragment sources: k = ks*16 + 2t + (j&1) + 8*(j>>1) -> staged-tile address of
+    // tap (dy,dx), channel c for pixel g of this warp's row.  Taps beyond 9*CIN alias tap 0: their
+    // weights are zero, so the (finite) value read there does not matter.
+    const float *src[KS][4];
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const int x = xb + 32 * j;
-            uint32_t o[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int c = cb * 8 + 2 * e;
-                float a = fmaf(acc[j][2 * e], ssc[c], ssh[c]);
-                float b = fmaf(acc[j][2 * e + 1], ssc[c + 1], ssh[c + 1]);
-                a = a > 0.0f ? a : 0.0f;
-                b = b > 0.0f ? b : 0.0f;
-                o[e] = pack_bf16(a, b);
-            }
-            if (x < W)
-                *reinterpret_cast<uint4 *>(out + ((((size_t)n * (COUT / 8) + cb) * H + y) * W + x) * 8) =
-                    make_uint4(o[0], o[1], o[2], o[3]);
+            const int k = ks * 16 + 2 * t + (j & 1) + 8 * (j >> 1);
+            const int tap = (k < KTOT) ? k / CIN : 0, c = (k < KTOT) ? k % CIN : 0;
+            src[ks][j] = tile + (warp + tap / 3) * SROW + (g + tap % 3) * CIN + c;
         }
+    __syncthreads();
+    const int y = y0 + warp;
+    if (y >= H) return;
+    bf16 *orow = out + (((size_t)n * NT * H + y) * W + x0 + g) * 8 + 2 * t;
+    const size_t plane = (size_t)H * W * 8;
+#pragma unroll 2
+    for (int q = 0; q < FIRST_TW / 16; ++q) {
+        if (x0 + 16 * q >= W) break;
+        float acc[NT][4];
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[nt][e] = 0.0f;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+            // rows g / g+8 of the fragment = pixels 16q+g and 16q+g+8
+            uint32_t a[4];
+            a[0] = pack_bf16(src[ks][0][(16 * q) * CIN], src[ks][1][(16 * q) * CIN]);
+            a[1] = pack_bf16(src[ks][0][(16 * q + 8) * CIN], src[ks][1][(16 * q + 8) * CIN]);
+            a[2] = pack_bf16(src[ks][2][(16 * q) * CIN], src[ks][3][(16 * q) * CIN]);
+            a[3] = pack_bf16(src[ks][2][(16 * q + 8) * CIN], src[ks][3][(16 * q + 8) * CIN]);
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) mma_m16n8k16_bf16(acc[nt], a, bw[ks][nt][0], bw[ks][nt][1]);
+        }
+        // C fragment: (row g, cols 2t,2t+1), (row g+8, cols 2t,2t+1) -> channel block nt, channels 2t,2t+1
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const float v0 = fmaxf(fmaf(acc[nt][2 * r], sc[nt][0], sh[nt][0]), 0.0f);
+                const float v1 = fmaxf(fmaf(acc[nt][2 * r + 1], sc[nt][1], sh[nt][1]), 0.0f);
+                if (x0 + 16 * q + g + 8 * r < W)
+                    *reinterpret_cast<uint32_t *>(orow + nt * plane + (size_t)(16 * q + 8 * r) * 8) = pack_bf16(v0, v1);
+            }
     }
 }
 
@@ -727,14 +767,26 @@ int tc_run(sq_unet_s *u, bool dry, const float *in, int n, int hgt, int wid, flo
         snprintf(scope, sizeof scope, "UNet/down%d/conv2", l);
         SqLayer *c2 = layer_by_scope(u, scope);
         if (l == 0) {
-            const size_t sm = (size_t)(9 * u->cin * c1->cout + 2 * c1->cout) * sizeof(float);
-            const dim3 grid((W + 127) / 128, (H + 3) / 4, n);
-            switch (u->cin) {
-            case 1: first_conv_kernel<1><<<grid, 128, sm, st>>>(in, (const float *)c1->w_tc, c1->scale, c1->shift, t1[0], n, H, W, c1->cout); break;
-            case 2: first_conv_kernel<2><<<grid, 128, sm, st>>>(in, (const float *)c1->w_tc, c1->scale, c1->shift, t1[0], n, H, W, c1->cout); break;
-            case 3: first_conv_kernel<3><<<grid, 128, sm, st>>>(in, (const float *)c1->w_tc, c1->scale, c1->shift, t1[0], n, H, W, c1->cout); break;
-            default: first_conv_kernel<4><<<grid, 128, sm, st>>>(in, (const float *)c1->w_tc, c1->scale, c1->shift, t1[0], n, H, W, c1->cout); break;
+            const dim3 grid((W + FIRST_TW - 1) / FIRST_TW, (H + FIRST_ROWS - 1) / FIRST_ROWS, n);
+            const float *wf = (const float *)c1->w_tc;
+#define SQ_FIRST(CI, CO) first_conv_kernel<CI, CO><<<grid, 256, 0, st>>>(in, wf, c1->scale, c1->shift, t1[0], n, H, W)
+            const int key = u->cin * 1000 + c1->cout;
+            switch (key) {
+            case 1016: SQ_FIRST(1, 16); break;
+            case 1032: SQ_FIRST(1, 32); break;
+            case 1064: SQ_FIRST(1, 64); break;
+            case 2016: SQ_FIRST(2, 16); break;
+            case 2032: SQ_FIRST(2, 32); break;
+            case 3016: SQ_FIRST(3, 16); break;
+            case 3032: SQ_FIRST(3, 32); break;
+            case 3064: SQ_FIRST(3, 64); break;
+            case 4016: SQ_FIRST(4, 16); break;
+            case 4032: SQ_FIRST(4, 32); break;
+            default:
+                SQ_REQUIRE(false, SQ_EUNSUPPORTED, "bf16 mode: first conv %d -> %d channels not instantiated",
+                           u->cin, c1->cout);
             }
+#undef SQ_FIRST
             ++u->last_launches;
             SQ_CHECK_LAUNCH();
         } else {
