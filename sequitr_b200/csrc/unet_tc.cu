@@ -52,7 +52,8 @@ struct Cfg {
 };
 
 constexpr int MAX_STAGES = 8;
-constexpr int TC_THREADS = 192;
+constexpr int EPI_GROUPS = 2;                 // epilogue warp groups (4 warps each, one per TMEM lane quarter)
+constexpr int TC_THREADS = 64 + 128 * EPI_GROUPS;
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b)
 {
@@ -105,7 +106,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < nstages; ++i) { tc::mbar_init(&full_bar[i], 1); tc::mbar_init(&empty_bar[i], 1); }
-        for (int i = 0; i < 2; ++i) { tc::mbar_init(&tfull_bar[i], 1); tc::mbar_init(&tempty_bar[i], 4); }
+        for (int i = 0; i < 2; ++i) { tc::mbar_init(&tfull_bar[i], 1); tc::mbar_init(&tempty_bar[i], 4 * EPI_GROUPS); }
         tc::fence_barrier_init();
         tc::tma_prefetch_desc(&mapA0);
         tc::tma_prefetch_desc(&mapA1);
@@ -189,6 +190,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     } else {
         // ========================================================= epilogue
         const int q4 = warp & 3;                            // TMEM lane quarter this warp may read
+        const int half = (warp - 2) >> 2;                   // which epilogue group: splits the work items
         const int r = q4 * 32 + lane;                       // accumulator row = pixel of the sub-tile
         const int ph = r >> 3, pw = r & 7;
         const uint32_t lane_addr = (uint32_t)(q4 * 32) << 16;
@@ -209,6 +211,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                     for (int k = 0; k < HK; ++k) hl[k] = 0.0f;
 #pragma unroll 1
                     for (int c16 = 0; c16 < COUT / 16; ++c16) {
+                        if (EPI == EPI_HEAD ? ((j % EPI_GROUPS) != half)
+                                            : (((j * (COUT / 16) + c16) % EPI_GROUPS) != half)) continue;
                         uint32_t v[16];
                         tc::tmem_ld16(tmem_base + lane_addr + buf * C::ACC_COLS + j * COUT + c16 * 16, v);
                         tc::tmem_ld_wait();
@@ -268,7 +272,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                             }
                         }
                     }
-                    if (EPI == EPI_HEAD) {
+                    if (EPI == EPI_HEAD && (j % EPI_GROUPS) == half) {
                         const size_t p = ((size_t)n * H + y) * W + x;
                         int best = 0;
                         float m = -INFINITY;
@@ -308,6 +312,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                     const int Ho = 2 * H, Wo = 2 * W;
 #pragma unroll 1
                     for (int ky = 0; ky < 2; ++ky) {
+                        if (((j * 2 + ky) % EPI_GROUPS) != half) continue;
 #pragma unroll 1
                         for (int c8 = 0; c8 < COUT / 8; ++c8) {
                             uint32_t v0[8], v1[8];
