@@ -1,58 +1,71 @@
-// Label-and-localise on the GPU: union-find connected-component labelling with
+// Label-and-localise on the GPU: run-based union-find connected-component labelling with
 // centroid reduction.  Replaces the per-frame / per-class SciPy loop of
 // utils.CentroidWriter.write (reference utils.py:531-566: ndimage.label :547,
 // center_of_mass :550).  Integer work, bit-exact against the oracle.
 //
-// One pass handles ALL classes: two voxels are connected when they share a face
-// and carry the same non-zero value, so label(out == c) for every c falls out of
-// a single union-find whose roots are the minimum linear index of each component
-// (= the component's first voxel in raster order = SciPy's numbering order).
+// One pass handles ALL classes: two voxels are connected when they share a face and carry
+// the same non-zero value, so label(out == c) for every c falls out of a single union-find.
+// The mask is read as horizontal RUNS of equal non-zero value (a segmentation mask of a few
+// hundred cells has ~10^4 runs against 4*10^6 pixels): only the two run-extraction kernels
+// touch every voxel (1 B/voxel each, the second pass hits L2); everything else -- unions
+// between vertically (and, in 3-D, depth-) adjacent runs, path compression, ordering,
+// 64-bit centroid sums -- is O(runs).  Run slots are allocated in raster order by a prefix
+// sum, so the root of a component (minimum slot, atomicMin union) is the run holding the
+// component's first voxel in raster order = SciPy's numbering order.
 //
 // Kernels (HBM-bound; algorithmic traffic 1 B/voxel in, rows out):
-//   ccl_init      run-start labels inside 32-voxel row segments (warp ballot)
-//   ccl_merge     unions across segment / row / plane borders (atomicMin union-find)
-//   ccl_compress  full path compression + root count per 2048-voxel chunk
-//   ccl_scan      per-frame exclusive scan of the chunk counts
-//   ccl_emit      raster-ordered root list
-//   ccl_order     stable counting sort of the roots by class -> row index
-//   ccl_accum     warp-aggregated 64-bit sums (count, sum z, sum y, sum x) per row
+//   run_count     runs per 128-voxel row segment (4 voxels per lane + shuffles)
+//   scan_i32      per-frame exclusive scan (segment counts, then root counts)
+//   run_emit      run start / end lists in raster order, parent[i] = i
+//   run_merge     unions with overlapping runs of the previous row / previous plane
+//   run_compress  full path compression + root count per 2048-run chunk
+//   root_emit     raster-ordered root list
+//   ccl_order     stable counting sort of the roots by class -> table row index
+//   run_accum     64-bit sums (count, sum z, sum y, sum x) per row from run endpoints
 //   ccl_finalize  fp64 divide exactly as center_of_mass does, float32 rows
 #include "sq_common.cuh"
+#include <algorithm>
 
 namespace {
 
-constexpr int CHUNK = 2048;          // voxels per compress/emit block
+constexpr int SEG = 128;             // voxels per warp segment (4 per lane)
+constexpr int CHUNK = 2048;          // runs per compress/emit block
 constexpr int CHUNK_THREADS = 256;
 
 struct Dims {
     int n, D, H, W;
-    int vox;                          // D*H*W  (< 2^31)
-    int nchunks;
+    int rows;                         // D*H lines per frame
+    int vox;                          // rows*W  (< 2^31)
+    int nseg;                         // segments per line
+    int nsegs;                        // rows*nseg segments per frame
+    int maxruns;                      // run capacity per frame
+    int nchunks;                      // ceil(maxruns / CHUNK)
+    int vec;                          // 1: 32-bit mask loads are aligned
 };
 
-__device__ __forceinline__ int find_root(const int *L, int i)
+__device__ __forceinline__ int find_root(const int *P, int i)
 {
-    int p = __ldcg(L + i);
+    int p = __ldcg(P + i);
     while (p != i) {
         i = p;
-        p = __ldcg(L + i);
+        p = __ldcg(P + i);
     }
     return i;
 }
 
-// lock-free union by minimum index (Playne/Komura style)
-__device__ __forceinline__ void unite(int *L, int a, int b)
+// lock-free union by minimum slot (Playne/Komura style)
+__device__ __forceinline__ void unite(int *P, int a, int b)
 {
     bool done = false;
     while (!done) {
-        a = find_root(L, a);
-        b = find_root(L, b);
+        a = find_root(P, a);
+        b = find_root(P, b);
         if (a < b) {
-            int old = atomicMin(L + b, a);
+            int old = atomicMin(P + b, a);
             done = (old == b);
             b = old;
         } else if (b < a) {
-            int old = atomicMin(L + a, b);
+            int old = atomicMin(P + a, b);
             done = (old == a);
             a = old;
         } else {
@@ -61,105 +74,75 @@ __device__ __forceinline__ void unite(int *L, int a, int b)
     }
 }
 
-// grid (ceil(W/32), ceil(H/8), n*D), block (32, 8): one warp = 32 consecutive x
-__global__ void ccl_init(const uint8_t *__restrict__ mask, int *__restrict__ L, Dims dm)
+// start / end bits of the 4 voxels this lane owns in its segment; returns popc(start) | popc(end)<<16
+__device__ __forceinline__ unsigned segment_bits(const uint8_t *__restrict__ line, int x, int W, int vec,
+                                                 int lane, unsigned &sb, unsigned &eb)
 {
-    const int lane = threadIdx.x;
-    const int x = blockIdx.x * 32 + lane;
-    const int y = blockIdx.y * 8 + threadIdx.y;
-    const int zf = blockIdx.z;                    // frame * D + z
-    const int z = zf % dm.D;
-    const bool inside = (x < dm.W) && (y < dm.H);
-    const long long g = ((long long)zf * dm.H + y) * dm.W + x;
-    const uint8_t v = inside ? mask[g] : (uint8_t)0;
-    const uint8_t lv = (uint8_t)__shfl_up_sync(0xffffffffu, (int)v, 1);
-    const bool cont = (lane > 0) && (v != 0) && (lv == v);
-    const unsigned bits = __ballot_sync(0xffffffffu, cont);
-    if (!inside) return;
-    const unsigned m = ~bits & ((2u << lane) - 1u);
-    const int s = 31 - __clz(m);
-    const int idx = (z * dm.H + y) * dm.W + x;
-    if (v) L[g] = idx - (lane - s);            // background entries of L are never read
-}
-
-__global__ void ccl_merge(const uint8_t *__restrict__ mask, int *__restrict__ L, Dims dm)
-{
-    const int lane = threadIdx.x;
-    const int x = blockIdx.x * 32 + lane;
-    const int y = blockIdx.y * 8 + threadIdx.y;
-    const int zf = blockIdx.z;
-    const int z = zf % dm.D;
-    if (x >= dm.W || y >= dm.H) return;
-    const long long fo = (long long)(zf / dm.D) * dm.vox;      // frame offset
-    const uint8_t *mk = mask + fo;
-    int *Lf = L + fo;
-    const int idx = (z * dm.H + y) * dm.W + x;
-    const uint8_t v = mk[idx];
-    if (!v) return;
-    const bool left_same = (x > 0) && (mk[idx - 1] == v);
-    if (lane == 0 && left_same) unite(Lf, idx, idx - 1);
-    if (y > 0 && mk[idx - dm.W] == v) {
-        const bool covered = left_same && (mk[idx - dm.W - 1] == v);
-        if (!covered) unite(Lf, idx, idx - dm.W);
-    }
-    if (z > 0) {
-        const int plane = dm.H * dm.W;
-        if (mk[idx - plane] == v) {
-            const bool covered = left_same && (mk[idx - plane - 1] == v);
-            if (!covered) unite(Lf, idx, idx - plane);
-        }
-    }
-}
-
-__device__ __forceinline__ int block_sum_256(int v, int *sh)
-{
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
-    __syncthreads();
-    int r = 0;
-    if (threadIdx.x < 32) {
-        r = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : 0;
-        for (int o = 16; o > 0; o >>= 1) r += __shfl_down_sync(0xffffffffu, r, o);
-    }
-    return r;                                                  // valid in thread 0
-}
-
-// grid (nchunks, n), block 256
-__global__ void ccl_compress(const uint8_t *__restrict__ mask, int *__restrict__ L,
-                             int *__restrict__ chunk_count, Dims dm)
-{
-    __shared__ int sh[8];
-    int *Lf = L + (long long)blockIdx.y * dm.vox;
-    const uint8_t *mk = mask + (long long)blockIdx.y * dm.vox;
-    const int base = blockIdx.x * CHUNK;
-    int cnt = 0;
+    unsigned w = 0;
+    if (vec && x + 3 < W) {
+        w = *reinterpret_cast<const unsigned *>(line + x);
+    } else {
 #pragma unroll
-    for (int k = 0; k < CHUNK / CHUNK_THREADS; ++k) {
-        const int i = base + k * CHUNK_THREADS + threadIdx.x;
-        if (i < dm.vox && mk[i]) {
-            const int l = Lf[i];
-            const int r = find_root(Lf, i);
-            if (r != l) Lf[i] = r;
-            cnt += (r == i);
-        }
+        for (int k = 0; k < 4; ++k)
+            if (x + k < W) w |= (unsigned)line[x + k] << (8 * k);
     }
-    const int tot = block_sum_256(cnt, sh);
-    if (threadIdx.x == 0) chunk_count[blockIdx.y * dm.nchunks + blockIdx.x] = tot;
+    unsigned prev = __shfl_up_sync(0xffffffffu, w >> 24, 1);
+    unsigned next = __shfl_down_sync(0xffffffffu, w & 0xffu, 1);
+    if (lane == 0) prev = 0;                       // segment borders always cut a run
+    if (lane == 31) next = 0;
+    sb = 0;
+    eb = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const unsigned p = (w >> (8 * k)) & 0xffu;
+        const unsigned l = k ? (w >> (8 * (k - 1))) & 0xffu : prev;
+        const unsigned r = k < 3 ? (w >> (8 * (k + 1))) & 0xffu : next;
+        if (p && p != l) sb |= 1u << k;
+        if (p && p != r) eb |= 1u << k;
+    }
+    return (unsigned)__popc(sb) | ((unsigned)__popc(eb) << 16);
 }
 
-// grid (n), block 1024: exclusive scan of chunk counts of one frame
-__global__ void ccl_scan(const int *__restrict__ chunk_count, int *__restrict__ chunk_off,
-                         int *__restrict__ totals, Dims dm)
+__device__ __forceinline__ unsigned warp_inclusive_scan(unsigned v, int lane)
+{
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
+    }
+    return v;
+}
+
+// grid (ceil(nsegs/8), n), block 256: one warp per segment
+__global__ void run_count(const uint8_t *__restrict__ mask, int *__restrict__ seg_count, Dims dm)
+{
+    const int lane = threadIdx.x & 31;
+    const int s = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (s >= dm.nsegs) return;
+    const int line = s / dm.nseg, seg = s % dm.nseg;
+    const uint8_t *lp = mask + (long long)blockIdx.y * dm.vox + (long long)line * dm.W;
+    unsigned sb, eb;
+    const unsigned c = segment_bits(lp, seg * SEG + lane * 4, dm.W, dm.vec, lane, sb, eb);
+    const unsigned tot = warp_inclusive_scan(c & 0xffffu, lane);
+    if (lane == 31) seg_count[(long long)blockIdx.y * (dm.nsegs + 1) + s] = (int)tot;
+}
+
+// grid (n), block 1024: exclusive scan of `len` ints of one frame (stride `pitch`); the grand
+// total goes to out[len] (if sentinel) and totals[f]
+__global__ void scan_i32(const int *__restrict__ in, int *__restrict__ out, int *__restrict__ totals,
+                         int len, int pitch, int sentinel)
 {
     __shared__ int warp_sums[32];
     __shared__ int carry_sh;
     const int f = blockIdx.x;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int *src = in + (long long)f * pitch;
+    int *dst = out + (long long)f * pitch;
     if (threadIdx.x == 0) carry_sh = 0;
     __syncthreads();
-    for (int start = 0; start < dm.nchunks; start += 1024) {
+    for (int start = 0; start < len; start += 1024) {
         const int i = start + threadIdx.x;
-        const int v = (i < dm.nchunks) ? chunk_count[f * dm.nchunks + i] : 0;
+        const int v = (i < len) ? src[i] : 0;
         int s = v;
         for (int o = 1; o < 32; o <<= 1) {
             int t = __shfl_up_sync(0xffffffffu, s, o);
@@ -178,30 +161,143 @@ __global__ void ccl_scan(const int *__restrict__ chunk_count, int *__restrict__ 
         __syncthreads();
         const int carry = carry_sh;
         const int incl = s + (wid > 0 ? warp_sums[wid - 1] : 0);
-        if (i < dm.nchunks) chunk_off[f * dm.nchunks + i] = carry + incl - v;
+        if (i < len) dst[i] = carry + incl - v;
         __syncthreads();
         if (threadIdx.x == 1023) carry_sh = carry + incl;
         __syncthreads();
     }
-    if (threadIdx.x == 0) totals[f] = carry_sh;
+    if (threadIdx.x == 0) {
+        if (sentinel) dst[len] = carry_sh;
+        totals[f] = carry_sh;
+    }
 }
 
-// grid (nchunks, n), block 256: thread t owns 8 consecutive voxels (keeps raster order)
-__global__ void ccl_emit(const uint8_t *__restrict__ mask, const int *__restrict__ L,
-                         const int *__restrict__ chunk_count, const int *__restrict__ chunk_off,
-                         int *__restrict__ rootlist, Dims dm, int max_rows)
+// same launch shape as run_count: writes the runs of every segment at their raster-order slots
+__global__ void run_emit(const uint8_t *__restrict__ mask, const int *__restrict__ seg_off,
+                         int *__restrict__ run_start, int *__restrict__ run_end,
+                         int *__restrict__ parent, Dims dm)
+{
+    const int lane = threadIdx.x & 31;
+    const int s = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (s >= dm.nsegs) return;
+    const int f = blockIdx.y;
+    const int line = s / dm.nseg, seg = s % dm.nseg;
+    const uint8_t *lp = mask + (long long)f * dm.vox + (long long)line * dm.W;
+    const int x = seg * SEG + lane * 4;
+    unsigned sb, eb;
+    const unsigned c = segment_bits(lp, x, dm.W, dm.vec, lane, sb, eb);
+    const unsigned incl = warp_inclusive_scan(c, lane);
+    if (!(sb | eb)) return;
+    const long long rb = (long long)f * dm.maxruns;
+    const int base = seg_off[(long long)f * (dm.nsegs + 1) + s];
+    int is = base + (int)((incl - c) & 0xffffu), ie = base + (int)((incl - c) >> 16);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (sb & (1u << k)) {
+            run_start[rb + is] = line * dm.W + x + k;
+            parent[rb + is] = is;
+            ++is;
+        }
+        if (eb & (1u << k)) run_end[rb + ie++] = x + k;
+    }
+}
+
+// unions of run i with the overlapping same-class runs of line `pl` (frame-local pointers)
+__device__ __forceinline__ void merge_with_line(const uint8_t *mk, const int *seg_off,
+                                                const int *run_start, const int *run_end, int *parent,
+                                                const Dims &dm, int i, int pl, int x0, int x1, uint8_t c)
+{
+    const int jb = seg_off[pl * dm.nseg], je = seg_off[(pl + 1) * dm.nseg];
+    for (int j = jb; j < je; ++j) {
+        const int s = run_start[j];
+        const int xs = s - pl * dm.W;
+        if (xs > x1) break;                                    // runs of a line are sorted by x
+        if (run_end[j] >= x0 && mk[s] == c) unite(parent, i, j);
+    }
+}
+
+// grid (blocks, n): grid-stride over the runs of a frame
+__global__ void run_merge(const uint8_t *__restrict__ mask, const int *__restrict__ seg_off,
+                          const int *__restrict__ totals, const int *__restrict__ run_start,
+                          const int *__restrict__ run_end, int *__restrict__ parent, Dims dm)
+{
+    const int f = blockIdx.y;
+    const int R = totals[f];
+    const uint8_t *mk = mask + (long long)f * dm.vox;
+    const int *so = seg_off + (long long)f * (dm.nsegs + 1);
+    const int *rs = run_start + (long long)f * dm.maxruns;
+    const int *re = run_end + (long long)f * dm.maxruns;
+    int *pa = parent + (long long)f * dm.maxruns;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < R; i += gridDim.x * blockDim.x) {
+        const int s = rs[i];
+        const int line = s / dm.W, x0 = s - line * dm.W, x1 = re[i];
+        const uint8_t c = mk[s];
+        // a run cut by a segment border continues in the previous slot
+        if (x0 > 0 && (x0 % SEG) == 0 && i > 0) {
+            const int ps = rs[i - 1];
+            if (ps / dm.W == line && re[i - 1] == x0 - 1 && mk[ps] == c) unite(pa, i, i - 1);
+        }
+        const int y = line % dm.H;
+        if (y > 0) merge_with_line(mk, so, rs, re, pa, dm, i, line - 1, x0, x1, c);
+        if (line >= dm.H) merge_with_line(mk, so, rs, re, pa, dm, i, line - dm.H, x0, x1, c);
+    }
+}
+
+__device__ __forceinline__ int block_sum_256(int v, int *sh)
+{
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    int r = 0;
+    if (threadIdx.x < 32) {
+        r = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : 0;
+        for (int o = 16; o > 0; o >>= 1) r += __shfl_down_sync(0xffffffffu, r, o);
+    }
+    return r;                                                  // valid in thread 0
+}
+
+// grid (nchunks, n), block 256
+__global__ void run_compress(int *__restrict__ parent, const int *__restrict__ totals,
+                             int *__restrict__ chunk_count, Dims dm)
+{
+    __shared__ int sh[8];
+    const int f = blockIdx.y;
+    const int R = totals[f];
+    int *pa = parent + (long long)f * dm.maxruns;
+    const int base = blockIdx.x * CHUNK;
+    int cnt = 0;
+    if (base < R) {
+#pragma unroll
+        for (int k = 0; k < CHUNK / CHUNK_THREADS; ++k) {
+            const int i = base + k * CHUNK_THREADS + threadIdx.x;
+            if (i < R) {
+                const int l = pa[i];
+                const int r = find_root(pa, i);
+                if (r != l) pa[i] = r;
+                cnt += (r == i);
+            }
+        }
+    }
+    const int tot = block_sum_256(cnt, sh);
+    if (threadIdx.x == 0) chunk_count[(long long)f * (dm.nchunks + 1) + blockIdx.x] = tot;
+}
+
+// grid (nchunks, n), block 256: thread t owns 8 consecutive runs (keeps raster order)
+__global__ void root_emit(const int *__restrict__ parent, const int *__restrict__ totals,
+                          const int *__restrict__ chunk_count, const int *__restrict__ chunk_off,
+                          int *__restrict__ rootlist, Dims dm, int max_rows)
 {
     __shared__ int warp_sums[8];
     const int f = blockIdx.y;
-    if (chunk_count[f * dm.nchunks + blockIdx.x] == 0) return;
-    const int *Lf = L + (long long)f * dm.vox;
-    const uint8_t *mk = mask + (long long)f * dm.vox;
+    if (chunk_count[(long long)f * (dm.nchunks + 1) + blockIdx.x] == 0) return;
+    const int R = totals[f];
+    const int *pa = parent + (long long)f * dm.maxruns;
     const int base = blockIdx.x * CHUNK + threadIdx.x * 8;
     int flags = 0, cnt = 0;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         const int i = base + k;
-        if (i < dm.vox && mk[i] && Lf[i] == i) { flags |= 1 << k; ++cnt; }
+        if (i < R && pa[i] == i) { flags |= 1 << k; ++cnt; }
     }
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     int s = cnt;
@@ -213,7 +309,7 @@ __global__ void ccl_emit(const uint8_t *__restrict__ mask, const int *__restrict
     __syncthreads();
     int pre = 0;
     for (int w = 0; w < wid; ++w) pre += warp_sums[w];
-    int pos = chunk_off[f * dm.nchunks + blockIdx.x] + pre + s - cnt;
+    int pos = chunk_off[(long long)f * (dm.nchunks + 1) + blockIdx.x] + pre + s - cnt;
 #pragma unroll
     for (int k = 0; k < 8; ++k)
         if (flags & (1 << k)) {
@@ -222,33 +318,34 @@ __global__ void ccl_emit(const uint8_t *__restrict__ mask, const int *__restrict
         }
 }
 
-// grid (n), block 256: stable counting sort of the frame's roots by class value.
-// Writes L[root] = -2 - row, sorted_root, class_base.  The class histogram uses shared-memory
-// atomics; the stable rank of root j is base[class] + #(i < j with the same class).  For up to
-// ORDER_PAR roots every thread counts its predecessors in parallel (O(n^2/256), a few
-// microseconds for the hundreds of cells of a real frame); beyond that thread c walks the
-// raster-ordered list for class c.
+// grid (n), block 256: stable counting sort of the frame's root runs by class value.
+// Writes parent[root] = -2 - row, sorted_root (root run slot of each row), class_base.
+// The class histogram uses shared-memory atomics; the stable rank of root j is base[class] +
+// #(i < j with the same class).  For up to ORDER_PAR roots every thread counts its predecessors
+// in parallel (O(n^2/256), a few microseconds for the hundreds of cells of a real frame); beyond
+// that thread c walks the raster-ordered list for class c.
 constexpr int ORDER_PAR = 4096;
 
-__global__ void ccl_order(const uint8_t *__restrict__ mask, int *__restrict__ L,
-                          const int *__restrict__ rootlist, const int *__restrict__ totals,
-                          int *__restrict__ sorted_root, int *__restrict__ class_base,
-                          Dims dm, int max_rows)
+__global__ void ccl_order(const uint8_t *__restrict__ mask, const int *__restrict__ run_start,
+                          int *__restrict__ parent, const int *__restrict__ rootlist,
+                          const int *__restrict__ nroots, int *__restrict__ sorted_root,
+                          int *__restrict__ class_base, Dims dm, int max_rows)
 {
     __shared__ uint8_t cls[ORDER_PAR];
     __shared__ int cnt_sh[256];
     const int f = blockIdx.x;
     const int c = threadIdx.x;
-    const int n = min(totals[f], max_rows);
+    const int n = min(nroots[f], max_rows);
     const uint8_t *mk = mask + (long long)f * dm.vox;
-    int *Lf = L + (long long)f * dm.vox;
+    const int *rs = run_start + (long long)f * dm.maxruns;
+    int *pa = parent + (long long)f * dm.maxruns;
     const int *rl = rootlist + (long long)f * max_rows;
     int *sr = sorted_root + (long long)f * max_rows;
 
     cnt_sh[c] = 0;
     __syncthreads();
     for (int j = c; j < n; j += 256) {
-        const uint8_t v = mk[rl[j]];
+        const uint8_t v = mk[rs[rl[j]]];
         if (j < ORDER_PAR) cls[j] = v;
         atomicAdd(&cnt_sh[v], 1);
     }
@@ -268,80 +365,69 @@ __global__ void ccl_order(const uint8_t *__restrict__ mask, int *__restrict__ L,
             for (int i = 0; i < j; ++i) rank += (cls[i] == v);
             const int row = cnt_sh[v] + rank;
             const int r = rl[j];
-            Lf[r] = -2 - row;
+            pa[r] = -2 - row;
             sr[row] = r;
         }
     } else if (mine > 0) {
         int k = cnt_sh[c];
         for (int j = 0; j < n; ++j) {
             const int r = rl[j];
-            if (mk[r] == c) { Lf[r] = -2 - k; sr[k] = r; ++k; }
+            if (mk[rs[r]] == c) { pa[r] = -2 - k; sr[k] = r; ++k; }
         }
     }
 }
 
-__device__ __forceinline__ int sum_of_set_bit_positions(unsigned g)
+// grid (blocks, n): grid-stride over runs; closed-form sums from the run endpoints
+__global__ void run_accum(const uint8_t *__restrict__ mask, const int *__restrict__ totals,
+                          const int *__restrict__ run_start, const int *__restrict__ run_end,
+                          const int *__restrict__ parent, const int *__restrict__ class_base,
+                          unsigned long long *__restrict__ acc, int *__restrict__ labels_out, Dims dm,
+                          int max_rows)
 {
-    return __popc(g & 0xAAAAAAAAu) + 2 * __popc(g & 0xCCCCCCCCu) + 4 * __popc(g & 0xF0F0F0F0u) +
-           8 * __popc(g & 0xFF00FF00u) + 16 * __popc(g & 0xFFFF0000u);
-}
-
-// same launch shape as ccl_init
-__global__ void ccl_accum(const uint8_t *__restrict__ mask, const int *__restrict__ L,
-                          const int *__restrict__ class_base, unsigned long long *__restrict__ acc,
-                          int *__restrict__ labels_out, Dims dm, int max_rows)
-{
-    const int lane = threadIdx.x;
-    const int x = blockIdx.x * 32 + lane;
-    const int y = blockIdx.y * 8 + threadIdx.y;
-    const int zf = blockIdx.z;
-    const int z = zf % dm.D, f = zf / dm.D;
-    const bool inside = (x < dm.W) && (y < dm.H);
-    const long long fo = (long long)f * dm.vox;
-    const int idx = (z * dm.H + y) * dm.W + x;
-    int row = -1;
-    uint8_t v = 0;
-    if (inside) {
-        v = mask[fo + idx];
-        if (v) {
-            const int l = L[fo + idx];
-            if (l <= -2) row = -2 - l;
-            else if (l >= 0) {
-                const int rr = L[fo + l];
-                if (rr <= -2) row = -2 - rr;
-            }
+    const int f = blockIdx.y;
+    const int R = totals[f];
+    const int *rs = run_start + (long long)f * dm.maxruns;
+    const int *re = run_end + (long long)f * dm.maxruns;
+    const int *pa = parent + (long long)f * dm.maxruns;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < R; i += gridDim.x * blockDim.x) {
+        const int l = pa[i];
+        int row = -1;
+        if (l <= -2) row = -2 - l;
+        else {
+            const int rr = pa[l];
+            if (rr <= -2) row = -2 - rr;
         }
-        if (labels_out) labels_out[fo + idx] = (row >= 0) ? row - class_base[f * 256 + v] + 1 : 0;
-    }
-    const unsigned act = __ballot_sync(0xffffffffu, row >= 0);
-    if (row >= 0) {
-        const unsigned g = __match_any_sync(act, row);
-        if (lane == __ffs(g) - 1) {
-            const unsigned long long cnt = __popc(g);
-            unsigned long long *a = acc + ((long long)f * max_rows + row) * 4;
-            const int x0 = blockIdx.x * 32;
-            atomicAdd(a + 0, cnt);
-            if (dm.D > 1) atomicAdd(a + 1, cnt * (unsigned long long)z);
-            atomicAdd(a + 2, cnt * (unsigned long long)y);
-            atomicAdd(a + 3, cnt * (unsigned long long)x0 +
-                                 (unsigned long long)sum_of_set_bit_positions(g));
+        if (row < 0) continue;                                 // component beyond max_rows
+        const int s = rs[i];
+        const int line = s / dm.W, x0 = s - line * dm.W, x1 = re[i];
+        const unsigned long long len = (unsigned long long)(x1 - x0 + 1);
+        unsigned long long *a = acc + ((long long)f * max_rows + row) * 4;
+        atomicAdd(a + 0, len);
+        if (dm.D > 1) atomicAdd(a + 1, len * (unsigned long long)(line / dm.H));
+        atomicAdd(a + 2, len * (unsigned long long)(line % dm.H));
+        atomicAdd(a + 3, (unsigned long long)(x0 + x1) * len / 2);
+        if (labels_out) {
+            const int lab = row - class_base[f * 256 + mask[(long long)f * dm.vox + s]] + 1;
+            int *lo = labels_out + (long long)f * dm.vox + s;
+            for (int k = 0; k <= x1 - x0; ++k) lo[k] = lab;
         }
     }
 }
 
 // grid (ceil(max_rows/256), n)
-__global__ void ccl_finalize(const uint8_t *__restrict__ mask, const int *__restrict__ sorted_root,
+__global__ void ccl_finalize(const uint8_t *__restrict__ mask, const int *__restrict__ run_start,
+                             const int *__restrict__ sorted_root,
                              const unsigned long long *__restrict__ acc,
-                             const int *__restrict__ totals, float *__restrict__ table,
+                             const int *__restrict__ nroots, float *__restrict__ table,
                              int *__restrict__ counts, Dims dm, int max_rows, int frame0)
 {
     const int f = blockIdx.y;
     const int row = blockIdx.x * blockDim.x + threadIdx.x;
-    const int tot = totals[f];
+    const int tot = nroots[f];
     if (row == 0) counts[f] = tot;
     if (row >= min(tot, max_rows)) return;
     const int r = sorted_root[(long long)f * max_rows + row];
-    const unsigned long long c = mask[(long long)f * dm.vox + r];
+    const unsigned long long c = mask[(long long)f * dm.vox + run_start[(long long)f * dm.maxruns + r]];
     const unsigned long long *a = acc + ((long long)f * max_rows + row) * 4;
     // center_of_mass: sum(c * index) / sum(c), both exact integers in fp64
     const double den = (double)(c * a[0]);
@@ -356,7 +442,8 @@ __global__ void ccl_finalize(const uint8_t *__restrict__ mask, const int *__rest
 }
 
 struct Workspace {
-    int *L, *chunk_count, *chunk_off, *totals, *rootlist, *sorted_root, *class_base;
+    int *seg_count, *seg_off, *totals, *run_start, *run_end, *parent;
+    int *chunk_count, *chunk_off, *nroots, *rootlist, *sorted_root, *class_base;
     unsigned long long *acc;
     size_t bytes;
 };
@@ -365,10 +452,15 @@ Workspace carve(void *p, size_t avail, const Dims &dm, int max_rows)
 {
     SqArena a(p, avail);
     Workspace w;
-    w.L = a.take<int>((size_t)dm.n * dm.vox);
-    w.chunk_count = a.take<int>((size_t)dm.n * dm.nchunks);
-    w.chunk_off = a.take<int>((size_t)dm.n * dm.nchunks);
+    w.seg_count = a.take<int>((size_t)dm.n * (dm.nsegs + 1));
+    w.seg_off = a.take<int>((size_t)dm.n * (dm.nsegs + 1));
     w.totals = a.take<int>(dm.n);
+    w.run_start = a.take<int>((size_t)dm.n * dm.maxruns);
+    w.run_end = a.take<int>((size_t)dm.n * dm.maxruns);
+    w.parent = a.take<int>((size_t)dm.n * dm.maxruns);
+    w.chunk_count = a.take<int>((size_t)dm.n * (dm.nchunks + 1));
+    w.chunk_off = a.take<int>((size_t)dm.n * (dm.nchunks + 1));
+    w.nroots = a.take<int>(dm.n);
     w.rootlist = a.take<int>((size_t)dm.n * max_rows);
     w.sorted_root = a.take<int>((size_t)dm.n * max_rows);
     w.class_base = a.take<int>((size_t)dm.n * 256);
@@ -377,17 +469,25 @@ Workspace carve(void *p, size_t avail, const Dims &dm, int max_rows)
     return w;
 }
 
-int make_dims(int n, int d, int hgt, int wid, int max_rows, Dims *dm)
+int make_dims(int n, int d, int hgt, int wid, int max_rows, const void *mask, Dims *dm)
 {
     SQ_REQUIRE(n >= 1 && d >= 1 && hgt >= 1 && wid >= 1, SQ_EINVAL,
                "label: bad shape (%d,%d,%d,%d)", n, d, hgt, wid);
     SQ_REQUIRE(max_rows >= 1, SQ_EINVAL, "label: max_rows must be >= 1");
+    SQ_REQUIRE(n <= 65535, SQ_EINVAL, "label: more than 65535 frames per call");
     const long long vox = (long long)d * hgt * wid;
     SQ_REQUIRE(vox < (1ll << 31) - CHUNK, SQ_EINVAL, "label: frame too large (%lld voxels)", vox);
-    SQ_REQUIRE(d <= 65535, SQ_EINVAL, "label: depth %d > 65535", d);
     dm->n = n; dm->D = d; dm->H = hgt; dm->W = wid;
+    dm->rows = d * hgt;
     dm->vox = (int)vox;
-    dm->nchunks = sq_div_up(vox, CHUNK);
+    dm->nseg = sq_div_up(wid, SEG);
+    dm->nsegs = dm->rows * dm->nseg;
+    // worst case: alternating values, plus one cut per segment border
+    const long long mr = (long long)dm->rows * ((wid + 1) / 2 + dm->nseg);
+    SQ_REQUIRE(mr < (1ll << 31) - CHUNK, SQ_EINVAL, "label: frame too large");
+    dm->maxruns = (int)mr;
+    dm->nchunks = sq_div_up(mr, CHUNK);
+    dm->vec = (wid % 4 == 0) && (((uintptr_t)mask & 3u) == 0);
     return SQ_OK;
 }
 
@@ -398,7 +498,7 @@ extern "C" int sq_label_workspace_bytes(sq_handle_t h, int n, int d, int hgt, in
 {
     SQ_REQUIRE(h && bytes, SQ_EINVAL, "label: null handle/pointer");
     Dims dm;
-    SQ_TRY(make_dims(n, d, hgt, wid, max_rows, &dm));
+    SQ_TRY(make_dims(n, d, hgt, wid, max_rows, nullptr, &dm));
     *bytes = carve(nullptr, 0, dm, max_rows).bytes;
     return SQ_OK;
 }
@@ -410,46 +510,33 @@ extern "C" int sq_label_centroids(sq_handle_t h, const uint8_t *mask, int n, int
 {
     SQ_REQUIRE(h && mask && table && counts && ws, SQ_EINVAL, "label: null pointer");
     Dims dm;
-    SQ_TRY(make_dims(n, d, hgt, wid, max_rows, &dm));
+    SQ_TRY(make_dims(n, d, hgt, wid, max_rows, mask, &dm));
     Workspace w = carve(ws, ws_bytes, dm, max_rows);
     SQ_REQUIRE(w.bytes <= ws_bytes, SQ_ENOMEM, "label: workspace %zu < %zu bytes", ws_bytes, w.bytes);
     cudaStream_t st = (cudaStream_t)stream_;
 
-    // planes go on grid.z (max 65535): split very deep batches
-    const dim3 blk(32, 8);
-    const int planes = n * d;
     SQ_CUDA(cudaMemsetAsync(w.acc, 0, (size_t)n * max_rows * 4 * sizeof(unsigned long long), st));
-    for (int p0 = 0; p0 < planes; p0 += 65535 / d * d) {
-        // chunks of whole frames so that frame = zf / D stays valid
-        const int np = min(planes - p0, 65535 / d * d);
-        Dims sub = dm;
-        const long long off = (long long)(p0 / d) * dm.vox;
-        sub.n = np / d;
-        const dim3 grid(sq_div_up(wid, 32), sq_div_up(hgt, 8), np);
-        ccl_init<<<grid, blk, 0, st>>>(mask + off, w.L + off, sub);
-        ccl_merge<<<grid, blk, 0, st>>>(mask + off, w.L + off, sub);
-    }
+    if (labels) SQ_CUDA(cudaMemsetAsync(labels, 0, (size_t)n * dm.vox * sizeof(int32_t), st));
+    const dim3 seg_grid(sq_div_up(dm.nsegs, 8), n);
+    run_count<<<seg_grid, 256, 0, st>>>(mask, w.seg_count, dm);
+    scan_i32<<<n, 1024, 0, st>>>(w.seg_count, w.seg_off, w.totals, dm.nsegs, dm.nsegs + 1, 1);
+    run_emit<<<seg_grid, 256, 0, st>>>(mask, w.seg_off, w.run_start, w.run_end, w.parent, dm);
     SQ_CHECK_LAUNCH();
-    ccl_compress<<<dim3(dm.nchunks, n), CHUNK_THREADS, 0, st>>>(mask, w.L, w.chunk_count, dm);
-    ccl_scan<<<n, 1024, 0, st>>>(w.chunk_count, w.chunk_off, w.totals, dm);
-    ccl_emit<<<dim3(dm.nchunks, n), CHUNK_THREADS, 0, st>>>(mask, w.L, w.chunk_count, w.chunk_off,
-                                                           w.rootlist, dm, max_rows);
-    ccl_order<<<n, 256, 0, st>>>(mask, w.L, w.rootlist, w.totals, w.sorted_root, w.class_base,
-                                 dm, max_rows);
+    // O(runs) kernels: the run count lives on the device, so launch a fixed grid and stride
+    const int rblocks = std::min(dm.nchunks * (CHUNK / 256), 4 * h->sm_count);
+    run_merge<<<dim3(rblocks, n), 256, 0, st>>>(mask, w.seg_off, w.totals, w.run_start, w.run_end,
+                                                w.parent, dm);
+    run_compress<<<dim3(dm.nchunks, n), CHUNK_THREADS, 0, st>>>(w.parent, w.totals, w.chunk_count, dm);
+    scan_i32<<<n, 1024, 0, st>>>(w.chunk_count, w.chunk_off, w.nroots, dm.nchunks, dm.nchunks + 1, 0);
+    root_emit<<<dim3(dm.nchunks, n), CHUNK_THREADS, 0, st>>>(w.parent, w.totals, w.chunk_count,
+                                                            w.chunk_off, w.rootlist, dm, max_rows);
+    ccl_order<<<n, 256, 0, st>>>(mask, w.run_start, w.parent, w.rootlist, w.nroots, w.sorted_root,
+                                 w.class_base, dm, max_rows);
     SQ_CHECK_LAUNCH();
-    for (int p0 = 0; p0 < planes; p0 += 65535 / d * d) {
-        const int np = min(planes - p0, 65535 / d * d);
-        Dims sub = dm;
-        const int f0 = p0 / d;
-        const long long off = (long long)f0 * dm.vox;
-        sub.n = np / d;
-        const dim3 grid(sq_div_up(wid, 32), sq_div_up(hgt, 8), np);
-        ccl_accum<<<grid, blk, 0, st>>>(mask + off, w.L + off, w.class_base + f0 * 256,
-                                        w.acc + (long long)f0 * max_rows * 4,
-                                        labels ? labels + off : nullptr, sub, max_rows);
-    }
+    run_accum<<<dim3(rblocks, n), 256, 0, st>>>(mask, w.totals, w.run_start, w.run_end, w.parent,
+                                                w.class_base, w.acc, labels, dm, max_rows);
     ccl_finalize<<<dim3(sq_div_up(max_rows, 256), n), 256, 0, st>>>(
-        mask, w.sorted_root, w.acc, w.totals, table, counts, dm, max_rows, frame0);
+        mask, w.run_start, w.sorted_root, w.acc, w.nroots, table, counts, dm, max_rows, frame0);
     SQ_CHECK_LAUNCH();
     return SQ_OK;
 }
@@ -460,7 +547,7 @@ extern "C" int sq_label_centroids_host(sq_handle_t h, const uint8_t *mask_host, 
 {
     SQ_REQUIRE(h && mask_host && table_host && counts_host, SQ_EINVAL, "label_host: null pointer");
     Dims dm;
-    SQ_TRY(make_dims(n, d, hgt, wid, max_rows, &dm));
+    SQ_TRY(make_dims(n, d, hgt, wid, max_rows, nullptr, &dm));
     SQ_CUDA(cudaSetDevice(h->device));
     const size_t nvox = (size_t)n * dm.vox;
     SqArena probe(nullptr, 0);
