@@ -29,6 +29,7 @@
 #include "unet_plan.cuh"
 #include "tc_common.cuh"
 #include <algorithm>
+#include <cstdlib>
 
 namespace {
 
@@ -46,7 +47,11 @@ struct Cfg {
     static constexpr int B_BYTES = NT * 2 * COUT * 16;   // 16 input channels of the weights
     static constexpr int STAGE_BYTES = (A_BYTES + B_BYTES + 127) / 128 * 128;
     static constexpr int ACC_COLS = S * NQ * COUT;
-    static constexpr uint32_t LBO_A = PH * PW * 16, SBO_A = PW * 16;
+    // conv with an even number of sub-tiles: sub-tiles 2p and 2p+1 take the even / odd image rows
+    // of a 32-row block, so vertically adjacent pixels sit in the SAME accumulator lane (same
+    // thread) of two sub-tiles and the fused 2x2 max-pool needs no vertical shuffle
+    static constexpr bool ILV = !UP && (S % 2 == 0);
+    static constexpr uint32_t LBO_A = PH * PW * 16, SBO_A = (ILV ? 2 : 1) * PW * 16;
     static constexpr uint32_t LBO_B = COUT * 16, SBO_B = 128;
     static_assert(A_BYTES % 128 == 0, "TMA destination alignment");
 };
@@ -171,8 +176,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                     for (int j = 0; j < S; ++j) {
 #pragma unroll
                         for (int tp = 0; tp < C::NT; ++tp) {
-                            const uint32_t a_off = UP ? (uint32_t)(j * 16 * C::PW)
-                                                      : (uint32_t)((j * 16 + tp / 3) * C::PW + tp % 3);
+                            const int row0 = C::ILV ? 32 * (j / 2) + (j & 1) : j * 16;   // first image row
+                            const uint32_t a_off = UP ? (uint32_t)(row0 * C::PW)
+                                                      : (uint32_t)((row0 + tp / 3) * C::PW + tp % 3);
                             const int q = UP ? tp : 0;
                             tc::umma_bf16_parts(d0 + (j * C::NQ + q) * COUT, a_lo + a_off, a_hi,
                                                 b_lo + tp * 2 * COUT, b_hi, idesc,
@@ -201,9 +207,63 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             const int tx = t % tiles_x, ty = (t / tiles_x) % tiles_y, n = t / (tiles_x * tiles_y);
             tc::mbar_wait(&tfull_bar[buf], (it / NBUF) & 1);
             tc::tc_fence_after();
+            if (EPI == EPI_POOL) {
+                // sub-tile pair (2p, 2p+1) = image rows (y, y+1) in the same lane: store both rows of
+                // the activation, take the vertical max in registers, the horizontal max with one
+                // shuffle (lane^1) and let the even-x lanes store the pooled tensor
+                static_assert(EPI != EPI_POOL || C::ILV, "fused pool needs interleaved sub-tiles");
+#pragma unroll 1
+                for (int jp = 0; jp < S / 2; ++jp) {
+                    const int y = ty * C::TH + 32 * jp + 2 * ph, x = tx * 8 + pw;
+                    const bool valid = (y < H) && (x < W);
+#pragma unroll 1
+                    for (int c16 = 0; c16 < COUT / 16; ++c16) {
+                        if (((jp * (COUT / 16) + c16) % EPI_GROUPS) != half) continue;
+                        uint32_t v0[16], v1[16];
+                        const uint32_t col = tmem_base + lane_addr + buf * C::ACC_COLS + (2 * jp) * COUT + c16 * 16;
+                        tc::tmem_ld16(col, v0);
+                        tc::tmem_ld16(col + COUT, v1);
+                        tc::tmem_ld_wait();
+                        uint32_t o0[8], o1[8];
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            const float4 sc = *reinterpret_cast<const float4 *>(s_scale + c16 * 16 + 4 * g);
+                            const float4 sh = *reinterpret_cast<const float4 *>(s_shift + c16 * 16 + 4 * g);
+                            o0[2 * g] = pack_bf16(fmaxf(fmaf(__uint_as_float(v0[4 * g]), sc.x, sh.x), 0.0f),
+                                                  fmaxf(fmaf(__uint_as_float(v0[4 * g + 1]), sc.y, sh.y), 0.0f));
+                            o0[2 * g + 1] = pack_bf16(fmaxf(fmaf(__uint_as_float(v0[4 * g + 2]), sc.z, sh.z), 0.0f),
+                                                      fmaxf(fmaf(__uint_as_float(v0[4 * g + 3]), sc.w, sh.w), 0.0f));
+                            o1[2 * g] = pack_bf16(fmaxf(fmaf(__uint_as_float(v1[4 * g]), sc.x, sh.x), 0.0f),
+                                                  fmaxf(fmaf(__uint_as_float(v1[4 * g + 1]), sc.y, sh.y), 0.0f));
+                            o1[2 * g + 1] = pack_bf16(fmaxf(fmaf(__uint_as_float(v1[4 * g + 2]), sc.z, sh.z), 0.0f),
+                                                      fmaxf(fmaf(__uint_as_float(v1[4 * g + 3]), sc.w, sh.w), 0.0f));
+                        }
+                        if (valid) {
+                            bf16 *p = out + ((((size_t)n * CBo + c16 * 2) * H + y) * W + x) * 8;
+                            *reinterpret_cast<uint4 *>(p) = make_uint4(o0[0], o0[1], o0[2], o0[3]);
+                            *reinterpret_cast<uint4 *>(p + (size_t)H * W * 8) = make_uint4(o0[4], o0[5], o0[6], o0[7]);
+                            p += (size_t)W * 8;                       // row y + 1 (H is even)
+                            *reinterpret_cast<uint4 *>(p) = make_uint4(o1[0], o1[1], o1[2], o1[3]);
+                            *reinterpret_cast<uint4 *>(p + (size_t)H * W * 8) = make_uint4(o1[4], o1[5], o1[6], o1[7]);
+                        }
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const uint32_t m = bf162_max(o0[e], o1[e]);
+                            o0[e] = bf162_max(m, __shfl_xor_sync(0xffffffffu, m, 1));
+                        }
+                        if (valid && (lane & 1) == 0) {
+                            const int Hp = H >> 1, Wp = W >> 1;
+                            bf16 *p = out_pool + ((((size_t)n * CBo + c16 * 2) * Hp + (y >> 1)) * Wp + (x >> 1)) * 8;
+                            *reinterpret_cast<uint4 *>(p) = make_uint4(o0[0], o0[1], o0[2], o0[3]);
+                            *reinterpret_cast<uint4 *>(p + (size_t)Hp * Wp * 8) = make_uint4(o0[4], o0[5], o0[6], o0[7]);
+                        }
+                    }
+                }
+            } else
 #pragma unroll 1
             for (int j = 0; j < S; ++j) {
-                const int y = ty * C::TH + j * 16 + ph, x = tx * 8 + pw;
+                const int y = ty * C::TH + (C::ILV ? 32 * (j / 2) + 2 * ph + (j & 1) : j * 16 + ph);
+                const int x = tx * 8 + pw;
                 const bool valid = (y < H) && (x < W);
                 if (!UP) {
                     float hl[HK > 0 ? HK : 1];                     // fused head: running logits
@@ -256,20 +316,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                                 *reinterpret_cast<uint4 *>(p) = make_uint4(o[0], o[1], o[2], o[3]);
                                 *reinterpret_cast<uint4 *>(p + (size_t)H * W * 8) = make_uint4(o[4], o[5], o[6], o[7]);
                             }
-                            if (EPI == EPI_POOL) {
-                                // 2x2 max pool inside the warp: partner pixels are lane^1 (x) and lane^8 (y)
-#pragma unroll
-                                for (int e = 0; e < 8; ++e) {
-                                    uint32_t m = bf162_max(o[e], __shfl_xor_sync(0xffffffffu, o[e], 1));
-                                    o[e] = bf162_max(m, __shfl_xor_sync(0xffffffffu, m, 8));
-                                }
-                                if (valid && (lane & 9) == 0) {
-                                    const int Hp = H >> 1, Wp = W >> 1;
-                                    bf16 *p = out_pool + ((((size_t)n * CBo + c16 * 2) * Hp + (y >> 1)) * Wp + (x >> 1)) * 8;
-                                    *reinterpret_cast<uint4 *>(p) = make_uint4(o[0], o[1], o[2], o[3]);
-                                    *reinterpret_cast<uint4 *>(p + (size_t)Hp * Wp * 8) = make_uint4(o[4], o[5], o[6], o[7]);
-                                }
-                            }
+
                         }
                     }
                     if (EPI == EPI_HEAD && (j % EPI_GROUPS) == half) {
@@ -590,7 +637,7 @@ int launch_tc(sq_unet_s *u, const SqLayer &L, const bf16 *in0, int cb0, const bf
     if (in1) SQ_TRY(make_map(&m1, in1, nimg, cb1, H, W, C::PW, C::PH));
     else m1 = m0;
     static_assert(MINB * NBUF * C::ACC_COLS <= 512, "co-resident CTAs must fit in TMEM");
-    int nstages = std::min(MAX_STAGES, ((MINB == 2 ? 108 : 200) * 1024) / C::STAGE_BYTES);
+    int nstages = std::min(MAX_STAGES, ((MINB == 1 ? 200 : 216 / MINB) * 1024 - 2048) / C::STAGE_BYTES);
     nstages = std::max(nstages, 2);
     const size_t smem = (size_t)nstages * C::STAGE_BYTES + 1024;
     auto kern = conv_tc_kernel<COUT, S, UP, NBUF, MINB, EPI, HK>;
