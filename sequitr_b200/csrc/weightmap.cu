@@ -273,6 +273,282 @@ __global__ void inst_cols_weight(const int *__restrict__ labels, const int *__re
     out[idx] = (OutT)w;
 }
 
+// ------------------------------------------------------------------ cut-off (bounded) kernels
+// When the cut-off radius R (beyond which the exponential term cannot change the rounded
+// result) is small -- R = 32 for the reference's w0 = 10, sigma = 5 -- distances only matter up
+// to R, fit in a byte, and both phases become cheap:
+//   row pass   every row is turned into bit masks in shared memory (one ballot per 32 pixels);
+//              a pixel finds its nearest seed (W1) or its two nearest distinct labels (W3, via
+//              run-start / run-end masks) with a handful of clz/ffs on <= 4 words -- O(1) per
+//              pixel, fully parallel, 1 B/px (W1) or 10 B/px (W3) of L2-resident output;
+//   col pass   a block stages the (64 + 2R) x 32 window of that output in shared memory and
+//              scans +-dy with the exact early exit dy^2 >= best.  W1 weights depend on the
+//              integer d2 only, so the fp64 sqrt/exp is evaluated once per distinct value
+//              (<= R^2 + 1 of them, same expression as the general kernel) and looked up.
+constexpr int WR_MAX = 64;             // largest cut-off radius handled by the bounded kernels
+constexpr unsigned char INF8 = 255;
+constexpr int CT_W = 32, CT_H = 64;    // column-pass tile
+
+// highest set bit at index <= pos and >= lo in a word array (-1 if none)
+__device__ __forceinline__ int prev_set(const unsigned *w, int pos, int lo)
+{
+    if (pos < lo) return -1;
+    int wi = pos >> 5;
+    unsigned m = w[wi] & (0xffffffffu >> (31 - (pos & 31)));
+    const int wlo = lo >> 5;
+    while (true) {
+        if (m) {
+            const int r = (wi << 5) + 31 - __clz(m);
+            return r >= lo ? r : -1;
+        }
+        if (--wi < wlo) return -1;
+        m = w[wi];
+    }
+}
+// lowest set bit at index >= pos and <= hi (-1 if none)
+__device__ __forceinline__ int next_set(const unsigned *w, int pos, int hi)
+{
+    if (pos > hi) return -1;
+    int wi = pos >> 5;
+    unsigned m = w[wi] & (0xffffffffu << (pos & 31));
+    const int whi = hi >> 5;
+    while (true) {
+        if (m) {
+            const int r = (wi << 5) + __ffs(m) - 1;
+            return r <= hi ? r : -1;
+        }
+        if (++wi > whi) return -1;
+        m = w[wi];
+    }
+}
+
+// grid (hgt, n), block 256, dyn smem: ceil(wid/32) words.  g8 = row distance if <= R else 255
+__global__ void edt_rows_bits(const uint8_t *__restrict__ mask, unsigned char *__restrict__ g8,
+                              int *__restrict__ anyfg, int hgt, int wid, int R)
+{
+    extern __shared__ unsigned bits[];
+    const long long ro = ((long long)blockIdx.y * hgt + blockIdx.x) * wid;
+    const uint8_t *mk = mask + ro;
+    const int nw = (wid + 31) >> 5;
+    bool any = false;
+    for (int x = threadIdx.x; x < nw * 32; x += blockDim.x) {
+        const unsigned b = __ballot_sync(0xffffffffu, x < wid && mk[x] != 0);
+        if ((threadIdx.x & 31) == 0) bits[x >> 5] = b;
+        any |= b != 0;
+    }
+    if (any && (threadIdx.x & 31) == 0) anyfg[blockIdx.y] = 1;
+    __syncthreads();
+    for (int x = threadIdx.x; x < wid; x += blockDim.x) {
+        const int l = prev_set(bits, x, max(x - R, 0));
+        const int r = next_set(bits, x, min(x + R, wid - 1));
+        int d = INF8;
+        if (l >= 0) d = x - l;
+        if (r >= 0) d = min(d, r - x);
+        g8[ro + x] = (unsigned char)d;
+    }
+}
+
+__global__ void w1_table_kernel(double *__restrict__ table, int n, double w0e, double denom)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double d = sqrt((double)i);
+    table[i] = w0e * exp(-(d * d) / denom) + 0.0 + 1.0;
+}
+
+// grid (ceil(W/32), ceil(H/64), n), block 256, dyn smem (64 + 2R) * 32 bytes
+template <typename OutT>
+__global__ void __launch_bounds__(256)
+edt_cols_tile(const unsigned char *__restrict__ g8, const int *__restrict__ anyfg,
+              const double *__restrict__ table, OutT *__restrict__ out, int hgt, int wid, int R,
+              double w0e, double denom)
+{
+    extern __shared__ unsigned char gs[];
+    __shared__ int tile_min;
+    const int x0 = blockIdx.x * CT_W, y0 = blockIdx.y * CT_H;
+    const long long fo = (long long)blockIdx.z * hgt * wid;
+    const int rows = CT_H + 2 * R;
+    const int col = threadIdx.x & 31, x = x0 + col;
+    if (threadIdx.x == 0) tile_min = INF8;
+    __syncthreads();
+    int mn = INF8;
+    for (int r = threadIdx.x >> 5; r < rows; r += 8) {
+        const int yy = y0 - R + r;
+        unsigned char v = INF8;
+        if (yy >= 0 && yy < hgt && x < wid) v = g8[fo + (long long)yy * wid + x];
+        gs[r * CT_W + col] = v;
+        mn = min(mn, (int)v);
+    }
+    if (mn < INF8) atomicMin(&tile_min, mn);
+    __syncthreads();
+    const bool none = !anyfg[blockIdx.z];
+    const bool empty = (tile_min == INF8) && !none;     // nothing within reach of this tile
+    const unsigned R2 = (unsigned)R * R;
+    for (int ly = threadIdx.x >> 5; ly < CT_H; ly += 8) {
+        const int y = y0 + ly;
+        if (x >= wid || y >= hgt) continue;
+        const long long idx = fo + (long long)y * wid + x;
+        if (empty) { out[idx] = (OutT)1.0; continue; }
+        const unsigned char *gc = gs + (ly + R) * CT_W + col;
+        const unsigned g0 = gc[0];
+        if (g0 == 0) { out[idx] = (OutT)2.0; continue; }               // foreground (row distance 0)
+        unsigned best;
+        if (none) {
+            best = (unsigned)(y + 1) * (unsigned)(y + 1) + (unsigned)x * (unsigned)x;   // SciPy, no seed
+        } else {
+            best = (g0 == INF8) ? INF32 : g0 * g0;
+            for (int dy = 1; dy <= R; ++dy) {
+                const unsigned dy2 = (unsigned)dy * dy;
+                if (dy2 >= best) break;
+                const unsigned gu = gc[-dy * CT_W], gd = gc[dy * CT_W];
+                if (gu != INF8) best = min(best, dy2 + gu * gu);
+                if (gd != INF8) best = min(best, dy2 + gd * gd);
+            }
+        }
+        double w = 1.0;
+        if (best <= R2) w = __ldg(table + best);
+        else if (none) {          // seedless frame: R was clamped to the image size, evaluate directly
+            const double d = sqrt((double)best);
+            w = w0e * exp(-(d * d) / denom) + 0.0 + 1.0;
+        }
+        out[idx] = (OutT)w;
+    }
+}
+
+// W3 row pass.  grid (hgt, n), block 256, dyn smem: 2 * ceil(wid/32) words (run starts, run ends)
+__global__ void inst_rows_bits(const int *__restrict__ labels, int *__restrict__ la,
+                               int *__restrict__ lb, unsigned char *__restrict__ da,
+                               unsigned char *__restrict__ db, int hgt, int wid, int R)
+{
+    extern __shared__ unsigned bits[];
+    const long long ro = ((long long)blockIdx.y * hgt + blockIdx.x) * wid;
+    const int *lr = labels + ro;
+    const int nw = (wid + 31) >> 5;
+    unsigned *sbits = bits, *ebits = bits + nw;
+    for (int x = threadIdx.x; x < nw * 32; x += blockDim.x) {
+        int l = 0, lp = 0, ln = 0;
+        if (x < wid) {
+            l = lr[x];
+            lp = x > 0 ? lr[x - 1] : 0;
+            ln = x + 1 < wid ? lr[x + 1] : 0;
+        }
+        const bool fg = l > 0;
+        const unsigned s = __ballot_sync(0xffffffffu, fg && lp != l);
+        const unsigned e = __ballot_sync(0xffffffffu, fg && ln != l);
+        if ((threadIdx.x & 31) == 0) { sbits[x >> 5] = s; ebits[x >> 5] = e; }
+    }
+    __syncthreads();
+    for (int x = threadIdx.x; x < wid; x += blockDim.x) {
+        const int own = lr[x] > 0 ? lr[x] : 0;
+        Best2 b = {0, 0, INF32, INF32};
+        if (own) best2_insert(b, own, 0u);
+        const int lo = max(x - R, 0), hi = min(x + R, wid - 1);
+        // ---- to the left: walk run ends, skipping runs of a label already taken on this side
+        {
+            int pos = own ? prev_set(sbits, x, 0) - 1 : x;       // left of the own run
+            int first = own;
+            for (int it = 0; it < 48 && pos >= lo; ++it) {
+                const int e = prev_set(ebits, pos, lo);
+                if (e < 0) break;
+                const int l = lr[e];
+                if (l != first) {
+                    best2_insert(b, l, (unsigned)(x - e));
+                    if (first) break;                             // two distinct labels on this side
+                    first = l;
+                }
+                const int st = prev_set(sbits, e, 0);
+                if (st < 0) break;
+                pos = st - 1;                                     // jump over that run
+            }
+        }
+        // ---- to the right
+        {
+            int pos = x;
+            if (own) { const int e = next_set(ebits, x, wid - 1); pos = (e < 0 ? wid : e + 1); }
+            int first = own;
+            for (int it = 0; it < 48 && pos <= hi; ++it) {
+                const int s = next_set(sbits, pos, hi);
+                if (s < 0) break;
+                const int l = lr[s];
+                if (l != first) {
+                    best2_insert(b, l, (unsigned)(s - x));
+                    if (first) break;
+                    first = l;
+                }
+                const int e = next_set(ebits, s, wid - 1);
+                if (e < 0) break;
+                pos = e + 1;
+            }
+        }
+        la[ro + x] = b.la;
+        lb[ro + x] = b.lb;
+        da[ro + x] = b.la ? (unsigned char)min(b.da, 254u) : INF8;
+        db[ro + x] = b.lb ? (unsigned char)min(b.db, 254u) : INF8;
+    }
+}
+
+// grid (ceil(W/32), ceil(H/64), n), block 256, dyn smem (64 + 2R) * 32 * 10 bytes
+template <typename OutT>
+__global__ void __launch_bounds__(256)
+inst_cols_tile(const int *__restrict__ la, const int *__restrict__ lb,
+               const unsigned char *__restrict__ da, const unsigned char *__restrict__ db,
+               OutT *__restrict__ out, int hgt, int wid, int R, double w0, double denom, double wc0,
+               double wc1)
+{
+    extern __shared__ __align__(16) unsigned char ws_[];
+    const int rows = CT_H + 2 * R;
+    int *sla = reinterpret_cast<int *>(ws_);
+    int *slb = sla + rows * CT_W;
+    unsigned char *sda = reinterpret_cast<unsigned char *>(slb + rows * CT_W);
+    unsigned char *sdb = sda + rows * CT_W;
+    const int x0 = blockIdx.x * CT_W, y0 = blockIdx.y * CT_H;
+    const long long fo = (long long)blockIdx.z * hgt * wid;
+    const int col = threadIdx.x & 31, x = x0 + col;
+    for (int r = threadIdx.x >> 5; r < rows; r += 8) {
+        const int yy = y0 - R + r;
+        int l1 = 0, l2 = 0;
+        unsigned char d1 = INF8, d2 = INF8;
+        if (yy >= 0 && yy < hgt && x < wid) {
+            const long long j = fo + (long long)yy * wid + x;
+            l1 = la[j]; l2 = lb[j]; d1 = da[j]; d2 = db[j];
+        }
+        sla[r * CT_W + col] = l1; slb[r * CT_W + col] = l2;
+        sda[r * CT_W + col] = d1; sdb[r * CT_W + col] = d2;
+    }
+    __syncthreads();
+    const double reach = (double)(R + 1);
+    for (int ly = threadIdx.x >> 5; ly < CT_H; ly += 8) {
+        const int y = y0 + ly;
+        if (x >= wid || y >= hgt) continue;
+        const long long idx = fo + (long long)y * wid + x;
+        const int c0 = (ly + R) * CT_W + col;
+        if (sda[c0] == 0) { out[idx] = (OutT)wc1; continue; }        // foreground: row distance 0
+        Best2 b = {0, 0, INF32, INF32};
+        for (int dy = 0; dy <= R; ++dy) {
+            const unsigned dy2 = (unsigned)dy * dy;
+            if (dy2 >= b.db) break;
+#pragma unroll
+            for (int sgn = -1; sgn <= 1; sgn += 2) {
+                if (dy == 0 && sgn > 0) continue;
+                const int j = c0 + sgn * dy * CT_W;
+                const int l1 = sla[j];
+                if (l1) {
+                    const unsigned d = sda[j];
+                    best2_insert(b, l1, dy2 + d * d);
+                    const int l2 = slb[j];
+                    if (l2) { const unsigned e = sdb[j]; best2_insert(b, l2, dy2 + e * e); }
+                }
+            }
+        }
+        double w = wc0;
+        if (b.lb != 0) {
+            const double sum = sqrt((double)b.da) + sqrt((double)b.db);
+            if (sum <= reach) w = wc0 + w0 * exp(-(sum * sum) / denom);   // beyond: cannot change the result
+        }
+        out[idx] = (OutT)w;
+    }
+}
+
 // Radius beyond which |w0|*exp(-r^2/denom) is < 2^-bits * scale, i.e. cannot change
 // the rounded result (scale = magnitude of the class term it is added to).
 int cutoff_radius(double w0, double denom, double scale, int out_dtype, int maxdim)
@@ -313,6 +589,7 @@ extern "C" int sq_weightmap_workspace_bytes(sq_handle_t h, int n, int hgt, int w
     } else {
         a.take<unsigned short>(px);
         a.take<int>(n);
+        a.take<double>(WR_MAX * WR_MAX + 1);
     }
     *bytes = a.off;
     return SQ_OK;
@@ -328,6 +605,7 @@ extern "C" int sq_weightmap_edt(sq_handle_t h, const uint8_t *mask, int n, int h
     SqArena a(ws, ws_bytes);
     unsigned short *g = a.take<unsigned short>(px);
     int *anyfg = a.take<int>(n);
+    double *table = a.take<double>(WR_MAX * WR_MAX + 1);
     SQ_REQUIRE(a.ok(), SQ_ENOMEM, "weightmap_edt: workspace %zu < %zu bytes", ws_bytes, a.off);
     cudaStream_t st = (cudaStream_t)stream_;
     const double denom = 2.0 * sigma * sigma + 1e-99;          // pipeline.py:478
@@ -336,6 +614,22 @@ extern "C" int sq_weightmap_edt(sq_handle_t h, const uint8_t *mask, int n, int h
     const int rmax = d2 ? maxdim : cutoff_radius(w0e, denom, 1.0, out_dtype, maxdim);
 
     SQ_CUDA(cudaMemsetAsync(anyfg, 0, n * sizeof(int), st));
+    if (!d2 && rmax <= WR_MAX) {
+        // bounded path (the common case: R = 32 for w0 = 10, sigma = 5)
+        unsigned char *g8 = reinterpret_cast<unsigned char *>(g);
+        edt_rows_bits<<<dim3(hgt, n), 256, (size_t)((wid + 31) / 32) * 4, st>>>(mask, g8, anyfg, hgt, wid, rmax);
+        w1_table_kernel<<<sq_div_up(rmax * rmax + 1, 256), 256, 0, st>>>(table, rmax * rmax + 1, w0e, denom);
+        const dim3 tgrid(sq_div_up(wid, CT_W), sq_div_up(hgt, CT_H), n);
+        const size_t sm = (size_t)(CT_H + 2 * rmax) * CT_W;
+        if (out_dtype == SQ_F32)
+            edt_cols_tile<float><<<tgrid, 256, sm, st>>>(g8, anyfg, table, (float *)out, hgt, wid, rmax, w0e, denom);
+        else
+            edt_cols_tile<double><<<tgrid, 256, sm, st>>>(g8, anyfg, table, (double *)out, hgt, wid, rmax, w0e, denom);
+        SQ_CHECK_LAUNCH();
+        return SQ_OK;
+    }
+    if ((size_t)wid * sizeof(unsigned short) > 48 * 1024)
+        SQ_CUDA(cudaFuncSetAttribute(edt_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
     edt_rows<<<dim3(hgt, n), ROW_THREADS, (size_t)wid * sizeof(unsigned short), st>>>(
         mask, g, anyfg, hgt, wid);
     const dim3 grid(sq_div_up(wid, 32), sq_div_up(hgt, 8), n), blk(32, 8);
@@ -367,6 +661,23 @@ extern "C" int sq_weightmap_unet(sq_handle_t h, const int32_t *labels, int n, in
     // d1 + d2 >= d2 >= dy: once dy passes the cut-off the gap term cannot matter
     const int rmax = cutoff_radius(w0, denom, std::fabs(wc0), out_dtype, maxdim);
 
+    if (rmax <= WR_MAX) {
+        unsigned char *da8 = reinterpret_cast<unsigned char *>(da), *db8 = reinterpret_cast<unsigned char *>(db);
+        inst_rows_bits<<<dim3(hgt, n), 256, (size_t)((wid + 31) / 32) * 8, st>>>(labels, la, lb, da8, db8, hgt, wid, rmax);
+        const dim3 tgrid(sq_div_up(wid, CT_W), sq_div_up(hgt, CT_H), n);
+        const size_t sm = (size_t)(CT_H + 2 * rmax) * CT_W * 10;
+        if (out_dtype == SQ_F32) {
+            auto k = inst_cols_tile<float>;
+            if (sm > 48 * 1024) SQ_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            k<<<tgrid, 256, sm, st>>>(la, lb, da8, db8, (float *)out, hgt, wid, rmax, w0, denom, wc0, wc1);
+        } else {
+            auto k = inst_cols_tile<double>;
+            if (sm > 48 * 1024) SQ_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            k<<<tgrid, 256, sm, st>>>(la, lb, da8, db8, (double *)out, hgt, wid, rmax, w0, denom, wc0, wc1);
+        }
+        SQ_CHECK_LAUNCH();
+        return SQ_OK;
+    }
     inst_rows<<<dim3(hgt, n), ROW_THREADS, 0, st>>>(labels, la, lb, da, db, hgt, wid);
     const dim3 grid(sq_div_up(wid, 32), sq_div_up(hgt, 8), n), blk(32, 8);
     if (out_dtype == SQ_F32)
