@@ -164,6 +164,18 @@ int sq_unet_profile(sq_unet_t u, const float *in_dev, int n, int d, int hgt, int
                     const char **names_out, float *ms_out, double *flops_out,
                     int max_layers, int *n_layers);
 
+/* Weighted softmax cross-entropy of the head (training step of BASELINE config 5; consumes the
+ * per-pixel 'weights' map and the labels that networks/unet.py tr_augment :396-401 returns; the
+ * loss itself is not shipped by the reference).  logits_dev float32 (npix,K); labels_dev uint8
+ * (npix) class ids < K; weights_dev float32 (npix).
+ *   loss  = (1/npix) * sum_i w_i * (logsumexp(logits_i) - logits_i[label_i])      -> *loss_dev (float64)
+ *   grad  = w_i * (softmax(logits_i) - onehot(label_i)) / npix                    -> grad_dev (npix,K) or NULL
+ * The reduction order is fixed (deterministic).  workspace: sq_weighted_ce_workspace_bytes(). */
+int sq_weighted_ce_workspace_bytes(sq_handle_t h, size_t *bytes);
+int sq_weighted_ce(sq_handle_t h, const float *logits_dev, const uint8_t *labels_dev,
+                   const float *weights_dev, long long npix, int K, double *loss_dev,
+                   float *grad_dev, void *workspace_dev, size_t workspace_bytes, void *stream);
+
 /* The whole data-parallel hot path on HOST frames: H2D -> UNet -> argmax ->
  * label-and-localise -> D2H of the centroid tables (the call a Sequitr job
  * function makes per batch of frames).  frames_host float32 (n,hgt,wid,cin);

@@ -55,6 +55,9 @@ _SIGNATURES = {
     'sq_unet_profile': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_size_t,
                                 c_void_p, _P(c_char_p), _P(ctypes.c_float), _P(c_double), c_int,
                                 _P(c_int)]),
+    'sq_weighted_ce_workspace_bytes': (c_int, [c_void_p, _P(c_size_t)]),
+    'sq_weighted_ce': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_longlong, c_int, c_void_p,
+                       c_void_p, c_void_p, c_size_t, c_void_p]),
     'sq_segment_localise_host': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
                                          c_void_p, c_int, c_void_p]),
 }

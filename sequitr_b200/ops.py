@@ -106,6 +106,29 @@ def weightmap_unet(labels, w0=10., sigma=5., wc=None, out_dtype='float32', works
     return out
 
 
+def weighted_cross_entropy(logits, labels, weights, want_grad=True, workspace=None):
+    """Weighted softmax cross-entropy of the head on cuda tensors: logits float32 (...,K), labels
+    uint8 (...), weights float32 (...) (e.g. the GPU weight map).  Returns (loss float64 0-d tensor,
+    grad float32 like logits or None)."""
+    torch = _torch()
+    lib = _lib.load()
+    k = logits.shape[-1]
+    npix = logits.numel() // k
+    assert logits.is_cuda and logits.dtype == torch.float32 and logits.is_contiguous()
+    assert labels.dtype == torch.uint8 and labels.numel() == npix and labels.is_contiguous()
+    assert weights.dtype == torch.float32 and weights.numel() == npix and weights.is_contiguous()
+    hd = _lib.handle(logits.device.index)
+    need = ctypes.c_size_t()
+    _lib.check(lib.sq_weighted_ce_workspace_bytes(hd, ctypes.byref(need)))
+    ws = (workspace or _ws(('ce', logits.device.index))).get(need.value)
+    loss = torch.empty((), dtype=torch.float64, device=logits.device)
+    grad = torch.empty_like(logits) if want_grad else None
+    _lib.check(lib.sq_weighted_ce(hd, logits.data_ptr(), labels.data_ptr(), weights.data_ptr(), npix, k,
+                                  loss.data_ptr(), _lib.ptr(grad), ws.data_ptr(), ws.numel(),
+                                  _lib.stream_ptr()))
+    return loss, grad
+
+
 # ------------------------------------------------------------- host-buffer calls
 
 def label_centroids_host(mask, max_rows=4096, frame0=0, want_labels=False, device=None):
