@@ -90,8 +90,13 @@ __global__ void __launch_bounds__(TC_THREADS, MINB)
 conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                int ks0, int ks1, const bf16 *__restrict__ wts, const float *__restrict__ scale,
                const float *__restrict__ shift, bf16 *__restrict__ out, bf16 *__restrict__ out_pool,
-               HeadArgs head, int nimg, int H, int W, int relu, int nstages)
+               HeadArgs head, int nimg, int H, int W, int relu, int nstages, int D, int KZ,
+               int out_mul, int out_off)
 {
+    // Volumes: activations are [n][z][c/8][y][x][8]; a (z-slice, image) pair is one "image" np =
+    // n*D + z for tiling and for the epilogue, and a 3x3x3 conv is the same 9-tap stage run for
+    // KZ = 3 z-offsets: k-step q = kz*ksteps + ks loads the halo patch of slice z + kz - 1 (TMA
+    // zero-fills slices outside the volume) and the weights of depth tap kz.  Planar: D = KZ = 1.
     using C = Cfg<COUT, S, UP>;
     constexpr int TMEM_COLS = (NBUF * C::ACC_COLS <= 32) ? 32 : (NBUF * C::ACC_COLS <= 64) ? 64
                             : (NBUF * C::ACC_COLS <= 128) ? 128 : (NBUF * C::ACC_COLS <= 256) ? 256 : 512;
@@ -106,8 +111,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_x = (W + 7) >> 3, tiles_y = (H + C::TH - 1) / C::TH;
-    const int ntiles = nimg * tiles_x * tiles_y;
-    const int ksteps = ks0 + ks1;
+    const int ntiles = nimg * D * tiles_x * tiles_y;
+    const int ksteps = ks0 + ks1, qsteps = KZ * ksteps;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < nstages; ++i) { tc::mbar_init(&full_bar[i], 1); tc::mbar_init(&empty_bar[i], 1); }
@@ -134,15 +139,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             int stage = 0;
             uint32_t phase = 0;
             for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-                const int tx = t % tiles_x, ty = (t / tiles_x) % tiles_y, n = t / (tiles_x * tiles_y);
+                const int tx = t % tiles_x, ty = (t / tiles_x) % tiles_y, np = t / (tiles_x * tiles_y);
+                const int z = np % D, n = np / D;
                 const int x0 = tx * 8 - (UP ? 0 : 1), y0 = ty * C::TH - (UP ? 0 : 1);
-                for (int ks = 0; ks < ksteps; ++ks) {
+                for (int q = 0; q < qsteps; ++q) {
+                    const int kz = q / ksteps, ks = q - kz * ksteps;
+                    const int zc = z + kz - (KZ >> 1);
                     tc::mbar_wait(&empty_bar[stage], phase ^ 1);
                     tc::mbar_arrive_expect_tx(&full_bar[stage], C::A_BYTES + C::B_BYTES);
                     uint8_t *sA = smem + (size_t)stage * C::STAGE_BYTES;
-                    if (ks < ks0) tc::tma_load_4d(sA, &mapA0, &full_bar[stage], x0 * 8, y0, ks * 2, n);
-                    else          tc::tma_load_4d(sA, &mapA1, &full_bar[stage], x0 * 8, y0, (ks - ks0) * 2, n);
-                    tc::bulk_load(sA + C::A_BYTES, wts + (size_t)ks * (C::B_BYTES / 2), C::B_BYTES,
+                    if (ks < ks0) tc::tma_load_5d(sA, &mapA0, &full_bar[stage], x0 * 8, y0, ks * 2, zc, n);
+                    else          tc::tma_load_5d(sA, &mapA1, &full_bar[stage], x0 * 8, y0, (ks - ks0) * 2, zc, n);
+                    tc::bulk_load(sA + C::A_BYTES, wts + (size_t)q * (C::B_BYTES / 2), C::B_BYTES,
                                   &full_bar[stage]);
                     if (++stage == nstages) { stage = 0; phase ^= 1; }
                 }
@@ -162,7 +170,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             const int buf = it % NBUF;
             tc::mbar_wait(&tempty_bar[buf], ((it / NBUF) & 1) ^ 1);
             tc::tc_fence_after();
-            for (int ks = 0; ks < ksteps; ++ks) {
+            for (int ks = 0; ks < qsteps; ++ks) {
                 tc::mbar_wait(&full_bar[stage], phase);
                 tc::tc_fence_after();
                 if (tc::elect_one()) {
@@ -204,7 +212,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         int it = 0;
         for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
             const int buf = it % NBUF;
-            const int tx = t % tiles_x, ty = (t / tiles_x) % tiles_y, n = t / (tiles_x * tiles_y);
+            const int tx = t % tiles_x, ty = (t / tiles_x) % tiles_y;
+            const int n = (t / (tiles_x * tiles_y)) * out_mul + out_off;   // output "image" (n*D + z)
             tc::mbar_wait(&tfull_bar[buf], (it / NBUF) & 1);
             tc::tc_fence_after();
             if (EPI == EPI_POOL) {
@@ -527,6 +536,83 @@ __global__ void maxpool_bf16_kernel(const uint4 *__restrict__ in, uint4 *__restr
     out[i] = m;
 }
 
+// Volumes: first 3x3x3 conv, fp32 NDHWC input with few channels -> bf16 blocked [n*D+z][c/8][y][x][8].
+// One thread per voxel; weights ([27*CIN][COUT] fp32, bf16-rounded) are broadcast from shared memory.
+template <int COUT>
+__global__ void __launch_bounds__(128)
+first_conv3d_kernel(const float *__restrict__ in, const float *__restrict__ wf,
+                    const float *__restrict__ scale, const float *__restrict__ shift,
+                    bf16 *__restrict__ out, int nimg, int D, int H, int W, int CIN)
+{
+    extern __shared__ float sw3[];                      // [27*CIN][COUT] + scale[COUT] + shift[COUT]
+    const int KT = 27 * CIN;
+    for (int i = threadIdx.x; i < KT * COUT + 2 * COUT; i += blockDim.x)
+        sw3[i] = i < KT * COUT ? wf[i] : (i < KT * COUT + COUT ? scale[i - KT * COUT] : shift[i - KT * COUT - COUT]);
+    __syncthreads();
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= (long long)nimg * D * H * W) return;
+    const int x = (int)(p % W), y = (int)((p / W) % H), z = (int)((p / ((long long)W * H)) % D);
+    const long long n = p / ((long long)W * H * D);
+    float acc[COUT];
+#pragma unroll
+    for (int c = 0; c < COUT; ++c) acc[c] = 0.0f;
+    for (int kz = 0; kz < 3; ++kz) {
+        const int zz = z + kz - 1;
+        if (zz < 0 || zz >= D) continue;
+        for (int ky = 0; ky < 3; ++ky) {
+            const int yy = y + ky - 1;
+            if (yy < 0 || yy >= H) continue;
+            for (int kx = 0; kx < 3; ++kx) {
+                const int xx = x + kx - 1;
+                if (xx < 0 || xx >= W) continue;
+                const float *src = in + ((((size_t)n * D + zz) * H + yy) * W + xx) * CIN;
+                for (int c = 0; c < CIN; ++c) {
+                    const float v = __bfloat162float(__float2bfloat16_rn(__ldg(src + c)));
+                    const float4 *w4 = reinterpret_cast<const float4 *>(sw3 + (size_t)(((kz * 3 + ky) * 3 + kx) * CIN + c) * COUT);
+#pragma unroll
+                    for (int q = 0; q < COUT / 4; ++q) {
+                        const float4 w = w4[q];
+                        acc[4 * q] = fmaf(v, w.x, acc[4 * q]);
+                        acc[4 * q + 1] = fmaf(v, w.y, acc[4 * q + 1]);
+                        acc[4 * q + 2] = fmaf(v, w.z, acc[4 * q + 2]);
+                        acc[4 * q + 3] = fmaf(v, w.w, acc[4 * q + 3]);
+                    }
+                }
+            }
+        }
+    }
+    const float *sc = sw3 + KT * COUT, *sh = sc + COUT;
+    const long long np = n * D + z;
+#pragma unroll
+    for (int cb = 0; cb < COUT / 8; ++cb) {
+        uint4 o;
+        uint32_t *ow = reinterpret_cast<uint32_t *>(&o);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int c = cb * 8 + 2 * e;
+            ow[e] = pack_bf16(fmaxf(fmaf(acc[c], sc[c], sh[c]), 0.0f), fmaxf(fmaf(acc[c + 1], sc[c + 1], sh[c + 1]), 0.0f));
+        }
+        *reinterpret_cast<uint4 *>(out + ((((size_t)np * (COUT / 8) + cb) * H + y) * W + x) * 8) = o;
+    }
+}
+
+// Volumes: depth half of the 2x2x2 max pool.  in: [n][2*Do][plane] (the xy-pooled slices), out:
+// [n][Do][plane]; plane = (c/8)*h*w 16-byte vectors.
+__global__ void zpool_bf16_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ out, long long nvec,
+                                  long long plane)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nvec) return;
+    const long long s = i / plane, r = i - s * plane;          // s = n*Do + zo
+    const uint4 a = in[(2 * s) * plane + r], b = in[(2 * s + 1) * plane + r];
+    uint4 m;
+    m.x = bf162_max(a.x, b.x);
+    m.y = bf162_max(a.y, b.y);
+    m.z = bf162_max(a.z, b.z);
+    m.w = bf162_max(a.w, b.w);
+    out[i] = m;
+}
+
 __global__ void eltwise_bf16_kernel(const uint32_t *__restrict__ a, const uint32_t *__restrict__ b,
                                     long long n2, int op, uint32_t *__restrict__ out)
 {
@@ -610,31 +696,41 @@ int dev_upload(sq_unet_s *u, const void *src, size_t bytes, void **dst)
     return SQ_OK;
 }
 
-int make_map(CUtensorMap *m, const bf16 *ptr, int nimg, int CB, int H, int W, int PW, int PH)
+int make_map(CUtensorMap *m, const bf16 *ptr, int nimg, int D, int CB, int H, int W, int PW, int PH)
 {
     sq_encode_tiled_fn enc = sq_get_encode_tiled();
     SQ_REQUIRE(enc, SQ_ECUDA, "cuTensorMapEncodeTiled entry point not available");
-    cuuint64_t dims[4] = {(cuuint64_t)W * 8, (cuuint64_t)H, (cuuint64_t)CB, (cuuint64_t)nimg};
-    cuuint64_t strides[3] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)CB * H * W * 16};
-    cuuint32_t box[4] = {(cuuint32_t)PW * 8, (cuuint32_t)PH, 2, 1};
-    cuuint32_t es[4] = {1, 1, 1, 1};
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void *)ptr, dims, strides, box, es,
+    // act[n][z][c/8][y][x][8] as a 5-D tensor (x*8, y, c/8, z, n); planar stacks have D = 1
+    cuuint64_t dims[5] = {(cuuint64_t)W * 8, (cuuint64_t)H, (cuuint64_t)CB, (cuuint64_t)D, (cuuint64_t)nimg};
+    cuuint64_t strides[4] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)CB * H * W * 16,
+                             (cuuint64_t)D * CB * H * W * 16};
+    cuuint32_t box[5] = {(cuuint32_t)PW * 8, (cuuint32_t)PH, 2, 1, 1};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void *)ptr, dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    SQ_REQUIRE(r == CUDA_SUCCESS, SQ_ECUDA, "cuTensorMapEncodeTiled failed (%d) for (%d,%d,%d,%d)",
-               (int)r, nimg, CB, H, W);
+    SQ_REQUIRE(r == CUDA_SUCCESS, SQ_ECUDA, "cuTensorMapEncodeTiled failed (%d) for (%d,%d,%d,%d,%d)",
+               (int)r, nimg, D, CB, H, W);
     return SQ_OK;
 }
 
+// geometry of one launch: nimg volumes of D slices (planar: D = 1); KZ depth taps; up-conv output
+// image index = in_image * out_mul + out_off
+struct TcGeo {
+    int nimg, D, H, W, KZ, out_mul, out_off;
+    size_t w_off;                           // element offset into the layer's tensor-core weights
+};
+
 template <int COUT, int S, bool UP, int NBUF, int MINB, int EPI, int HK = 0>
 int launch_tc(sq_unet_s *u, const SqLayer &L, const bf16 *in0, int cb0, const bf16 *in1, int cb1,
-              bf16 *out, bf16 *out_pool, const HeadArgs &head, int nimg, int H, int W, int relu,
+              bf16 *out, bf16 *out_pool, const HeadArgs &head, const TcGeo &g, int relu,
               cudaStream_t st)
 {
     using C = Cfg<COUT, S, UP>;
+    const int nimg = g.nimg, H = g.H, W = g.W;
     CUtensorMap m0, m1;
-    SQ_TRY(make_map(&m0, in0, nimg, cb0, H, W, C::PW, C::PH));
-    if (in1) SQ_TRY(make_map(&m1, in1, nimg, cb1, H, W, C::PW, C::PH));
+    SQ_TRY(make_map(&m0, in0, nimg, g.D, cb0, H, W, C::PW, C::PH));
+    if (in1) SQ_TRY(make_map(&m1, in1, nimg, g.D, cb1, H, W, C::PW, C::PH));
     else m1 = m0;
     static_assert(MINB * NBUF * C::ACC_COLS <= 512, "co-resident CTAs must fit in TMEM");
     int nstages = std::min(MAX_STAGES, ((MINB == 1 ? 200 : 216 / MINB) * 1024 - 2048) / C::STAGE_BYTES);
@@ -646,10 +742,11 @@ int launch_tc(sq_unet_s *u, const SqLayer &L, const bf16 *in0, int cb0, const bf
         SQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
-    const int tiles = nimg * ((W + 7) / 8) * ((H + C::TH - 1) / C::TH);
+    const int tiles = nimg * g.D * ((W + 7) / 8) * ((H + C::TH - 1) / C::TH);
     const int grid = std::min(tiles, MINB * u->h->sm_count);
-    kern<<<grid, TC_THREADS, smem, st>>>(m0, m1, cb0 / 2, in1 ? cb1 / 2 : 0, (const bf16 *)L.w_tc, L.scale,
-                                         L.shift, out, out_pool, head, nimg, H, W, relu, nstages);
+    kern<<<grid, TC_THREADS, smem, st>>>(m0, m1, cb0 / 2, in1 ? cb1 / 2 : 0, (const bf16 *)L.w_tc + g.w_off, L.scale,
+                                         L.shift, out, out_pool, head, nimg, H, W, relu, nstages, g.D, g.KZ,
+                                         g.out_mul, g.out_off);
     ++u->last_launches;
     SQ_CHECK_LAUNCH();
     return SQ_OK;
@@ -657,15 +754,15 @@ int launch_tc(sq_unet_s *u, const SqLayer &L, const bf16 *in0, int cb0, const bf
 
 template <int COUT, int S, int MINB>
 int conv3x3_epi(sq_unet_s *u, const SqLayer &L, const bf16 *in0, int c0, const bf16 *in1, int c1,
-                bf16 *out, bf16 *out_pool, const HeadArgs *head, int nimg, int H, int W, cudaStream_t st)
+                bf16 *out, bf16 *out_pool, const HeadArgs *head, const TcGeo &g, cudaStream_t st)
 {
     const HeadArgs none = {nullptr, 0, nullptr, nullptr, nullptr};
     if (head) {
         if constexpr (COUT <= 32) {
             switch (head->K) {
-            case 2: return launch_tc<COUT, S, false, 2, MINB, EPI_HEAD, 2>(u, L, in0, c0 / 8, in1, c1 / 8, out, nullptr, *head, nimg, H, W, 1, st);
-            case 3: return launch_tc<COUT, S, false, 2, MINB, EPI_HEAD, 3>(u, L, in0, c0 / 8, in1, c1 / 8, out, nullptr, *head, nimg, H, W, 1, st);
-            case 4: return launch_tc<COUT, S, false, 2, MINB, EPI_HEAD, 4>(u, L, in0, c0 / 8, in1, c1 / 8, out, nullptr, *head, nimg, H, W, 1, st);
+            case 2: return launch_tc<COUT, S, false, 2, MINB, EPI_HEAD, 2>(u, L, in0, c0 / 8, in1, c1 / 8, out, nullptr, *head, g, 1, st);
+            case 3: return launch_tc<COUT, S, false, 2, MINB, EPI_HEAD, 3>(u, L, in0, c0 / 8, in1, c1 / 8, out, nullptr, *head, g, 1, st);
+            case 4: return launch_tc<COUT, S, false, 2, MINB, EPI_HEAD, 4>(u, L, in0, c0 / 8, in1, c1 / 8, out, nullptr, *head, g, 1, st);
             }
         }
         SQ_REQUIRE(false, SQ_EUNSUPPORTED, "fused head supports filters[0] <= 32 and 2..4 classes");
@@ -673,37 +770,36 @@ int conv3x3_epi(sq_unet_s *u, const SqLayer &L, const bf16 *in0, int c0, const b
     if (out_pool) {
         if constexpr (COUT <= 128)
             return launch_tc<COUT, S, false, 2, MINB, EPI_POOL>(u, L, in0, c0 / 8, in1, c1 / 8, out, out_pool,
-                                                                none, nimg, H, W, 1, st);
+                                                                none, g, 1, st);
         else
             SQ_REQUIRE(false, SQ_EUNSUPPORTED, "fused pool needs filters <= 128");
     }
     return launch_tc<COUT, S, false, 2, MINB, EPI_STORE>(u, L, in0, c0 / 8, in1, c1 / 8, out, nullptr, none,
-                                                         nimg, H, W, 1, st);
+                                                         g, 1, st);
 }
 
 // out_pool != NULL: also write the 2x2 max-pooled tensor; head != NULL: fused 1x1 head, no `out`.
 int conv3x3_tc(sq_unet_s *u, const SqLayer &L, const bf16 *in0, int c0, const bf16 *in1, int c1,
-               bf16 *out, bf16 *out_pool, const HeadArgs *head, int nimg, int H, int W, cudaStream_t st)
+               bf16 *out, bf16 *out_pool, const HeadArgs *head, const TcGeo &g, cudaStream_t st)
 {
     switch (L.cout) {
-    case 16:  return conv3x3_epi<16, 4, 2>(u, L, in0, c0, in1, c1, out, out_pool, head, nimg, H, W, st);
-    case 32:  return conv3x3_epi<32, 4, 2>(u, L, in0, c0, in1, c1, out, out_pool, head, nimg, H, W, st);
-    case 64:  return conv3x3_epi<64, 2, 2>(u, L, in0, c0, in1, c1, out, out_pool, head, nimg, H, W, st);
-    case 128: return conv3x3_epi<128, 2, 1>(u, L, in0, c0, in1, c1, out, out_pool, head, nimg, H, W, st);
-    case 256: return conv3x3_epi<256, 1, 1>(u, L, in0, c0, in1, c1, out, out_pool, head, nimg, H, W, st);
+    case 16:  return conv3x3_epi<16, 4, 2>(u, L, in0, c0, in1, c1, out, out_pool, head, g, st);
+    case 32:  return conv3x3_epi<32, 4, 2>(u, L, in0, c0, in1, c1, out, out_pool, head, g, st);
+    case 64:  return conv3x3_epi<64, 2, 2>(u, L, in0, c0, in1, c1, out, out_pool, head, g, st);
+    case 128: return conv3x3_epi<128, 2, 1>(u, L, in0, c0, in1, c1, out, out_pool, head, g, st);
+    case 256: return conv3x3_epi<256, 1, 1>(u, L, in0, c0, in1, c1, out, out_pool, head, g, st);
     }
     SQ_REQUIRE(false, SQ_EUNSUPPORTED, "bf16 mode: unsupported filter count %d", L.cout);
 }
 
-int upconv_tc(sq_unet_s *u, const SqLayer &L, const bf16 *in, bf16 *out, int nimg, int H, int W,
-              cudaStream_t st)
+int upconv_tc(sq_unet_s *u, const SqLayer &L, const bf16 *in, bf16 *out, const TcGeo &g, cudaStream_t st)
 {
     const HeadArgs none = {nullptr, 0, nullptr, nullptr, nullptr};
     switch (L.cout) {
-    case 16:  return launch_tc<16, 2, true, 2, 2, EPI_STORE>(u, L, in, L.cin0 / 8, nullptr, 0, out, nullptr, none, nimg, H, W, 0, st);
-    case 32:  return launch_tc<32, 1, true, 2, 2, EPI_STORE>(u, L, in, L.cin0 / 8, nullptr, 0, out, nullptr, none, nimg, H, W, 0, st);
-    case 64:  return launch_tc<64, 1, true, 2, 1, EPI_STORE>(u, L, in, L.cin0 / 8, nullptr, 0, out, nullptr, none, nimg, H, W, 0, st);
-    case 128: return launch_tc<128, 1, true, 1, 1, EPI_STORE>(u, L, in, L.cin0 / 8, nullptr, 0, out, nullptr, none, nimg, H, W, 0, st);
+    case 16:  return launch_tc<16, 2, true, 2, 2, EPI_STORE>(u, L, in, L.cin0 / 8, nullptr, 0, out, nullptr, none, g, 0, st);
+    case 32:  return launch_tc<32, 1, true, 2, 2, EPI_STORE>(u, L, in, L.cin0 / 8, nullptr, 0, out, nullptr, none, g, 0, st);
+    case 64:  return launch_tc<64, 1, true, 2, 1, EPI_STORE>(u, L, in, L.cin0 / 8, nullptr, 0, out, nullptr, none, g, 0, st);
+    case 128: return launch_tc<128, 1, true, 1, 1, EPI_STORE>(u, L, in, L.cin0 / 8, nullptr, 0, out, nullptr, none, g, 0, st);
     }
     SQ_REQUIRE(false, SQ_EUNSUPPORTED, "bf16 mode: unsupported up-conv filter count %d", L.cout);
 }
@@ -728,40 +824,41 @@ int sq_tc_destroy(sq_unet_s *u)
 // fp32 upload, so L.scale / L.shift already hold the folded epilogue).
 int sq_tc_finalize(sq_unet_s *u)
 {
-    SQ_REQUIRE(u->ndim == 2, SQ_EUNSUPPORTED,
-               "bf16 tensor-core mode implements UNet2D; use compute='fp32' for UNet3D");
     SQ_REQUIRE(u->cin <= 4, SQ_EUNSUPPORTED, "bf16 mode: num_inputs must be <= 4 (got %d)", u->cin);
     for (int f : u->filters)
         SQ_REQUIRE(f == 16 || f == 32 || f == 64 || f == 128 || f == 256, SQ_EUNSUPPORTED,
                    "bf16 mode: filters must be in {16,32,64,128,256} (got %d)", f);
+    const int KZ = (u->ndim == 3) ? 3 : 1, UZ = (u->ndim == 3) ? 2 : 1;
     for (SqLayer &L : u->layers) {
         const std::vector<float> &k = u->host[L.scope + "/kernel"].data;
         const int C = L.cin0 + L.cin1, CO = L.cout;
         if (L.kind == SqLayer::CONV && C % 16 == 0) {
-            // [ks][tap][kb][co][8]  <-  HWIO kernel[tap][ci][co]
-            std::vector<uint16_t> w((size_t)9 * C * CO);
-            for (int ks = 0; ks < C / 16; ++ks)
-                for (int tp = 0; tp < 9; ++tp)
-                    for (int kb = 0; kb < 2; ++kb)
-                        for (int co = 0; co < CO; ++co)
-                            for (int e = 0; e < 8; ++e) {
-                                const int ci = ks * 16 + kb * 8 + e;
-                                w[((((size_t)ks * 9 + tp) * 2 + kb) * CO + co) * 8 + e] =
-                                    host_bf16(k[((size_t)tp * C + ci) * CO + co]);
-                            }
+            // [kz][ks][tap9][kb][co][8]  <-  (D)HWIO kernel[kz*9 + tap9][ci][co]
+            std::vector<uint16_t> w((size_t)KZ * 9 * C * CO);
+            for (int kz = 0; kz < KZ; ++kz)
+                for (int ks = 0; ks < C / 16; ++ks)
+                    for (int tp = 0; tp < 9; ++tp)
+                        for (int kb = 0; kb < 2; ++kb)
+                            for (int co = 0; co < CO; ++co)
+                                for (int e = 0; e < 8; ++e) {
+                                    const int ci = ks * 16 + kb * 8 + e;
+                                    w[(((((size_t)kz * (C / 16) + ks) * 9 + tp) * 2 + kb) * CO + co) * 8 + e] =
+                                        host_bf16(k[((size_t)(kz * 9 + tp) * C + ci) * CO + co]);
+                                }
             SQ_TRY(dev_upload(u, w.data(), w.size() * 2, &L.w_tc));
         } else if (L.kind == SqLayer::UPCONV) {
-            // [ks][tap][kb][co][8]  <-  TF conv_transpose kernel[tap][co][ci]
-            std::vector<uint16_t> w((size_t)4 * C * CO);
-            for (int ks = 0; ks < C / 16; ++ks)
-                for (int tp = 0; tp < 4; ++tp)
-                    for (int kb = 0; kb < 2; ++kb)
-                        for (int co = 0; co < CO; ++co)
-                            for (int e = 0; e < 8; ++e) {
-                                const int ci = ks * 16 + kb * 8 + e;
-                                w[((((size_t)ks * 4 + tp) * 2 + kb) * CO + co) * 8 + e] =
-                                    host_bf16(k[((size_t)tp * CO + co) * C + ci]);
-                            }
+            // [kz][ks][tap4][kb][co][8]  <-  TF conv_transpose kernel[kz*4 + tap4][co][ci]
+            std::vector<uint16_t> w((size_t)UZ * 4 * C * CO);
+            for (int kz = 0; kz < UZ; ++kz)
+                for (int ks = 0; ks < C / 16; ++ks)
+                    for (int tp = 0; tp < 4; ++tp)
+                        for (int kb = 0; kb < 2; ++kb)
+                            for (int co = 0; co < CO; ++co)
+                                for (int e = 0; e < 8; ++e) {
+                                    const int ci = ks * 16 + kb * 8 + e;
+                                    w[(((((size_t)kz * (C / 16) + ks) * 4 + tp) * 2 + kb) * CO + co) * 8 + e] =
+                                        host_bf16(k[((size_t)(kz * 4 + tp) * CO + co) * C + ci]);
+                                }
             SQ_TRY(dev_upload(u, w.data(), w.size() * 2, &L.w_tc));
         } else {
             // first conv / head: CUDA-core kernels read fp32 copies of the bf16-rounded weights
@@ -782,19 +879,23 @@ int sq_tc_finalize(sq_unet_s *u)
 
 namespace {
 
-int tc_run(sq_unet_s *u, bool dry, const float *in, int n, int hgt, int wid, float *probs,
+int tc_run(sq_unet_s *u, bool dry, const float *in, int n, int dep, int hgt, int wid, float *probs,
            uint8_t *mask, float *logits, void *ws, size_t ws_bytes, cudaStream_t st, size_t *need)
 {
     SqArena a(dry ? nullptr : ws, dry ? 0 : ws_bytes);
     const int nl = u->nlev;
-    std::vector<bf16 *> t1(nl), skip(nl), pooled(nl, nullptr), up(nl, nullptr), merged(nl, nullptr),
-        ut(nl, nullptr), uo(nl, nullptr);
+    const bool vol = u->ndim == 3;
+    const int KZ = vol ? 3 : 1;
+    auto depth = [&](int l) { return vol ? (dep >> l) : 1; };
+    std::vector<bf16 *> t1(nl), skip(nl), pooled(nl, nullptr), xyp(nl, nullptr), up(nl, nullptr),
+        merged(nl, nullptr), ut(nl, nullptr), uo(nl, nullptr);
     for (int l = 0; l < nl; ++l) {
-        const size_t px = (size_t)n * (hgt >> l) * (wid >> l);
+        const size_t px = (size_t)n * depth(l) * (hgt >> l) * (wid >> l);
         const size_t f = u->filters[l];
         t1[l] = a.take<bf16>(px * f);
         skip[l] = a.take<bf16>(px * f);
         if (l > 0) pooled[l] = a.take<bf16>(px * u->filters[l - 1]);
+        if (l > 0 && vol) xyp[l] = a.take<bf16>(2 * px * u->filters[l - 1]);   // xy-pooled, full depth
         if (l < nl - 1) {
             up[l] = a.take<bf16>(px * f);
             if (u->bridge >= SQ_BRIDGE_ADD && u->bridge <= SQ_BRIDGE_SUB) merged[l] = a.take<bf16>(px * f);
@@ -812,13 +913,30 @@ int tc_run(sq_unet_s *u, bool dry, const float *in, int n, int hgt, int wid, flo
     char scope[64];
     std::vector<char> pool_fused(nl + 1, 0);
     for (int l = 0; l < nl; ++l) {
-        const int H = hgt >> l, W = wid >> l;
-        const long long px = (long long)n * H * W;
+        const int D = depth(l), H = hgt >> l, W = wid >> l;
+        const long long px = (long long)n * D * H * W;
+        const TcGeo geo = {n, D, H, W, KZ, 1, 0, 0};
         snprintf(scope, sizeof scope, "UNet/down%d/conv1", l);
         SqLayer *c1 = layer_by_scope(u, scope);
         snprintf(scope, sizeof scope, "UNet/down%d/conv2", l);
         SqLayer *c2 = layer_by_scope(u, scope);
-        if (l == 0) {
+        if (l == 0 && vol) {
+            const float *wf = (const float *)c1->w_tc;
+            const size_t sm = (size_t)(27 * u->cin + 2) * c1->cout * sizeof(float);
+            const unsigned grid = (unsigned)((px + 127) / 128);
+#define SQ_FIRST3(CO) first_conv3d_kernel<CO><<<grid, 128, sm, st>>>(in, wf, c1->scale, c1->shift, t1[0], n, D, H, W, u->cin)
+            switch (c1->cout) {
+            case 16: SQ_FIRST3(16); break;
+            case 32: SQ_FIRST3(32); break;
+            case 64: SQ_FIRST3(64); break;
+            default:
+                SQ_REQUIRE(false, SQ_EUNSUPPORTED, "bf16 mode: first 3-D conv -> %d channels not instantiated",
+                           c1->cout);
+            }
+#undef SQ_FIRST3
+            ++u->last_launches;
+            SQ_CHECK_LAUNCH();
+        } else if (l == 0) {
             const dim3 grid((W + FIRST_TW - 1) / FIRST_TW, (H + FIRST_ROWS - 1) / FIRST_ROWS, n);
             const float *wf = (const float *)c1->w_tc;
 #define SQ_FIRST(CI, CO) first_conv_kernel<CI, CO><<<grid, 256, 0, st>>>(in, wf, c1->scale, c1->shift, t1[0], n, H, W)
@@ -842,37 +960,58 @@ int tc_run(sq_unet_s *u, bool dry, const float *in, int n, int hgt, int wid, flo
             ++u->last_launches;
             SQ_CHECK_LAUNCH();
         } else {
+            const int fp = u->filters[l - 1];
             if (!pool_fused[l]) {
-                const long long nvec = px * (u->filters[l - 1] / 8);
+                // xy pool over every slice of the level above (2*D of them in a volume)
+                const long long nvec = px * (vol ? 2 : 1) * (fp / 8);
                 maxpool_bf16_kernel<<<(unsigned)((nvec + threads - 1) / threads), threads, 0, st>>>(
-                    (const uint4 *)skip[l - 1], (uint4 *)pooled[l], nvec, H, W);
+                    (const uint4 *)skip[l - 1], (uint4 *)(vol ? xyp[l] : pooled[l]), nvec, H, W);
                 ++u->last_launches;
                 SQ_CHECK_LAUNCH();
-                sq_timer_mark(u, st, "maxpool", 0);
             }
-            SQ_TRY(conv3x3_tc(u, *c1, pooled[l], c1->cin0, nullptr, 0, t1[l], nullptr, nullptr, n, H, W, st));
+            if (vol) {
+                const long long nvec = px * (fp / 8), plane = (long long)(fp / 8) * H * W;
+                zpool_bf16_kernel<<<(unsigned)((nvec + threads - 1) / threads), threads, 0, st>>>(
+                    (const uint4 *)xyp[l], (uint4 *)pooled[l], nvec, plane);
+                ++u->last_launches;
+                SQ_CHECK_LAUNCH();
+            }
+            if (vol || !pool_fused[l]) sq_timer_mark(u, st, "maxpool", 0);
+            SQ_TRY(conv3x3_tc(u, *c1, pooled[l], c1->cin0, nullptr, 0, t1[l], nullptr, nullptr, geo, st));
         }
         sq_timer_mark(u, st, c1->scope.c_str(), c1->flops_per_px * px);
-        // the level's second conv also emits the pooled tensor the next level starts from
+        // the level's second conv also emits the (xy-)pooled tensor the next level starts from
         const bool fuse_pool = (l < nl - 1) && c2->cout <= 128;
         if (l < nl - 1) pool_fused[l + 1] = fuse_pool;
-        SQ_TRY(conv3x3_tc(u, *c2, t1[l], c2->cin0, nullptr, 0, skip[l], fuse_pool ? pooled[l + 1] : nullptr,
-                          nullptr, n, H, W, st));
+        bf16 *pool_dst = !fuse_pool ? nullptr : (vol ? xyp[l + 1] : pooled[l + 1]);
+        SQ_TRY(conv3x3_tc(u, *c2, t1[l], c2->cin0, nullptr, 0, skip[l], pool_dst, nullptr, geo, st));
         sq_timer_mark(u, st, c2->scope.c_str(), c2->flops_per_px * px);
     }
     SqLayer *head = layer_by_scope(u, "UNet/to_image");
     const bool head_fused = nl >= 2 && head->cout >= 2 && head->cout <= 4 && u->filters[0] <= 32;
     const bf16 *cur = skip[nl - 1];
     for (int l = nl - 2; l >= 0; --l) {
-        const int H = hgt >> l, W = wid >> l;
-        const long long px = (long long)n * H * W;
+        const int D = depth(l), H = hgt >> l, W = wid >> l;
+        const long long px = (long long)n * D * H * W;
+        const TcGeo geo = {n, D, H, W, KZ, 1, 0, 0};
         snprintf(scope, sizeof scope, "UNet/up%d/upscale", l);
         SqLayer *us = layer_by_scope(u, scope);
         snprintf(scope, sizeof scope, "UNet/up%d/conv1", l);
         SqLayer *c1 = layer_by_scope(u, scope);
         snprintf(scope, sizeof scope, "UNet/up%d/conv2", l);
         SqLayer *c2 = layer_by_scope(u, scope);
-        SQ_TRY(upconv_tc(u, *us, cur, up[l], n, H / 2, W / 2, st));
+        if (vol) {
+            // 2x2x2 transposed conv = one planar 2x2 up-conv per output depth parity kz: input slice
+            // s = n*D/2 + z feeds output slice 2*s + kz with the weights of depth tap kz
+            const size_t wslice = (size_t)4 * us->cin0 * us->cout;
+            for (int kz = 0; kz < 2; ++kz) {
+                const TcGeo gu = {n * (D / 2), 1, H / 2, W / 2, 1, 2, kz, kz * wslice};
+                SQ_TRY(upconv_tc(u, *us, cur, up[l], gu, st));
+            }
+        } else {
+            const TcGeo gu = {n, 1, H / 2, W / 2, 1, 1, 0, 0};
+            SQ_TRY(upconv_tc(u, *us, cur, up[l], gu, st));
+        }
         sq_timer_mark(u, st, us->scope.c_str(), us->flops_per_px * px);
         const bf16 *in0 = up[l], *in1 = nullptr;
         if (u->bridge == SQ_BRIDGE_CONCAT) {
@@ -886,26 +1025,27 @@ int tc_run(sq_unet_s *u, bool dry, const float *in, int n, int hgt, int wid, flo
             sq_timer_mark(u, st, "bridge", 0);
             in0 = merged[l];
         }
-        SQ_TRY(conv3x3_tc(u, *c1, in0, c1->cin0, in1, c1->cin1, ut[l], nullptr, nullptr, n, H, W, st));
+        SQ_TRY(conv3x3_tc(u, *c1, in0, c1->cin0, in1, c1->cin1, ut[l], nullptr, nullptr, geo, st));
         sq_timer_mark(u, st, c1->scope.c_str(), c1->flops_per_px * px);
         if (l == 0 && head_fused) {
             // last conv of the net: 1x1 head + softmax + argmax run in its epilogue
             const HeadArgs ha = {(const float *)head->w_tc, head->cout, logits, probs, mask};
-            SQ_TRY(conv3x3_tc(u, *c2, ut[l], c2->cin0, nullptr, 0, nullptr, nullptr, &ha, n, H, W, st));
+            SQ_TRY(conv3x3_tc(u, *c2, ut[l], c2->cin0, nullptr, 0, nullptr, nullptr, &ha, geo, st));
             sq_timer_mark(u, st, c2->scope.c_str(), (c2->flops_per_px + head->flops_per_px) * px);
             return SQ_OK;
         }
-        SQ_TRY(conv3x3_tc(u, *c2, ut[l], c2->cin0, nullptr, 0, uo[l], nullptr, nullptr, n, H, W, st));
+        SQ_TRY(conv3x3_tc(u, *c2, ut[l], c2->cin0, nullptr, 0, uo[l], nullptr, nullptr, geo, st));
         sq_timer_mark(u, st, c2->scope.c_str(), c2->flops_per_px * px);
         cur = uo[l];
     }
-    const long long px0 = (long long)hgt * wid;
+    const long long px0 = (long long)hgt * wid, nslices = (long long)n * depth(0);
     const size_t sm = (size_t)(head->cin0 * head->cout + head->cout) * sizeof(float);
-    head_bf16_kernel<<<(unsigned)((px0 * n + 127) / 128), 128, sm, st>>>(
-        cur, (const float *)head->w_tc, head->shift, head->cin0, head->cout, px0, n, logits, probs, mask);
+    head_bf16_kernel<<<(unsigned)((px0 * nslices + 127) / 128), 128, sm, st>>>(
+        cur, (const float *)head->w_tc, head->shift, head->cin0, head->cout, px0, (int)nslices, logits, probs,
+        mask);
     ++u->last_launches;
     SQ_CHECK_LAUNCH();
-    sq_timer_mark(u, st, head->scope.c_str(), head->flops_per_px * px0 * n);
+    sq_timer_mark(u, st, head->scope.c_str(), head->flops_per_px * px0 * nslices);
     return SQ_OK;
 }
 
@@ -913,13 +1053,11 @@ int tc_run(sq_unet_s *u, bool dry, const float *in, int n, int hgt, int wid, flo
 
 int sq_tc_workspace_bytes(sq_unet_s *u, int n, int d, int hgt, int wid, size_t *bytes)
 {
-    (void)d;
-    return tc_run(u, true, nullptr, n, hgt, wid, nullptr, nullptr, nullptr, nullptr, 0, nullptr, bytes);
+    return tc_run(u, true, nullptr, n, d, hgt, wid, nullptr, nullptr, nullptr, nullptr, 0, nullptr, bytes);
 }
 
 int sq_tc_forward(sq_unet_s *u, const float *in, int n, int d, int hgt, int wid, float *probs,
                   uint8_t *mask, float *logits, void *ws, size_t ws_bytes, cudaStream_t st)
 {
-    (void)d;
-    return tc_run(u, false, in, n, hgt, wid, probs, mask, logits, ws, ws_bytes, st, nullptr);
+    return tc_run(u, false, in, n, d, hgt, wid, probs, mask, logits, ws, ws_bytes, st, nullptr);
 }

@@ -116,7 +116,7 @@ def volumes(n, d, h, w, cin=1, seed=4321):
     zz, yy, xx = np.mgrid[0:d, 0:h, 0:w]
     for v in range(n):
         for _ in range(nballs):
-            r = rng.uniform(3.0, min(8.0, d / 2.0))
+            r = rng.uniform(min(3.0, d / 4.0), max(3.0, min(8.0, d / 2.0)))
             c = rng.uniform([0, 0, 0], [d, h, w])
             dist = np.sqrt((zz - c[0]) ** 2 + (yy - c[1]) ** 2 + (xx - c[2]) ** 2)
             out[v] += (np.clip(r - dist + 0.5, 0, 1) * 3.0).astype(np.float32)[..., None]

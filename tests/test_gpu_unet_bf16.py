@@ -121,6 +121,30 @@ def test_unsupported_configs_fail_loudly(sq):
     net = UNet2D({'filters': (8, 16), 'shape': (16, 16), 'bridge': 'concat', 'compute': 'bf16'})
     with pytest.raises(NotImplementedError):
         net.predict(np.zeros((1, 16, 16, 1), np.float32))
-    net3 = UNet3D({'filters': (16, 32), 'shape': (16, 16, 8), 'bridge': 'concat', 'compute': 'bf16'})
+    net3 = UNet3D({'filters': (8, 16), 'shape': (16, 16, 8), 'bridge': 'concat', 'compute': 'bf16'})
     with pytest.raises(NotImplementedError):
         net3.predict(np.zeros((1, 8, 16, 16, 1), np.float32))
+
+
+@pytest.mark.parametrize('filters,bridge,k,dhw', [
+    ((16, 32), 'concat', 2, (8, 32, 40)),           # fused head, fused xy pool + depth pool
+    ((16, 32, 64), 'concat', 3, (8, 24, 48)),
+    ((16, 32), 'eltwise_add', 2, (4, 16, 24)),
+    ((32, 64), None, 10, (6, 16, 16)),              # stand-alone head
+])
+def test_unet3d_volumes(sq, filters, bridge, k, dhw):
+    """UNet3D on tensor cores: 3x3x3 convs as three depth taps of the planar kernel (5-D TMA,
+    zero-filled outside the volume), 2x2x2 up-conv as two planar launches, depth pool kernel."""
+    from sequitr_b200.networks import UNet3D
+    d, h, wd = dhw
+    w = synth.unet_weights(filters, 1, k, ndim=3, bridge=bridge, seed=9)
+    x = synth.volumes(2, d, h, wd, 1)
+    net = UNet3D({'filters': filters, 'shape': (h, wd, d), 'bridge': bridge, 'num_outputs': k,
+                  'compute': 'bf16'})
+    net.load_weights(w)
+    out = net.predict(x)
+    ref = unet_c.unet_forward(x, w, filters, bridge, contract='bf16')
+    assert out['logits'].shape == ref['logits'].shape == (2, d, h, wd, k)
+    _compare(out, ref, 'unet3d %s' % (filters,))
+    one = net.predict(x[1:2])                                  # volume-independent
+    np.testing.assert_array_equal(out['logits'][1:2], one['logits'])
