@@ -78,6 +78,177 @@ __global__ void probe_tma(const __grid_constant__ CUtensorMap map, int c0, int c
     for (int i = threadIdx.x; i < bytes; i += blockDim.x) out[i] = smem[i];
 }
 
+// MMA issue-rate probe: one thread issues `reps` back-to-back 128 x N x 16 MMAs (operands in shared
+// memory, `ntap` different A start offsets round-robin, accumulating into `nacc` accumulators
+// round-robin) and times them with clock64: the cost model behind DESIGN.md section 4.
+__global__ void __launch_bounds__(128, 4)
+probe_rate(int N, int reps, uint32_t lbo_a, uint32_t sbo_a, int ntap, uint32_t tap_stride, int nacc,
+           int a_bytes, long long *out)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid * 4; i < a_bytes + 8192; i += 128 * 4)
+        *(uint32_t *)(smem + i) = 0x3c003c00u + (uint32_t)(i * 2654435761u >> 28);   // small bf16 values
+    if (tid == 0) { tc::mbar_init(&bar, 1); tc::fence_barrier_init(); }
+    if (warp == 0) { tc::tmem_alloc(&tmem_base, 128); tc::tmem_relinquish(); }
+    tc::fence_proxy_async();
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tb = tmem_base;
+    if (tid == 0) {
+        const uint32_t base = tc::smem_u32(smem);
+        const uint32_t idesc = tc::instr_desc_bf16(128, N);
+        const uint64_t bdesc = tc::smem_desc(base + a_bytes, N * 16, 128);
+        const long long t0 = clock64();
+        // descriptors precomputed; 6 MMAs per loop trip (taps round-robin, accumulators alternate)
+        uint64_t ad[3];
+        for (int k = 0; k < 3; ++k) ad[k] = tc::smem_desc(base + (k % ntap) * tap_stride, lbo_a, sbo_a);
+        const uint32_t d1 = tb + (nacc > 1 ? N : 0);
+        for (int i = 0; i < reps; i += 6) {
+            tc::umma_bf16(tb, ad[0], bdesc, idesc, 1);
+            tc::umma_bf16(d1, ad[1], bdesc, idesc, 1);
+            tc::umma_bf16(tb, ad[2], bdesc, idesc, 1);
+            tc::umma_bf16(d1, ad[0], bdesc, idesc, 1);
+            tc::umma_bf16(tb, ad[1], bdesc, idesc, 1);
+            tc::umma_bf16(d1, ad[2], bdesc, idesc, 1);
+        }
+        tc::umma_commit(&bar);
+        tc::mbar_wait(&bar, 0);
+        out[blockIdx.x] = clock64() - t0;
+    }
+    __syncthreads();
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tb, 128);
+}
+
+// TMA load-rate probe: the conv kernels' producer loop alone (5-D box loads into an smem ring, a
+// consumer thread that frees each stage as soon as it lands), to measure bytes/clk/SM per box shape.
+__global__ void __launch_bounds__(160, 4)
+probe_tma_rate(const __grid_constant__ CUtensorMap map, int box_bytes, int nst, int tiles_x, int tiles_y,
+               int nimg, int step_x, int step_y, int xoff, int ksteps, int nprod, long long *out)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t full_bar[16], empty_bar[16];
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < nst; ++i) { tc::mbar_init(&full_bar[i], 1); tc::mbar_init(&empty_bar[i], 1); }
+        tc::fence_barrier_init();
+    }
+    __syncthreads();
+    const int ntiles = nimg * tiles_x * tiles_y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long t0 = clock64();
+    if (warp < nprod && lane == 0) {
+        // producer warp `warp` issues the loads of global steps i = warp, warp + nprod, ...
+        long long i = 0;
+        for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+            const int tx = t % tiles_x, ty = (t / tiles_x) % tiles_y, n = t / (tiles_x * tiles_y);
+            for (int ks = 0; ks < ksteps; ++ks, ++i) {
+                if ((int)(i % nprod) != warp) continue;
+                const int stage = (int)(i % nst);
+                const uint32_t phase = (uint32_t)((i / nst) & 1);
+                tc::mbar_wait(&empty_bar[stage], phase ^ 1);
+                tc::mbar_arrive_expect_tx(&full_bar[stage], box_bytes);
+                tc::tma_load_5d(smem + (size_t)stage * box_bytes, &map, &full_bar[stage], (tx * step_x + xoff) * 8,
+                                ty * step_y - 1, ks * 2, 0, n);
+            }
+        }
+    } else if (warp == 4 && lane == 0) {
+        int stage = 0; uint32_t phase = 0;
+        for (int t = blockIdx.x; t < ntiles; t += gridDim.x)
+            for (int ks = 0; ks < ksteps; ++ks) {
+                tc::mbar_wait(&full_bar[stage], phase);
+                tc::mbar_arrive(&empty_bar[stage]);
+                if (++stage == nst) { stage = 0; phase ^= 1; }
+            }
+        out[blockIdx.x] = clock64() - t0;
+    }
+}
+
+// TMEM read-rate probe: every warp of the CTA streams its lane quarter of the 512 TMEM columns with
+// tcgen05.ld 32x32b.x16 (or .x32 via two back-to-back x16 on adjacent columns), `depth` loads in flight
+// before each wait.
+template <int DEPTH>
+__global__ void __launch_bounds__(512, 1)
+probe_ldtm(int reps, long long *out, uint32_t *sink)
+{
+    __shared__ uint32_t tmem_base;
+    const int warp = threadIdx.x >> 5;
+    if (warp == 0) { tc::tmem_alloc(&tmem_base, 512); tc::tmem_relinquish(); }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tb = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    uint32_t acc = 0;
+    const long long t0 = clock64();
+    for (int r = 0; r < reps; ++r) {
+        uint32_t v[DEPTH][16];
+#pragma unroll
+        for (int d = 0; d < DEPTH; ++d) tc::tmem_ld16(tb + ((r * DEPTH + d) * 16) % 512, v[d]);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int d = 0; d < DEPTH; ++d) acc ^= v[d][0] ^ v[d][15];
+    }
+    const long long t1 = clock64();
+    if ((threadIdx.x & 31) == 0) out[blockIdx.x * 16 + warp] = t1 - t0;
+    if (acc == 0x12345678u) sink[0] = acc;
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem_base, 512);
+}
+
+// Do tcgen05.mma and tcgen05.ld overlap?  Warp 0 lane 0 issues `reps` MMAs (N columns at TMEM col 0..),
+// warps 4..4+ldw-1 meanwhile stream tcgen05.ld from columns 256.. of the same CTA's TMEM.
+__global__ void __launch_bounds__(384, 1)
+probe_overlap(int N, int reps, int ldw, int ldreps, long long *out, uint32_t *sink)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid * 4; i < 16384; i += 384 * 4) *(uint32_t *)(smem + i) = 0x3c003c00u;
+    if (tid == 0) { tc::mbar_init(&bar, 1); tc::fence_barrier_init(); }
+    if (warp == 0) { tc::tmem_alloc(&tmem_base, 512); tc::tmem_relinquish(); }
+    tc::fence_proxy_async();
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tb = tmem_base;
+    const long long t0 = clock64();
+    if (tid == 0) {
+        const uint32_t base = tc::smem_u32(smem);
+        const uint32_t idesc = tc::instr_desc_bf16(128, N);
+        const uint64_t ad = tc::smem_desc(base, 2048, 128), bd = tc::smem_desc(base + 4096, N * 16, 128);
+        for (int i = 0; i < reps; i += 4) {
+            tc::umma_bf16(tb, ad, bd, idesc, 1);
+            tc::umma_bf16(tb + 128, ad, bd, idesc, 1);
+            tc::umma_bf16(tb, ad, bd, idesc, 1);
+            tc::umma_bf16(tb + 128, ad, bd, idesc, 1);
+        }
+        tc::umma_commit(&bar);
+        tc::mbar_wait(&bar, 0);
+        out[blockIdx.x * 2] = clock64() - t0;
+    } else if (warp >= 4 && warp < 4 + ldw) {
+        uint32_t acc = 0;
+        const uint32_t lb = tb + 256 + ((uint32_t)((warp & 3) * 32) << 16);
+        for (int r = 0; r < ldreps; ++r) {
+            uint32_t v0[16], v1[16];
+            tc::tmem_ld16(lb + (r * 32) % 256, v0);
+            tc::tmem_ld16(lb + (r * 32 + 16) % 256, v1);
+            tc::tmem_ld_wait();
+            acc ^= v0[3] ^ v1[7];
+        }
+        if (acc == 0x12345678u) sink[0] = acc;
+        if (tid == 128) out[blockIdx.x * 2 + 1] = clock64() - t0;
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tb, 512);
+}
+
 static uint16_t f2bf(float f)
 {
     uint32_t u;
@@ -246,6 +417,135 @@ int main(int argc, char **argv)
         }
         printf("PROBE tma VERDICT %s\n", fails ? "MISMATCH" : "OK");
         return fails;
+    }
+    if (!strcmp(which, "rate")) {
+        long long *dout;
+        CK(cudaMalloc(&dout, 1024 * sizeof(long long)));
+        const int reps = 6 * 700;
+        CK(cudaFuncSetAttribute(probe_rate, cudaFuncAttributeMaxDynamicSharedMemorySize, 50 * 1024));
+        struct { const char *name; uint32_t lbo, sbo; int ntap; uint32_t tstride; int a_bytes; } lay[3] = {
+            {"9tap PW=10 (sbo 160)", 18 * 10 * 16, 160, 9, 16, 2 * 18 * 10 * 16 + 1024},
+            {"9tap ILV   (sbo 320)", 34 * 10 * 16, 320, 9, 16, 2 * 34 * 10 * 16 + 1024},
+            {"xc 3tap    (sbo 128)", 18 * 16 * 16, 128, 3, 256, 2 * 18 * 16 * 16 + 1024}};
+        const int Ns[5] = {16, 32, 48, 64, 96};
+        for (int l = 0; l < 3; ++l)
+            for (int ni = 0; ni < 5; ++ni)
+                for (int ctas = 1; ctas <= 4; ++ctas) {
+                    const int N = Ns[ni], nacc = (N <= 64) ? 2 : 1;
+                    const int grid = 148 * ctas;
+                    const int smem = lay[l].a_bytes + 8192 + 1024;
+                    probe_rate<<<grid, 128, smem>>>(N, reps, lay[l].lbo, lay[l].sbo, lay[l].ntap, lay[l].tstride,
+                                                    nacc, lay[l].a_bytes, dout);
+                    CK(cudaGetLastError());
+                    CK(cudaDeviceSynchronize());
+                    std::vector<long long> h(grid);
+                    CK(cudaMemcpy(h.data(), dout, grid * sizeof(long long), cudaMemcpyDeviceToHost));
+                    long long mx = 0;
+                    double avg = 0;
+                    for (long long v : h) { mx = v > mx ? v : mx; avg += (double)v / grid; }
+                    // per-SM cost of one MMA = elapsed / (reps * ctas co-resident)
+                    printf("PROBE rate %-22s N=%3d ctas/SM=%d  clk/MMA per CTA %.1f  per SM %.1f  (tensor floor %.1f)\n",
+                           lay[l].name, N, ctas, avg / reps, avg / reps / ctas, N / 2.0);
+                }
+        return 0;
+    }
+    if (!strcmp(which, "tmarate")) {
+        // activation tensor [n=4][cb=4][2048][2048][8] bf16 = 537 MB (streams from HBM)
+        const int NB = 4, CB = 4, H = 2048, W = 2048;
+        uint16_t *dg;
+        CK(cudaMalloc(&dg, (size_t)NB * CB * H * W * 16));
+        CK(cudaMemset(dg, 0x3c, (size_t)NB * CB * H * W * 16));
+        long long *dout;
+        CK(cudaMalloc(&dout, 1024 * sizeof(long long)));
+        sq_encode_tiled_fn enc = sq_get_encode_tiled();
+        CK(cudaFuncSetAttribute(probe_tma_rate, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        struct { const char *name; int pw, ph, step_x, step_y, xoff; } sh[7] = {
+            {"9tap S=4: 10 x 66 (x0-1)", 10, 66, 8, 64, -1},
+            {"9tap S=2: 10 x 34 (x0-1)", 10, 34, 8, 32, -1},
+            {"xc   S=2: 16 x 18 (x0-1)", 16, 18, 14, 16, -1},
+            {"xc   S=1: 16 x 10 (x0-1)", 16, 10, 14, 8, -1},
+            {"aligned : 16 x 18 (x0)", 16, 18, 16, 16, 0},
+            {"wide    : 32 x 18 (x0)", 32, 18, 32, 16, 0},
+            {"wide    : 32 x 34 (x0)", 32, 34, 32, 32, 0}};
+        for (int i = 0; i < 7; ++i) {
+            CUtensorMap map;
+            cuuint64_t dims[5] = {(cuuint64_t)W * 8, (cuuint64_t)H, (cuuint64_t)CB, 1, (cuuint64_t)NB};
+            cuuint64_t strides[4] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)CB * H * W * 16,
+                                     (cuuint64_t)CB * H * W * 16};
+            cuuint32_t box[5] = {(cuuint32_t)sh[i].pw * 8, (cuuint32_t)sh[i].ph, 2, 1, 1};
+            cuuint32_t es[5] = {1, 1, 1, 1, 1};
+            CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, dg, dims, strides, box, es,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) { printf("encode failed %d\n", (int)r); return 1; }
+            const int box_bytes = sh[i].pw * sh[i].ph * 2 * 16;
+            const int tiles_x = (W + sh[i].step_x - 1) / sh[i].step_x, tiles_y = H / sh[i].step_y;
+            for (int ctas = 1; ctas <= 2; ++ctas)
+                for (int nprod = 1; nprod <= 4; nprod *= 2) {
+                    int nst = 100 * 1024 / box_bytes / 4 * 4;          // a stage belongs to ONE producer
+                    nst = nst > 16 ? 16 : (nst < 4 ? 4 : nst);
+                    if (ctas == 2 && nst * box_bytes > 100 * 1024) continue;
+                    const int grid = 148 * ctas, ksteps = 2;
+                    probe_tma_rate<<<grid, 160, nst * box_bytes + 1024>>>(map, box_bytes, nst, tiles_x, tiles_y, NB,
+                                                                          sh[i].step_x, sh[i].step_y, sh[i].xoff, ksteps,
+                                                                          nprod, dout);
+                    CK(cudaGetLastError());
+                    CK(cudaDeviceSynchronize());
+                    std::vector<long long> h(grid);
+                    CK(cudaMemcpy(h.data(), dout, grid * sizeof(long long), cudaMemcpyDeviceToHost));
+                    long long mx = 0;
+                    for (long long v : h) mx = v > mx ? v : mx;
+                    const double bytes = (double)NB * tiles_x * tiles_y * ksteps * box_bytes;
+                    printf("PROBE tmarate %-26s box %5d B  ctas/SM=%d stages=%2d producers=%d: %.1f B/clk/SM  (%.0f clk, %.2f GB moved)\n",
+                           sh[i].name, box_bytes, ctas, nst, nprod, bytes / 148.0 / (double)mx, (double)mx, bytes / 1e9);
+                }
+        }
+        return 0;
+    }
+    if (!strcmp(which, "ldtm")) {
+        long long *dout;
+        uint32_t *sink;
+        CK(cudaMalloc(&dout, 148 * 16 * sizeof(long long)));
+        CK(cudaMalloc(&sink, 4));
+        const int reps = 2000;
+        for (int depth = 1; depth <= 4; depth *= 2)
+            for (int warps = 4; warps <= 16; warps *= 2) {
+                if (depth == 1) probe_ldtm<1><<<148, warps * 32>>>(reps, dout, sink);
+                else if (depth == 2) probe_ldtm<2><<<148, warps * 32>>>(reps, dout, sink);
+                else probe_ldtm<4><<<148, warps * 32>>>(reps, dout, sink);
+                CK(cudaGetLastError());
+                CK(cudaDeviceSynchronize());
+                std::vector<long long> h(148 * 16);
+                CK(cudaMemcpy(h.data(), dout, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+                long long mx = 0;
+                for (int b = 0; b < 148; ++b) for (int w = 0; w < warps; ++w) mx = h[b * 16 + w] > mx ? h[b * 16 + w] : mx;
+                const double bytes = (double)reps * depth * warps * 32 * 16 * 4;
+                printf("PROBE ldtm 32x32b.x16  warps/SM=%2d loads in flight/warp=%d: %.1f B/clk/SM (%.1f clk per x16 load per warp)\n",
+                       warps, depth, bytes / (double)mx, (double)mx / (reps * depth));
+            }
+        return 0;
+    }
+    if (!strcmp(which, "overlap")) {
+        long long *dout;
+        uint32_t *sink;
+        CK(cudaMalloc(&dout, 148 * 2 * sizeof(long long)));
+        CK(cudaMalloc(&sink, 4));
+        CK(cudaFuncSetAttribute(probe_overlap, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 1024));
+        const int reps = 4000;
+        for (int N = 16; N <= 128; N *= 2)
+            for (int ldw = 0; ldw <= 8; ldw += 4) {
+                CK(cudaMemset(dout, 0, 148 * 2 * sizeof(long long)));
+                probe_overlap<<<148, 384, 17 * 1024>>>(N, reps, ldw, 4000, dout, sink);
+                CK(cudaGetLastError());
+                CK(cudaDeviceSynchronize());
+                std::vector<long long> h(148 * 2);
+                CK(cudaMemcpy(h.data(), dout, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+                double am = 0, al = 0;
+                for (int b = 0; b < 148; ++b) { am += h[b * 2] / 148.0; al += h[b * 2 + 1] / 148.0; }
+                printf("PROBE overlap N=%3d  ld warps=%d: %.1f clk/MMA; ld warps: %.1f clk per pair of x16 loads\n", N, ldw,
+                       am / reps, ldw ? al / 4000 : 0.0);
+            }
+        return 0;
     }
     printf("unknown case %s\n", which);
     return 1;

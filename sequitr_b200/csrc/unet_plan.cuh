@@ -20,6 +20,7 @@ struct SqLayer {
     float *w = nullptr, *scale = nullptr, *shift = nullptr;
     // tensor-core device weights (bf16, re-laid-out; see unet_tc.cu)
     void *w_tc = nullptr;
+    void *w_xc = nullptr;         // x-combined layout for Cout <= 32 convs (conv_xc_kernel)
 };
 
 struct SqLayerTimer {

@@ -408,6 +408,358 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     }
 }
 
+// ------------------------------------------------- x-combined 3x3 conv (Cout <= 32)
+// With N = Cout <= 32 the 128 x N x 16 MMA above is bound by its A-operand fetch (4 KB from shared
+// memory per instruction, ~32 clk) rather than by the tensor math (N/2 clk), and a 3x3 conv pays
+// that fetch nine times per 16 input channels.  This variant folds the three horizontal taps into
+// the N dimension instead: B_ky = [(kx, co)][ci] has N = 3*Cout rows, so ONE instruction per row
+// tap ky computes, for every INPUT pixel of the tile, its contribution to the three outputs it
+// feeds (D'[xi][kx][co]); three instructions per k-step instead of nine, each with 3x the math per
+// fetched byte.  The epilogue finishes the conv with two lane shuffles:
+//     out[x][co] = D'[x-1][0][co] + D'[x][1][co] + D'[x+1][2][co]
+// which is why a sub-tile is 8 rows x 16 INPUT columns (one warp = 2 rows of 16 lanes; the outer
+// two columns are the x halo and produce no output): 8 x 14 outputs per 128-lane accumulator.
+template <int COUT, int S, bool PADACC = true>
+struct XCfg {
+    static constexpr int N = 3 * COUT;                   // MMA N: (kx, co)
+    static constexpr int TW = 14, TH = 8 * S;            // output tile (pixels)
+    static constexpr int PW = 16, PH = TH + 2;           // input patch incl. halo
+    static constexpr int A_BYTES = 2 * PH * PW * 16;     // 16 input channels of the patch
+    static constexpr int B_BYTES = 3 * 2 * N * 16;       // 3 row taps x 16 input channels x N
+    static constexpr int STAGE_BYTES = (A_BYTES + B_BYTES + 127) / 128 * 128;   // streaming weights
+    static constexpr int ACC_STRIDE = !PADACC ? N : (N <= 64) ? 64 : 128;   // TMEM columns per sub-tile
+    static constexpr int ACC_COLS = S * ACC_STRIDE;
+    static constexpr uint32_t LBO_A = PH * PW * 16, SBO_A = 128;   // 8-pixel groups are contiguous
+    static constexpr uint32_t LBO_B = N * 16, SBO_B = 128;
+    static_assert(A_BYTES % 128 == 0, "TMA destination alignment");
+};
+
+constexpr int XC_MAX_STAGES = 12;
+
+template <int COUT, int S, int NBUF, int MINB, int EPI, int HK, bool PADACC, int KPS, int ZPS>
+__global__ void __launch_bounds__(TC_THREADS, MINB)
+conv_xc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
+               int ks0, int ks1, const bf16 *__restrict__ wts, const float *__restrict__ scale,
+               const float *__restrict__ shift, bf16 *__restrict__ out, bf16 *__restrict__ out_pool,
+               HeadArgs head, int nimg, int H, int W, int nstages, int D, int KZ, int wres, long long *phase_dbg)
+{
+    // phase_dbg (build with -DSQ_XC_PHASE_DIAG, run with SQ_XC_PHASE=1; diagnostics only): per-CTA
+    // clocks each role spends waiting / working (scripts/xc_phase.py, profiles/r1_xc_phase.log)
+#ifdef SQ_XC_PHASE_DIAG
+#define XC_T0() const long long t_ = phase_dbg ? clock64() : 0
+#define XC_ACC(var) if (phase_dbg) var += clock64() - t_
+#else
+#define XC_T0() do { } while (0)
+#define XC_ACC(var) do { } while (0)
+#endif
+    // The weights of ALL k-steps (wres bytes) are loaded once per CTA and stay in shared memory; the
+    // ring stages carry activation patches only (with tiles this small, re-fetching the weights per
+    // tile would make the kernel L2-bandwidth bound).
+    // One TMA instruction costs ~450-500 clk of issue time per SM whatever the box size
+    // (profiles/r1_tma_rate_probe_*), so small boxes starve the MMA pipe.  A ring stage therefore
+    // holds ZPS x KPS 16-channel k-steps fetched by ONE box: KPS pairs of channel blocks (box
+    // channel-block extent 2*KPS) and, for volumes, all ZPS = 3 depth taps (box z extent 3, slices
+    // outside the volume zero-filled).  ZPS = 1: depth taps (if any) are separate stages.
+    using C = XCfg<COUT, S, PADACC>;
+    constexpr int A_STAGE = ZPS * KPS * C::A_BYTES;
+    constexpr int TMEM_COLS = (NBUF * C::ACC_COLS <= 64) ? 64 : (NBUF * C::ACC_COLS <= 128) ? 128
+                            : (NBUF * C::ACC_COLS <= 256) ? 256 : 512;
+    static_assert(NBUF * C::ACC_COLS <= 512, "TMEM overflow");
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+    __shared__ uint64_t full_bar[XC_MAX_STAGES], empty_bar[XC_MAX_STAGES], tfull_bar[2], tempty_bar[2], w_bar;
+    __shared__ uint32_t tmem_base_sh;
+    __shared__ __align__(16) float s_scale[COUT], s_shift[COUT];
+    __shared__ __align__(16) float s_head[EPI == EPI_HEAD ? COUT * HK + HK : 4];   // [k][c] then bias[k]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_x = (W + C::TW - 1) / C::TW, tiles_y = (H + C::TH - 1) / C::TH;
+    const int ntiles = nimg * D * tiles_x * tiles_y;
+    const int ksteps = ks0 + ks1, qsteps = KZ * ksteps;
+    const int zgroups = KZ / ZPS;                           // depth-tap groups fetched as separate stages
+    uint8_t *ring = smem + ((wres + 127) & ~127);           // stages start after the resident weights
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < nstages; ++i) { tc::mbar_init(&full_bar[i], 1); tc::mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < 2; ++i) { tc::mbar_init(&tfull_bar[i], 1); tc::mbar_init(&tempty_bar[i], 4 * EPI_GROUPS); }
+        tc::mbar_init(&w_bar, 1);
+        tc::fence_barrier_init();
+        tc::tma_prefetch_desc(&mapA0);
+        tc::tma_prefetch_desc(&mapA1);
+    }
+    if (warp == 1) { tc::tmem_alloc(&tmem_base_sh, TMEM_COLS); tc::tmem_relinquish(); }
+    for (int i = threadIdx.x; i < COUT; i += TC_THREADS) { s_scale[i] = scale[i]; s_shift[i] = shift[i]; }
+    if (EPI == EPI_HEAD) {
+        for (int i = threadIdx.x; i < COUT * HK; i += TC_THREADS) s_head[(i % HK) * COUT + i / HK] = head.w[i];
+        for (int i = threadIdx.x; i < HK; i += TC_THREADS) s_head[COUT * HK + i] = head.w[COUT * HK + i];
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = tmem_base_sh;
+
+    if (warp == 0) {
+        // ===================================================== TMA producer
+        if (lane == 0) {
+#ifdef SQ_XC_PHASE_DIAG
+            long long d_wait0 = 0, d_work = 0;
+#endif
+            tc::mbar_arrive_expect_tx(&w_bar, (uint32_t)wres);
+            for (int q = 0; q < qsteps; ++q)
+                tc::bulk_load(smem + (size_t)q * C::B_BYTES, wts + (size_t)q * (C::B_BYTES / 2), C::B_BYTES, &w_bar);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+                const int tx = t % tiles_x, ty = (t / tiles_x) % tiles_y, np = t / (tiles_x * tiles_y);
+                const int z = np % D, n = np / D;
+                const int x0 = tx * C::TW - 1, y0 = ty * C::TH - 1;
+                for (int zg = 0; zg < zgroups; ++zg) {
+                    const int zc = z + zg - (KZ >> 1);      // first slice of the box (ZPS = 3: z - 1)
+                    for (int ks = 0; ks < ksteps; ks += KPS) {
+                        { XC_T0(); tc::mbar_wait(&empty_bar[stage], phase ^ 1); XC_ACC(d_wait0); }
+                        XC_T0();
+                        tc::mbar_arrive_expect_tx(&full_bar[stage], A_STAGE);
+                        uint8_t *sA = ring + (size_t)stage * A_STAGE;
+                        if (ks < ks0) tc::tma_load_5d(sA, &mapA0, &full_bar[stage], x0 * 8, y0, ks * 2, zc, n);
+                        else          tc::tma_load_5d(sA, &mapA1, &full_bar[stage], x0 * 8, y0, (ks - ks0) * 2, zc, n);
+                        XC_ACC(d_work);
+                        if (++stage == nstages) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+#ifdef SQ_XC_PHASE_DIAG
+            if (phase_dbg) { phase_dbg[blockIdx.x * 8 + 0] = d_wait0; phase_dbg[blockIdx.x * 8 + 1] = d_work; }
+#endif
+        }
+    } else if (warp == 1) {
+        // ======================================================= MMA issuer
+        const uint32_t idesc = tc::instr_desc_bf16(128, C::N);
+        const uint32_t a_hi = ((C::SBO_A >> 4) & 0x3FFFu) | (1u << 14);
+        const uint32_t b_hi = ((C::SBO_B >> 4) & 0x3FFFu) | (1u << 14);
+        int stage = 0;
+        uint32_t phase = 0;
+        int it = 0;
+        tc::mbar_wait(&w_bar, 0);
+#ifdef SQ_XC_PHASE_DIAG
+        long long d_wait0 = 0, d_wait1 = 0, d_work = 0;
+#endif
+        for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+            const int buf = it % NBUF;
+            { XC_T0(); tc::mbar_wait(&tempty_bar[buf], ((it / NBUF) & 1) ^ 1); XC_ACC(d_wait0); }
+            tc::tc_fence_after();
+            for (int zg = 0; zg < zgroups; ++zg) {
+                for (int ks = 0; ks < ksteps; ks += KPS) {
+                    { XC_T0(); tc::mbar_wait(&full_bar[stage], phase); XC_ACC(d_wait1); }
+                    tc::tc_fence_after();
+                    XC_T0();
+                    if (tc::elect_one()) {
+                        const uint32_t a_base = tc::smem_u32(ring + (size_t)stage * A_STAGE);
+                        const uint32_t a_lo = ((a_base >> 4) & 0x3FFFu) | (((C::LBO_A >> 4) & 0x3FFFu) << 16);
+                        const uint32_t d0 = tmem_base + buf * C::ACC_COLS;
+                        const uint32_t first = (zg > 0 || ks > 0) ? 1u : 0u;
+#pragma unroll
+                        for (int dz = 0; dz < ZPS; ++dz) {
+                            // weights of k-step q = (depth tap) * ksteps + ks (+ kk)
+                            const uint32_t b_base = tc::smem_u32(smem) + (uint32_t)(((zg * ZPS + dz) * ksteps + ks) * C::B_BYTES);
+                            const uint32_t b_lo = ((b_base >> 4) & 0x3FFFu) | (((C::LBO_B >> 4) & 0x3FFFu) << 16);
+#pragma unroll
+                            for (int kk = 0; kk < KPS; ++kk) {
+#pragma unroll
+                                for (int j = 0; j < S; ++j) {
+#pragma unroll
+                                    for (int ky = 0; ky < 3; ++ky)
+                                        tc::umma_bf16_parts(d0 + j * C::ACC_STRIDE,
+                                                            a_lo + (uint32_t)((dz * KPS + kk) * (C::A_BYTES >> 4) + (j * 8 + ky) * C::PW), a_hi,
+                                                            b_lo + (uint32_t)(kk * (C::B_BYTES >> 4) + ky * 2 * C::N), b_hi, idesc,
+                                                            (ky == 0 && kk == 0 && dz == 0) ? first : 1u);
+                                }
+                            }
+                        }
+                        tc::umma_commit(&empty_bar[stage]);
+                    }
+                    __syncwarp();
+                    XC_ACC(d_work);
+                    if (++stage == nstages) { stage = 0; phase ^= 1; }
+                }
+            }
+            if (tc::elect_one()) tc::umma_commit(&tfull_bar[buf]);
+            __syncwarp();
+        }
+#ifdef SQ_XC_PHASE_DIAG
+        if (phase_dbg && lane == 0) {
+            phase_dbg[blockIdx.x * 8 + 2] = d_wait0; phase_dbg[blockIdx.x * 8 + 3] = d_wait1; phase_dbg[blockIdx.x * 8 + 4] = d_work;
+        }
+#endif
+    } else {
+        // ========================================================= epilogue
+        const int q4 = warp & 3;                            // TMEM lane quarter this warp may read
+        const int half = (warp - 2) >> 2;                   // epilogue group
+        const int ph = q4 * 2 + (lane >> 4), pw = lane & 15;   // sub-tile row, INPUT column of this lane
+        const uint32_t lane_addr = (uint32_t)(q4 * 32) << 16;
+        constexpr int CBo = COUT / 8, NC16 = COUT / 16;
+        const bool colok = (pw >= 1) && (pw <= C::TW);
+        const size_t plane = (size_t)H * W * 8;
+        // tile coordinates advance incrementally (no division in the loop)
+        const int tpi = tiles_x * tiles_y, gstep = (int)gridDim.x;
+        int tx = (int)blockIdx.x % tiles_x, ty = ((int)blockIdx.x / tiles_x) % tiles_y, n = (int)blockIdx.x / tpi;
+        const int dtx = gstep % tiles_x, dty = (gstep / tiles_x) % tiles_y, dn = gstep / tpi;
+        int it = 0;
+#ifdef SQ_XC_PHASE_DIAG
+        long long d_wait0 = 0, d_work = 0;
+#endif
+        for (int t = blockIdx.x; t < ntiles; t += gstep, ++it) {
+            const int buf = it % NBUF;
+            { XC_T0(); tc::mbar_wait(&tfull_bar[buf], (it / NBUF) & 1); XC_ACC(d_wait0); }
+            tc::tc_fence_after();
+            XC_T0();
+            const int x = tx * C::TW + pw - 1;
+            const bool xok = colok && (x < W);
+            const uint32_t tbase = tmem_base + lane_addr + buf * C::ACC_COLS;
+            if (EPI != EPI_HEAD) {
+#pragma unroll
+                for (int i = 0; i < (S * NC16 + EPI_GROUPS - 1) / EPI_GROUPS; ++i) {
+                    const int item = i * EPI_GROUPS + half;             // (sub-tile, 16-channel chunk)
+                    if (item >= S * NC16) break;
+                    const int j = item / NC16, c16 = item % NC16;
+                    const int y = ty * C::TH + j * 8 + ph;
+                    const bool valid = xok && (y < H);
+                    uint32_t a0[16], a1[16], a2[16];
+                    const uint32_t col = tbase + j * C::ACC_STRIDE + c16 * 16;
+                    tc::tmem_ld16(col, a0);
+                    tc::tmem_ld16(col + COUT, a1);
+                    tc::tmem_ld16(col + 2 * COUT, a2);
+                    tc::tmem_ld_wait();
+                    uint32_t o[8];
+                    const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.0f, 0.0f);
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        const float4 sc = *reinterpret_cast<const float4 *>(s_scale + c16 * 16 + 4 * g);
+                        const float4 sh = *reinterpret_cast<const float4 *>(s_shift + c16 * 16 + 4 * g);
+                        float v[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            v[e] = __shfl_up_sync(0xffffffffu, __uint_as_float(a0[4 * g + e]), 1) +
+                                   __uint_as_float(a1[4 * g + e]) +
+                                   __shfl_down_sync(0xffffffffu, __uint_as_float(a2[4 * g + e]), 1);
+                        // ReLU after the bf16 rounding (max commutes with the monotone rounding)
+                        __nv_bfloat162 p0 = __hmax2(__floats2bfloat162_rn(fmaf(v[0], sc.x, sh.x), fmaf(v[1], sc.y, sh.y)), zero2);
+                        __nv_bfloat162 p1 = __hmax2(__floats2bfloat162_rn(fmaf(v[2], sc.z, sh.z), fmaf(v[3], sc.w, sh.w)), zero2);
+                        o[2 * g] = *reinterpret_cast<uint32_t *>(&p0);
+                        o[2 * g + 1] = *reinterpret_cast<uint32_t *>(&p1);
+                    }
+                    if (valid) {
+                        bf16 *p = out + ((((size_t)n * CBo + c16 * 2) * H + y) * W + x) * 8;
+                        *reinterpret_cast<uint4 *>(p) = make_uint4(o[0], o[1], o[2], o[3]);
+                        *reinterpret_cast<uint4 *>(p + plane) = make_uint4(o[4], o[5], o[6], o[7]);
+                    }
+                    if (EPI == EPI_POOL) {
+                        // rows (y, y+1) sit 16 lanes apart, columns (x, x+1) in lanes (pw, pw+1), pw odd
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const uint32_t m = bf162_max(o[e], __shfl_xor_sync(0xffffffffu, o[e], 16));
+                            o[e] = bf162_max(m, __shfl_down_sync(0xffffffffu, m, 1));
+                        }
+                        if (valid && lane < 16 && (pw & 1)) {
+                            const int Hp = H >> 1, Wp = W >> 1;
+                            bf16 *p = out_pool + ((((size_t)n * CBo + c16 * 2) * Hp + (y >> 1)) * Wp + (x >> 1)) * 8;
+                            *reinterpret_cast<uint4 *>(p) = make_uint4(o[0], o[1], o[2], o[3]);
+                            *reinterpret_cast<uint4 *>(p + (size_t)Hp * Wp * 8) = make_uint4(o[4], o[5], o[6], o[7]);
+                        }
+                    }
+                }
+            } else {
+#pragma unroll 1
+                for (int j = half; j < S; j += EPI_GROUPS) {
+                    const int y = ty * C::TH + j * 8 + ph;
+                    const bool valid = xok && (y < H);
+                    float hl[HK > 0 ? HK : 1];
+#pragma unroll
+                    for (int k = 0; k < HK; ++k) hl[k] = 0.0f;
+#pragma unroll 1
+                    for (int c16 = 0; c16 < NC16; ++c16) {
+                        uint32_t a0[16], a1[16], a2[16];
+                        const uint32_t col = tbase + j * C::ACC_STRIDE + c16 * 16;
+                        tc::tmem_ld16(col, a0);
+                        tc::tmem_ld16(col + COUT, a1);
+                        tc::tmem_ld16(col + 2 * COUT, a2);
+                        tc::tmem_ld_wait();
+                        float f[16];
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            const float4 sc = *reinterpret_cast<const float4 *>(s_scale + c16 * 16 + 4 * g);
+                            const float4 sh = *reinterpret_cast<const float4 *>(s_shift + c16 * 16 + 4 * g);
+                            float v[4];
+#pragma unroll
+                            for (int e = 0; e < 4; ++e)
+                                v[e] = __shfl_up_sync(0xffffffffu, __uint_as_float(a0[4 * g + e]), 1) +
+                                       __uint_as_float(a1[4 * g + e]) +
+                                       __shfl_down_sync(0xffffffffu, __uint_as_float(a2[4 * g + e]), 1);
+                            // the head consumes the activation as it would have been stored (bf16)
+                            const float2 t0 = __bfloat1622float2(__floats2bfloat162_rn(
+                                fmaxf(fmaf(v[0], sc.x, sh.x), 0.0f), fmaxf(fmaf(v[1], sc.y, sh.y), 0.0f)));
+                            const float2 t1 = __bfloat1622float2(__floats2bfloat162_rn(
+                                fmaxf(fmaf(v[2], sc.z, sh.z), 0.0f), fmaxf(fmaf(v[3], sc.w, sh.w), 0.0f)));
+                            f[4 * g] = t0.x; f[4 * g + 1] = t0.y; f[4 * g + 2] = t1.x; f[4 * g + 3] = t1.y;
+                        }
+#pragma unroll
+                        for (int k = 0; k < HK; ++k) {
+                            const float4 *wk = reinterpret_cast<const float4 *>(s_head + k * COUT + c16 * 16);
+#pragma unroll
+                            for (int g = 0; g < 4; ++g) {
+                                const float4 w4 = wk[g];
+                                hl[k] = fmaf(f[4 * g], w4.x, hl[k]);
+                                hl[k] = fmaf(f[4 * g + 1], w4.y, hl[k]);
+                                hl[k] = fmaf(f[4 * g + 2], w4.z, hl[k]);
+                                hl[k] = fmaf(f[4 * g + 3], w4.w, hl[k]);
+                            }
+                        }
+                    }
+                    const size_t p = ((size_t)n * H + y) * W + x;
+                    int best = 0;
+                    float m = -INFINITY;
+#pragma unroll
+                    for (int k = 0; k < HK; ++k) {
+                        hl[k] += s_head[COUT * HK + k];
+                        if (hl[k] > m) { m = hl[k]; best = k; }
+                    }
+                    if (valid && head.mask) head.mask[p] = (uint8_t)best;
+                    if (valid && head.logits) {
+#pragma unroll
+                        for (int k = 0; k < HK; ++k) head.logits[p * HK + k] = hl[k];
+                    }
+                    if (valid && head.probs) {
+                        float sum = 0.0f;
+#pragma unroll
+                        for (int k = 0; k < HK; ++k) { hl[k] = expf(hl[k] - m); sum += hl[k]; }
+#pragma unroll
+                        for (int k = 0; k < HK; ++k) head.probs[p * HK + k] = hl[k] / sum;
+                    }
+                }
+            }
+            tx += dtx;
+            if (tx >= tiles_x) { tx -= tiles_x; ++ty; }
+            ty += dty;
+            if (ty >= tiles_y) { ty -= tiles_y; ++n; }
+            n += dn;
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&tempty_bar[buf]);
+            XC_ACC(d_work);
+        }
+#ifdef SQ_XC_PHASE_DIAG
+        if (phase_dbg && warp == 2 && lane == 0) { phase_dbg[blockIdx.x * 8 + 5] = d_wait0; phase_dbg[blockIdx.x * 8 + 6] = d_work; }
+#endif
+    }
+#undef XC_T0
+#undef XC_ACC
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tc::tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
 // ------------------------------------------------------- bandwidth-bound kernels
 // First conv: fp32 NHWC input with few channels -> bf16 blocked.  K = 9*CIN (9 or 27) is far
 // too small for a tcgen05 tile, and on CUDA cores the layer is instruction-bound (144 FMA per
@@ -428,29 +780,34 @@ __device__ __forceinline__ void mma_m16n8k16_bf16(float *c, const uint32_t *a, u
 constexpr int FIRST_ROWS = 8;              // rows per block (one warp per row)
 constexpr int FIRST_TW = 128;              // pixels per block row
 
-template <int CIN, int COUT>
+template <int CIN, int COUT, int KZ>
 __global__ void __launch_bounds__(256)
 first_conv_kernel(const float *__restrict__ in, const float *__restrict__ wf,
                   const float *__restrict__ scale, const float *__restrict__ shift,
-                  bf16 *__restrict__ out, int nimg, int H, int W)
+                  bf16 *__restrict__ out, int nimg, int D, int H, int W)
 {
-    constexpr int KTOT = 9 * CIN, KS = (KTOT + 15) / 16, NT = COUT / 8;
+    // KZ = 1: planar 3x3 (D = 1); KZ = 3: 3x3x3 on slice z of a volume, taps ordered (kz, ky, kx)
+    constexpr int KTOT = 9 * KZ * CIN, KS = (KTOT + 15) / 16, NT = COUT / 8;
     constexpr int SROW = (FIRST_TW + 2) * CIN + 2;            // staged row pitch (floats)
-    __shared__ float tile[(FIRST_ROWS + 2) * SROW];
+    constexpr int SSLICE = (FIRST_ROWS + 2) * SROW;
+    __shared__ float tile[KZ * SSLICE];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
-    const int n = blockIdx.z, x0 = blockIdx.x * FIRST_TW, y0 = blockIdx.y * FIRST_ROWS;
+    const int np = blockIdx.z, x0 = blockIdx.x * FIRST_TW, y0 = blockIdx.y * FIRST_ROWS;
+    const int z = np % D;
 
-    // stage the (ROWS+2) x (TW+2) input halo tile once (zero outside the image = SAME padding)
-    const float *img = in + (size_t)n * H * W * CIN;
-    for (int i = threadIdx.x; i < (FIRST_ROWS + 2) * (FIRST_TW + 2) * CIN; i += 256) {
-        const int ry = i / ((FIRST_TW + 2) * CIN), rx = i % ((FIRST_TW + 2) * CIN);
-        const int yy = y0 + ry - 1, e = (x0 - 1) * CIN + rx;
+    // stage the KZ x (ROWS+2) x (TW+2) input halo tile once (zero outside the image = SAME padding)
+    constexpr int ROWF = (FIRST_TW + 2) * CIN;
+    for (int i = threadIdx.x; i < KZ * (FIRST_ROWS + 2) * ROWF; i += 256) {
+        const int kz = i / ((FIRST_ROWS + 2) * ROWF), r = i % ((FIRST_ROWS + 2) * ROWF);
+        const int ry = r / ROWF, rx = r % ROWF;
+        const int zz = z + kz - (KZ >> 1), yy = y0 + ry - 1, e = (x0 - 1) * CIN + rx;
         float v = 0.0f;
-        if (yy >= 0 && yy < H && e >= 0 && e < W * CIN) v = __ldg(img + (size_t)yy * W * CIN + e);
-        tile[ry * SROW + rx] = v;
+        if (zz >= 0 && zz < D && yy >= 0 && yy < H && e >= 0 && e < W * CIN)
+            v = __ldg(in + ((size_t)(np + zz - z) * H + yy) * W * CIN + e);
+        tile[kz * SSLICE + ry * SROW + rx] = v;
     }
-    // B fragments: b0 = (k = 2t, 2t+1 ; n = g), b1 = (k = 2t+8, 2t+9 ; n = g); zero beyond 9*CIN
+    // B fragments: b0 = (k = 2t, 2t+1 ; n = g), b1 = (k = 2t+8, 2t+9 ; n = g); zero beyond KTOT
     uint32_t bw[KS][NT][2];
 #pragma unroll
     for (int ks = 0; ks < KS; ++ks)
@@ -469,7 +826,7 @@ first_conv_kernel(const float *__restrict__ in, const float *__restrict__ wf,
 #pragma unroll
         for (int e = 0; e < 2; ++e) { sc[nt][e] = scale[nt * 8 + 2 * t + e]; sh[nt][e] = shift[nt * 8 + 2 * t + e]; }
     // this thread's A-fragment sources: k = ks*16 + 2t + (j&1) + 8*(j>>1) -> staged-tile address of
-    // tap (dy,dx), channel c for pixel g of this warp's row.  Taps beyond 9*CIN alias tap 0: their
+    // tap (dz,dy,dx), channel c for pixel g of this warp's row.  Taps beyond KTOT alias tap 0: their
     // weights are zero, so the (finite) value read there does not matter.
     const float *src[KS][4];
 #pragma unroll
@@ -478,12 +835,13 @@ first_conv_kernel(const float *__restrict__ in, const float *__restrict__ wf,
         for (int j = 0; j < 4; ++j) {
             const int k = ks * 16 + 2 * t + (j & 1) + 8 * (j >> 1);
             const int tap = (k < KTOT) ? k / CIN : 0, c = (k < KTOT) ? k % CIN : 0;
-            src[ks][j] = tile + (warp + tap / 3) * SROW + (g + tap % 3) * CIN + c;
+            const int tz = tap / 9, tr = tap % 9;
+            src[ks][j] = tile + tz * SSLICE + (warp + tr / 3) * SROW + (g + tr % 3) * CIN + c;
         }
     __syncthreads();
     const int y = y0 + warp;
     if (y >= H) return;
-    bf16 *orow = out + (((size_t)n * NT * H + y) * W + x0 + g) * 8 + 2 * t;
+    bf16 *orow = out + (((size_t)np * NT * H + y) * W + x0 + g) * 8 + 2 * t;
     const size_t plane = (size_t)H * W * 8;
 #pragma unroll 2
     for (int q = 0; q < FIRST_TW / 16; ++q) {
@@ -696,7 +1054,8 @@ int dev_upload(sq_unet_s *u, const void *src, size_t bytes, void **dst)
     return SQ_OK;
 }
 
-int make_map(CUtensorMap *m, const bf16 *ptr, int nimg, int D, int CB, int H, int W, int PW, int PH)
+int make_map(CUtensorMap *m, const bf16 *ptr, int nimg, int D, int CB, int H, int W, int PW, int PH,
+             int box_cb = 2, int box_z = 1)
 {
     sq_encode_tiled_fn enc = sq_get_encode_tiled();
     SQ_REQUIRE(enc, SQ_ECUDA, "cuTensorMapEncodeTiled entry point not available");
@@ -704,7 +1063,7 @@ int make_map(CUtensorMap *m, const bf16 *ptr, int nimg, int D, int CB, int H, in
     cuuint64_t dims[5] = {(cuuint64_t)W * 8, (cuuint64_t)H, (cuuint64_t)CB, (cuuint64_t)D, (cuuint64_t)nimg};
     cuuint64_t strides[4] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)CB * H * W * 16,
                              (cuuint64_t)D * CB * H * W * 16};
-    cuuint32_t box[5] = {(cuuint32_t)PW * 8, (cuuint32_t)PH, 2, 1, 1};
+    cuuint32_t box[5] = {(cuuint32_t)PW * 8, (cuuint32_t)PH, (cuuint32_t)box_cb, (cuuint32_t)box_z, 1};
     cuuint32_t es[5] = {1, 1, 1, 1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void *)ptr, dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
@@ -778,10 +1137,127 @@ int conv3x3_epi(sq_unet_s *u, const SqLayer &L, const bf16 *in0, int c0, const b
                                                          g, 1, st);
 }
 
+constexpr int SQ_NOT_APPLICABLE = 1;        // launch_xc: configuration does not fit, use the 9-tap kernel
+
+template <int COUT, int S, int NBUF, int MINB, int EPI, int HK, bool PADACC, int KPS, int ZPS>
+int launch_xc_k(sq_unet_s *u, const SqLayer &L, const bf16 *in0, int cb0, const bf16 *in1, int cb1,
+                bf16 *out, bf16 *out_pool, const HeadArgs &head, const TcGeo &g, cudaStream_t st)
+{
+    using C = XCfg<COUT, S, PADACC>;
+    const int nimg = g.nimg, H = g.H, W = g.W;
+    CUtensorMap m0, m1;
+    SQ_TRY(make_map(&m0, in0, nimg, g.D, cb0, H, W, C::PW, C::PH, 2 * KPS, ZPS));
+    if (in1) SQ_TRY(make_map(&m1, in1, nimg, g.D, cb1, H, W, C::PW, C::PH, 2 * KPS, ZPS));
+    else m1 = m0;
+    static_assert(MINB * NBUF * C::ACC_COLS <= 512, "co-resident CTAs must fit in TMEM");
+    const int budget = (MINB == 1 ? 200 : 216 / MINB) * 1024 - 2048;
+    const int qsteps = g.KZ * (cb0 + (in1 ? cb1 : 0)) / 2;
+    const int wres = qsteps * C::B_BYTES, stage_bytes = ZPS * KPS * C::A_BYTES;
+    const int nstages = std::min(XC_MAX_STAGES, (budget - wres) / stage_bytes);
+    SQ_REQUIRE(nstages >= 2 && g.KZ % ZPS == 0, SQ_ESTATE, "conv_xc: configuration does not fit");
+    const size_t smem = (size_t)wres + (size_t)nstages * stage_bytes + 1024;
+    auto kern = conv_xc_kernel<COUT, S, NBUF, MINB, EPI, HK, PADACC, KPS, ZPS>;
+    static size_t attr_smem = 0;
+    if (smem > attr_smem) {
+        SQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_smem = smem;
+    }
+    const int tiles = nimg * g.D * ((W + C::TW - 1) / C::TW) * ((H + C::TH - 1) / C::TH);
+    const int grid = std::min(tiles, MINB * u->h->sm_count);
+    long long *phase_dbg = nullptr;
+#ifdef SQ_XC_PHASE_DIAG
+    if (getenv("SQ_XC_PHASE")) {
+        SQ_CUDA(cudaMalloc(&phase_dbg, (size_t)grid * 8 * sizeof(long long)));
+        SQ_CUDA(cudaMemset(phase_dbg, 0, (size_t)grid * 8 * sizeof(long long)));
+    }
+#endif
+    kern<<<grid, TC_THREADS, smem, st>>>(m0, m1, cb0 / 2, in1 ? cb1 / 2 : 0, (const bf16 *)L.w_xc, L.scale,
+                                         L.shift, out, out_pool, head, nimg, H, W, nstages, g.D, g.KZ, wres,
+                                         phase_dbg);
+    ++u->last_launches;
+    SQ_CHECK_LAUNCH();
+    if (phase_dbg) {
+        // diagnostics: average clocks per tile each role spent waiting / working
+        SQ_CUDA(cudaStreamSynchronize(st));
+        std::vector<long long> h((size_t)grid * 8);
+        SQ_CUDA(cudaMemcpy(h.data(), phase_dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+        SQ_CUDA(cudaFree(phase_dbg));
+        double a[8] = {0};
+        for (int b2 = 0; b2 < grid; ++b2) for (int i = 0; i < 8; ++i) a[i] += (double)h[(size_t)b2 * 8 + i] / grid;
+        const double tpc = (double)tiles / grid;
+        fprintf(stderr, "xc_phase %s Cout=%d S=%d KPS=%d ZPS=%d stages=%d tiles/CTA=%.0f | per tile clk: producer wait_empty %.0f issue %.0f | "
+                "mma wait_tempty %.0f wait_full %.0f issue %.0f | epilogue wait_tfull %.0f work %.0f\n", L.scope.c_str(), COUT, S, KPS, ZPS,
+                nstages, tpc, a[0] / tpc, a[1] / tpc, a[2] / tpc, a[3] / tpc, a[4] / tpc, a[5] / tpc, a[6] / tpc);
+    }
+    return SQ_OK;
+}
+
+// Pick the largest box that fits: all three depth taps (volumes) and two channel-block pairs per
+// stage if at least two stages remain next to the resident weights; SQ_NOT_APPLICABLE if even
+// single-k-step stages do not fit.
+template <int COUT, int S, int NBUF, int MINB, int EPI, int HK, bool PADACC>
+int launch_xc(sq_unet_s *u, const SqLayer &L, const bf16 *in0, int cb0, const bf16 *in1, int cb1,
+              bf16 *out, bf16 *out_pool, const HeadArgs &head, const TcGeo &g, cudaStream_t st)
+{
+    using C = XCfg<COUT, S, PADACC>;
+    const int budget = (MINB == 1 ? 200 : 216 / MINB) * 1024 - 2048;
+    const int qsteps = g.KZ * (cb0 + (in1 ? cb1 : 0)) / 2;
+    const int room = budget - qsteps * C::B_BYTES;
+    const bool pairable = (cb0 % 4 == 0) && (!in1 || cb1 % 4 == 0);
+    auto fits = [&](int zps, int kps) { return room >= 2 * zps * kps * C::A_BYTES; };
+#define SQ_XC_GO(KPS, ZPS) \
+    return launch_xc_k<COUT, S, NBUF, MINB, EPI, HK, PADACC, KPS, ZPS>(u, L, in0, cb0, in1, cb1, out, out_pool, head, g, st)
+    if (g.KZ == 3) {
+        if (pairable && fits(3, 2)) SQ_XC_GO(2, 3);
+        if (fits(3, 1)) SQ_XC_GO(1, 3);
+    }
+    if (pairable && fits(1, 2)) SQ_XC_GO(2, 1);
+    if (fits(1, 1)) SQ_XC_GO(1, 1);
+#undef SQ_XC_GO
+    return SQ_NOT_APPLICABLE;
+}
+
+template <int COUT, int S, int NBUF, int MINB, bool PADACC = true>
+int conv3x3_xc(sq_unet_s *u, const SqLayer &L, const bf16 *in0, int c0, const bf16 *in1, int c1,
+               bf16 *out, bf16 *out_pool, const HeadArgs *head, const TcGeo &g, cudaStream_t st)
+{
+    const HeadArgs none = {nullptr, 0, nullptr, nullptr, nullptr};
+    if (head) {
+        switch (head->K) {
+        case 2: return launch_xc<COUT, S, NBUF, MINB, EPI_HEAD, 2, PADACC>(u, L, in0, c0 / 8, in1, c1 / 8, out, nullptr, *head, g, st);
+        case 3: return launch_xc<COUT, S, NBUF, MINB, EPI_HEAD, 3, PADACC>(u, L, in0, c0 / 8, in1, c1 / 8, out, nullptr, *head, g, st);
+        case 4: return launch_xc<COUT, S, NBUF, MINB, EPI_HEAD, 4, PADACC>(u, L, in0, c0 / 8, in1, c1 / 8, out, nullptr, *head, g, st);
+        }
+        SQ_REQUIRE(false, SQ_EUNSUPPORTED, "fused head supports 2..4 classes");
+    }
+    if (out_pool)
+        return launch_xc<COUT, S, NBUF, MINB, EPI_POOL, 0, PADACC>(u, L, in0, c0 / 8, in1, c1 / 8, out, out_pool, none, g, st);
+    return launch_xc<COUT, S, NBUF, MINB, EPI_STORE, 0, PADACC>(u, L, in0, c0 / 8, in1, c1 / 8, out, nullptr, none, g, st);
+}
+
+int xc_variant()
+{
+    // SQ_XC=0 disables the x-combined kernels, SQ_XC=2 forces them (A/B measurements, tests)
+    const char *e = getenv("SQ_XC");
+    return e ? atoi(e) : 1;
+}
+
 // out_pool != NULL: also write the 2x2 max-pooled tensor; head != NULL: fused 1x1 head, no `out`.
 int conv3x3_tc(sq_unet_s *u, const SqLayer &L, const bf16 *in0, int c0, const bf16 *in1, int c1,
                bf16 *out, bf16 *out_pool, const HeadArgs *head, const TcGeo &g, cudaStream_t st)
 {
+    // x-combined kernel: its MMA phase costs ~0.4x the 9-tap kernel's per k-step, but its epilogue reads
+    // 3x the accumulator columns and tcgen05.ld moves only 64 B/clk/SM (3.4 clk/px at Cout 16, 6.9 at
+    // Cout 32, against 2.7-2.8 clk/px PER K-STEP of 9-tap MMAs): it wins from 2 k-steps per tile at
+    // Cout 16 and from 3 at Cout 32 (profiles/r1_xc_ablation.log).  SQ_XC=0 disables it, 2 forces it.
+    const int v = xc_variant();
+    const int qsteps = g.KZ * ((c0 + c1) / 16);
+    if (L.w_xc && v > 0 && (qsteps >= (L.cout == 16 ? 2 : 3) || v == 2)) {
+        int r = SQ_NOT_APPLICABLE;
+        if (L.cout == 16) r = conv3x3_xc<16, 2, 2, 2>(u, L, in0, c0, in1, c1, out, out_pool, head, g, st);
+        if (L.cout == 32) r = conv3x3_xc<32, 1, 2, 2>(u, L, in0, c0, in1, c1, out, out_pool, head, g, st);
+        if (r != SQ_NOT_APPLICABLE) return r;
+    }
     switch (L.cout) {
     case 16:  return conv3x3_epi<16, 4, 2>(u, L, in0, c0, in1, c1, out, out_pool, head, g, st);
     case 32:  return conv3x3_epi<32, 4, 2>(u, L, in0, c0, in1, c1, out, out_pool, head, g, st);
@@ -846,6 +1322,23 @@ int sq_tc_finalize(sq_unet_s *u)
                                         host_bf16(k[((size_t)(kz * 9 + tp) * C + ci) * CO + co]);
                                 }
             SQ_TRY(dev_upload(u, w.data(), w.size() * 2, &L.w_tc));
+            if (CO <= 32) {
+                // x-combined layout: [kz][ks][ky][kb][(kx, co)][8]
+                std::vector<uint16_t> x((size_t)KZ * 9 * C * CO);
+                const int N = 3 * CO;
+                for (int kz = 0; kz < KZ; ++kz)
+                    for (int ks = 0; ks < C / 16; ++ks)
+                        for (int ky = 0; ky < 3; ++ky)
+                            for (int kb = 0; kb < 2; ++kb)
+                                for (int kx = 0; kx < 3; ++kx)
+                                    for (int co = 0; co < CO; ++co)
+                                        for (int e = 0; e < 8; ++e) {
+                                            const int ci = ks * 16 + kb * 8 + e;
+                                            x[((((((size_t)kz * (C / 16) + ks) * 3 + ky) * 2 + kb) * N) + kx * CO + co) * 8 + e] =
+                                                host_bf16(k[((size_t)(kz * 9 + ky * 3 + kx) * C + ci) * CO + co]);
+                                        }
+                SQ_TRY(dev_upload(u, x.data(), x.size() * 2, &L.w_xc));
+            }
         } else if (L.kind == SqLayer::UPCONV) {
             // [kz][ks][tap4][kb][co][8]  <-  TF conv_transpose kernel[kz*4 + tap4][co][ci]
             std::vector<uint16_t> w((size_t)UZ * 4 * C * CO);
@@ -922,24 +1415,35 @@ int tc_run(sq_unet_s *u, bool dry, const float *in, int n, int dep, int hgt, int
         SqLayer *c2 = layer_by_scope(u, scope);
         if (l == 0 && vol) {
             const float *wf = (const float *)c1->w_tc;
-            const size_t sm = (size_t)(27 * u->cin + 2) * c1->cout * sizeof(float);
-            const unsigned grid = (unsigned)((px + 127) / 128);
+            const int key = u->cin * 1000 + c1->cout;
+            const dim3 g3((W + FIRST_TW - 1) / FIRST_TW, (H + FIRST_ROWS - 1) / FIRST_ROWS, n * D);
+            SQ_REQUIRE((long long)n * D <= 65535, SQ_EINVAL, "unet(bf16): more than 65535 slices per call");
+#define SQ_FIRST3M(CI, CO) first_conv_kernel<CI, CO, 3><<<g3, 256, 0, st>>>(in, wf, c1->scale, c1->shift, t1[0], n, D, H, W)
+            if (key == 1016) SQ_FIRST3M(1, 16);
+            else if (key == 1032) SQ_FIRST3M(1, 32);
+            else if (key == 2016) SQ_FIRST3M(2, 16);
+            else {
+                // other channel counts: one thread per voxel on CUDA cores
+                const size_t sm = (size_t)(27 * u->cin + 2) * c1->cout * sizeof(float);
+                const unsigned grid = (unsigned)((px + 127) / 128);
 #define SQ_FIRST3(CO) first_conv3d_kernel<CO><<<grid, 128, sm, st>>>(in, wf, c1->scale, c1->shift, t1[0], n, D, H, W, u->cin)
-            switch (c1->cout) {
-            case 16: SQ_FIRST3(16); break;
-            case 32: SQ_FIRST3(32); break;
-            case 64: SQ_FIRST3(64); break;
-            default:
-                SQ_REQUIRE(false, SQ_EUNSUPPORTED, "bf16 mode: first 3-D conv -> %d channels not instantiated",
-                           c1->cout);
-            }
+                switch (c1->cout) {
+                case 16: SQ_FIRST3(16); break;
+                case 32: SQ_FIRST3(32); break;
+                case 64: SQ_FIRST3(64); break;
+                default:
+                    SQ_REQUIRE(false, SQ_EUNSUPPORTED, "bf16 mode: first 3-D conv -> %d channels not instantiated",
+                               c1->cout);
+                }
 #undef SQ_FIRST3
+            }
+#undef SQ_FIRST3M
             ++u->last_launches;
             SQ_CHECK_LAUNCH();
         } else if (l == 0) {
             const dim3 grid((W + FIRST_TW - 1) / FIRST_TW, (H + FIRST_ROWS - 1) / FIRST_ROWS, n);
             const float *wf = (const float *)c1->w_tc;
-#define SQ_FIRST(CI, CO) first_conv_kernel<CI, CO><<<grid, 256, 0, st>>>(in, wf, c1->scale, c1->shift, t1[0], n, H, W)
+#define SQ_FIRST(CI, CO) first_conv_kernel<CI, CO, 1><<<grid, 256, 0, st>>>(in, wf, c1->scale, c1->shift, t1[0], n, 1, H, W)
             const int key = u->cin * 1000 + c1->cout;
             switch (key) {
             case 1016: SQ_FIRST(1, 16); break;

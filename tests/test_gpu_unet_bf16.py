@@ -126,21 +126,22 @@ def test_unsupported_configs_fail_loudly(sq):
         net3.predict(np.zeros((1, 8, 16, 16, 1), np.float32))
 
 
-@pytest.mark.parametrize('filters,bridge,k,dhw', [
-    ((16, 32), 'concat', 2, (8, 32, 40)),           # fused head, fused xy pool + depth pool
-    ((16, 32, 64), 'concat', 3, (8, 24, 48)),
-    ((16, 32), 'eltwise_add', 2, (4, 16, 24)),
-    ((32, 64), None, 10, (6, 16, 16)),              # stand-alone head
+@pytest.mark.parametrize('filters,bridge,k,dhw,cin', [
+    ((16, 32), 'concat', 2, (8, 32, 40), 1),        # fused head, fused xy pool + depth pool
+    ((16, 32, 64), 'concat', 3, (8, 24, 48), 1),
+    ((16, 32), 'eltwise_add', 2, (4, 16, 24), 2),
+    ((32, 64), None, 10, (6, 16, 16), 1),           # stand-alone head
+    ((16, 32), 'concat', 2, (4, 24, 136), 3),       # CUDA-core first conv; wider than one block
 ])
-def test_unet3d_volumes(sq, filters, bridge, k, dhw):
+def test_unet3d_volumes(sq, filters, bridge, k, dhw, cin):
     """UNet3D on tensor cores: 3x3x3 convs as three depth taps of the planar kernel (5-D TMA,
     zero-filled outside the volume), 2x2x2 up-conv as two planar launches, depth pool kernel."""
     from sequitr_b200.networks import UNet3D
     d, h, wd = dhw
-    w = synth.unet_weights(filters, 1, k, ndim=3, bridge=bridge, seed=9)
-    x = synth.volumes(2, d, h, wd, 1)
-    net = UNet3D({'filters': filters, 'shape': (h, wd, d), 'bridge': bridge, 'num_outputs': k,
-                  'compute': 'bf16'})
+    w = synth.unet_weights(filters, cin, k, ndim=3, bridge=bridge, seed=9)
+    x = synth.volumes(2, d, h, wd, cin)
+    net = UNet3D({'filters': filters, 'shape': (h, wd, d), 'bridge': bridge, 'num_inputs': cin,
+                  'num_outputs': k, 'compute': 'bf16'})
     net.load_weights(w)
     out = net.predict(x)
     ref = unet_c.unet_forward(x, w, filters, bridge, contract='bf16')
@@ -148,3 +149,22 @@ def test_unet3d_volumes(sq, filters, bridge, k, dhw):
     _compare(out, ref, 'unet3d %s' % (filters,))
     one = net.predict(x[1:2])                                  # volume-independent
     np.testing.assert_array_equal(out['logits'][1:2], one['logits'])
+
+
+@pytest.mark.parametrize('xc', ['0', '2'])
+def test_both_conv_kernels_cover_every_layer(sq, monkeypatch, xc):
+    """Cout <= 32 convs have two tcgen05 kernels (9-tap and x-combined, picked by k-steps per tile);
+    SQ_XC=0 / SQ_XC=2 force one or the other on every such layer, incl. fused pool and fused head."""
+    monkeypatch.setenv('SQ_XC', xc)
+    filters = (16, 32, 64)
+    for bridge, cin, k, shape in (('concat', 1, 2, (64, 88)), ('eltwise_add', 3, 3, (48, 80))):
+        w = synth.unet_weights(filters, cin, k, bridge=bridge, seed=21)
+        x = synth.frames(2, shape[0], shape[1], cin, seed=8, n_objects=4)
+        out = _net(filters, shape, bridge, cin, k, w).predict(x)
+        _compare(out, unet_c.unet_forward(x, w, filters, bridge, contract='bf16'), 'SQ_XC=%s %s' % (xc, bridge))
+    from sequitr_b200.networks import UNet3D
+    w = synth.unet_weights((16, 32), 1, 2, ndim=3, bridge='concat', seed=4)
+    x = synth.volumes(1, 4, 24, 40, 1)
+    net = UNet3D({'filters': (16, 32), 'shape': (24, 40, 4), 'bridge': 'concat', 'compute': 'bf16'})
+    net.load_weights(w)
+    _compare(net.predict(x), unet_c.unet_forward(x, w, (16, 32), 'concat', contract='bf16'), 'SQ_XC=%s 3d' % xc)
