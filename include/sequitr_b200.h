@@ -164,6 +164,29 @@ int sq_unet_profile(sq_unet_t u, const float *in_dev, int n, int d, int hgt, int
                     const char **names_out, float *ms_out, double *flops_out,
                     int max_layers, int *n_layers);
 
+/* Pre-inference clean-up pipes (the step right before the UNet).  Stacks
+ * are float32 (n,h,w,c) channels-last on the device; workspace: sq_prep_workspace_bytes(n, c).
+ *   sq_image_norm        replaces ImageNorm.pipe        (reference pipeline.py:338-356): per image and
+ *                        channel (x - mean) / std, population std, float32 arithmetic on float32 moments
+ *                        (the reference's 1e-99 epsilon vanishes in float32 too); in may equal out.
+ *   sq_image_outliers    replaces ImageOutliers.pipe    (pipeline.py:266-296): size x size median
+ *                        (scipy.ndimage.median_filter: 'reflect' boundary, window origin size/2, rank
+ *                        size*size/2); pixels with |x - median| > threshold take the median.  size 1..5;
+ *                        in and out must differ.  Bit-exact.
+ *   sq_image_bgsubtract  replaces ImageBGSubtract.pipe  (pipeline.py:360-405): least-squares quadratic
+ *                        surface over (column, row) subtracted from a single-channel image; fp64 fit;
+ *                        out_dtype SQ_F64 (the reference's result dtype) or SQ_F32.
+ *   sq_image_pipe_host   the same three on host buffers (which = 0 norm, 1 outliers, 2 background). */
+int sq_prep_workspace_bytes(sq_handle_t h, int n, int c, size_t *bytes);
+int sq_image_norm(sq_handle_t h, const float *in_dev, float *out_dev, int n, int hgt, int wid, int c,
+                  void *workspace_dev, size_t workspace_bytes, void *stream);
+int sq_image_outliers(sq_handle_t h, const float *in_dev, float *out_dev, int n, int hgt, int wid, int c,
+                      int size, double threshold, void *stream);
+int sq_image_bgsubtract(sq_handle_t h, const float *in_dev, void *out_dev, int out_dtype, int n, int hgt,
+                        int wid, void *workspace_dev, size_t workspace_bytes, void *stream);
+int sq_image_pipe_host(sq_handle_t h, int which, const float *in_host, void *out_host, int out_dtype,
+                       int n, int hgt, int wid, int c, int size, double threshold);
+
 /* Weighted softmax cross-entropy of the head (training step of BASELINE config 5; consumes the
  * per-pixel 'weights' map and the labels that networks/unet.py tr_augment :396-401 returns; the
  * loss itself is not shipped by the reference).  logits_dev float32 (npix,K); labels_dev uint8

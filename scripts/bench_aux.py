@@ -39,12 +39,16 @@ def timeit(fn, reps=10):
     return e0.elapsed_time(e1) / reps
 
 
+frames_d = torch.from_numpy(synth.frames(4, H, W, 1, seed=5)).cuda().repeat(N // 4, 1, 1, 1).contiguous()
 px = N * H * W
 rows = []
 for name, fn, bpp in (
         ('weightmap_edt  W1 (u8 -> f32)', lambda: ops.weightmap_edt(mask_d, 10., 5., 'float32'), 5),
         ('weightmap_edt  W1 (u8 -> f64)', lambda: ops.weightmap_edt(mask_d, 10., 5., 'float64'), 9),
         ('weightmap_unet W3 (i32 -> f32)', lambda: ops.weightmap_unet(lab_d, 10., 5., None, 'float32'), 8),
+        ('ImageNorm      (f32 -> f32)', lambda: ops.image_norm(frames_d), 8),
+        ('ImageOutliers  (f32 -> f32, 2x2 median)', lambda: ops.image_outliers(frames_d, 2, 5.), 8),
+        ('ImageBGSubtract (f32 -> f32)', lambda: ops.image_bgsubtract(frames_d, 'float32'), 8),
         ('label_centroids L1 (u8 -> rows)', lambda: ops.label_centroids(cls_d, max_rows=2048), 1),
         ('label_centroids L1 (+ label matrix)', lambda: ops.label_centroids(cls_d, max_rows=2048, want_labels=True), 5)):
     ms = timeit(fn)

@@ -11,6 +11,9 @@
 * ``unet_kat.npz``       -- a small known-answer test of the plain-C UNet oracle
   (seeded input/weights -> logits/mask), to detect drift of the numeric contract.
 
+* ``prep_ref.npz``       -- inputs + outputs of the REFERENCE's ``ImageNorm`` / ``ImageOutliers`` /
+  ``ImageBGSubtract`` pipes (pre-inference clean-up).
+
 The /root/reference tree does not travel to the GPU box; these files do.
 """
 import os
@@ -46,9 +49,36 @@ def weightmap_cases():
     return cases
 
 
+def prep_cases():
+    rng = np.random.default_rng(11)
+    cases = {}
+    yy, xx = np.mgrid[0:72, 0:96]
+    cam = 120 + 0.05 * xx + 0.11 * yy + 4e-4 * xx * yy - 3e-4 * yy * yy + rng.standard_normal((72, 96)) * 3
+    cam[10, 20] += 400.0                 # hot pixels, one on the border, one in a corner
+    cam[0, 50] += 250.0
+    cam[71, 95] -= 300.0
+    cases['camera72x96'] = cam.astype(np.float32)
+    cases['noise33x31'] = (rng.standard_normal((33, 31)) * 7 + 50).astype(np.float32)
+    rgb = (rng.standard_normal((40, 48, 3)) * np.array([1., 5., 20.]) + np.array([0., 10., -30.])).astype(np.float32)
+    rgb[7, 9, 1] = 300.0
+    cases['rgb40x48x3'] = rgb
+    return cases
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = ref_loader.load_reference_pipeline()
+
+    pr = {}
+    for name, img in prep_cases().items():
+        pr['in_' + name] = img
+        pr['norm_' + name] = ref.ImageNorm()(img.copy())
+        pr['outl2_' + name] = ref.ImageOutliers()(img.copy())
+        pr['outl3_' + name] = ref.ImageOutliers(sigma=3, threshold=2.)(img.copy())
+        if img.ndim == 2:
+            pr['bg_' + name] = ref.ImageBGSubtract()(img.copy())
+    np.savez_compressed(os.path.join(OUT, 'prep_ref.npz'), **pr)
+    print('prep_ref.npz', len(pr), 'arrays')
 
     wm = {}
     for name, mask in weightmap_cases().items():

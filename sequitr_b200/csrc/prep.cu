@@ -1,0 +1,351 @@
+// Pre-inference clean-up pipes: the step right before the UNet.
+//   ImageNorm        reference pipeline.py:338-356   (x - mean) / std per image and channel
+//   ImageOutliers    reference pipeline.py:266-296   hot-pixel removal against a size x size median
+//   ImageBGSubtract  reference pipeline.py:360-405   least-squares quadratic background surface
+// All three are HBM-bound: one or two streaming passes over a float32 (N,H,W,C) stack.
+#include "sq_common.cuh"
+#include <cmath>
+
+namespace {
+
+constexpr int PREP_BLOCKS = 128;          // partial-sum blocks per image
+constexpr int PREP_THREADS = 256;
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// block-wide sums of NV values per thread; result valid in thread 0
+template <int NV>
+__device__ __forceinline__ void block_sum(double (&v)[NV], double *sm)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        v[i] = warp_sum(v[i]);
+        if (lane == 0) sm[warp * NV + i] = v[i];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            double s = 0.0;
+            for (int w = 0; w < PREP_THREADS / 32; ++w) s += sm[w * NV + i];
+            v[i] = s;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ ImageNorm
+// pass 1: per (image, channel, block) partial sum and sum of squares in fp64
+__global__ void __launch_bounds__(PREP_THREADS)
+norm_partial(const float *__restrict__ in, long long npix, int C, double *__restrict__ part)
+{
+    __shared__ double sm[PREP_THREADS / 32 * 2];
+    const int n = blockIdx.y, c = blockIdx.z;
+    const float *img = in + (size_t)n * npix * C + c;
+    double v[2] = {0.0, 0.0};
+    for (long long p = (long long)blockIdx.x * PREP_THREADS + threadIdx.x; p < npix;
+         p += (long long)PREP_BLOCKS * PREP_THREADS) {
+        const double x = (double)__ldg(img + p * C);
+        v[0] += x;
+        v[1] = fma(x, x, v[1]);
+    }
+    block_sum<2>(v, sm);
+    if (threadIdx.x == 0) {
+        double *o = part + (((size_t)n * C + c) * PREP_BLOCKS + blockIdx.x) * 2;
+        o[0] = v[0];
+        o[1] = v[1];
+    }
+}
+
+// pass 2: mean / std -> float32 (the dtype numpy's float32 reductions return, pipeline.py:353-355)
+__global__ void norm_final(const double *__restrict__ part, long long npix, int nc, float2 *__restrict__ stats)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nc) return;
+    double s = 0.0, q = 0.0;
+    for (int b = 0; b < PREP_BLOCKS; ++b) { s += part[((size_t)i * PREP_BLOCKS + b) * 2]; q += part[((size_t)i * PREP_BLOCKS + b) * 2 + 1]; }
+    const double mean = s / (double)npix;
+    double var = q / (double)npix - mean * mean;
+    if (var < 0.0) var = 0.0;
+    stats[i] = make_float2((float)mean, (float)sqrt(var));
+}
+
+// pass 3: float32 arithmetic exactly as numpy does it on a float32 image (epsilon 1e-99 vanishes in
+// float32, pipeline.py:350,354-355: a constant image divides by zero there too)
+__global__ void norm_apply(const float *__restrict__ in, float *__restrict__ out, long long npix, int C,
+                           const float2 *__restrict__ stats, long long total)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const long long n = i / (npix * C);
+    const int c = (int)(i % C);
+    const float2 st = stats[n * C + c];
+    out[i] = __fdiv_rn(__fsub_rn(in[i], st.x), st.y);
+}
+
+// -------------------------------------------------------------- ImageOutliers
+// scipy.ndimage.median_filter(x, size): window = offsets -(size/2) .. -(size/2)+size-1 per axis, 'reflect'
+// boundary (d c b a | a b c d | d c b a), value of rank (size*size)/2; pipeline.py:287-294.
+__device__ __forceinline__ int reflect_idx(int i, int n)
+{
+    if (n == 1) return 0;
+    while (i < 0 || i >= n) i = (i < 0) ? (-i - 1) : (2 * n - 1 - i);
+    return i;
+}
+
+template <int K>
+__global__ void outliers_kernel(const float *__restrict__ in, float *__restrict__ out, int H, int W, int C,
+                                float threshold, long long total)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int c = (int)(i % C);
+    long long r = i / C;
+    const int x = (int)(r % W);
+    r /= W;
+    const int y = (int)(r % H);
+    const long long n = r / H;
+    const float *img = in + (size_t)n * H * W * C + c;
+    float v[K * K];
+#pragma unroll
+    for (int dy = 0; dy < K; ++dy) {
+        const int yy = reflect_idx(y - K / 2 + dy, H);
+#pragma unroll
+        for (int dx = 0; dx < K; ++dx) {
+            const int xx = reflect_idx(x - K / 2 + dx, W);
+            v[dy * K + dx] = __ldg(img + ((size_t)yy * W + xx) * C);
+        }
+    }
+    // partial selection sort up to the median rank
+    constexpr int RANK = (K * K) / 2;
+#pragma unroll
+    for (int a = 0; a <= RANK; ++a) {
+#pragma unroll
+        for (int b = a + 1; b < K * K; ++b) {
+            const float lo = fminf(v[a], v[b]), hi = fmaxf(v[a], v[b]);
+            v[a] = lo;
+            v[b] = hi;
+        }
+    }
+    const float med = v[RANK], raw = in[i];
+    out[i] = (fabsf(__fsub_rn(raw, med)) > threshold) ? med : raw;
+}
+
+// ------------------------------------------------------------ ImageBGSubtract
+// Least-squares fit of I(u,v) ~ k0 + k1 u + k2 v + k3 u^2 + k4 uv + k5 v^2 (u = column, v = row,
+// pipeline.py:384-401).  The reference inverts the raw normal matrix; here the same surface is fitted in
+// centred, scaled coordinates (s = (u - cu)/su, t = (v - cv)/sv), which is well conditioned, so the
+// result agrees with the reference to ~1e-12 (tests) without reproducing its conditioning.
+struct BgGram {
+    double g[36];             // Gram matrix of the basis {1, s, t, s^2, st, t^2} over the pixel grid
+    double cu, cv, su, sv;
+};
+
+__device__ __forceinline__ void bg_basis(double s, double t, double *b)
+{
+    b[0] = 1.0; b[1] = s; b[2] = t; b[3] = s * s; b[4] = s * t; b[5] = t * t;
+}
+
+__global__ void __launch_bounds__(PREP_THREADS)
+bg_partial(const float *__restrict__ in, int H, int W, BgGram G, double *__restrict__ part)
+{
+    __shared__ double sm[PREP_THREADS / 32 * 6];
+    const int n = blockIdx.y;
+    const float *img = in + (size_t)n * H * W;
+    const long long npix = (long long)H * W;
+    double v[6] = {0, 0, 0, 0, 0, 0};
+    for (long long p = (long long)blockIdx.x * PREP_THREADS + threadIdx.x; p < npix;
+         p += (long long)PREP_BLOCKS * PREP_THREADS) {
+        const int x = (int)(p % W), y = (int)(p / W);
+        const double I = (double)__ldg(img + p);
+        double b[6];
+        bg_basis(((double)x - G.cu) / G.su, ((double)y - G.cv) / G.sv, b);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) v[k] = fma(b[k], I, v[k]);
+    }
+    block_sum<6>(v, sm);
+    if (threadIdx.x == 0)
+        for (int k = 0; k < 6; ++k) part[((size_t)n * PREP_BLOCKS + blockIdx.x) * 6 + k] = v[k];
+}
+
+// one thread per image: reduce the partial moments, solve the 6x6 normal equations (Gaussian elimination
+// with partial pivoting, fp64)
+__global__ void bg_solve(const double *__restrict__ part, BgGram G, int nimg, double *__restrict__ coef)
+{
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= nimg) return;
+    double a[6][7];
+    for (int i = 0; i < 6; ++i) {
+        for (int j = 0; j < 6; ++j) a[i][j] = G.g[i * 6 + j];
+        double s = 0.0;
+        for (int b = 0; b < PREP_BLOCKS; ++b) s += part[((size_t)n * PREP_BLOCKS + b) * 6 + i];
+        a[i][6] = s;
+    }
+    for (int c = 0; c < 6; ++c) {
+        int piv = c;
+        for (int r = c + 1; r < 6; ++r) if (fabs(a[r][c]) > fabs(a[piv][c])) piv = r;
+        if (piv != c) for (int j = 0; j < 7; ++j) { const double t = a[c][j]; a[c][j] = a[piv][j]; a[piv][j] = t; }
+        const double d = a[c][c];
+        for (int r = c + 1; r < 6; ++r) {
+            const double f = (d != 0.0) ? a[r][c] / d : 0.0;
+            for (int j = c; j < 7; ++j) a[r][j] -= f * a[c][j];
+        }
+    }
+    double k[6];
+    for (int c = 5; c >= 0; --c) {
+        double s = a[c][6];
+        for (int j = c + 1; j < 6; ++j) s -= a[c][j] * k[j];
+        k[c] = (a[c][c] != 0.0) ? s / a[c][c] : 0.0;
+    }
+    for (int i = 0; i < 6; ++i) coef[(size_t)n * 6 + i] = k[i];
+}
+
+template <typename OutT>
+__global__ void bg_apply(const float *__restrict__ in, OutT *__restrict__ out, int H, int W, BgGram G,
+                         const double *__restrict__ coef, long long total)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int x = (int)(i % W), y = (int)((i / W) % H);
+    const long long n = i / ((long long)W * H);
+    const double *k = coef + n * 6;
+    double b[6];
+    bg_basis(((double)x - G.cu) / G.su, ((double)y - G.cv) / G.sv, b);
+    double bg = 0.0;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) bg = fma(k[j], b[j], bg);
+    out[i] = (OutT)((double)in[i] - bg);
+}
+
+int check_stack(sq_handle_t h, int n, int hgt, int wid, int c)
+{
+    SQ_REQUIRE(h, SQ_EINVAL, "null handle");
+    SQ_REQUIRE(n >= 1 && hgt >= 1 && wid >= 1 && c >= 1 && c <= 16, SQ_EINVAL,
+               "image stack: bad geometry n=%d h=%d w=%d c=%d", n, hgt, wid, c);
+    return SQ_OK;
+}
+
+}  // namespace
+
+extern "C" int sq_prep_workspace_bytes(sq_handle_t h, int n, int c, size_t *bytes)
+{
+    SQ_REQUIRE(h && bytes, SQ_EINVAL, "prep_workspace_bytes: null pointer");
+    SQ_REQUIRE(n >= 1 && c >= 1, SQ_EINVAL, "prep_workspace_bytes: bad geometry");
+    SqArena a(nullptr, 0);
+    a.take<double>((size_t)n * c * PREP_BLOCKS * 6);
+    a.take<double>((size_t)n * c * 8);
+    *bytes = a.off;
+    return SQ_OK;
+}
+
+extern "C" int sq_image_norm(sq_handle_t h, const float *in, float *out, int n, int hgt, int wid, int c,
+                             void *ws, size_t ws_bytes, void *stream)
+{
+    SQ_TRY(check_stack(h, n, hgt, wid, c));
+    SQ_REQUIRE(in && out && ws, SQ_EINVAL, "image_norm: null pointer");
+    SQ_CUDA(cudaSetDevice(h->device));
+    SqArena a(ws, ws_bytes);
+    double *part = a.take<double>((size_t)n * c * PREP_BLOCKS * 6);
+    float2 *stats = (float2 *)a.take<double>((size_t)n * c * 8);
+    SQ_REQUIRE(a.ok(), SQ_ENOMEM, "image_norm: workspace %zu < %zu bytes", ws_bytes, a.off);
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long npix = (long long)hgt * wid, total = npix * c * n;
+    norm_partial<<<dim3(PREP_BLOCKS, n, c), PREP_THREADS, 0, st>>>(in, npix, c, part);
+    SQ_CHECK_LAUNCH();
+    norm_final<<<(n * c + 127) / 128, 128, 0, st>>>(part, npix, n * c, stats);
+    SQ_CHECK_LAUNCH();
+    norm_apply<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in, out, npix, c, stats, total);
+    SQ_CHECK_LAUNCH();
+    return SQ_OK;
+}
+
+extern "C" int sq_image_outliers(sq_handle_t h, const float *in, float *out, int n, int hgt, int wid, int c,
+                                 int size, double threshold, void *stream)
+{
+    SQ_TRY(check_stack(h, n, hgt, wid, c));
+    SQ_REQUIRE(in && out && in != out, SQ_EINVAL, "image_outliers: needs distinct in / out buffers");
+    SQ_REQUIRE(size >= 1 && size <= 5, SQ_EUNSUPPORTED, "image_outliers: median size %d not in 1..5", size);
+    SQ_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long total = (long long)n * hgt * wid * c;
+    const unsigned grid = (unsigned)((total + 255) / 256);
+    const float thr = (float)threshold;
+    switch (size) {
+    case 1: outliers_kernel<1><<<grid, 256, 0, st>>>(in, out, hgt, wid, c, thr, total); break;
+    case 2: outliers_kernel<2><<<grid, 256, 0, st>>>(in, out, hgt, wid, c, thr, total); break;
+    case 3: outliers_kernel<3><<<grid, 256, 0, st>>>(in, out, hgt, wid, c, thr, total); break;
+    case 4: outliers_kernel<4><<<grid, 256, 0, st>>>(in, out, hgt, wid, c, thr, total); break;
+    default: outliers_kernel<5><<<grid, 256, 0, st>>>(in, out, hgt, wid, c, thr, total); break;
+    }
+    SQ_CHECK_LAUNCH();
+    return SQ_OK;
+}
+
+extern "C" int sq_image_bgsubtract(sq_handle_t h, const float *in, void *out, int out_dtype, int n, int hgt,
+                                   int wid, void *ws, size_t ws_bytes, void *stream)
+{
+    SQ_TRY(check_stack(h, n, hgt, wid, 1));
+    SQ_REQUIRE(in && out && ws, SQ_EINVAL, "image_bgsubtract: null pointer");
+    SQ_REQUIRE(out_dtype == SQ_F32 || out_dtype == SQ_F64, SQ_EINVAL, "image_bgsubtract: bad out_dtype");
+    SQ_REQUIRE(hgt >= 3 && wid >= 3, SQ_EINVAL, "image_bgsubtract: a quadratic surface needs >= 3x3 pixels");
+    SQ_CUDA(cudaSetDevice(h->device));
+    SqArena a(ws, ws_bytes);
+    double *part = a.take<double>((size_t)n * PREP_BLOCKS * 6);
+    double *coef = a.take<double>((size_t)n * 8);
+    SQ_REQUIRE(a.ok(), SQ_ENOMEM, "image_bgsubtract: workspace %zu < %zu bytes", ws_bytes, a.off);
+    // Gram matrix of the centred basis: separable power sums over columns and rows
+    BgGram G;
+    G.cu = 0.5 * (wid - 1); G.cv = 0.5 * (hgt - 1);
+    G.su = 0.5 * wid; G.sv = 0.5 * hgt;
+    double px[5] = {0, 0, 0, 0, 0}, py[5] = {0, 0, 0, 0, 0};
+    for (int x = 0; x < wid; ++x) { const double s = (x - G.cu) / G.su; double p = 1.0; for (int e = 0; e < 5; ++e) { px[e] += p; p *= s; } }
+    for (int y = 0; y < hgt; ++y) { const double t = (y - G.cv) / G.sv; double p = 1.0; for (int e = 0; e < 5; ++e) { py[e] += p; p *= t; } }
+    const int es[6] = {0, 1, 0, 2, 1, 0}, et[6] = {0, 0, 1, 0, 1, 2};   // basis i = s^es[i] * t^et[i]
+    for (int i = 0; i < 6; ++i)
+        for (int j = 0; j < 6; ++j) G.g[i * 6 + j] = px[es[i] + es[j]] * py[et[i] + et[j]];
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long total = (long long)n * hgt * wid;
+    bg_partial<<<dim3(PREP_BLOCKS, n), PREP_THREADS, 0, st>>>(in, hgt, wid, G, part);
+    SQ_CHECK_LAUNCH();
+    bg_solve<<<(n + 63) / 64, 64, 0, st>>>(part, G, n, coef);
+    SQ_CHECK_LAUNCH();
+    const unsigned grid = (unsigned)((total + 255) / 256);
+    if (out_dtype == SQ_F32) bg_apply<float><<<grid, 256, 0, st>>>(in, (float *)out, hgt, wid, G, coef, total);
+    else bg_apply<double><<<grid, 256, 0, st>>>(in, (double *)out, hgt, wid, G, coef, total);
+    SQ_CHECK_LAUNCH();
+    return SQ_OK;
+}
+
+// Host-buffer form of the three pipes: which = 0 norm, 1 outliers, 2 background subtract.  `out_host`
+// is float32 (n,h,w,c) except for background subtraction with out_dtype SQ_F64.
+extern "C" int sq_image_pipe_host(sq_handle_t h, int which, const float *in_host, void *out_host, int out_dtype,
+                                  int n, int hgt, int wid, int c, int size, double threshold)
+{
+    SQ_TRY(check_stack(h, n, hgt, wid, c));
+    SQ_REQUIRE(in_host && out_host, SQ_EINVAL, "image_pipe_host: null pointer");
+    SQ_REQUIRE(which >= 0 && which <= 2, SQ_EINVAL, "image_pipe_host: unknown pipe %d", which);
+    SQ_REQUIRE(which != 2 || c == 1, SQ_EINVAL, "image_pipe_host: background subtraction takes one channel");
+    SQ_CUDA(cudaSetDevice(h->device));
+    const size_t count = (size_t)n * hgt * wid * c;
+    const size_t osz = (which == 2 && out_dtype == SQ_F64) ? 8 : 4;
+    size_t ws_bytes = 0;
+    SQ_TRY(sq_prep_workspace_bytes(h, n, c, &ws_bytes));
+    SQ_TRY(sq_reserve_device(h, sq_align_up(count * 4) + sq_align_up(count * osz) + ws_bytes + 1024));
+    SqArena a(h->dev_arena, h->dev_arena_bytes);
+    float *in = a.take<float>(count);
+    char *out = a.take<char>(count * osz);
+    void *ws = a.take<char>(ws_bytes);
+    cudaStream_t st = h->stream;
+    SQ_CUDA(cudaMemcpyAsync(in, in_host, count * 4, cudaMemcpyHostToDevice, st));
+    if (which == 0) SQ_TRY(sq_image_norm(h, in, (float *)out, n, hgt, wid, c, ws, ws_bytes, st));
+    else if (which == 1) SQ_TRY(sq_image_outliers(h, in, (float *)out, n, hgt, wid, c, size, threshold, st));
+    else SQ_TRY(sq_image_bgsubtract(h, in, out, out_dtype, n, hgt, wid, ws, ws_bytes, st));
+    SQ_CUDA(cudaMemcpyAsync(out_host, out, count * osz, cudaMemcpyDeviceToHost, st));
+    SQ_CUDA(cudaStreamSynchronize(st));
+    return SQ_OK;
+}

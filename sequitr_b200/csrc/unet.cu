@@ -538,8 +538,17 @@ extern "C" int sq_segment_localise_host(sq_unet_t u, const float *frames_host, i
     // input) overlaps the UNet of chunk c (compute stream); label-and-localise then runs once
     // over the whole batch of masks and only the small centroid tables travel back.
     const size_t px1 = (size_t)hgt * wid, px = (size_t)n * px1;
+    // Chunk schedule 1, 1, 2, 4, 4, ...: the first copy (the only one nothing can hide) is one frame.
     const int ch = n >= 8 ? 4 : (n >= 2 ? n / 2 : 1);
-    const int nchunks = (n + ch - 1) / ch;
+    std::vector<int> chunk_of;
+    for (int done = 0; done < n;) {
+        int c = ch;
+        if (n >= 8) c = chunk_of.size() < 2 ? 1 : (chunk_of.size() == 2 ? 2 : ch);
+        c = std::min(c, n - done);
+        chunk_of.push_back(c);
+        done += c;
+    }
+    const int nchunks = (int)chunk_of.size();
     size_t unet_ws = 0, lab_ws = 0;
     SQ_TRY(sq_unet_workspace_bytes(u, ch, 1, hgt, wid, &unet_ws));
     SQ_TRY(sq_label_workspace_bytes(h, n, 1, hgt, wid, max_rows, &lab_ws));
@@ -557,9 +566,9 @@ extern "C" int sq_segment_localise_host(sq_unet_t u, const float *frames_host, i
     void *w1 = a.take<char>(unet_ws);
     void *w2 = a.take<char>(lab_ws);
     cudaStream_t st = h->stream, cs = h->copy_stream;
-    for (int c = 0; c < nchunks; ++c) {
+    for (int c = 0, f0 = 0; c < nchunks; f0 += chunk_of[c], ++c) {
         const int b = c & 1;
-        const int f0 = c * ch, nc = (n - f0 < ch) ? n - f0 : ch;
+        const int nc = chunk_of[c];
         float *buf = frames + (size_t)b * ch * px1 * u->cin;
         if (c >= 2) SQ_CUDA(cudaStreamWaitEvent(cs, h->ev_done[b], 0));     // buffer b is free again
         SQ_CUDA(cudaMemcpyAsync(buf, frames_host + (size_t)f0 * px1 * u->cin,

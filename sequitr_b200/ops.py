@@ -129,7 +129,76 @@ def weighted_cross_entropy(logits, labels, weights, want_grad=True, workspace=No
     return loss, grad
 
 
+def _stack_geometry(x):
+    torch = _torch()
+    assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 4
+    return tuple(int(v) for v in x.shape)
+
+
+def image_norm(x, out=None, workspace=None):
+    """ImageNorm on a float32 cuda stack (N,H,W,C): (x - mean) / std per image and channel."""
+    torch = _torch()
+    lib = _lib.load()
+    n, h, w, c = _stack_geometry(x)
+    hd = _lib.handle(x.device.index)
+    need = ctypes.c_size_t()
+    _lib.check(lib.sq_prep_workspace_bytes(hd, n, c, ctypes.byref(need)))
+    ws = (workspace or _ws(('prep', x.device.index))).get(need.value)
+    out = torch.empty_like(x) if out is None else out
+    _lib.check(lib.sq_image_norm(hd, x.data_ptr(), out.data_ptr(), n, h, w, c, ws.data_ptr(), ws.numel(),
+                                 _lib.stream_ptr()))
+    return out
+
+
+def image_outliers(x, size=2, threshold=5.):
+    """ImageOutliers on a float32 cuda stack (N,H,W,C): hot pixels replaced by the local median."""
+    torch = _torch()
+    lib = _lib.load()
+    n, h, w, c = _stack_geometry(x)
+    out = torch.empty_like(x)
+    _lib.check(lib.sq_image_outliers(_lib.handle(x.device.index), x.data_ptr(), out.data_ptr(), n, h, w, c,
+                                     int(size), float(threshold), _lib.stream_ptr()))
+    return out
+
+
+def image_bgsubtract(x, out_dtype='float32', workspace=None):
+    """ImageBGSubtract on a float32 cuda stack (N,H,W,1): minus the least-squares quadratic surface."""
+    torch = _torch()
+    lib = _lib.load()
+    n, h, w, c = _stack_geometry(x)
+    if c != 1:
+        raise ValueError('image_bgsubtract takes single-channel stacks (N,H,W,1)')
+    hd = _lib.handle(x.device.index)
+    need = ctypes.c_size_t()
+    _lib.check(lib.sq_prep_workspace_bytes(hd, n, c, ctypes.byref(need)))
+    ws = (workspace or _ws(('prep', x.device.index))).get(need.value)
+    out = torch.empty(x.shape, dtype=torch.float32 if out_dtype == 'float32' else torch.float64, device=x.device)
+    _lib.check(lib.sq_image_bgsubtract(hd, x.data_ptr(), out.data_ptr(),
+                                       _lib.F32 if out_dtype == 'float32' else _lib.F64, n, h, w,
+                                       ws.data_ptr(), ws.numel(), _lib.stream_ptr()))
+    return out
+
+
 # ------------------------------------------------------------- host-buffer calls
+
+def image_pipe_host(which, image, size=2, threshold=5., out_dtype='float32', device=None):
+    """which in ('norm', 'outliers', 'bgsubtract'); image float32 ndarray (H,W,C) or (N,H,W,C)."""
+    lib = _lib.load()
+    image = np.ascontiguousarray(image, dtype=np.float32)
+    squeeze = image.ndim == 3
+    if squeeze:
+        image = image[None]
+    if image.ndim != 4:
+        raise ValueError('image_pipe_host: (H,W,C) or (N,H,W,C) float32 images')
+    n, h, w, c = image.shape
+    code = {'norm': 0, 'outliers': 1, 'bgsubtract': 2}[which]
+    f64 = (code == 2 and out_dtype == 'float64')
+    out = np.empty(image.shape, dtype=np.float64 if f64 else np.float32)
+    _lib.check(lib.sq_image_pipe_host(_lib.handle(device), code, image.ctypes.data, out.ctypes.data,
+                                      _lib.F64 if f64 else _lib.F32, n, h, w, c, int(size), float(threshold)))
+    return out[0] if squeeze else out
+
+
 
 def label_centroids_host(mask, max_rows=4096, frame0=0, want_labels=False, device=None):
     """mask: uint8 ndarray (N,H,W) / (N,D,H,W).  Returns list of per-frame (n_i,5) float32

@@ -74,6 +74,50 @@ def _binary_plane(image, who):
     return np.ascontiguousarray(m != 0).astype(np.uint8)
 
 
+class ImageOutliers(ImagePipe):
+    """ ImageOutliers (pipeline.py:266-296): remove hot pixels by comparing the raw image with a
+    ``sigma`` x ``sigma`` median-filtered copy; where they differ by more than ``threshold`` the
+    pixel takes the median value.  Runs on the GPU (``sq_image_outliers``), bit-exact with the
+    reference's SciPy path; like the reference it updates ``image`` in place and returns it. """
+
+    def __init__(self, sigma=2, threshold=5.):
+        ImagePipe.__init__(self)
+        self.sigma = sigma
+        self.threshold = threshold
+
+    def pipe(self, image):
+        image[...] = ops.image_pipe_host('outliers', image, size=self.sigma, threshold=self.threshold)
+        return image
+
+
+class ImageNorm(ImagePipe):
+    """ ImageNorm (pipeline.py:338-356): subtract the mean and divide by the standard deviation, per
+    channel.  Runs on the GPU (``sq_image_norm``); in place like the reference. """
+
+    def __init__(self):
+        ImagePipe.__init__(self)
+        self.epsilon = 1e-99
+
+    def pipe(self, image):
+        image[...] = ops.image_pipe_host('norm', image)
+        return image
+
+
+class ImageBGSubtract(ImagePipe):
+    """ ImageBGSubtract (pipeline.py:360-405): estimate the background as a second-order polynomial
+    surface (least squares over every pixel) and subtract it.  Runs on the GPU
+    (``sq_image_bgsubtract``); returns a new (H,W,1) float64 array like the reference. """
+
+    def __init__(self):
+        ImagePipe.__init__(self)
+
+    def pipe(self, image):
+        if image.shape[-1] != 1:
+            # np.ravel(image) against an (H*W)-row design matrix (pipeline.py:398) only works for 1 channel
+            raise ValueError('ImageBGSubtract: single-channel images only')
+        return ops.image_pipe_host('bgsubtract', image, out_dtype='float64')
+
+
 class ImageWeightMap(ImagePipe):
     """ ImageWeightMap (pipeline.py:455-479): exponential decay away from the edges of
     binary objects, w = w0*(1-m)*exp(-d^2/(2 sigma^2)) + m + 1 with d the exact

@@ -1,0 +1,93 @@
+"""Pre-inference pipes on the GPU against the reference's outputs.
+
+ImageOutliers is comparison/selection only -> bit-exact.  ImageNorm: the GPU takes the moments in
+fp64 and rounds them to float32, NumPy sums in float32 pairwise; the two float32 means / stds can
+differ in the last ulp, which moves a normalised value by <= ~1e-6 relative (tolerance 4e-6 + 4e-6 |x|).
+ImageBGSubtract: fp64 fit, |difference| <= 1e-8 on backgrounds ~1e2..1e3.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import prep_oracle as po
+
+pytestmark = pytest.mark.gpu
+
+
+def _golden(golden_dir):
+    return np.load(os.path.join(golden_dir, 'prep_ref.npz'))
+
+
+def _close_norm(got, ref):
+    assert got.dtype == ref.dtype == np.float32 and got.shape == ref.shape
+    np.testing.assert_allclose(got, ref, rtol=4e-6, atol=4e-6)
+
+
+def test_pipes_match_reference_golden(sq, golden_dir):
+    from sequitr_b200 import pipeline
+    g = _golden(golden_dir)
+    for name in [k[3:] for k in g.files if k.startswith('in_')]:
+        img = g['in_' + name]
+        _close_norm(pipeline.ImageNorm()(img.copy()), g['norm_' + name])
+        got = pipeline.ImageOutliers()(img.copy())
+        assert got.dtype == np.float32
+        np.testing.assert_array_equal(got, g['outl2_' + name])
+        np.testing.assert_array_equal(pipeline.ImageOutliers(sigma=3, threshold=2.)(img.copy()), g['outl3_' + name])
+        if 'bg_' + name in g.files:
+            bg = pipeline.ImageBGSubtract()(img.copy())
+            assert bg.dtype == np.float64 and bg.shape == g['bg_' + name].shape
+            np.testing.assert_allclose(bg, g['bg_' + name], rtol=0, atol=1e-8)
+
+
+def test_in_place_semantics_and_pipeline(sq):
+    """ImageNorm / ImageOutliers update the caller's array like the reference; ImageBGSubtract does not."""
+    from sequitr_b200 import pipeline
+    rng = np.random.default_rng(3)
+    img = (rng.standard_normal((48, 40, 1)) * 4 + 20).astype(np.float32)
+    img[5, 5, 0] = 500.
+    keep = img.copy()
+    out = pipeline.ImageOutliers()(img)
+    assert out is img and img[5, 5, 0] != 500.
+    np.testing.assert_array_equal(img, po.image_outliers(keep))
+    out = pipeline.ImageNorm()(img)
+    assert out is img and abs(float(img.mean())) < 1e-5 and abs(float(img.std()) - 1) < 1e-5
+    before = img.copy()
+    bg = pipeline.ImageBGSubtract()(img)
+    assert bg is not img
+    np.testing.assert_array_equal(img, before)
+    with pytest.raises(ValueError):
+        pipeline.ImageBGSubtract()(np.zeros((8, 8, 3), np.float32))
+
+
+@pytest.mark.parametrize('size', [1, 2, 3, 4, 5])
+def test_outliers_every_median_size_and_tiny_images(sq, size):
+    from sequitr_b200 import ops
+    rng = np.random.default_rng(size)
+    for shape in ((1, 1, 1), (2, 3, 1), (5, 4, 2), (37, 53, 3)):
+        img = (rng.standard_normal(shape) * 3).astype(np.float32)
+        got = ops.image_pipe_host('outliers', img, size=size, threshold=1.5)
+        np.testing.assert_array_equal(got, po.image_outliers(img, size, 1.5))
+
+
+def test_full_size_stack_on_device(sq):
+    """BASELINE's frame size, batch of 4, device-resident tensors."""
+    import torch
+    from sequitr_b200 import ops, synth
+    x = synth.frames(4, 2048, 2048, 1, seed=99) * 37.0 + 500.0
+    yy, xx = np.mgrid[0:2048, 0:2048]
+    x[..., 0] += (0.02 * xx + 0.01 * yy + 3e-6 * xx * yy).astype(np.float32)
+    x = x.astype(np.float32)
+    xd = torch.from_numpy(x).cuda()
+    nrm = ops.image_norm(xd).cpu().numpy()
+    for i in range(4):
+        _close_norm(nrm[i], po.image_norm(x[i]))
+    out = ops.image_outliers(xd, 2, 5.).cpu().numpy()
+    np.testing.assert_array_equal(out[1], po.image_outliers(x[1], 2, 5.))
+    bg = ops.image_bgsubtract(xd, out_dtype='float64').cpu().numpy()
+    np.testing.assert_allclose(bg[2], po.image_bgsubtract(x[2]), rtol=0, atol=1e-7)
+    bg32 = ops.image_bgsubtract(xd, out_dtype='float32').cpu().numpy()
+    np.testing.assert_allclose(bg32[2], po.image_bgsubtract(x[2]).astype(np.float32), rtol=0, atol=1e-4)
+    # in-place normalisation (in == out) is allowed
+    ops.image_norm(xd, out=xd)
+    np.testing.assert_array_equal(xd.cpu().numpy(), nrm)
