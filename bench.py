@@ -234,6 +234,23 @@ def main():
     h2d = B * H * W * 4
     d2h = B * max_rows * 5 * 4 + B * 4
 
+    # ---- same call on RAW uint16 camera frames (what dataio.OctopusData.frames_raw delivers): 2 bytes
+    #      per pixel cross PCIe, widening + ImageNorm run on the device (informational, not the headline)
+    raw = torch.empty((CALL_STEPS * B, H, W), dtype=torch.uint16).pin_memory()
+    raw.numpy()[...] = np.clip(frames_np[..., 0] * 400.0 + 3000.0, 0, 65535).astype(np.uint16)
+    raw_np = raw.numpy()
+    for _ in range(2):
+        net.segment_and_localise(raw_np, frame0=lo, max_rows=max_rows, normalise=True)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(Kc):
+        net.segment_and_localise(raw_np, frame0=lo + i * CALL_STEPS * B, max_rows=max_rows, normalise=True)
+    torch.cuda.synchronize()
+    dtr = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(dtr, op=dist.ReduceOp.MAX)
+    e2e_raw = world * B * Ke / float(dtr.item())
+
     # ---- roofline of the dominant (tensor-core) kernel family: per-layer CUDA events on the
     #      stream the kernels run on, same batch as the timed step
     roofline = None
@@ -259,7 +276,7 @@ def main():
         achieved = dense_fl / (dense_ms * 1e-3) / 1e12
         roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                     "frac": achieved / peak, "traffic": None,
-                    "kernel": "conv_tc_kernel<COUT,S,UP,NBUF> (tcgen05 3x3 conv + up-conv, %d launches "
+                    "kernel": "conv_tc_kernel / conv_xc_kernel family (tcgen05 3x3 conv + up-conv, %d launches "
                               "per step)" % (n_dense // reps),
                     "peak_source": which,
                     "avg_launch_ms": dense_ms / n_dense,
@@ -287,6 +304,9 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": Ke, "steps_per_call": CALL_STEPS},
+            "e2e_raw_u16": {"value": e2e_raw, "unit": "frames/s", "h2d_bytes_per_step": B * H * W * 2,
+                            "d2h_bytes_per_step": d2h,
+                            "note": "uint16 host frames, widened + ImageNorm on the device"},
             "gpu_launches": launches_per_step * K,
             "roofline": roofline,
             "cpu_baseline": cpu,

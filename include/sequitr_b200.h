@@ -56,6 +56,8 @@ typedef struct sq_unet_s   *sq_unet_t;
 /* output dtype of the weight maps */
 #define SQ_F32 0
 #define SQ_F64 1
+#define SQ_U8  2   /* raw camera frames (dataio/octopus.py:236: 'uint' + bit depth) */
+#define SQ_U16 3
 
 /* ------------------------------------------------------------------ runtime */
 const char *sq_version(void);
@@ -206,6 +208,18 @@ int sq_weighted_ce(sq_handle_t h, const float *logits_dev, const uint8_t *labels
 int sq_segment_localise_host(sq_unet_t u, const float *frames_host, int n, int hgt, int wid,
                              int frame0, float *table_host, int32_t *counts_host, int max_rows,
                              uint8_t *mask_host);
+
+/* Same path on RAW camera frames as the reference's readers deliver them (dataio/octopus.py:236-247:
+ * uint8 / uint16 memmap, one channel): the frames cross PCIe in their stored type (1 or 2 bytes per
+ * pixel instead of 4), are widened to float32 on the device (exact) and, when normalise != 0, pass
+ * through ImageNorm (sq_image_norm) before the UNet.  in_dtype: SQ_U8, SQ_U16 or SQ_F32. */
+int sq_segment_localise_raw_host(sq_unet_t u, const void *frames_host, int in_dtype, int normalise, int n,
+                                 int hgt, int wid, int frame0, float *table_host, int32_t *counts_host,
+                                 int max_rows, uint8_t *mask_host);
+
+/* Widen a raw stack to float32 on the device: in_dtype SQ_U8 / SQ_U16 (SQ_F32 copies). */
+int sq_image_cast(sq_handle_t h, const void *in_dev, int in_dtype, float *out_dev, long long count,
+                  void *stream);
 
 #ifdef __cplusplus
 }

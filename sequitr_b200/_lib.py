@@ -17,7 +17,7 @@ HEADER_PATH = os.path.join(os.path.dirname(_HERE), 'include', 'sequitr_b200.h')
 SQ_OK, SQ_EINVAL, SQ_ECUDA, SQ_ENOMEM, SQ_EOVERFLOW, SQ_EUNSUPPORTED, SQ_ESTATE = 0, -1, -2, -3, -4, -5, -6
 BRIDGE_CODES = {None: 0, 'eltwise_add': 1, 'eltwise_mul': 2, 'eltwise_sub': 3, 'concat': 4}
 MODE_FP32_EXACT, MODE_BF16_TC = 0, 1
-F32, F64 = 0, 1
+F32, F64, U8, U16 = 0, 1, 2, 3
 
 c_int, c_void_p, c_size_t, c_double, c_char_p = (ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t,
                                                  ctypes.c_double, ctypes.c_char_p)
@@ -67,6 +67,9 @@ _SIGNATURES = {
                                     c_size_t, c_void_p]),
     'sq_image_pipe_host': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                    c_int, c_double]),
+    'sq_segment_localise_raw_host': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
+                                             c_void_p, c_int, c_void_p]),
+    'sq_image_cast': (c_int, [c_void_p, c_void_p, c_int, c_void_p, ctypes.c_longlong, c_void_p]),
     'sq_segment_localise_host': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
                                          c_void_p, c_int, c_void_p]),
 }

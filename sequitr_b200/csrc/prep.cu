@@ -222,6 +222,13 @@ __global__ void bg_apply(const float *__restrict__ in, OutT *__restrict__ out, i
     out[i] = (OutT)((double)in[i] - bg);
 }
 
+template <typename T>
+__global__ void cast_kernel(const T *__restrict__ in, float *__restrict__ out, long long count)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) out[i] = (float)in[i];
+}
+
 int check_stack(sq_handle_t h, int n, int hgt, int wid, int c)
 {
     SQ_REQUIRE(h, SQ_EINVAL, "null handle");
@@ -231,6 +238,22 @@ int check_stack(sq_handle_t h, int n, int hgt, int wid, int c)
 }
 
 }  // namespace
+
+extern "C" int sq_image_cast(sq_handle_t h, const void *in, int in_dtype, float *out, long long count,
+                             void *stream)
+{
+    SQ_REQUIRE(h && in && out && count >= 0, SQ_EINVAL, "image_cast: bad arguments");
+    SQ_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned grid = (unsigned)((count + 255) / 256);
+    if (count == 0) return SQ_OK;
+    if (in_dtype == SQ_U8) cast_kernel<uint8_t><<<grid, 256, 0, st>>>((const uint8_t *)in, out, count);
+    else if (in_dtype == SQ_U16) cast_kernel<uint16_t><<<grid, 256, 0, st>>>((const uint16_t *)in, out, count);
+    else if (in_dtype == SQ_F32) SQ_CUDA(cudaMemcpyAsync(out, in, (size_t)count * 4, cudaMemcpyDeviceToDevice, st));
+    else SQ_REQUIRE(false, SQ_EINVAL, "image_cast: in_dtype must be SQ_U8, SQ_U16 or SQ_F32");
+    SQ_CHECK_LAUNCH();
+    return SQ_OK;
+}
 
 extern "C" int sq_prep_workspace_bytes(sq_handle_t h, int n, int c, size_t *bytes)
 {

@@ -525,19 +525,23 @@ extern "C" int sq_unet_profile(sq_unet_t u, const float *in, int n, int d, int h
     return SQ_OK;
 }
 
-extern "C" int sq_segment_localise_host(sq_unet_t u, const float *frames_host, int n, int hgt,
-                                        int wid, int frame0, float *table_host,
-                                        int32_t *counts_host, int max_rows, uint8_t *mask_host)
+extern "C" int sq_segment_localise_raw_host(sq_unet_t u, const void *frames_host, int in_dtype, int normalise,
+                                            int n, int hgt, int wid, int frame0, float *table_host,
+                                            int32_t *counts_host, int max_rows, uint8_t *mask_host)
 {
     SQ_TRY(check_geometry(u, n, 1, hgt, wid));
     SQ_REQUIRE(u->ndim == 2, SQ_EUNSUPPORTED, "segment_localise_host: planar stacks only");
     SQ_REQUIRE(frames_host && table_host && counts_host, SQ_EINVAL, "segment_localise_host: null pointer");
+    SQ_REQUIRE(in_dtype == SQ_F32 || in_dtype == SQ_U8 || in_dtype == SQ_U16, SQ_EINVAL,
+               "segment_localise_host: in_dtype must be SQ_F32, SQ_U8 or SQ_U16");
     sq_handle_s *h = u->h;
     SQ_CUDA(cudaSetDevice(h->device));
     // Frames stream through in chunks: the H2D copy of chunk c+1 (copy stream, double-buffered
     // input) overlaps the UNet of chunk c (compute stream); label-and-localise then runs once
     // over the whole batch of masks and only the small centroid tables travel back.
     const size_t px1 = (size_t)hgt * wid, px = (size_t)n * px1;
+    const size_t esz = in_dtype == SQ_U8 ? 1 : (in_dtype == SQ_U16 ? 2 : 4);
+    const bool staged = in_dtype != SQ_F32 || normalise;      // raw chunk -> float32 chunk on the device
     // Chunk schedule 1, 1, 2, 4, 4, ...: the first copy (the only one nothing can hide) is one frame.
     const int ch = n >= 8 ? 4 : (n >= 2 ? n / 2 : 1);
     std::vector<int> chunk_of;
@@ -549,33 +553,47 @@ extern "C" int sq_segment_localise_host(sq_unet_t u, const float *frames_host, i
         done += c;
     }
     const int nchunks = (int)chunk_of.size();
-    size_t unet_ws = 0, lab_ws = 0;
+    size_t unet_ws = 0, lab_ws = 0, prep_ws = 0;
     SQ_TRY(sq_unet_workspace_bytes(u, ch, 1, hgt, wid, &unet_ws));
     SQ_TRY(sq_label_workspace_bytes(h, n, 1, hgt, wid, max_rows, &lab_ws));
+    SQ_TRY(sq_prep_workspace_bytes(h, ch, u->cin, &prep_ws));
+    const size_t chunk_elems = (size_t)ch * px1 * u->cin;
     SqArena probe(nullptr, 0);
-    probe.take<float>(2 * ch * px1 * u->cin);
+    probe.take<char>(2 * chunk_elems * esz);
+    if (staged) probe.take<float>(chunk_elems);
     probe.take<uint8_t>(px);
     probe.take<float>((size_t)n * max_rows * 5);
     probe.take<int32_t>(n);
-    SQ_TRY(sq_reserve_device(h, probe.off + sq_align_up(unet_ws) + sq_align_up(lab_ws) + 1024));
+    SQ_TRY(sq_reserve_device(h, probe.off + sq_align_up(unet_ws) + sq_align_up(lab_ws) + sq_align_up(prep_ws) + 1024));
     SqArena a(h->dev_arena, h->dev_arena_bytes);
-    float *frames = a.take<float>(2 * ch * px1 * u->cin);
+    char *frames = a.take<char>(2 * chunk_elems * esz);
+    float *stage = staged ? a.take<float>(chunk_elems) : nullptr;
     uint8_t *mask = a.take<uint8_t>(px);
     float *table = a.take<float>((size_t)n * max_rows * 5);
     int32_t *counts = a.take<int32_t>(n);
     void *w1 = a.take<char>(unet_ws);
     void *w2 = a.take<char>(lab_ws);
+    void *w3 = a.take<char>(prep_ws);
     cudaStream_t st = h->stream, cs = h->copy_stream;
     for (int c = 0, f0 = 0; c < nchunks; f0 += chunk_of[c], ++c) {
         const int b = c & 1;
         const int nc = chunk_of[c];
-        float *buf = frames + (size_t)b * ch * px1 * u->cin;
+        const size_t elems = (size_t)nc * px1 * u->cin;
+        char *buf = frames + (size_t)b * chunk_elems * esz;
         if (c >= 2) SQ_CUDA(cudaStreamWaitEvent(cs, h->ev_done[b], 0));     // buffer b is free again
-        SQ_CUDA(cudaMemcpyAsync(buf, frames_host + (size_t)f0 * px1 * u->cin,
-                                (size_t)nc * px1 * u->cin * sizeof(float), cudaMemcpyHostToDevice, cs));
+        SQ_CUDA(cudaMemcpyAsync(buf, (const char *)frames_host + (size_t)f0 * px1 * u->cin * esz, elems * esz,
+                                cudaMemcpyHostToDevice, cs));
         SQ_CUDA(cudaEventRecord(h->ev_h2d[b], cs));
         SQ_CUDA(cudaStreamWaitEvent(st, h->ev_h2d[b], 0));
-        SQ_TRY(sq_unet_forward(u, buf, nc, 1, hgt, wid, nullptr, mask + (size_t)f0 * px1, nullptr, w1,
+        const float *net_in = (const float *)buf;
+        if (staged) {
+            // widen (exact for 8/16-bit integers) and optionally normalise; the raw buffer is free as
+            // soon as the cast has run, the float32 stage is consumed in stream order
+            SQ_TRY(sq_image_cast(h, buf, in_dtype, stage, (long long)elems, st));
+            if (normalise) SQ_TRY(sq_image_norm(h, stage, stage, nc, hgt, wid, u->cin, w3, prep_ws, st));
+            net_in = stage;
+        }
+        SQ_TRY(sq_unet_forward(u, net_in, nc, 1, hgt, wid, nullptr, mask + (size_t)f0 * px1, nullptr, w1,
                                unet_ws, st));
         SQ_CUDA(cudaEventRecord(h->ev_done[b], st));
     }
@@ -591,4 +609,12 @@ extern "C" int sq_segment_localise_host(sq_unet_t u, const float *frames_host, i
                    "segment_localise: frame %d has %d components > max_rows=%d", frame0 + i,
                    counts_host[i], max_rows);
     return SQ_OK;
+}
+
+extern "C" int sq_segment_localise_host(sq_unet_t u, const float *frames_host, int n, int hgt,
+                                        int wid, int frame0, float *table_host,
+                                        int32_t *counts_host, int max_rows, uint8_t *mask_host)
+{
+    return sq_segment_localise_raw_host(u, frames_host, SQ_F32, 0, n, hgt, wid, frame0, table_host, counts_host,
+                                        max_rows, mask_host);
 }

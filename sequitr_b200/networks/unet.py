@@ -393,21 +393,32 @@ class UNet(object):
         """uint8 class mask (N,[D,]H,W)."""
         return self.predict(features, want=('mask',))['mask']
 
-    def segment_and_localise(self, frames, frame0=0, max_rows=4096, return_mask=False):
+    def segment_and_localise(self, frames, frame0=0, max_rows=4096, return_mask=False, normalise=False):
         """The whole hot path on HOST frames (2-D): H2D -> UNet -> argmax -> label-and-
-        localise -> D2H.  frames float32 (N,H,W,Cin).  Returns the list of per-frame
-        (n_i,5) float32 centroid tables (rows as utils.CentroidWriter writes them)."""
+        localise -> D2H.  frames float32 (N,H,W,Cin), or RAW uint8 / uint16 camera frames as the
+        readers in ``dataio`` deliver them (they then cross PCIe in 1-2 bytes per pixel and are
+        widened on the device).  ``normalise`` applies ImageNorm per frame on the device first.
+        Returns the list of per-frame (n_i,5) float32 centroid tables (rows as
+        utils.CentroidWriter writes them)."""
         plan = self._ensure_plan()
         lib = _lib.load()
-        frames = np.ascontiguousarray(self._as_input(np.asarray(frames)), dtype=np.float32)
+        frames = np.asarray(frames)
+        if frames.dtype == np.uint8:
+            code = _lib.U8
+        elif frames.dtype == np.uint16:
+            code = _lib.U16
+        else:
+            code = _lib.F32
+            frames = frames.astype(np.float32, copy=False)
+        frames = np.ascontiguousarray(self._as_input(frames))
         n, h, w = frames.shape[:3]
         mask = np.empty((n, h, w), dtype=np.uint8) if return_mask else None
         while True:
             table = np.empty((n, max_rows, 5), dtype=np.float32)
             counts = np.empty((n,), dtype=np.int32)
-            st = lib.sq_segment_localise_host(plan, frames.ctypes.data, n, h, w, frame0,
-                                              table.ctypes.data, counts.ctypes.data, max_rows,
-                                              _lib.ptr(mask))
+            st = lib.sq_segment_localise_raw_host(plan, frames.ctypes.data, code, int(bool(normalise)), n, h, w,
+                                                  frame0, table.ctypes.data, counts.ctypes.data, max_rows,
+                                                  _lib.ptr(mask))
             if st == _lib.SQ_EOVERFLOW:
                 max_rows = int(counts.max())
                 continue

@@ -91,3 +91,40 @@ def test_full_size_stack_on_device(sq):
     # in-place normalisation (in == out) is allowed
     ops.image_norm(xd, out=xd)
     np.testing.assert_array_equal(xd.cpu().numpy(), nrm)
+
+
+def test_raw_camera_frames_through_the_hot_path(sq, tmp_path):
+    """uint16 / uint8 frames (dataio.OctopusData.frames_raw) cross PCIe as stored and are widened -- and
+    optionally normalised -- on the device: identical tables and masks to the float32 route."""
+    import torch
+    from sequitr_b200 import ops, synth
+    from sequitr_b200.dataio import OctopusData, write_octopus_stream
+    from sequitr_b200.networks import UNet2D
+    filters = (16, 32, 64)
+    net = UNet2D({'filters': filters, 'shape': (96, 128), 'bridge': 'concat', 'compute': 'bf16'})
+    net.load_weights(synth.blob_detector_weights(filters, 1, 2, seed=1))
+    x = synth.frames(10, 96, 128, 1, seed=3, n_objects=5)[..., 0]
+    raw = np.clip(x * 400.0 + 3000.0, 0, 65535).astype(np.uint16)
+    stem = str(tmp_path / 'BF_pos0_')
+    write_octopus_stream(stem, raw, frames_per_file=4)
+    batch = OctopusData(stem).frames_raw(0, 10)
+    np.testing.assert_array_equal(batch, raw)
+    # no normalisation: same as handing the float32 copy of the integers
+    t_raw, m_raw = net.segment_and_localise(batch, return_mask=True)
+    t_f32, m_f32 = net.segment_and_localise(batch.astype(np.float32), return_mask=True)
+    np.testing.assert_array_equal(m_raw, m_f32)
+    for a, b in zip(t_raw, t_f32):
+        np.testing.assert_array_equal(a, b)
+    # with ImageNorm on the device == image_norm then the float route (same kernels, same bits)
+    t_n, m_n = net.segment_and_localise(batch, return_mask=True, normalise=True)
+    xn = ops.image_norm(torch.from_numpy(batch.astype(np.float32)[..., None]).cuda()).cpu().numpy()
+    t_ref, m_ref = net.segment_and_localise(xn, return_mask=True)
+    np.testing.assert_array_equal(m_n, m_ref)
+    for a, b in zip(t_n, t_ref):
+        np.testing.assert_array_equal(a, b)
+    assert sum(len(t) for t in t_n) >= 10                  # the discs are found on normalised frames
+    # 8-bit stream
+    raw8 = (raw >> 6).astype(np.uint8)
+    t8, m8 = net.segment_and_localise(raw8, return_mask=True, normalise=True)
+    x8 = ops.image_norm(torch.from_numpy(raw8.astype(np.float32)[..., None]).cuda()).cpu().numpy()
+    np.testing.assert_array_equal(m8, net.segment_and_localise(x8, return_mask=True)[1])

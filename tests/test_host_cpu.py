@@ -173,3 +173,35 @@ def test_synthetic_generators_are_seeded():
     assert label(lab > 0)[1] == lab.max()          # >= 2 px gaps: binary and instance views agree
     w = synth.blob_detector_weights((8, 16), 1, 2)
     assert set(k.rsplit('/', 1)[0] for k in w) == set(synth.unet_layer_names((8, 16)))
+
+
+def test_octopus_stream_reader(tmp_path):
+    """dataio.OctopusData on a synthetic stream: file ranges, contiguous mode, headers, float frames
+    (reference dataio/octopus.py:171-247) and raw batches across file boundaries."""
+    from sequitr_b200.dataio import OctopusData, write_octopus_stream
+    rng = np.random.default_rng(0)
+    frames = rng.integers(0, 4096, size=(7, 12, 20), dtype=np.uint16)
+    stem = str(tmp_path / 'BF_pos0_')
+    assert write_octopus_stream(stem, frames, frames_per_file=3, extra={'X': np.arange(7) * 0.5}) == 3
+    write_octopus_stream(stem, frames[:2], first_file=5)          # a later, non-contiguous file
+    o = OctopusData(stem)
+    assert len(o) == 7 and o.bit_depth == 16 and o.framesize == (12, 20) and o.filelist == [0, 1, 2]
+    assert o.header_keys[:4] == ['N', 'H', 'W', 'Bit_Depth'] and o.header(0)['X'] == '0.0'
+    for i in (0, 2, 3, 6):
+        assert o[i].dtype == np.float64
+        np.testing.assert_array_equal(o[i], frames[i].astype(float))
+    assert o.info(4)['N'] == 4 and o.info(4)['X'] == '2.0'
+    np.testing.assert_array_equal(o.frames_raw(1, 5), frames[1:6])
+    assert o.frames_raw(5, 10).shape == (2, 12, 20) and o.frames_raw(0, 7).dtype == np.uint16
+    assert len(OctopusData(stem, contiguous=False)) == 9
+    with pytest.raises(IndexError):
+        o[7]
+    with pytest.raises(IOError):
+        OctopusData(str(tmp_path / 'missing_'))
+    write_octopus_stream(stem, frames[:1], first_file=3, age=0)   # still being written: ignored
+    assert o.refresh() is False
+    frames8 = rng.integers(0, 255, size=(2, 6, 6), dtype=np.uint8)
+    write_octopus_stream(str(tmp_path / 'GFP_'), frames8)
+    o8 = OctopusData(str(tmp_path / 'GFP_'))
+    assert o8.bit_depth == 8
+    np.testing.assert_array_equal(o8.to_array(), frames8)
