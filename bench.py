@@ -33,6 +33,24 @@ sys.path.insert(0, ROOT)
 FILTERS = (16, 32, 64, 128, 256)
 H = W = 2048
 FLOP_PER_FRAME = 92000.0 * H * W
+
+
+def dense_layer_bytes(filters=FILTERS, px=H * W, classes_mask_bytes=1):
+    """Algorithmic (compulsory) HBM bytes of the tcgen05 layers per frame, layer by layer: every layer
+    reads its bf16 input(s) once and writes its bf16 output once; the last conv
+    writes only the 1 B/px class mask (fused head).  The first conv (CUDA cores) is not included."""
+    nl, total = len(filters), 0.0
+    for l, f in enumerate(filters):
+        p = px / 4 ** l
+        if l > 0:
+            total += p * 2 * (filters[l - 1] + f)                       # down{l}/conv1
+        total += p * 2 * (f + f) + (p / 4 * 2 * f if l < nl - 1 else 0)    # conv2 (+ pooled copy)
+    for l in range(nl - 2, -1, -1):
+        p, f = px / 4 ** l, filters[l]
+        total += p / 4 * 2 * filters[l + 1] + p * 2 * f                # upscale
+        total += p * 2 * (2 * f + f)                                   # conv1 on concat(up, skip)
+        total += p * 2 * f + (p * 2 * f if l > 0 else p * classes_mask_bytes)
+    return total
 METRIC = "frames/sec 2048^2 UNet2D seg+localize"
 
 
@@ -253,7 +271,7 @@ def main():
 
     # ---- roofline of the dominant (tensor-core) kernel family: per-layer CUDA events on the
     #      stream the kernels run on, same batch as the timed step
-    roofline = None
+    roofline = roofline_hbm = None
     if rank == 0:
         peaks = {}
         try:
@@ -282,6 +300,21 @@ def main():
                     "avg_launch_ms": dense_ms / n_dense,
                     "dense_ms_per_step": dense_ms / reps,
                     "flops_per_step": dense_fl / reps}
+        # The same launches against HBM: layer by layer this net is bandwidth-bound at levels 0-1
+        # (64-128 B moved per pixel for 4.6-37 kFLOP), so the byte roofline is reported next to the
+        # tensor one.  traffic = ncu dram bytes per launch of the same family (profiles/).
+        hbm_peak = peaks.get('hbm_gbs') or 6650.0
+        alg_bytes = dense_layer_bytes() * B
+        try:
+            traffic = json.load(open(os.path.join(ROOT, 'profiles', 'r1_conv_traffic.json')))['avg_dram_bytes_per_launch']
+        except Exception:
+            traffic = None
+        roofline["traffic"] = traffic
+        roofline_hbm = {"bound": "hbm", "achieved": alg_bytes / (dense_ms / reps * 1e-3) / 1e9, "peak": hbm_peak,
+                        "unit": "GB/s", "frac": alg_bytes / (dense_ms / reps * 1e-3) / 1e9 / hbm_peak,
+                        "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes / (n_dense // reps),
+                        "kernel": "same 21 launches, compulsory bf16 activation bytes (each layer reads its "
+                                  "inputs once, writes its output once)"}
 
     # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same workload
     cpu = None
@@ -309,6 +342,7 @@ def main():
                             "note": "uint16 host frames, widened + ImageNorm on the device"},
             "gpu_launches": launches_per_step * K,
             "roofline": roofline,
+            "roofline_hbm": roofline_hbm if roofline else None,
             "cpu_baseline": cpu,
             "tensor_frac_of_frame_flops": value / world * FLOP_PER_FRAME / 1e12 / (roofline or {}).get("peak", 1.0)
             if roofline else None,
