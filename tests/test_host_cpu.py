@@ -205,3 +205,59 @@ def test_octopus_stream_reader(tmp_path):
     o8 = OctopusData(str(tmp_path / 'GFP_'))
     assert o8.bit_depth == 8
     np.testing.assert_array_equal(o8.to_array(), frames8)
+
+
+def test_micromanager_position_reader(tmp_path):
+    """dataio.MicromanagerReader on a synthetic Micro-Manager 2.0 position folder (reference
+    dataio/micromanager.py:30-262) and the baseline TIFF reader it sits on."""
+    from sequitr_b200.dataio import (MicromanagerReader, read_tiff, write_tiff, write_micromanager_position)
+    rng = np.random.default_rng(1)
+    frames = rng.integers(0, 65535, size=(5, 14, 22), dtype=np.uint16)
+    gfp = rng.integers(0, 255, size=(5, 14, 22), dtype=np.uint8)
+    pos = str(tmp_path / 'Pos0')
+    write_micromanager_position(pos, frames, channel_index=0, n_channels=2)
+    write_micromanager_position(pos, gfp, channel_index=1, n_channels=2)
+    r = MicromanagerReader(pos, channel=0)
+    assert len(r) == 5 and r.dtype == np.uint16 and (r.width, r.height) == (22, 14)
+    for i in range(5):
+        np.testing.assert_array_equal(r[i], frames[i])
+    np.testing.assert_array_equal(r.frames_raw(1, 3), frames[1:4])
+    assert r.frames_raw(3, 10).shape == (2, 14, 22)
+    m = r.get_metadata(2)
+    assert m['filename'].endswith('time000000002_z000.tif') and m['x_position'] == 20.0
+    assert abs(m['timestamp'] - r.metadata.start_time - 3.275) < 1e-6
+    assert r.metadata.shape == (5, 1, 22, 14)
+    g = MicromanagerReader(pos, channel=1)
+    assert g.dtype == np.uint8
+    np.testing.assert_array_equal(g[4], gfp[4])
+    assert len(MicromanagerReader(pos)) == 10                      # no channel filter: both channels
+    with pytest.raises(IndexError):
+        r[5]
+    w = rng.standard_normal((9, 7)).astype(np.float32)             # float32 weight maps (weightmap.py:205)
+    write_tiff(str(tmp_path / 'w.tif'), w)
+    np.testing.assert_array_equal(read_tiff(str(tmp_path / 'w.tif')), w)
+    big = struct_be_tiff(tmp_path, frames[0])
+    np.testing.assert_array_equal(read_tiff(big), frames[0])
+
+
+def struct_be_tiff(tmp_path, img):
+    """A big-endian, two-strip TIFF written by hand (the reader must not depend on its own writer)."""
+    import struct
+    h, w = img.shape
+    rows0 = h // 2
+    s0 = img[:rows0].astype('>u2').tobytes()
+    s1 = img[rows0:].astype('>u2').tobytes()
+    off0, off1 = 8, 8 + len(s0)
+    extra = off1 + len(s1)                       # strip offsets / counts arrays live after the pixel data
+    ifd = extra + 16
+    entries = [(256, 3, 1, w << 16), (257, 3, 1, h << 16), (258, 3, 1, 16 << 16), (259, 3, 1, 1 << 16),
+               (273, 4, 2, extra), (277, 3, 1, 1 << 16), (278, 3, 1, rows0 << 16), (279, 4, 2, extra + 8)]
+    path = str(tmp_path / 'be.tif')
+    with open(path, 'wb') as fh:
+        fh.write(b'MM' + struct.pack('>HI', 42, ifd) + s0 + s1)
+        fh.write(struct.pack('>IIII', off0, off1, len(s0), len(s1)))
+        fh.write(struct.pack('>H', len(entries)))
+        for tag, typ, cnt, val in entries:
+            fh.write(struct.pack('>HHII', tag, typ, cnt, val))
+        fh.write(struct.pack('>I', 0))
+    return path
