@@ -8,7 +8,7 @@
 
 namespace {
 
-constexpr int PREP_BLOCKS = 128;          // partial-sum blocks per image
+constexpr int PREP_BLOCKS = 512;          // partial-sum blocks per image (>= 3 per SM even for one frame)
 constexpr int PREP_THREADS = 256;
 
 __device__ __forceinline__ double warp_sum(double v)
@@ -48,11 +48,26 @@ norm_partial(const float *__restrict__ in, long long npix, int C, double *__rest
     const int n = blockIdx.y, c = blockIdx.z;
     const float *img = in + (size_t)n * npix * C + c;
     double v[2] = {0.0, 0.0};
-    for (long long p = (long long)blockIdx.x * PREP_THREADS + threadIdx.x; p < npix;
-         p += (long long)PREP_BLOCKS * PREP_THREADS) {
-        const double x = (double)__ldg(img + p * C);
-        v[0] += x;
-        v[1] = fma(x, x, v[1]);
+    if (C == 1 && (npix & 3) == 0) {
+        // single channel: 16-byte loads, four independent accumulators per moment
+        const float4 *img4 = reinterpret_cast<const float4 *>(img);
+        double s0 = 0, s1 = 0, s2 = 0, s3 = 0, q0 = 0, q1 = 0, q2 = 0, q3 = 0;
+        for (long long p = (long long)blockIdx.x * PREP_THREADS + threadIdx.x; p < (npix >> 2);
+             p += (long long)PREP_BLOCKS * PREP_THREADS) {
+            const float4 f = __ldg(img4 + p);
+            const double a = f.x, b = f.y, cc = f.z, d = f.w;
+            s0 += a; s1 += b; s2 += cc; s3 += d;
+            q0 = fma(a, a, q0); q1 = fma(b, b, q1); q2 = fma(cc, cc, q2); q3 = fma(d, d, q3);
+        }
+        v[0] = (s0 + s1) + (s2 + s3);
+        v[1] = (q0 + q1) + (q2 + q3);
+    } else {
+        for (long long p = (long long)blockIdx.x * PREP_THREADS + threadIdx.x; p < npix;
+             p += (long long)PREP_BLOCKS * PREP_THREADS) {
+            const double x = (double)__ldg(img + p * C);
+            v[0] += x;
+            v[1] = fma(x, x, v[1]);
+        }
     }
     block_sum<2>(v, sm);
     if (threadIdx.x == 0) {
@@ -65,10 +80,14 @@ norm_partial(const float *__restrict__ in, long long npix, int C, double *__rest
 // pass 2: mean / std -> float32 (the dtype numpy's float32 reductions return, pipeline.py:353-355)
 __global__ void norm_final(const double *__restrict__ part, long long npix, int nc, float2 *__restrict__ stats)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    // one warp per (image, channel); fixed summation order -> deterministic
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (i >= nc) return;
     double s = 0.0, q = 0.0;
-    for (int b = 0; b < PREP_BLOCKS; ++b) { s += part[((size_t)i * PREP_BLOCKS + b) * 2]; q += part[((size_t)i * PREP_BLOCKS + b) * 2 + 1]; }
+    for (int b = lane; b < PREP_BLOCKS; b += 32) { s += part[((size_t)i * PREP_BLOCKS + b) * 2]; q += part[((size_t)i * PREP_BLOCKS + b) * 2 + 1]; }
+    s = warp_sum(s);
+    q = warp_sum(q);
+    if (lane != 0) return;
     const double mean = s / (double)npix;
     double var = q / (double)npix - mean * mean;
     if (var < 0.0) var = 0.0;
@@ -77,15 +96,31 @@ __global__ void norm_final(const double *__restrict__ part, long long npix, int 
 
 // pass 3: float32 arithmetic exactly as numpy does it on a float32 image (epsilon 1e-99 vanishes in
 // float32, pipeline.py:350,354-355: a constant image divides by zero there too)
-__global__ void norm_apply(const float *__restrict__ in, float *__restrict__ out, long long npix, int C,
-                           const float2 *__restrict__ stats, long long total)
+__global__ void norm_apply(const float *__restrict__ in, float *__restrict__ out, long long per_image, int C,
+                           const float2 *__restrict__ stats)
 {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    const long long n = i / (npix * C);
-    const int c = (int)(i % C);
-    const float2 st = stats[n * C + c];
-    out[i] = __fdiv_rn(__fsub_rn(in[i], st.x), st.y);
+    // grid (chunks, n): per_image = pixels * C values of image blockIdx.y
+    const int n = blockIdx.y;
+    const float *src = in + (size_t)n * per_image;
+    float *dst = out + (size_t)n * per_image;
+    if (C == 1 && (per_image & 3) == 0) {
+        const float2 st = stats[n];
+        const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+        if (i >= (per_image >> 2)) return;
+        float4 f = reinterpret_cast<const float4 *>(src)[i];
+        f.x = __fdiv_rn(__fsub_rn(f.x, st.x), st.y);
+        f.y = __fdiv_rn(__fsub_rn(f.y, st.x), st.y);
+        f.z = __fdiv_rn(__fsub_rn(f.z, st.x), st.y);
+        f.w = __fdiv_rn(__fsub_rn(f.w, st.x), st.y);
+        reinterpret_cast<float4 *>(dst)[i] = f;
+    } else {
+        for (int k = 0; k < 4; ++k) {
+            const long long i = ((long long)blockIdx.x * 4 + k) * blockDim.x + threadIdx.x;
+            if (i >= per_image) return;
+            const float2 st = stats[n * C + (int)(i % C)];
+            dst[i] = __fdiv_rn(__fsub_rn(src[i], st.x), st.y);
+        }
+    }
 }
 
 // -------------------------------------------------------------- ImageOutliers
@@ -99,17 +134,14 @@ __device__ __forceinline__ int reflect_idx(int i, int n)
 }
 
 template <int K>
-__global__ void outliers_kernel(const float *__restrict__ in, float *__restrict__ out, int H, int W, int C,
-                                float threshold, long long total)
+__global__ void __launch_bounds__(256)
+outliers_kernel(const float *__restrict__ in, float *__restrict__ out, int H, int W, int C, float threshold)
 {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    const int c = (int)(i % C);
-    long long r = i / C;
-    const int x = (int)(r % W);
-    r /= W;
-    const int y = (int)(r % H);
-    const long long n = r / H;
+    // grid (ceil(W*C/256), H, n): one thread per (pixel, channel) of a row
+    const int xc = blockIdx.x * 256 + threadIdx.x;
+    if (xc >= W * C) return;
+    const int y = blockIdx.y, n = blockIdx.z;
+    const int x = xc / C, c = xc - x * C;
     const float *img = in + (size_t)n * H * W * C + c;
     float v[K * K];
 #pragma unroll
@@ -132,8 +164,36 @@ __global__ void outliers_kernel(const float *__restrict__ in, float *__restrict_
             v[b] = hi;
         }
     }
+    const size_t i = ((size_t)n * H + y) * W * C + xc;
     const float med = v[RANK], raw = in[i];
     out[i] = (fabsf(__fsub_rn(raw, med)) > threshold) ? med : raw;
+}
+
+// Single-channel 2x2 fast path (the reference's default sigma = 2): one thread = 4 consecutive pixels,
+// 16-byte loads of rows y-1 and y plus the left neighbours; rank 2 of 4 = second largest.
+__global__ void __launch_bounds__(256)
+outliers2_c1_kernel(const float *__restrict__ in, float *__restrict__ out, int H, int W, float threshold)
+{
+    const int x4 = (blockIdx.x * 256 + threadIdx.x) * 4;
+    if (x4 >= W) return;
+    const int y = blockIdx.y, n = blockIdx.z;
+    const float *r1 = in + ((size_t)n * H + y) * W;                      // row y
+    const float *r0 = in + ((size_t)n * H + (y > 0 ? y - 1 : 0)) * W;    // row y-1 (reflect: -1 -> 0)
+    const float4 a = __ldg(reinterpret_cast<const float4 *>(r0 + x4));
+    const float4 b = __ldg(reinterpret_cast<const float4 *>(r1 + x4));
+    const int xl = x4 > 0 ? x4 - 1 : 0;                                  // column x-1 (reflect)
+    const float top[5] = {__ldg(r0 + xl), a.x, a.y, a.z, a.w};
+    const float bot[5] = {__ldg(r1 + xl), b.x, b.y, b.z, b.w};
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float M1 = fmaxf(top[j], top[j + 1]), m1 = fminf(top[j], top[j + 1]);
+        const float M2 = fmaxf(bot[j], bot[j + 1]), m2 = fminf(bot[j], bot[j + 1]);
+        const float med = fmaxf(fminf(M1, M2), fmaxf(m1, m2));
+        const float raw = bot[j + 1];
+        o[j] = (fabsf(__fsub_rn(raw, med)) > threshold) ? med : raw;
+    }
+    *reinterpret_cast<float4 *>(out + ((size_t)n * H + y) * W + x4) = make_float4(o[0], o[1], o[2], o[3]);
 }
 
 // ------------------------------------------------------------ ImageBGSubtract
@@ -151,22 +211,47 @@ __device__ __forceinline__ void bg_basis(double s, double t, double *b)
     b[0] = 1.0; b[1] = s; b[2] = t; b[3] = s * s; b[4] = s * t; b[5] = t * t;
 }
 
+// Each block sums whole rows: per row r0 = sum I, r1 = sum I s, r2 = sum I s^2 (3 FMAs per pixel), then
+// the six moments pick up the row's t powers once per row.
 __global__ void __launch_bounds__(PREP_THREADS)
 bg_partial(const float *__restrict__ in, int H, int W, BgGram G, double *__restrict__ part)
 {
     __shared__ double sm[PREP_THREADS / 32 * 6];
     const int n = blockIdx.y;
     const float *img = in + (size_t)n * H * W;
-    const long long npix = (long long)H * W;
+    const double isu = 1.0 / G.su, isv = 1.0 / G.sv;
     double v[6] = {0, 0, 0, 0, 0, 0};
-    for (long long p = (long long)blockIdx.x * PREP_THREADS + threadIdx.x; p < npix;
-         p += (long long)PREP_BLOCKS * PREP_THREADS) {
-        const int x = (int)(p % W), y = (int)(p / W);
-        const double I = (double)__ldg(img + p);
-        double b[6];
-        bg_basis(((double)x - G.cu) / G.su, ((double)y - G.cv) / G.sv, b);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // one warp per row, rows strided over all warps of the image
+    for (int y = blockIdx.x * (PREP_THREADS / 32) + warp; y < H; y += PREP_BLOCKS * (PREP_THREADS / 32)) {
+        const float *row = img + (size_t)y * W;
+        double r0 = 0.0, r1 = 0.0, r2 = 0.0;
+        if ((W & 3) == 0 && ((uintptr_t)img & 15) == 0) {
+            for (int x = lane * 4; x < W; x += 128) {
+                const float4 f = __ldg(reinterpret_cast<const float4 *>(row + x));
+                const float fv[4] = {f.x, f.y, f.z, f.w};
 #pragma unroll
-        for (int k = 0; k < 6; ++k) v[k] = fma(b[k], I, v[k]);
+                for (int j = 0; j < 4; ++j) {
+                    const double I = (double)fv[j];
+                    const double s = ((double)(x + j) - G.cu) * isu;
+                    const double Is = I * s;
+                    r0 += I;
+                    r1 += Is;
+                    r2 = fma(Is, s, r2);
+                }
+            }
+        } else
+        for (int x = lane; x < W; x += 32) {
+            const double I = (double)__ldg(row + x);
+            const double s = ((double)x - G.cu) * isu;
+            const double Is = I * s;
+            r0 += I;
+            r1 += Is;
+            r2 = fma(Is, s, r2);
+        }
+        const double t = ((double)y - G.cv) * isv;
+        v[0] += r0; v[1] += r1; v[3] += r2;
+        v[2] = fma(t, r0, v[2]); v[4] = fma(t, r1, v[4]); v[5] = fma(t * t, r0, v[5]);
     }
     block_sum<6>(v, sm);
     if (threadIdx.x == 0)
@@ -177,14 +262,19 @@ bg_partial(const float *__restrict__ in, int H, int W, BgGram G, double *__restr
 // with partial pivoting, fp64)
 __global__ void bg_solve(const double *__restrict__ part, BgGram G, int nimg, double *__restrict__ coef)
 {
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= nimg) return;
+    // one block of 6 warps per image: warp i reduces moment i, thread 0 solves
+    __shared__ double rhs[6];
+    const int n = blockIdx.x, i = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double s = 0.0;
+    for (int b = lane; b < PREP_BLOCKS; b += 32) s += part[((size_t)n * PREP_BLOCKS + b) * 6 + i];
+    s = warp_sum(s);
+    if (lane == 0) rhs[i] = s;
+    __syncthreads();
+    if (threadIdx.x != 0) return;
     double a[6][7];
-    for (int i = 0; i < 6; ++i) {
-        for (int j = 0; j < 6; ++j) a[i][j] = G.g[i * 6 + j];
-        double s = 0.0;
-        for (int b = 0; b < PREP_BLOCKS; ++b) s += part[((size_t)n * PREP_BLOCKS + b) * 6 + i];
-        a[i][6] = s;
+    for (int r = 0; r < 6; ++r) {
+        for (int j = 0; j < 6; ++j) a[r][j] = G.g[r * 6 + j];
+        a[r][6] = rhs[r];
     }
     for (int c = 0; c < 6; ++c) {
         int piv = c;
@@ -206,20 +296,35 @@ __global__ void bg_solve(const double *__restrict__ part, BgGram G, int nimg, do
 }
 
 template <typename OutT>
-__global__ void bg_apply(const float *__restrict__ in, OutT *__restrict__ out, int H, int W, BgGram G,
-                         const double *__restrict__ coef, long long total)
+__global__ void __launch_bounds__(256)
+bg_apply(const float *__restrict__ in, OutT *__restrict__ out, int H, int W, BgGram G,
+         const double *__restrict__ coef)
 {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    const int x = (int)(i % W), y = (int)((i / W) % H);
-    const long long n = i / ((long long)W * H);
-    const double *k = coef + n * 6;
-    double b[6];
-    bg_basis(((double)x - G.cu) / G.su, ((double)y - G.cv) / G.sv, b);
-    double bg = 0.0;
+    // grid (ceil(W/1024), H, n), 4 consecutive pixels per thread:
+    // bg = (k0 + k2 t + k5 t^2) + s (k1 + k4 t + k3 s)
+    const int x0 = (blockIdx.x * 256 + threadIdx.x) * 4;
+    if (x0 >= W) return;
+    const int y = blockIdx.y, n = blockIdx.z;
+    const double *k = coef + (size_t)n * 6;
+    const double t = ((double)y - G.cv) * (1.0 / G.sv), isu = 1.0 / G.su;
+    const double a = fma(t, fma(t, k[5], k[2]), k[0]), b = fma(t, k[4], k[1]), c = k[3];
+    const size_t i0 = ((size_t)n * H + y) * W + x0;
+    const bool vec = (W & 3) == 0 && ((uintptr_t)in & 15) == 0;
+    float v[4];
+    if (vec) {
+        const float4 f = *reinterpret_cast<const float4 *>(in + i0);
+        v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+    } else {
+        for (int j = 0; j < 4; ++j) v[j] = (x0 + j < W) ? in[i0 + j] : 0.0f;
+    }
+    OutT o[4];
 #pragma unroll
-    for (int j = 0; j < 6; ++j) bg = fma(k[j], b[j], bg);
-    out[i] = (OutT)((double)in[i] - bg);
+    for (int j = 0; j < 4; ++j) {
+        const double s = ((double)(x0 + j) - G.cu) * isu;
+        o[j] = (OutT)((double)v[j] - fma(s, fma(s, c, b), a));
+    }
+    for (int j = 0; j < 4; ++j)
+        if (x0 + j < W) out[i0 + j] = o[j];
 }
 
 template <typename T>
@@ -280,9 +385,9 @@ extern "C" int sq_image_norm(sq_handle_t h, const float *in, float *out, int n, 
     const long long npix = (long long)hgt * wid, total = npix * c * n;
     norm_partial<<<dim3(PREP_BLOCKS, n, c), PREP_THREADS, 0, st>>>(in, npix, c, part);
     SQ_CHECK_LAUNCH();
-    norm_final<<<(n * c + 127) / 128, 128, 0, st>>>(part, npix, n * c, stats);
+    norm_final<<<(n * c + 3) / 4, 128, 0, st>>>(part, npix, n * c, stats);
     SQ_CHECK_LAUNCH();
-    norm_apply<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in, out, npix, c, stats, total);
+    norm_apply<<<dim3((unsigned)((npix * c + 1023) / 1024), n), 256, 0, st>>>(in, out, npix * c, c, stats);
     SQ_CHECK_LAUNCH();
     return SQ_OK;
 }
@@ -295,15 +400,21 @@ extern "C" int sq_image_outliers(sq_handle_t h, const float *in, float *out, int
     SQ_REQUIRE(size >= 1 && size <= 5, SQ_EUNSUPPORTED, "image_outliers: median size %d not in 1..5", size);
     SQ_CUDA(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
-    const long long total = (long long)n * hgt * wid * c;
-    const unsigned grid = (unsigned)((total + 255) / 256);
+    SQ_REQUIRE(hgt <= 65535 && n <= 65535, SQ_EINVAL, "image_outliers: more than 65535 rows / images");
+    const dim3 grid((unsigned)((wid * c + 255) / 256), (unsigned)hgt, (unsigned)n);
     const float thr = (float)threshold;
+    if (size == 2 && c == 1 && (wid & 3) == 0 && (((uintptr_t)in | (uintptr_t)out) & 15) == 0) {
+        outliers2_c1_kernel<<<dim3((unsigned)((wid / 4 + 255) / 256), (unsigned)hgt, (unsigned)n), 256, 0, st>>>(
+            in, out, hgt, wid, thr);
+        SQ_CHECK_LAUNCH();
+        return SQ_OK;
+    }
     switch (size) {
-    case 1: outliers_kernel<1><<<grid, 256, 0, st>>>(in, out, hgt, wid, c, thr, total); break;
-    case 2: outliers_kernel<2><<<grid, 256, 0, st>>>(in, out, hgt, wid, c, thr, total); break;
-    case 3: outliers_kernel<3><<<grid, 256, 0, st>>>(in, out, hgt, wid, c, thr, total); break;
-    case 4: outliers_kernel<4><<<grid, 256, 0, st>>>(in, out, hgt, wid, c, thr, total); break;
-    default: outliers_kernel<5><<<grid, 256, 0, st>>>(in, out, hgt, wid, c, thr, total); break;
+    case 1: outliers_kernel<1><<<grid, 256, 0, st>>>(in, out, hgt, wid, c, thr); break;
+    case 2: outliers_kernel<2><<<grid, 256, 0, st>>>(in, out, hgt, wid, c, thr); break;
+    case 3: outliers_kernel<3><<<grid, 256, 0, st>>>(in, out, hgt, wid, c, thr); break;
+    case 4: outliers_kernel<4><<<grid, 256, 0, st>>>(in, out, hgt, wid, c, thr); break;
+    default: outliers_kernel<5><<<grid, 256, 0, st>>>(in, out, hgt, wid, c, thr); break;
     }
     SQ_CHECK_LAUNCH();
     return SQ_OK;
@@ -335,11 +446,12 @@ extern "C" int sq_image_bgsubtract(sq_handle_t h, const float *in, void *out, in
     const long long total = (long long)n * hgt * wid;
     bg_partial<<<dim3(PREP_BLOCKS, n), PREP_THREADS, 0, st>>>(in, hgt, wid, G, part);
     SQ_CHECK_LAUNCH();
-    bg_solve<<<(n + 63) / 64, 64, 0, st>>>(part, G, n, coef);
+    bg_solve<<<n, 192, 0, st>>>(part, G, n, coef);
     SQ_CHECK_LAUNCH();
-    const unsigned grid = (unsigned)((total + 255) / 256);
-    if (out_dtype == SQ_F32) bg_apply<float><<<grid, 256, 0, st>>>(in, (float *)out, hgt, wid, G, coef, total);
-    else bg_apply<double><<<grid, 256, 0, st>>>(in, (double *)out, hgt, wid, G, coef, total);
+    SQ_REQUIRE(hgt <= 65535 && n <= 65535, SQ_EINVAL, "image_bgsubtract: more than 65535 rows / images");
+    const dim3 grid((unsigned)((wid + 1023) / 1024), (unsigned)hgt, (unsigned)n);
+    if (out_dtype == SQ_F32) bg_apply<float><<<grid, 256, 0, st>>>(in, (float *)out, hgt, wid, G, coef);
+    else bg_apply<double><<<grid, 256, 0, st>>>(in, (double *)out, hgt, wid, G, coef);
     SQ_CHECK_LAUNCH();
     return SQ_OK;
 }

@@ -168,3 +168,31 @@ def test_both_conv_kernels_cover_every_layer(sq, monkeypatch, xc):
     net = UNet3D({'filters': (16, 32), 'shape': (24, 40, 4), 'bridge': 'concat', 'compute': 'bf16'})
     net.load_weights(w)
     _compare(net.predict(x), unet_c.unet_forward(x, w, (16, 32), 'concat', contract='bf16'), 'SQ_XC=%s 3d' % xc)
+
+
+@pytest.mark.parametrize('name,n,shape,cin,k', [
+    ('C1: 1024^2 x 1ch, 2 classes', 2, (1024, 1024), 1, 2),
+    ('C4: 1600x1200 x 3ch (BF+GFP+RFP), 3 classes', 1, (1600, 1200), 3, 3),
+])
+def test_baseline_config_sizes_against_fp32_exact_mode(sq, name, n, shape, cin, k):
+    """BASELINE configs[0] and configs[3] at their full frame sizes: the CPU oracle is too slow here, so
+    the fp32 exact GPU mode (bit-verified against the oracle at small sizes) stands in for it; the
+    centroid tables from OUR mask must equal SciPy's on the same mask (bit-exact)."""
+    from oracle import centroid_oracle
+    from sequitr_b200.networks import UNet2D
+    filters = (16, 32, 64, 128, 256)
+    w = synth.blob_detector_weights(filters, cin, k, seed=1)
+    x = synth.frames(n, shape[0], shape[1], cin, seed=21)
+    net = _net(filters, shape, 'concat', cin, k, w)
+    a = net.predict(x, want=('probs', 'mask'))
+    net32 = UNet2D({'filters': filters, 'shape': shape, 'bridge': 'concat', 'num_inputs': cin,
+                    'num_outputs': k, 'compute': 'fp32'})
+    net32.load_weights(w)
+    b = net32.predict(x, want=('probs', 'mask'))
+    assert (a['mask'] != b['mask']).mean() < 5e-4, name
+    assert np.abs(a['probs'] - b['probs']).mean() < 2e-3, name
+    tables, mask = net.segment_and_localise(x, return_mask=True)
+    np.testing.assert_array_equal(mask, a['mask'])
+    assert sum(len(t) for t in tables) >= 20, name
+    for t, want in zip(tables, centroid_oracle.centroid_tables(mask)):
+        np.testing.assert_array_equal(t, want)
