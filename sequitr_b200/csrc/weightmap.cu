@@ -322,14 +322,18 @@ __device__ __forceinline__ int next_set(const unsigned *w, int pos, int hi)
     }
 }
 
-// grid (hgt, n), block 256, dyn smem: ceil(wid/32) words.  g8 = row distance if <= R else 255
+// grid (hgt, n), block 256, dyn smem: (ceil(wid/32) + 4) words.  g8 = row distance if <= R else 255.
+// Each pixel builds the 64-bit windows [x-63, x] and [x, x+63] of the row's foreground bit mask (two
+// zero words pad each end) and takes one clz / ffs: O(1), no loops (R <= WR_MAX = 64).
 __global__ void edt_rows_bits(const uint8_t *__restrict__ mask, unsigned char *__restrict__ g8,
                               int *__restrict__ anyfg, int hgt, int wid, int R)
 {
-    extern __shared__ unsigned bits[];
+    extern __shared__ unsigned bits_raw[];
+    unsigned *bits = bits_raw + 2;                       // bits[-2..-1] and bits[nw..nw+1] are zero
     const long long ro = ((long long)blockIdx.y * hgt + blockIdx.x) * wid;
     const uint8_t *mk = mask + ro;
     const int nw = (wid + 31) >> 5;
+    if (threadIdx.x < 2) { bits_raw[threadIdx.x] = 0u; bits[nw + threadIdx.x] = 0u; }
     bool any = false;
     for (int x = threadIdx.x; x < nw * 32; x += blockDim.x) {
         const unsigned b = __ballot_sync(0xffffffffu, x < wid && mk[x] != 0);
@@ -339,12 +343,20 @@ __global__ void edt_rows_bits(const uint8_t *__restrict__ mask, unsigned char *_
     if (any && (threadIdx.x & 31) == 0) anyfg[blockIdx.y] = 1;
     __syncthreads();
     for (int x = threadIdx.x; x < wid; x += blockDim.x) {
-        const int l = prev_set(bits, x, max(x - R, 0));
-        const int r = next_set(bits, x, min(x + R, wid - 1));
-        int d = INF8;
-        if (l >= 0) d = x - l;
-        if (r >= 0) d = min(d, r - x);
-        g8[ro + x] = (unsigned char)d;
+        const int wi = x >> 5, sh = x & 31;
+        const unsigned wm2 = bits[wi - 2], wm1 = bits[wi - 1], w0 = bits[wi], wp1 = bits[wi + 1], wp2 = bits[wi + 2];
+        // left window: bit 63 = pixel x, bit 63-k = pixel x-k
+        const unsigned lhi = __funnelshift_l(wm1, w0, 31 - sh);          // pixels x-31 .. x
+        const unsigned llo = __funnelshift_l(wm2, wm1, 31 - sh);         // pixels x-63 .. x-32
+        const unsigned long long L = ((unsigned long long)lhi << 32) | llo;
+        // right window: bit k = pixel x+k
+        const unsigned rlo = __funnelshift_r(w0, wp1, sh);               // pixels x .. x+31
+        const unsigned rhi = __funnelshift_r(wp1, wp2, sh);              // pixels x+32 .. x+63
+        const unsigned long long Rw = ((unsigned long long)rhi << 32) | rlo;
+        int d = 1 << 20;
+        if (L) d = __clzll((long long)L);
+        if (Rw) d = min(d, __ffsll((long long)Rw) - 1);
+        g8[ro + x] = (unsigned char)(d <= R ? d : INF8);
     }
 }
 
@@ -356,53 +368,96 @@ __global__ void w1_table_kernel(double *__restrict__ table, int n, double w0e, d
     table[i] = w0e * exp(-(d * d) / denom) + 0.0 + 1.0;
 }
 
-// grid (ceil(W/32), ceil(H/64), n), block 256, dyn smem (64 + 2R) * 32 bytes
+// grid (ceil(W/32), ceil(H/64), n), block 256, dyn smem (rows8 + rows8/8) * 32 * 2 bytes with
+// rows8 = 64 + 2R rounded up to 8.  The window is staged as SQUARED row distances (uint16, 0xFFFF =
+// none within R) plus the minimum of every 8-row block, and a pixel scans block by block outwards:
+// a block whose lower bound dy_min^2 + block_min cannot beat the current best is skipped with one
+// load, so a pixel far from every object costs ~2R/8 loads instead of 2R, and one next to an object
+// opens one or two blocks.  Every candidate is a real pixel, so the minimum is exact whenever it is
+// <= R^2; beyond R the weight is exactly 1.
+constexpr unsigned short INF16S = 0xFFFFu;
+
 template <typename OutT>
 __global__ void __launch_bounds__(256)
 edt_cols_tile(const unsigned char *__restrict__ g8, const int *__restrict__ anyfg,
               const double *__restrict__ table, OutT *__restrict__ out, int hgt, int wid, int R,
               double w0e, double denom)
 {
-    extern __shared__ unsigned char gs[];
+    extern __shared__ __align__(16) unsigned short gs2[];
     __shared__ int tile_min;
     const int x0 = blockIdx.x * CT_W, y0 = blockIdx.y * CT_H;
     const long long fo = (long long)blockIdx.z * hgt * wid;
-    const int rows = CT_H + 2 * R;
-    const int col = threadIdx.x & 31, x = x0 + col;
-    if (threadIdx.x == 0) tile_min = INF8;
+    const int rows = CT_H + 2 * R, nblk = (rows + 7) >> 3, rows8 = nblk * 8;
+    unsigned short *bm = gs2 + rows8 * CT_W;             // [nblk][32] block minima
+    const int col = threadIdx.x & 31, x = x0 + col, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) tile_min = 0xFFFF;
     __syncthreads();
-    int mn = INF8;
-    for (int r = threadIdx.x >> 5; r < rows; r += 8) {
+    int mn = 0xFFFF;
+    for (int r = warp; r < rows8; r += 8) {
         const int yy = y0 - R + r;
-        unsigned char v = INF8;
-        if (yy >= 0 && yy < hgt && x < wid) v = g8[fo + (long long)yy * wid + x];
-        gs[r * CT_W + col] = v;
+        unsigned short v = INF16S;
+        if (r < rows && yy >= 0 && yy < hgt && x < wid) {
+            const unsigned g = g8[fo + (long long)yy * wid + x];
+            if (g != INF8) v = (unsigned short)(g * g);
+        }
+        gs2[r * CT_W + col] = v;
         mn = min(mn, (int)v);
     }
-    if (mn < INF8) atomicMin(&tile_min, mn);
+    if (mn < 0xFFFF) atomicMin(&tile_min, mn);
+    __syncthreads();
+    for (int b = warp; b < nblk; b += 8) {
+        unsigned m = INF16S;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) m = min(m, (unsigned)gs2[(b * 8 + k) * CT_W + col]);
+        bm[b * CT_W + col] = (unsigned short)m;
+    }
     __syncthreads();
     const bool none = !anyfg[blockIdx.z];
-    const bool empty = (tile_min == INF8) && !none;     // nothing within reach of this tile
+    const bool empty = (tile_min == 0xFFFF) && !none;    // nothing within reach of this tile
     const unsigned R2 = (unsigned)R * R;
-    for (int ly = threadIdx.x >> 5; ly < CT_H; ly += 8) {
+    for (int ly = warp; ly < CT_H; ly += 8) {
         const int y = y0 + ly;
         if (x >= wid || y >= hgt) continue;
         const long long idx = fo + (long long)y * wid + x;
         if (empty) { out[idx] = (OutT)1.0; continue; }
-        const unsigned char *gc = gs + (ly + R) * CT_W + col;
-        const unsigned g0 = gc[0];
+        const int p = ly + R;                                            // this pixel's window row
+        const unsigned g0 = gs2[p * CT_W + col];
         if (g0 == 0) { out[idx] = (OutT)2.0; continue; }               // foreground (row distance 0)
         unsigned best;
         if (none) {
             best = (unsigned)(y + 1) * (unsigned)(y + 1) + (unsigned)x * (unsigned)x;   // SciPy, no seed
         } else {
-            best = (g0 == INF8) ? INF32 : g0 * g0;
-            for (int dy = 1; dy <= R; ++dy) {
-                const unsigned dy2 = (unsigned)dy * dy;
-                if (dy2 >= best) break;
-                const unsigned gu = gc[-dy * CT_W], gd = gc[dy * CT_W];
-                if (gu != INF8) best = min(best, dy2 + gu * gu);
-                if (gd != INF8) best = min(best, dy2 + gd * gd);
+            best = g0;                                                   // 0xFFFF if nothing in this row
+            const int bo = p >> 3, off = p & 7;
+            // own block
+            if (bm[bo * CT_W + col] < best) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int dy = k - off;
+                    best = min(best, (unsigned)(dy * dy) + gs2[(bo * 8 + k) * CT_W + col]);
+                }
+            }
+            // blocks above / below, nearest first
+            for (int k = 1; k < nblk; ++k) {
+                const int du = off + 8 * k - 7, dd = 8 * k - off;        // nearest row of block bo-k / bo+k
+                const unsigned du2 = (unsigned)(du * du), dd2 = (unsigned)(dd * dd);
+                if ((du2 >= best && dd2 >= best) || (du > R && dd > R)) break;   // rows beyond R cannot matter
+                if (bo - k >= 0 && du2 + bm[(bo - k) * CT_W + col] < best) {
+                    const unsigned short *gr = gs2 + ((bo - k) * 8) * CT_W + col;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int dy = du + 7 - j;                       // row j of the block
+                        best = min(best, (unsigned)(dy * dy) + gr[j * CT_W]);
+                    }
+                }
+                if (bo + k < nblk && dd2 + bm[(bo + k) * CT_W + col] < best) {
+                    const unsigned short *gr = gs2 + ((bo + k) * 8) * CT_W + col;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int dy = dd + j;
+                        best = min(best, (unsigned)(dy * dy) + gr[j * CT_W]);
+                    }
+                }
             }
         }
         double w = 1.0;
@@ -487,7 +542,10 @@ __global__ void inst_rows_bits(const int *__restrict__ labels, int *__restrict__
     }
 }
 
-// grid (ceil(W/32), ceil(H/64), n), block 256, dyn smem (64 + 2R) * 32 * 10 bytes
+// grid (ceil(W/32), ceil(H/64), n), block 256, dyn smem rows8 * 32 * 10 + (rows8/8) * 32 bytes.
+// Same block-by-block scan as edt_cols_tile: the minimum nearest-label distance of every 8-row block
+// bounds BOTH candidates of its rows from below, so a block is opened only if
+// dy_min^2 + block_min^2 < the current second-best squared distance.
 template <typename OutT>
 __global__ void __launch_bounds__(256)
 inst_cols_tile(const int *__restrict__ la, const int *__restrict__ lb,
@@ -496,19 +554,20 @@ inst_cols_tile(const int *__restrict__ la, const int *__restrict__ lb,
                double wc1)
 {
     extern __shared__ __align__(16) unsigned char ws_[];
-    const int rows = CT_H + 2 * R;
+    const int rows = CT_H + 2 * R, nblk = (rows + 7) >> 3, rows8 = nblk * 8;
     int *sla = reinterpret_cast<int *>(ws_);
-    int *slb = sla + rows * CT_W;
-    unsigned char *sda = reinterpret_cast<unsigned char *>(slb + rows * CT_W);
-    unsigned char *sdb = sda + rows * CT_W;
+    int *slb = sla + rows8 * CT_W;
+    unsigned char *sda = reinterpret_cast<unsigned char *>(slb + rows8 * CT_W);
+    unsigned char *sdb = sda + rows8 * CT_W;
+    unsigned char *bm = sdb + rows8 * CT_W;              // [nblk][32] block minima of sda
     const int x0 = blockIdx.x * CT_W, y0 = blockIdx.y * CT_H;
     const long long fo = (long long)blockIdx.z * hgt * wid;
-    const int col = threadIdx.x & 31, x = x0 + col;
-    for (int r = threadIdx.x >> 5; r < rows; r += 8) {
+    const int col = threadIdx.x & 31, x = x0 + col, warp = threadIdx.x >> 5;
+    for (int r = warp; r < rows8; r += 8) {
         const int yy = y0 - R + r;
         int l1 = 0, l2 = 0;
         unsigned char d1 = INF8, d2 = INF8;
-        if (yy >= 0 && yy < hgt && x < wid) {
+        if (r < rows && yy >= 0 && yy < hgt && x < wid) {
             const long long j = fo + (long long)yy * wid + x;
             l1 = la[j]; l2 = lb[j]; d1 = da[j]; d2 = db[j];
         }
@@ -516,28 +575,48 @@ inst_cols_tile(const int *__restrict__ la, const int *__restrict__ lb,
         sda[r * CT_W + col] = d1; sdb[r * CT_W + col] = d2;
     }
     __syncthreads();
+    for (int b = warp; b < nblk; b += 8) {
+        unsigned m = INF8;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) m = min(m, (unsigned)sda[(b * 8 + k) * CT_W + col]);
+        bm[b * CT_W + col] = (unsigned char)m;
+    }
+    __syncthreads();
     const double reach = (double)(R + 1);
-    for (int ly = threadIdx.x >> 5; ly < CT_H; ly += 8) {
+    for (int ly = warp; ly < CT_H; ly += 8) {
         const int y = y0 + ly;
         if (x >= wid || y >= hgt) continue;
         const long long idx = fo + (long long)y * wid + x;
-        const int c0 = (ly + R) * CT_W + col;
-        if (sda[c0] == 0) { out[idx] = (OutT)wc1; continue; }        // foreground: row distance 0
+        const int p = ly + R;
+        if (sda[p * CT_W + col] == 0) { out[idx] = (OutT)wc1; continue; }        // foreground: row distance 0
         Best2 b = {0, 0, INF32, INF32};
-        for (int dy = 0; dy <= R; ++dy) {
-            const unsigned dy2 = (unsigned)dy * dy;
-            if (dy2 >= b.db) break;
+        const int bo = p >> 3, off = p & 7;
+        auto scan_block = [&](int blk, int dy0, int step) {      // rows j = 0..7 at vertical offset dy0 + step*j
 #pragma unroll
-            for (int sgn = -1; sgn <= 1; sgn += 2) {
-                if (dy == 0 && sgn > 0) continue;
-                const int j = c0 + sgn * dy * CT_W;
-                const int l1 = sla[j];
+            for (int j = 0; j < 8; ++j) {
+                const int q = (blk * 8 + j) * CT_W + col;
+                const int l1 = sla[q];
                 if (l1) {
-                    const unsigned d = sda[j];
+                    const int dy = dy0 + step * j;
+                    const unsigned dy2 = (unsigned)(dy * dy), d = sda[q];
                     best2_insert(b, l1, dy2 + d * d);
-                    const int l2 = slb[j];
-                    if (l2) { const unsigned e = sdb[j]; best2_insert(b, l2, dy2 + e * e); }
+                    const int l2 = slb[q];
+                    if (l2) { const unsigned e = sdb[q]; best2_insert(b, l2, dy2 + e * e); }
                 }
+            }
+        };
+        if (bm[bo * CT_W + col] != INF8) scan_block(bo, -off, 1);
+        for (int k = 1; k < nblk; ++k) {
+            const int du = off + 8 * k - 7, dd = 8 * k - off;    // nearest row of block bo-k / bo+k
+            const unsigned du2 = (unsigned)(du * du), dd2 = (unsigned)(dd * dd);
+            if ((du2 >= b.db && dd2 >= b.db) || (du > R && dd > R)) break;       // rows beyond R cannot matter
+            if (bo - k >= 0) {
+                const unsigned m = bm[(bo - k) * CT_W + col];
+                if (m != INF8 && du2 + m * m < b.db) scan_block(bo - k, du + 7, -1);
+            }
+            if (bo + k < nblk) {
+                const unsigned m = bm[(bo + k) * CT_W + col];
+                if (m != INF8 && dd2 + m * m < b.db) scan_block(bo + k, dd, 1);
             }
         }
         double w = wc0;
@@ -617,10 +696,11 @@ extern "C" int sq_weightmap_edt(sq_handle_t h, const uint8_t *mask, int n, int h
     if (!d2 && rmax <= WR_MAX) {
         // bounded path (the common case: R = 32 for w0 = 10, sigma = 5)
         unsigned char *g8 = reinterpret_cast<unsigned char *>(g);
-        edt_rows_bits<<<dim3(hgt, n), 256, (size_t)((wid + 31) / 32) * 4, st>>>(mask, g8, anyfg, hgt, wid, rmax);
+        edt_rows_bits<<<dim3(hgt, n), 256, (size_t)((wid + 31) / 32 + 4) * 4, st>>>(mask, g8, anyfg, hgt, wid, rmax);
         w1_table_kernel<<<sq_div_up(rmax * rmax + 1, 256), 256, 0, st>>>(table, rmax * rmax + 1, w0e, denom);
         const dim3 tgrid(sq_div_up(wid, CT_W), sq_div_up(hgt, CT_H), n);
-        const size_t sm = (size_t)(CT_H + 2 * rmax) * CT_W;
+        const int rows8 = (CT_H + 2 * rmax + 7) / 8 * 8;
+        const size_t sm = (size_t)(rows8 + rows8 / 8) * CT_W * sizeof(unsigned short);
         if (out_dtype == SQ_F32)
             edt_cols_tile<float><<<tgrid, 256, sm, st>>>(g8, anyfg, table, (float *)out, hgt, wid, rmax, w0e, denom);
         else
@@ -665,7 +745,8 @@ extern "C" int sq_weightmap_unet(sq_handle_t h, const int32_t *labels, int n, in
         unsigned char *da8 = reinterpret_cast<unsigned char *>(da), *db8 = reinterpret_cast<unsigned char *>(db);
         inst_rows_bits<<<dim3(hgt, n), 256, (size_t)((wid + 31) / 32) * 8, st>>>(labels, la, lb, da8, db8, hgt, wid, rmax);
         const dim3 tgrid(sq_div_up(wid, CT_W), sq_div_up(hgt, CT_H), n);
-        const size_t sm = (size_t)(CT_H + 2 * rmax) * CT_W * 10;
+        const int rows8 = (CT_H + 2 * rmax + 7) / 8 * 8;
+        const size_t sm = (size_t)rows8 * CT_W * 10 + (size_t)(rows8 / 8) * CT_W;
         if (out_dtype == SQ_F32) {
             auto k = inst_cols_tile<float>;
             if (sm > 48 * 1024) SQ_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
