@@ -595,14 +595,16 @@ inst_cols_tile(const int *__restrict__ la, const int *__restrict__ lb,
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const int q = (blk * 8 + j) * CT_W + col;
-                const int l1 = sla[q];
-                if (l1) {
-                    const int dy = dy0 + step * j;
-                    const unsigned dy2 = (unsigned)(dy * dy), d = sda[q];
-                    best2_insert(b, l1, dy2 + d * d);
-                    const int l2 = slb[q];
-                    if (l2) { const unsigned e = sdb[q]; best2_insert(b, l2, dy2 + e * e); }
-                }
+                const unsigned d = sda[q];
+                if (d == INF8) continue;                       // no label within R in this row
+                const int dy = dy0 + step * j;
+                const unsigned dy2 = (unsigned)(dy * dy), c1 = dy2 + d * d;
+                if (c1 >= b.db) continue;                      // cannot change either of the two best
+                best2_insert(b, sla[q], c1);
+                const unsigned e = sdb[q];
+                if (e == INF8) continue;
+                const unsigned c2 = dy2 + e * e;
+                if (c2 < b.db) best2_insert(b, slb[q], c2);
             }
         };
         if (bm[bo * CT_W + col] != INF8) scan_block(bo, -off, 1);
