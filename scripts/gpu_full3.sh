@@ -10,3 +10,6 @@ timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.json 2> gpu
 echo "bench exit $?"; cat gpurun_out/bench.json; tail -3 gpurun_out/bench.err
 timeout 600 python scripts/bench_configs.py > gpurun_out/configs.log 2>&1; grep -v '^\[' gpurun_out/configs.log
 timeout 600 python scripts/bench_aux.py > gpurun_out/aux.log 2>&1; grep -v '^{' gpurun_out/aux.log
+timeout 600 python scripts/bench_config4.py > gpurun_out/config4.log 2>&1
+echo "c4 exit $?"; grep -v '^{' gpurun_out/config4.log
+timeout 300 python scripts/profile_layers.py > gpurun_out/layers.log 2>&1; cat gpurun_out/layers.log
