@@ -173,6 +173,7 @@ def main():
     from sequitr_b200.networks import UNet2D
 
     torch.cuda.set_device(local)
+    numa_cpus = shard.bind_to_gpu_numa(local) if world > 1 else None     # one worker per GPU, near its GPU
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', rank=rank, world_size=world,
@@ -333,7 +334,8 @@ def main():
                                    "concat bridge, 2 classes (BASELINE configs[2])",
                        "frames_per_step_per_gpu": B, "objects_per_step": n_obj,
                        "l2": "inputs (134 MB/step) and activations (>10 GB/step) exceed the 126 MB L2",
-                       "sharding": "contiguous frame range per rank, no collective"},
+                       "sharding": "contiguous frame range per rank, no collective",
+                       "worker_cpus": len(numa_cpus) if numa_cpus else None},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": Ke, "steps_per_call": CALL_STEPS},

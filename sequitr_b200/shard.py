@@ -17,3 +17,25 @@ def merge_tables(per_rank_tables):
     for tables in per_rank_tables:
         out.extend(tables)
     return out
+
+
+def bind_to_gpu_numa(device_index):
+    """Pin the calling worker process to the CPUs NVML reports as closest to GPU ``device_index`` (one
+    worker per GPU, the reference's model: core.py:41-42), so that the pinned frame buffers it allocates
+    afterwards are first-touched on that GPU's NUMA node and eight workers do not share one socket's
+    memory bandwidth.  Returns the CPU set, or None when NVML / affinity control is unavailable."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * i + b for i, w in enumerate(mask) for b in range(64) if (int(w) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return None
