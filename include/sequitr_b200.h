@@ -182,6 +182,9 @@ int sq_unet_profile(sq_unet_t u, const float *in_dev, int n, int d, int hgt, int
 int sq_prep_workspace_bytes(sq_handle_t h, int n, int c, size_t *bytes);
 int sq_image_norm(sq_handle_t h, const float *in_dev, float *out_dev, int n, int hgt, int wid, int c,
                   void *workspace_dev, size_t workspace_bytes, void *stream);
+/* sq_image_norm on a stack stored as SQ_F32, SQ_U16 or SQ_U8 (raw camera counts are widened on load). */
+int sq_image_norm_raw(sq_handle_t h, const void *in_dev, int in_dtype, float *out_dev, int n, int hgt, int wid,
+                      int c, void *workspace_dev, size_t workspace_bytes, void *stream);
 int sq_image_outliers(sq_handle_t h, const float *in_dev, float *out_dev, int n, int hgt, int wid, int c,
                       int size, double threshold, void *stream);
 int sq_image_bgsubtract(sq_handle_t h, const float *in_dev, void *out_dev, int out_dtype, int n, int hgt,

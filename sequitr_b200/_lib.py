@@ -61,6 +61,8 @@ _SIGNATURES = {
     'sq_prep_workspace_bytes': (c_int, [c_void_p, c_int, c_int, _P(c_size_t)]),
     'sq_image_norm': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_size_t,
                               c_void_p]),
+    'sq_image_norm_raw': (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
+                                  c_size_t, c_void_p]),
     'sq_image_outliers': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_double,
                                   c_void_p]),
     'sq_image_bgsubtract': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,

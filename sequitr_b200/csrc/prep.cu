@@ -39,22 +39,39 @@ __device__ __forceinline__ void block_sum(double (&v)[NV], double *sm)
     }
 }
 
+// four consecutive stored values (float32, or raw uint16 / uint8 camera counts) as floats, one load
+template <typename T> __device__ __forceinline__ float4 load4(const T *p);
+template <> __device__ __forceinline__ float4 load4<float>(const float *p)
+{
+    return __ldg(reinterpret_cast<const float4 *>(p));
+}
+template <> __device__ __forceinline__ float4 load4<uint16_t>(const uint16_t *p)
+{
+    const uint2 u = __ldg(reinterpret_cast<const uint2 *>(p));
+    return make_float4((float)(u.x & 0xffffu), (float)(u.x >> 16), (float)(u.y & 0xffffu), (float)(u.y >> 16));
+}
+template <> __device__ __forceinline__ float4 load4<uint8_t>(const uint8_t *p)
+{
+    const unsigned u = __ldg(reinterpret_cast<const unsigned *>(p));
+    return make_float4((float)(u & 0xffu), (float)((u >> 8) & 0xffu), (float)((u >> 16) & 0xffu), (float)(u >> 24));
+}
+
 // ------------------------------------------------------------------ ImageNorm
 // pass 1: per (image, channel, block) partial sum and sum of squares in fp64
+template <typename T>
 __global__ void __launch_bounds__(PREP_THREADS)
-norm_partial(const float *__restrict__ in, long long npix, int C, double *__restrict__ part)
+norm_partial(const T *__restrict__ in, long long npix, int C, double *__restrict__ part)
 {
     __shared__ double sm[PREP_THREADS / 32 * 2];
     const int n = blockIdx.y, c = blockIdx.z;
-    const float *img = in + (size_t)n * npix * C + c;
+    const T *img = in + (size_t)n * npix * C + c;
     double v[2] = {0.0, 0.0};
     if (C == 1 && (npix & 3) == 0) {
         // single channel: 16-byte loads, four independent accumulators per moment
-        const float4 *img4 = reinterpret_cast<const float4 *>(img);
         double s0 = 0, s1 = 0, s2 = 0, s3 = 0, q0 = 0, q1 = 0, q2 = 0, q3 = 0;
         for (long long p = (long long)blockIdx.x * PREP_THREADS + threadIdx.x; p < (npix >> 2);
              p += (long long)PREP_BLOCKS * PREP_THREADS) {
-            const float4 f = __ldg(img4 + p);
+            const float4 f = load4<T>(img + 4 * p);
             const double a = f.x, b = f.y, cc = f.z, d = f.w;
             s0 += a; s1 += b; s2 += cc; s3 += d;
             q0 = fma(a, a, q0); q1 = fma(b, b, q1); q2 = fma(cc, cc, q2); q3 = fma(d, d, q3);
@@ -64,7 +81,7 @@ norm_partial(const float *__restrict__ in, long long npix, int C, double *__rest
     } else {
         for (long long p = (long long)blockIdx.x * PREP_THREADS + threadIdx.x; p < npix;
              p += (long long)PREP_BLOCKS * PREP_THREADS) {
-            const double x = (double)__ldg(img + p * C);
+            const double x = (double)img[p * C];
             v[0] += x;
             v[1] = fma(x, x, v[1]);
         }
@@ -96,18 +113,19 @@ __global__ void norm_final(const double *__restrict__ part, long long npix, int 
 
 // pass 3: float32 arithmetic exactly as numpy does it on a float32 image (epsilon 1e-99 vanishes in
 // float32, pipeline.py:350,354-355: a constant image divides by zero there too)
-__global__ void norm_apply(const float *__restrict__ in, float *__restrict__ out, long long per_image, int C,
+template <typename T>
+__global__ void norm_apply(const T *__restrict__ in, float *__restrict__ out, long long per_image, int C,
                            const float2 *__restrict__ stats)
 {
     // grid (chunks, n): per_image = pixels * C values of image blockIdx.y
     const int n = blockIdx.y;
-    const float *src = in + (size_t)n * per_image;
+    const T *src = in + (size_t)n * per_image;
     float *dst = out + (size_t)n * per_image;
     if (C == 1 && (per_image & 3) == 0) {
         const float2 st = stats[n];
         const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
         if (i >= (per_image >> 2)) return;
-        float4 f = reinterpret_cast<const float4 *>(src)[i];
+        float4 f = load4<T>(src + 4 * i);
         f.x = __fdiv_rn(__fsub_rn(f.x, st.x), st.y);
         f.y = __fdiv_rn(__fsub_rn(f.y, st.x), st.y);
         f.z = __fdiv_rn(__fsub_rn(f.z, st.x), st.y);
@@ -118,7 +136,7 @@ __global__ void norm_apply(const float *__restrict__ in, float *__restrict__ out
             const long long i = ((long long)blockIdx.x * 4 + k) * blockDim.x + threadIdx.x;
             if (i >= per_image) return;
             const float2 st = stats[n * C + (int)(i % C)];
-            dst[i] = __fdiv_rn(__fsub_rn(src[i], st.x), st.y);
+            dst[i] = __fdiv_rn(__fsub_rn((float)src[i], st.x), st.y);
         }
     }
 }
@@ -330,8 +348,13 @@ bg_apply(const float *__restrict__ in, OutT *__restrict__ out, int H, int W, BgG
 template <typename T>
 __global__ void cast_kernel(const T *__restrict__ in, float *__restrict__ out, long long count)
 {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < count) out[i] = (float)in[i];
+    // 4 values per thread (the caller guarantees 16-byte aligned buffers); scalar tail
+    const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i + 3 < count) {
+        *reinterpret_cast<float4 *>(out + i) = load4<T>(in + i);
+    } else {
+        for (long long j = i; j < count; ++j) out[j] = (float)in[j];
+    }
 }
 
 int check_stack(sq_handle_t h, int n, int hgt, int wid, int c)
@@ -350,7 +373,7 @@ extern "C" int sq_image_cast(sq_handle_t h, const void *in, int in_dtype, float 
     SQ_REQUIRE(h && in && out && count >= 0, SQ_EINVAL, "image_cast: bad arguments");
     SQ_CUDA(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
-    const unsigned grid = (unsigned)((count + 255) / 256);
+    const unsigned grid = (unsigned)((count + 1023) / 1024);
     if (count == 0) return SQ_OK;
     if (in_dtype == SQ_U8) cast_kernel<uint8_t><<<grid, 256, 0, st>>>((const uint8_t *)in, out, count);
     else if (in_dtype == SQ_U16) cast_kernel<uint16_t><<<grid, 256, 0, st>>>((const uint16_t *)in, out, count);
@@ -371,8 +394,20 @@ extern "C" int sq_prep_workspace_bytes(sq_handle_t h, int n, int c, size_t *byte
     return SQ_OK;
 }
 
-extern "C" int sq_image_norm(sq_handle_t h, const float *in, float *out, int n, int hgt, int wid, int c,
-                             void *ws, size_t ws_bytes, void *stream)
+template <typename T>
+int norm_launch(const T *in, float *out, int n, long long npix, int c, double *part, float2 *stats, cudaStream_t st)
+{
+    norm_partial<T><<<dim3(PREP_BLOCKS, n, c), PREP_THREADS, 0, st>>>(in, npix, c, part);
+    SQ_CHECK_LAUNCH();
+    norm_final<<<(n * c + 3) / 4, 128, 0, st>>>(part, npix, n * c, stats);
+    SQ_CHECK_LAUNCH();
+    norm_apply<T><<<dim3((unsigned)((npix * c + 1023) / 1024), n), 256, 0, st>>>(in, out, npix * c, c, stats);
+    SQ_CHECK_LAUNCH();
+    return SQ_OK;
+}
+
+extern "C" int sq_image_norm_raw(sq_handle_t h, const void *in, int in_dtype, float *out, int n, int hgt,
+                                 int wid, int c, void *ws, size_t ws_bytes, void *stream)
 {
     SQ_TRY(check_stack(h, n, hgt, wid, c));
     SQ_REQUIRE(in && out && ws, SQ_EINVAL, "image_norm: null pointer");
@@ -382,14 +417,17 @@ extern "C" int sq_image_norm(sq_handle_t h, const float *in, float *out, int n, 
     float2 *stats = (float2 *)a.take<double>((size_t)n * c * 8);
     SQ_REQUIRE(a.ok(), SQ_ENOMEM, "image_norm: workspace %zu < %zu bytes", ws_bytes, a.off);
     cudaStream_t st = (cudaStream_t)stream;
-    const long long npix = (long long)hgt * wid, total = npix * c * n;
-    norm_partial<<<dim3(PREP_BLOCKS, n, c), PREP_THREADS, 0, st>>>(in, npix, c, part);
-    SQ_CHECK_LAUNCH();
-    norm_final<<<(n * c + 3) / 4, 128, 0, st>>>(part, npix, n * c, stats);
-    SQ_CHECK_LAUNCH();
-    norm_apply<<<dim3((unsigned)((npix * c + 1023) / 1024), n), 256, 0, st>>>(in, out, npix * c, c, stats);
-    SQ_CHECK_LAUNCH();
-    return SQ_OK;
+    const long long npix = (long long)hgt * wid;
+    if (in_dtype == SQ_F32) return norm_launch((const float *)in, out, n, npix, c, part, stats, st);
+    if (in_dtype == SQ_U16) return norm_launch((const uint16_t *)in, out, n, npix, c, part, stats, st);
+    if (in_dtype == SQ_U8) return norm_launch((const uint8_t *)in, out, n, npix, c, part, stats, st);
+    SQ_REQUIRE(false, SQ_EINVAL, "image_norm: in_dtype must be SQ_F32, SQ_U16 or SQ_U8");
+}
+
+extern "C" int sq_image_norm(sq_handle_t h, const float *in, float *out, int n, int hgt, int wid, int c,
+                             void *ws, size_t ws_bytes, void *stream)
+{
+    return sq_image_norm_raw(h, in, SQ_F32, out, n, hgt, wid, c, ws, ws_bytes, stream);
 }
 
 extern "C" int sq_image_outliers(sq_handle_t h, const float *in, float *out, int n, int hgt, int wid, int c,

@@ -589,8 +589,8 @@ extern "C" int sq_segment_localise_raw_host(sq_unet_t u, const void *frames_host
         if (staged) {
             // widen (exact for 8/16-bit integers) and optionally normalise; the raw buffer is free as
             // soon as the cast has run, the float32 stage is consumed in stream order
-            SQ_TRY(sq_image_cast(h, buf, in_dtype, stage, (long long)elems, st));
-            if (normalise) SQ_TRY(sq_image_norm(h, stage, stage, nc, hgt, wid, u->cin, w3, prep_ws, st));
+            if (normalise) SQ_TRY(sq_image_norm_raw(h, buf, in_dtype, stage, nc, hgt, wid, u->cin, w3, prep_ws, st));
+            else SQ_TRY(sq_image_cast(h, buf, in_dtype, stage, (long long)elems, st));
             net_in = stage;
         }
         SQ_TRY(sq_unet_forward(u, net_in, nc, 1, hgt, wid, nullptr, mask + (size_t)f0 * px1, nullptr, w1,
