@@ -123,7 +123,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     }
     if (warp == 1) { tc::tmem_alloc(&tmem_base_sh, TMEM_COLS); tc::tmem_relinquish(); }
     for (int i = threadIdx.x; i < COUT; i += TC_THREADS) { s_scale[i] = scale[i]; s_shift[i] = shift[i]; }
-    if (EPI == EPI_HEAD) {
+    if constexpr (EPI == EPI_HEAD) {
         // global layout is [c][k] (+ bias); keep it transposed so one class is 16 contiguous floats
         for (int i = threadIdx.x; i < COUT * HK; i += TC_THREADS) s_head[(i % HK) * COUT + i / HK] = head.w[i];
         for (int i = threadIdx.x; i < HK; i += TC_THREADS) s_head[COUT * HK + i] = head.w[COUT * HK + i];
@@ -298,7 +298,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                             o[2 * g] = pack_bf16(a, b);
                             o[2 * g + 1] = pack_bf16(c, d);
                         }
-                        if (EPI == EPI_HEAD) {
+                        if constexpr (EPI == EPI_HEAD) {
                             // the head consumes the activation as it would have been stored (bf16)
                             float f[16];
 #pragma unroll
@@ -489,7 +489,7 @@ conv_xc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     }
     if (warp == 1) { tc::tmem_alloc(&tmem_base_sh, TMEM_COLS); tc::tmem_relinquish(); }
     for (int i = threadIdx.x; i < COUT; i += TC_THREADS) { s_scale[i] = scale[i]; s_shift[i] = shift[i]; }
-    if (EPI == EPI_HEAD) {
+    if constexpr (EPI == EPI_HEAD) {
         for (int i = threadIdx.x; i < COUT * HK; i += TC_THREADS) s_head[(i % HK) * COUT + i / HK] = head.w[i];
         for (int i = threadIdx.x; i < HK; i += TC_THREADS) s_head[COUT * HK + i] = head.w[COUT * HK + i];
     }
@@ -777,7 +777,7 @@ __device__ __forceinline__ void mma_m16n8k16_bf16(float *c, const uint32_t *a, u
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-constexpr int FIRST_ROWS = 8;              // rows per block (one warp per row)
+constexpr int FIRST_ROWS = 8;              // rows per block (one warp per row; a multiple of 8)
 constexpr int FIRST_TW = 128;              // pixels per block row
 
 template <int CIN, int COUT, int KZ>
@@ -828,7 +828,7 @@ first_conv_kernel(const float *__restrict__ in, const float *__restrict__ wf,
     // this thread's A-fragment sources: k = ks*16 + 2t + (j&1) + 8*(j>>1) -> staged-tile address of
     // tap (dz,dy,dx), channel c for pixel g of this warp's row.  Taps beyond KTOT alias tap 0: their
     // weights are zero, so the (finite) value read there does not matter.
-    const float *src[KS][4];
+    int src[KS][4];                                      // offsets into `tile` (keeps the loads LDS)
 #pragma unroll
     for (int ks = 0; ks < KS; ++ks)
 #pragma unroll
@@ -836,42 +836,46 @@ first_conv_kernel(const float *__restrict__ in, const float *__restrict__ wf,
             const int k = ks * 16 + 2 * t + (j & 1) + 8 * (j >> 1);
             const int tap = (k < KTOT) ? k / CIN : 0, c = (k < KTOT) ? k % CIN : 0;
             const int tz = tap / 9, tr = tap % 9;
-            src[ks][j] = tile + tz * SSLICE + (warp + tr / 3) * SROW + (g + tr % 3) * CIN + c;
+            src[ks][j] = tz * SSLICE + (warp + tr / 3) * SROW + (g + tr % 3) * CIN + c;
         }
     __syncthreads();
-    const int y = y0 + warp;
-    if (y >= H) return;
-    bf16 *orow = out + (((size_t)np * NT * H + y) * W + x0 + g) * 8 + 2 * t;
     const size_t plane = (size_t)H * W * 8;
+#pragma unroll 1
+    for (int rr = 0; rr < FIRST_ROWS; rr += 8) {
+        const int y = y0 + warp + rr;
+        if (y >= H) return;
+        const int roff = rr * SROW;                      // this row's offset in the staged tile
+        bf16 *orow = out + (((size_t)np * NT * H + y) * W + x0 + g) * 8 + 2 * t;
 #pragma unroll 2
-    for (int q = 0; q < FIRST_TW / 16; ++q) {
-        if (x0 + 16 * q >= W) break;
-        float acc[NT][4];
+        for (int q = 0; q < FIRST_TW / 16; ++q) {
+            if (x0 + 16 * q >= W) break;
+            float acc[NT][4];
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt)
+            for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
-            for (int e = 0; e < 4; ++e) acc[nt][e] = 0.0f;
+                for (int e = 0; e < 4; ++e) acc[nt][e] = 0.0f;
 #pragma unroll
-        for (int ks = 0; ks < KS; ++ks) {
-            // rows g / g+8 of the fragment = pixels 16q+g and 16q+g+8
-            uint32_t a[4];
-            a[0] = pack_bf16(src[ks][0][(16 * q) * CIN], src[ks][1][(16 * q) * CIN]);
-            a[1] = pack_bf16(src[ks][0][(16 * q + 8) * CIN], src[ks][1][(16 * q + 8) * CIN]);
-            a[2] = pack_bf16(src[ks][2][(16 * q) * CIN], src[ks][3][(16 * q) * CIN]);
-            a[3] = pack_bf16(src[ks][2][(16 * q + 8) * CIN], src[ks][3][(16 * q + 8) * CIN]);
+            for (int ks = 0; ks < KS; ++ks) {
+                // rows g / g+8 of the fragment = pixels 16q+g and 16q+g+8
+                uint32_t a[4];
+                a[0] = pack_bf16(tile[src[ks][0] + roff + (16 * q) * CIN], tile[src[ks][1] + roff + (16 * q) * CIN]);
+                a[1] = pack_bf16(tile[src[ks][0] + roff + (16 * q + 8) * CIN], tile[src[ks][1] + roff + (16 * q + 8) * CIN]);
+                a[2] = pack_bf16(tile[src[ks][2] + roff + (16 * q) * CIN], tile[src[ks][3] + roff + (16 * q) * CIN]);
+                a[3] = pack_bf16(tile[src[ks][2] + roff + (16 * q + 8) * CIN], tile[src[ks][3] + roff + (16 * q + 8) * CIN]);
 #pragma unroll
-            for (int nt = 0; nt < NT; ++nt) mma_m16n8k16_bf16(acc[nt], a, bw[ks][nt][0], bw[ks][nt][1]);
-        }
-        // C fragment: (row g, cols 2t,2t+1), (row g+8, cols 2t,2t+1) -> channel block nt, channels 2t,2t+1
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                const float v0 = fmaxf(fmaf(acc[nt][2 * r], sc[nt][0], sh[nt][0]), 0.0f);
-                const float v1 = fmaxf(fmaf(acc[nt][2 * r + 1], sc[nt][1], sh[nt][1]), 0.0f);
-                if (x0 + 16 * q + g + 8 * r < W)
-                    *reinterpret_cast<uint32_t *>(orow + nt * plane + (size_t)(16 * q + 8 * r) * 8) = pack_bf16(v0, v1);
+                for (int nt = 0; nt < NT; ++nt) mma_m16n8k16_bf16(acc[nt], a, bw[ks][nt][0], bw[ks][nt][1]);
             }
+            // C fragment: (row g, cols 2t,2t+1), (row g+8, cols 2t,2t+1) -> channel block nt, channels 2t,2t+1
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    const float v0 = fmaxf(fmaf(acc[nt][2 * r], sc[nt][0], sh[nt][0]), 0.0f);
+                    const float v1 = fmaxf(fmaf(acc[nt][2 * r + 1], sc[nt][1], sh[nt][1]), 0.0f);
+                    if (x0 + 16 * q + g + 8 * r < W)
+                        *reinterpret_cast<uint32_t *>(orow + nt * plane + (size_t)(16 * q + 8 * r) * 8) = pack_bf16(v0, v1);
+                }
+        }
     }
 }
 
@@ -1096,10 +1100,11 @@ int launch_tc(sq_unet_s *u, const SqLayer &L, const bf16 *in0, int cb0, const bf
     nstages = std::max(nstages, 2);
     const size_t smem = (size_t)nstages * C::STAGE_BYTES + 1024;
     auto kern = conv_tc_kernel<COUT, S, UP, NBUF, MINB, EPI, HK>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static size_t attr_smem[64] = {0};          // the attribute is per device: one slot per device id
+    size_t &have = attr_smem[u->h->device & 63];
+    if (smem > have) {
         SQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
+        have = smem;
     }
     const int tiles = nimg * g.D * ((W + 7) / 8) * ((H + C::TH - 1) / C::TH);
     const int grid = std::min(tiles, MINB * u->h->sm_count);
@@ -1157,10 +1162,11 @@ int launch_xc_k(sq_unet_s *u, const SqLayer &L, const bf16 *in0, int cb0, const 
     SQ_REQUIRE(nstages >= 2 && g.KZ % ZPS == 0, SQ_ESTATE, "conv_xc: configuration does not fit");
     const size_t smem = (size_t)wres + (size_t)nstages * stage_bytes + 1024;
     auto kern = conv_xc_kernel<COUT, S, NBUF, MINB, EPI, HK, PADACC, KPS, ZPS>;
-    static size_t attr_smem = 0;
-    if (smem > attr_smem) {
+    static size_t attr_smem[64] = {0};          // the attribute is per device: one slot per device id
+    size_t &have = attr_smem[u->h->device & 63];
+    if (smem > have) {
         SQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_smem = smem;
+        have = smem;
     }
     const int tiles = nimg * g.D * ((W + C::TW - 1) / C::TW) * ((H + C::TH - 1) / C::TH);
     const int grid = std::min(tiles, MINB * u->h->sm_count);
