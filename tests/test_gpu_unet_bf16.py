@@ -196,3 +196,39 @@ def test_baseline_config_sizes_against_fp32_exact_mode(sq, name, n, shape, cin, 
     assert sum(len(t) for t in tables) >= 20, name
     for t, want in zip(tables, centroid_oracle.centroid_tables(mask)):
         np.testing.assert_array_equal(t, want)
+
+
+@pytest.mark.parametrize('seed', range(12))
+def test_random_geometries(sq, seed):
+    """Seeded random planar / volumetric nets: odd tile remainders in every direction (tiles are 8 or
+    14 columns wide and 8..64 rows tall), every bridge, 1-4 input channels, 2-4 or many classes, with
+    both Cout <= 32 kernels in play through the default dispatch."""
+    from sequitr_b200.networks import UNet2D, UNet3D
+    rng = np.random.default_rng(1000 + seed)
+    vol = seed % 3 == 2
+    nl = int(rng.integers(2, 4 if vol else 5))
+    filters = tuple([16, 32, 64, 128][:nl]) if rng.random() < 0.7 else tuple([32, 64, 128][:min(nl, 3)])
+    nl = len(filters)
+    m = 2 ** (nl - 1)
+    bridge = [None, 'concat', 'concat', 'eltwise_add', 'eltwise_mul', 'eltwise_sub'][int(rng.integers(0, 6))]
+    cin = int(rng.integers(1, 3 if vol else 5))
+    k = int(rng.choice([2, 2, 3, 4, 7]))
+    h = m * int(rng.integers(1, 1 + (40 if vol else 120) // m))
+    w = m * int(rng.integers(1, 1 + (56 if vol else 160) // m))
+    n = int(rng.integers(1, 3))
+    weights = synth.unet_weights(filters, cin, k, ndim=3 if vol else 2, bridge=bridge,
+                                 affine=bool(rng.integers(0, 2)), seed=seed)
+    if vol:
+        d = m * int(rng.integers(1, 1 + 8 // m))
+        x = synth.volumes(n, d, h, w, cin, seed=seed)
+        net = UNet3D({'filters': filters, 'shape': (h, w, d), 'bridge': bridge, 'num_inputs': cin,
+                      'num_outputs': k, 'compute': 'bf16'})
+    else:
+        x = synth.frames(n, h, w, cin, seed=seed, n_objects=3)
+        net = UNet2D({'filters': filters, 'shape': (h, w), 'bridge': bridge, 'num_inputs': cin,
+                      'num_outputs': k, 'compute': 'bf16'})
+    net.load_weights(weights)
+    out = net.predict(x)
+    ref = unet_c.unet_forward(x, weights, filters, bridge, contract='bf16')
+    _compare(out, ref, 'seed %d: %s filters=%s bridge=%s cin=%d k=%d shape=%s' %
+             (seed, '3d' if vol else '2d', filters, bridge, cin, k, x.shape))
