@@ -1,28 +1,33 @@
 // SQ_MODE_BF16_TC: the UNet on 5th-generation tensor cores (tcgen05 + TMEM + TMA).
 //
-// Data layout in HBM: activations are bf16, channel-blocked "NC/8HW8":
-//     act[n][c/8][y][x][c%8]
+// Data layout in HBM: activations are bf16, channel-blocked "NC/8HW8" (volumes: N D C/8 H W 8):
+//     act[n][z][c/8][y][x][c%8]
 // so that (a) a pixel's 8-channel slice is one 16-byte core-matrix row, (b) a TMA
-// box (8*PW, PH, 2 blocks, 1 image) lands in shared memory as [2][PH][PW][8] --
+// box (8*PW, PH, 2 blocks, 1 slice, 1 image) lands in shared memory as [2][PH][PW][8] --
 // already a canonical K-major, no-swizzle UMMA operand whose rows are pixels -- and
 // (c) shifting the descriptor start address by (ky*PW + kx)*16 bytes selects the
 // 3x3 tap (ky,kx).  Each halo patch is therefore read from L2/HBM ONCE per 16 input
 // channels and multiplied 9 times from shared memory; SAME zero padding is TMA's
-// out-of-bounds fill; the skip-concat is just a second tensor map (k-steps
-// ks0..ks0+ks1 read the skip tensor), no concatenated tensor ever exists.
+// out-of-bounds fill (also across slices of a volume); the skip-concat is just a second
+// tensor map (k-steps ks0..ks0+ks1 read the skip tensor), no concatenated tensor ever exists.
 //
-// One persistent, warp-specialised kernel template does every dense layer:
-//   warp 0      TMA producer   (patch via cp.async.bulk.tensor.4d, weights via cp.async.bulk)
-//   warp 1      MMA issuer     (tcgen05.mma kind::f16, M=128 pixels x N=Cout, K=16 per step)
-//   warps 2-5   epilogue       (tcgen05.ld -> scale/shift/ReLU -> bf16 -> 16-byte stores)
+// Two persistent, warp-specialised kernel templates do every dense layer:
+//   warp 0      TMA producer   (patch via cp.async.bulk.tensor.5d, weights via cp.async.bulk)
+//   warp 1      MMA issuer     (tcgen05.mma kind::f16, M=128 pixels, K=16 per instruction)
+//   warps 2-9   epilogue       (tcgen05.ld -> scale/shift/ReLU -> bf16 -> 16-byte stores;
+//                               two groups of four warps, one warp per TMEM lane quarter)
 // with an smem ring (full/empty mbarriers) and double-buffered TMEM accumulators
 // (tmem_full/tmem_empty) so the epilogue of tile i overlaps the MMAs of tile i+1.
-//   conv 3x3 : tile = 8 x (16*S) pixels, 9 taps accumulate into one accumulator
-//   up-conv  : 2x2 stride-2 transposed conv = 4 independent 1x1 GEMMs (one per
-//              output sub-position), 4 accumulators, scattered 2x upsampled store
-// The first conv (Cin = 1 or 3: K = 9..27, not tensor-core material), the 2x2 max
-// pool, the element-wise bridges and the 1x1 head + softmax + argmax are
-// bandwidth-bound CUDA-core kernels on the same layout.
+//   conv_tc_kernel  conv 3x3(x3): tile = 8 x (16*S) pixels, N = Cout, 9 taps accumulate into one
+//                   accumulator per sub-tile; up-conv 2x2 stride 2 = 4 independent 1x1 GEMMs (one per
+//                   output sub-position), scattered 2x upsampled store
+//   conv_xc_kernel  conv 3x3(x3) for Cout <= 32 with several k-steps per tile: the three horizontal
+//                   taps folded into N = 3*Cout (3 MMAs per k-step), combined by lane shuffles in the
+//                   epilogue; weights resident in shared memory
+// Epilogue variants: plain store, store + fused 2x2 max-pool, fused 1x1 head + softmax + argmax.
+// The first conv (Cin <= 4: K = 9..108 -- warp-level mma.sync on a staged halo tile), the depth
+// half of the 2x2x2 pool, the element-wise bridges and the stand-alone head are bandwidth-bound
+// CUDA-core kernels on the same layout.
 //
 // Numeric contract (oracle/unet_c.py contract='bf16'): inputs, weights and every
 // stored activation are bf16 (RNE); accumulation and the scale/shift epilogue are fp32.
