@@ -232,7 +232,7 @@ def main():
     #      not 8 frames at a time); inside, frames stream through in 4-frame chunks so the H2D
     #      copy of a chunk overlaps the UNet of the previous one.  Every step's frames are copied
     #      from pinned host memory and every step's centroid table is read back.
-    CALL_STEPS = 4
+    CALL_STEPS = int(os.environ.get('SQ_BENCH_CALL_STEPS', 4))
     big = torch.empty((CALL_STEPS * B, H, W, 1), dtype=torch.float32).pin_memory()
     for j in range(CALL_STEPS):
         big[j * B:(j + 1) * B] = host_pool
