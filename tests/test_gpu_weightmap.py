@@ -58,6 +58,28 @@ def test_w1_float32_output_and_cutoff(sq):
         np.testing.assert_allclose(got32, ref.astype(np.float32), rtol=1.2e-7, atol=0)
 
 
+@pytest.mark.parametrize('seed', range(8))
+def test_w1_random_shapes_and_radii(sq, seed):
+    """Bounded (cut-off radius) kernels on random shapes: widths that are / are not multiples of 16 and
+    32 (the two row-pass kernels), sparse to dense masks, radii from 2 to the 64-pixel limit and beyond
+    (general kernels), several frames per call."""
+    from sequitr_b200 import ops
+    rng = np.random.default_rng(50 + seed)
+    h = int(rng.integers(1, 220))
+    w = int(rng.choice([16, 48, 80, 112, 176, 272])) if seed % 2 == 0 else int(rng.integers(1, 300))
+    n = int(rng.integers(1, 4))
+    p = float(rng.choice([0.0005, 0.005, 0.05, 0.4]))
+    m = rng.random((n, h, w)) < p
+    if seed == 3:
+        m[1 % n] = False                                         # a seedless frame among seeded ones
+    for (w0, s) in ((10., 5.), (10., float(rng.choice([0.4, 2., 9., 14.]))), (1e-3, 3.)):
+        ref = np.stack([wo.weightmap_w1(f, w0, s)[..., 0] for f in m])
+        got64 = ops.weightmap_edt_host(m, w0, s, out_dtype='float64')
+        np.testing.assert_allclose(got64, ref, rtol=RTOL64, atol=0)
+        got32 = ops.weightmap_edt_host(m, w0, s, out_dtype='float32')
+        np.testing.assert_allclose(got32, ref.astype(np.float32), rtol=1.2e-7, atol=0)
+
+
 def test_w1_full_size_2048(sq):
     from sequitr_b200 import ops
     lab = synth.instance_labels(2048, 2048, 600, seed=1)
