@@ -108,6 +108,26 @@ def test_w3_matches_oracle(sq, shape, n, seed):
         np.testing.assert_allclose(got32, ref.astype(np.float32), rtol=1.2e-7, atol=0)
 
 
+@pytest.mark.parametrize('seed', range(6))
+def test_w3_random_label_images(sq, seed):
+    """Random instance-label images: noise labels (touching instances, single pixels, many labels per
+    row), discs, widths around the 32-pixel tile and word sizes, several radii (bounded and general)."""
+    from sequitr_b200 import ops
+    rng = np.random.default_rng(70 + seed)
+    h, w = int(rng.integers(1, 150)), int(rng.integers(1, 200))
+    if seed % 2 == 0:
+        lab = np.where(rng.random((h, w)) < float(rng.choice([0.01, 0.1, 0.5])),
+                       rng.integers(1, 6, size=(h, w)), 0).astype(np.int32)
+    else:
+        lab = synth.instance_labels(max(h, 24), max(w, 24), 8, seed=seed, rmin=2, rmax=6).astype(np.int32)
+    for (w0, s, wc) in ((10., 5., None), (10., float(rng.choice([0.5, 2., 12.])), (0.25, 1.5))):
+        ref = wo.weightmap_w3(lab, w0, s, wc)
+        got = ops.weightmap_unet_host(lab, w0, s, wc, out_dtype='float64')
+        np.testing.assert_allclose(got, ref, rtol=RTOL64, atol=0)
+        got32 = ops.weightmap_unet_host(lab, w0, s, wc, out_dtype='float32')
+        np.testing.assert_allclose(got32, ref.astype(np.float32), rtol=1.2e-7, atol=0)
+
+
 def test_w3_edge_cases_and_properties(sq):
     from sequitr_b200 import ops, pipeline
     empty = np.zeros((40, 50), np.int32)
