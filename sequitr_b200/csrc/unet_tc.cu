@@ -90,8 +90,10 @@ struct HeadArgs {
     uint8_t *mask;             // optional, (n,H,W)
 };
 
-template <int COUT, int S, bool UP, int NBUF, int MINB, int EPI, int HK>
-__global__ void __launch_bounds__(TC_THREADS, MINB)
+// NMMA = MMA-issuing warps (warps 1..NMMA; sub-tile j belongs to warp 1 + j % NMMA): one thread sustains
+// one MMA per ~45-65 clk, which a single-CTA-per-SM kernel with a 64 clk pipe time (Cout = 128) cannot hide.
+template <int COUT, int S, bool UP, int NBUF, int MINB, int EPI, int HK, int NMMA>
+__global__ void __launch_bounds__(TC_THREADS + 32 * (NMMA - 1), MINB)
 conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                int ks0, int ks1, const bf16 *__restrict__ wts, const float *__restrict__ scale,
                const float *__restrict__ shift, bf16 *__restrict__ out, bf16 *__restrict__ out_pool,
@@ -120,18 +122,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     const int ksteps = ks0 + ks1, qsteps = KZ * ksteps;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < nstages; ++i) { tc::mbar_init(&full_bar[i], 1); tc::mbar_init(&empty_bar[i], 1); }
-        for (int i = 0; i < 2; ++i) { tc::mbar_init(&tfull_bar[i], 1); tc::mbar_init(&tempty_bar[i], 4 * EPI_GROUPS); }
+        for (int i = 0; i < nstages; ++i) { tc::mbar_init(&full_bar[i], 1); tc::mbar_init(&empty_bar[i], NMMA); }
+        for (int i = 0; i < 2; ++i) { tc::mbar_init(&tfull_bar[i], NMMA); tc::mbar_init(&tempty_bar[i], 4 * EPI_GROUPS); }
         tc::fence_barrier_init();
         tc::tma_prefetch_desc(&mapA0);
         tc::tma_prefetch_desc(&mapA1);
     }
     if (warp == 1) { tc::tmem_alloc(&tmem_base_sh, TMEM_COLS); tc::tmem_relinquish(); }
-    for (int i = threadIdx.x; i < COUT; i += TC_THREADS) { s_scale[i] = scale[i]; s_shift[i] = shift[i]; }
+    for (int i = threadIdx.x; i < COUT; i += blockDim.x) { s_scale[i] = scale[i]; s_shift[i] = shift[i]; }
     if constexpr (EPI == EPI_HEAD) {
         // global layout is [c][k] (+ bias); keep it transposed so one class is 16 contiguous floats
-        for (int i = threadIdx.x; i < COUT * HK; i += TC_THREADS) s_head[(i % HK) * COUT + i / HK] = head.w[i];
-        for (int i = threadIdx.x; i < HK; i += TC_THREADS) s_head[COUT * HK + i] = head.w[COUT * HK + i];
+        for (int i = threadIdx.x; i < COUT * HK; i += blockDim.x) s_head[(i % HK) * COUT + i / HK] = head.w[i];
+        for (int i = threadIdx.x; i < HK; i += blockDim.x) s_head[COUT * HK + i] = head.w[COUT * HK + i];
     }
     tc::tc_fence_before();
     __syncthreads();
@@ -161,8 +163,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 }
             }
         }
-    } else if (warp == 1) {
-        // ======================================================= MMA issuer
+    } else if (warp <= NMMA) {
+        // ======================================================= MMA issuer(s)
         // The whole warp walks the loop converged (all lanes poll the barriers); one elected
         // lane issues.  Descriptors = per-stage base + compile-time offset (one add each).
         const uint32_t idesc = tc::instr_desc_bf16(128, COUT);
@@ -187,6 +189,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                     const uint32_t first = (ks > 0) ? 1u : 0u;
 #pragma unroll
                     for (int j = 0; j < S; ++j) {
+                        if (NMMA > 1 && (j % NMMA) != warp - 1) continue;
 #pragma unroll
                         for (int tp = 0; tp < C::NT; ++tp) {
                             const int row0 = C::ILV ? 32 * (j / 2) + (j & 1) : j * 16;   // first image row
@@ -209,7 +212,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     } else {
         // ========================================================= epilogue
         const int q4 = warp & 3;                            // TMEM lane quarter this warp may read
-        const int half = (warp - 2) >> 2;                   // which epilogue group: splits the work items
+        const int half = (warp - 1 - NMMA) >> 2;            // which epilogue group: splits the work items
         const int r = q4 * 32 + lane;                       // accumulator row = pixel of the sub-tile
         const int ph = r >> 3, pw = r & 7;
         const uint32_t lane_addr = (uint32_t)(q4 * 32) << 16;
@@ -1089,7 +1092,7 @@ struct TcGeo {
     size_t w_off;                           // element offset into the layer's tensor-core weights
 };
 
-template <int COUT, int S, bool UP, int NBUF, int MINB, int EPI, int HK = 0>
+template <int COUT, int S, bool UP, int NBUF, int MINB, int EPI, int HK = 0, int NMMA = 1>
 int launch_tc(sq_unet_s *u, const SqLayer &L, const bf16 *in0, int cb0, const bf16 *in1, int cb1,
               bf16 *out, bf16 *out_pool, const HeadArgs &head, const TcGeo &g, int relu,
               cudaStream_t st)
@@ -1104,7 +1107,8 @@ int launch_tc(sq_unet_s *u, const SqLayer &L, const bf16 *in0, int cb0, const bf
     int nstages = std::min(MAX_STAGES, ((MINB == 1 ? 200 : 216 / MINB) * 1024 - 2048) / C::STAGE_BYTES);
     nstages = std::max(nstages, 2);
     const size_t smem = (size_t)nstages * C::STAGE_BYTES + 1024;
-    auto kern = conv_tc_kernel<COUT, S, UP, NBUF, MINB, EPI, HK>;
+    static_assert(NMMA == 1 || S % NMMA == 0, "sub-tiles must split evenly over the MMA warps");
+    auto kern = conv_tc_kernel<COUT, S, UP, NBUF, MINB, EPI, HK, NMMA>;
     static size_t attr_smem[64] = {0};          // the attribute is per device: one slot per device id
     size_t &have = attr_smem[u->h->device & 63];
     if (smem > have) {
@@ -1113,7 +1117,7 @@ int launch_tc(sq_unet_s *u, const SqLayer &L, const bf16 *in0, int cb0, const bf
     }
     const int tiles = nimg * g.D * ((W + 7) / 8) * ((H + C::TH - 1) / C::TH);
     const int grid = std::min(tiles, MINB * u->h->sm_count);
-    kern<<<grid, TC_THREADS, smem, st>>>(m0, m1, cb0 / 2, in1 ? cb1 / 2 : 0, (const bf16 *)L.w_tc + g.w_off, L.scale,
+    kern<<<grid, TC_THREADS + 32 * (NMMA - 1), smem, st>>>(m0, m1, cb0 / 2, in1 ? cb1 / 2 : 0, (const bf16 *)L.w_tc + g.w_off, L.scale,
                                          L.shift, out, out_pool, head, nimg, H, W, relu, nstages, g.D, g.KZ,
                                          g.out_mul, g.out_off);
     ++u->last_launches;
@@ -1121,7 +1125,7 @@ int launch_tc(sq_unet_s *u, const SqLayer &L, const bf16 *in0, int cb0, const bf
     return SQ_OK;
 }
 
-template <int COUT, int S, int MINB>
+template <int COUT, int S, int MINB, int NMMA = 1>
 int conv3x3_epi(sq_unet_s *u, const SqLayer &L, const bf16 *in0, int c0, const bf16 *in1, int c1,
                 bf16 *out, bf16 *out_pool, const HeadArgs *head, const TcGeo &g, cudaStream_t st)
 {
@@ -1138,13 +1142,13 @@ int conv3x3_epi(sq_unet_s *u, const SqLayer &L, const bf16 *in0, int c0, const b
     }
     if (out_pool) {
         if constexpr (COUT <= 128)
-            return launch_tc<COUT, S, false, 2, MINB, EPI_POOL>(u, L, in0, c0 / 8, in1, c1 / 8, out, out_pool,
-                                                                none, g, 1, st);
+            return launch_tc<COUT, S, false, 2, MINB, EPI_POOL, 0, NMMA>(u, L, in0, c0 / 8, in1, c1 / 8, out, out_pool,
+                                                                         none, g, 1, st);
         else
             SQ_REQUIRE(false, SQ_EUNSUPPORTED, "fused pool needs filters <= 128");
     }
-    return launch_tc<COUT, S, false, 2, MINB, EPI_STORE>(u, L, in0, c0 / 8, in1, c1 / 8, out, nullptr, none,
-                                                         g, 1, st);
+    return launch_tc<COUT, S, false, 2, MINB, EPI_STORE, 0, NMMA>(u, L, in0, c0 / 8, in1, c1 / 8, out, nullptr, none,
+                                                                  g, 1, st);
 }
 
 constexpr int SQ_NOT_APPLICABLE = 1;        // launch_xc: configuration does not fit, use the 9-tap kernel
@@ -1273,7 +1277,7 @@ int conv3x3_tc(sq_unet_s *u, const SqLayer &L, const bf16 *in0, int c0, const bf
     case 16:  return conv3x3_epi<16, 4, 2>(u, L, in0, c0, in1, c1, out, out_pool, head, g, st);
     case 32:  return conv3x3_epi<32, 4, 2>(u, L, in0, c0, in1, c1, out, out_pool, head, g, st);
     case 64:  return conv3x3_epi<64, 2, 2>(u, L, in0, c0, in1, c1, out, out_pool, head, g, st);
-    case 128: return conv3x3_epi<128, 2, 1>(u, L, in0, c0, in1, c1, out, out_pool, head, g, st);
+    case 128: return conv3x3_epi<128, 2, 1, 2>(u, L, in0, c0, in1, c1, out, out_pool, head, g, st);   // 2 MMA warps
     case 256: return conv3x3_epi<256, 1, 1>(u, L, in0, c0, in1, c1, out, out_pool, head, g, st);
     }
     SQ_REQUIRE(false, SQ_EUNSUPPORTED, "bf16 mode: unsupported filter count %d", L.cout);
