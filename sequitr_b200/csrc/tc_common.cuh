@@ -173,6 +173,36 @@ __device__ __forceinline__ void umma_commit(uint64_t *bar)
                      smem_u32(bar))
                  : "memory");
 }
+// same, arriving on the barrier at this CTA-relative address in every CTA of `cta_mask` (cluster)
+__device__ __forceinline__ void umma_commit_mc(uint64_t *bar, uint16_t cta_mask)
+{
+    asm volatile(
+        "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+            smem_u32(bar)),
+        "h"(cta_mask)
+        : "memory");
+}
+// bulk copy global -> the same shared-memory offset of every CTA in `cta_mask`; each destination CTA's
+// barrier (same offset) receives the complete_tx for `bytes`
+__device__ __forceinline__ void bulk_load_mc(void *dst, const void *src, uint32_t bytes, uint64_t *bar,
+                                             uint16_t cta_mask)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::
+            "r"(smem_u32(dst)),
+        "l"((uint64_t)src), "r"(bytes), "r"(smem_u32(bar)), "h"(cta_mask)
+        : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
 __device__ __forceinline__ void tmem_ld_wait()
 {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");

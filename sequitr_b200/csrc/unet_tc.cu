@@ -92,7 +92,12 @@ struct HeadArgs {
 
 // NMMA = MMA-issuing warps (warps 1..NMMA; sub-tile j belongs to warp 1 + j % NMMA): one thread sustains
 // one MMA per ~45-65 clk, which a single-CTA-per-SM kernel with a 64 clk pipe time (Cout = 128) cannot hide.
-template <int COUT, int S, bool UP, int NBUF, int MINB, int EPI, int HK, int NMMA>
+// CL = launched as clusters of two CTAs that walk their (different) pixel tiles in lock-step and share
+// every weight stage: each CTA fetches HALF of the stage's weights and multicasts it into both CTAs'
+// shared memory, halving the L2 -> SM weight traffic that otherwise caps the Cout >= 128 layers (36.8 /
+// 73.7 KB of weights per k-step and 128-256 pixel tile).  A stage is free when the MMAs of BOTH CTAs
+// have retired (tcgen05.commit multicast onto both CTAs' `empty` barriers).
+template <int COUT, int S, bool UP, int NBUF, int MINB, int EPI, int HK, int NMMA, bool CL>
 __global__ void __launch_bounds__(TC_THREADS + 32 * (NMMA - 1), MINB)
 conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                int ks0, int ks1, const bf16 *__restrict__ wts, const float *__restrict__ scale,
@@ -122,7 +127,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     const int ksteps = ks0 + ks1, qsteps = KZ * ksteps;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < nstages; ++i) { tc::mbar_init(&full_bar[i], 1); tc::mbar_init(&empty_bar[i], NMMA); }
+        for (int i = 0; i < nstages; ++i) { tc::mbar_init(&full_bar[i], 1); tc::mbar_init(&empty_bar[i], NMMA * (CL ? 2 : 1)); }
         for (int i = 0; i < 2; ++i) { tc::mbar_init(&tfull_bar[i], NMMA); tc::mbar_init(&tempty_bar[i], 4 * EPI_GROUPS); }
         tc::fence_barrier_init();
         tc::tma_prefetch_desc(&mapA0);
@@ -139,13 +144,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem_base = tmem_base_sh;
+    // lock-step tile loop for clusters: both CTAs run the same number of iterations; an iteration whose
+    // tile index is past the end loads zero-filled patches (image coordinate out of range) and stores nothing
+    const int iters = CL ? (ntiles + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const uint32_t crank = CL ? tc::cluster_ctarank() : 0u;
+    if (CL) tc::cluster_sync_all();                         // peer barriers are initialised
 
     if (warp == 0) {
         // ===================================================== TMA producer
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+            for (int t = blockIdx.x, i = 0; CL ? (i < iters) : (t < ntiles); t += gridDim.x, ++i) {
                 const int tx = t % tiles_x, ty = (t / tiles_x) % tiles_y, np = t / (tiles_x * tiles_y);
                 const int z = np % D, n = np / D;
                 const int x0 = tx * 8 - (UP ? 0 : 1), y0 = ty * C::TH - (UP ? 0 : 1);
@@ -157,8 +167,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                     uint8_t *sA = smem + (size_t)stage * C::STAGE_BYTES;
                     if (ks < ks0) tc::tma_load_5d(sA, &mapA0, &full_bar[stage], x0 * 8, y0, ks * 2, zc, n);
                     else          tc::tma_load_5d(sA, &mapA1, &full_bar[stage], x0 * 8, y0, (ks - ks0) * 2, zc, n);
-                    tc::bulk_load(sA + C::A_BYTES, wts + (size_t)q * (C::B_BYTES / 2), C::B_BYTES,
-                                  &full_bar[stage]);
+                    if (CL)      // my half of the weights, into both CTAs
+                        tc::bulk_load_mc(sA + C::A_BYTES + crank * (C::B_BYTES / 2),
+                                         wts + (size_t)q * (C::B_BYTES / 2) + crank * (C::B_BYTES / 4), C::B_BYTES / 2,
+                                         &full_bar[stage], (uint16_t)3);
+                    else
+                        tc::bulk_load(sA + C::A_BYTES, wts + (size_t)q * (C::B_BYTES / 2), C::B_BYTES,
+                                      &full_bar[stage]);
                     if (++stage == nstages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -173,7 +188,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         int stage = 0;
         uint32_t phase = 0;
         int it = 0;
-        for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+        for (int t = blockIdx.x; CL ? (it < iters) : (t < ntiles); t += gridDim.x, ++it) {
             const int buf = it % NBUF;
             tc::mbar_wait(&tempty_bar[buf], ((it / NBUF) & 1) ^ 1);
             tc::tc_fence_after();
@@ -201,7 +216,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                                                 (UP || tp == 0) ? first : 1u);
                         }
                     }
-                    tc::umma_commit(&empty_bar[stage]);      // smem slot reusable once these MMAs retire
+                    // smem slot reusable once these MMAs retire (in both CTAs of a cluster)
+                    if (CL) tc::umma_commit_mc(&empty_bar[stage], (uint16_t)3);
+                    else tc::umma_commit(&empty_bar[stage]);
                 }
                 __syncwarp();
                 if (++stage == nstages) { stage = 0; phase ^= 1; }
@@ -218,8 +235,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         const uint32_t lane_addr = (uint32_t)(q4 * 32) << 16;
         const int CBo = COUT / 8;
         int it = 0;
-        for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+        for (int t = blockIdx.x; CL ? (it < iters) : (t < ntiles); t += gridDim.x, ++it) {
             const int buf = it % NBUF;
+            const bool live = !CL || t < ntiles;
             const int tx = t % tiles_x, ty = (t / tiles_x) % tiles_y;
             const int n = (t / (tiles_x * tiles_y)) * out_mul + out_off;   // output "image" (n*D + z)
             tc::mbar_wait(&tfull_bar[buf], (it / NBUF) & 1);
@@ -232,7 +250,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
 #pragma unroll 1
                 for (int jp = 0; jp < S / 2; ++jp) {
                     const int y = ty * C::TH + 32 * jp + 2 * ph, x = tx * 8 + pw;
-                    const bool valid = (y < H) && (x < W);
+                    const bool valid = live && (y < H) && (x < W);
 #pragma unroll 1
                     for (int c16 = 0; c16 < COUT / 16; ++c16) {
                         if (((jp * (COUT / 16) + c16) % EPI_GROUPS) != half) continue;
@@ -281,7 +299,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             for (int j = 0; j < S; ++j) {
                 const int y = ty * C::TH + (C::ILV ? 32 * (j / 2) + 2 * ph + (j & 1) : j * 16 + ph);
                 const int x = tx * 8 + pw;
-                const bool valid = (y < H) && (x < W);
+                const bool valid = live && (y < H) && (x < W);
                 if (!UP) {
                     float hl[HK > 0 ? HK : 1];                     // fused head: running logits
 #pragma unroll
@@ -414,6 +432,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         __syncwarp();
         tc::tmem_dealloc(tmem_base, TMEM_COLS);
     }
+    if (CL) tc::cluster_sync_all();                         // the peer may still signal this CTA's barriers
 }
 
 // ------------------------------------------------- x-combined 3x3 conv (Cout <= 32)
@@ -1092,7 +1111,7 @@ struct TcGeo {
     size_t w_off;                           // element offset into the layer's tensor-core weights
 };
 
-template <int COUT, int S, bool UP, int NBUF, int MINB, int EPI, int HK = 0, int NMMA = 1>
+template <int COUT, int S, bool UP, int NBUF, int MINB, int EPI, int HK = 0, int NMMA = 1, bool CL = false>
 int launch_tc(sq_unet_s *u, const SqLayer &L, const bf16 *in0, int cb0, const bf16 *in1, int cb1,
               bf16 *out, bf16 *out_pool, const HeadArgs &head, const TcGeo &g, int relu,
               cudaStream_t st)
@@ -1104,28 +1123,55 @@ int launch_tc(sq_unet_s *u, const SqLayer &L, const bf16 *in0, int cb0, const bf
     if (in1) SQ_TRY(make_map(&m1, in1, nimg, g.D, cb1, H, W, C::PW, C::PH));
     else m1 = m0;
     static_assert(MINB * NBUF * C::ACC_COLS <= 512, "co-resident CTAs must fit in TMEM");
+    static_assert(NMMA == 1 || S % NMMA == 0, "sub-tiles must split evenly over the MMA warps");
+    static_assert(!CL || (MINB == 1 && !UP), "cluster variant: one CTA per SM, 3x3 convs");
     int nstages = std::min(MAX_STAGES, ((MINB == 1 ? 200 : 216 / MINB) * 1024 - 2048) / C::STAGE_BYTES);
     nstages = std::max(nstages, 2);
     const size_t smem = (size_t)nstages * C::STAGE_BYTES + 1024;
-    static_assert(NMMA == 1 || S % NMMA == 0, "sub-tiles must split evenly over the MMA warps");
-    auto kern = conv_tc_kernel<COUT, S, UP, NBUF, MINB, EPI, HK, NMMA>;
+    auto kern = conv_tc_kernel<COUT, S, UP, NBUF, MINB, EPI, HK, NMMA, CL>;
     static size_t attr_smem[64] = {0};          // the attribute is per device: one slot per device id
     size_t &have = attr_smem[u->h->device & 63];
     if (smem > have) {
         SQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         have = smem;
     }
+    const int threads = TC_THREADS + 32 * (NMMA - 1);
     const int tiles = nimg * g.D * ((W + 7) / 8) * ((H + C::TH - 1) / C::TH);
-    const int grid = std::min(tiles, MINB * u->h->sm_count);
-    kern<<<grid, TC_THREADS + 32 * (NMMA - 1), smem, st>>>(m0, m1, cb0 / 2, in1 ? cb1 / 2 : 0, (const bf16 *)L.w_tc + g.w_off, L.scale,
+    if (CL) {
+        // persistent clusters: as many CTA pairs as can be co-resident (GPCs with an odd SM count leave one out)
+        cudaLaunchConfig_t cfg = {};
+        cfg.blockDim = dim3((unsigned)threads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        static int max_clusters[64] = {0};
+        int &mc = max_clusters[u->h->device & 63];
+        if (mc == 0) {
+            cfg.gridDim = dim3((unsigned)(2 * (u->h->sm_count / 2)));
+            SQ_CUDA(cudaOccupancyMaxActiveClusters(&mc, kern, &cfg));
+            SQ_REQUIRE(mc >= 1, SQ_ECUDA, "conv_tc: no 2-CTA cluster fits on this device");
+        }
+        const int grid = 2 * std::min(mc, (tiles + 1) / 2);
+        cfg.gridDim = dim3((unsigned)grid);
+        SQ_CUDA(cudaLaunchKernelEx(&cfg, kern, m0, m1, cb0 / 2, in1 ? cb1 / 2 : 0, (const bf16 *)L.w_tc + g.w_off,
+                                   (const float *)L.scale, (const float *)L.shift, out, out_pool, head, nimg, H, W,
+                                   relu, nstages, g.D, g.KZ, g.out_mul, g.out_off));
+    } else {
+        const int grid = std::min(tiles, MINB * u->h->sm_count);
+        kern<<<grid, threads, smem, st>>>(m0, m1, cb0 / 2, in1 ? cb1 / 2 : 0, (const bf16 *)L.w_tc + g.w_off, L.scale,
                                          L.shift, out, out_pool, head, nimg, H, W, relu, nstages, g.D, g.KZ,
                                          g.out_mul, g.out_off);
+    }
     ++u->last_launches;
     SQ_CHECK_LAUNCH();
     return SQ_OK;
 }
 
-template <int COUT, int S, int MINB, int NMMA = 1>
+template <int COUT, int S, int MINB, int NMMA = 1, bool CL = false>
 int conv3x3_epi(sq_unet_s *u, const SqLayer &L, const bf16 *in0, int c0, const bf16 *in1, int c1,
                 bf16 *out, bf16 *out_pool, const HeadArgs *head, const TcGeo &g, cudaStream_t st)
 {
@@ -1142,12 +1188,12 @@ int conv3x3_epi(sq_unet_s *u, const SqLayer &L, const bf16 *in0, int c0, const b
     }
     if (out_pool) {
         if constexpr (COUT <= 128)
-            return launch_tc<COUT, S, false, 2, MINB, EPI_POOL, 0, NMMA>(u, L, in0, c0 / 8, in1, c1 / 8, out, out_pool,
+            return launch_tc<COUT, S, false, 2, MINB, EPI_POOL, 0, NMMA, CL>(u, L, in0, c0 / 8, in1, c1 / 8, out, out_pool,
                                                                          none, g, 1, st);
         else
             SQ_REQUIRE(false, SQ_EUNSUPPORTED, "fused pool needs filters <= 128");
     }
-    return launch_tc<COUT, S, false, 2, MINB, EPI_STORE, 0, NMMA>(u, L, in0, c0 / 8, in1, c1 / 8, out, nullptr, none,
+    return launch_tc<COUT, S, false, 2, MINB, EPI_STORE, 0, NMMA, CL>(u, L, in0, c0 / 8, in1, c1 / 8, out, nullptr, none,
                                                                   g, 1, st);
 }
 
@@ -1257,6 +1303,12 @@ int xc_variant()
     return e ? atoi(e) : 1;
 }
 
+bool use_clusters()
+{
+    const char *e = getenv("SQ_CLUSTER");       // SQ_CLUSTER=0: plain launches (A/B measurements)
+    return !(e && atoi(e) == 0);
+}
+
 // out_pool != NULL: also write the 2x2 max-pooled tensor; head != NULL: fused 1x1 head, no `out`.
 int conv3x3_tc(sq_unet_s *u, const SqLayer &L, const bf16 *in0, int c0, const bf16 *in1, int c1,
                bf16 *out, bf16 *out_pool, const HeadArgs *head, const TcGeo &g, cudaStream_t st)
@@ -1277,8 +1329,12 @@ int conv3x3_tc(sq_unet_s *u, const SqLayer &L, const bf16 *in0, int c0, const bf
     case 16:  return conv3x3_epi<16, 4, 2>(u, L, in0, c0, in1, c1, out, out_pool, head, g, st);
     case 32:  return conv3x3_epi<32, 4, 2>(u, L, in0, c0, in1, c1, out, out_pool, head, g, st);
     case 64:  return conv3x3_epi<64, 2, 2>(u, L, in0, c0, in1, c1, out, out_pool, head, g, st);
-    case 128: return conv3x3_epi<128, 2, 1, 2>(u, L, in0, c0, in1, c1, out, out_pool, head, g, st);   // 2 MMA warps
-    case 256: return conv3x3_epi<256, 1, 1>(u, L, in0, c0, in1, c1, out, out_pool, head, g, st);
+    case 128:   // 2 MMA warps; weight multicast across CTA pairs unless SQ_CLUSTER=0
+        if (use_clusters()) return conv3x3_epi<128, 2, 1, 2, true>(u, L, in0, c0, in1, c1, out, out_pool, head, g, st);
+        return conv3x3_epi<128, 2, 1, 2>(u, L, in0, c0, in1, c1, out, out_pool, head, g, st);
+    case 256:
+        if (use_clusters()) return conv3x3_epi<256, 1, 1, 1, true>(u, L, in0, c0, in1, c1, out, out_pool, head, g, st);
+        return conv3x3_epi<256, 1, 1>(u, L, in0, c0, in1, c1, out, out_pool, head, g, st);
     }
     SQ_REQUIRE(false, SQ_EUNSUPPORTED, "bf16 mode: unsupported filter count %d", L.cout);
 }
