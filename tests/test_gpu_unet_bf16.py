@@ -232,3 +232,16 @@ def test_random_geometries(sq, seed):
     ref = unet_c.unet_forward(x, weights, filters, bridge, contract='bf16')
     _compare(out, ref, 'seed %d: %s filters=%s bridge=%s cin=%d k=%d shape=%s' %
              (seed, '3d' if vol else '2d', filters, bridge, cin, k, x.shape))
+
+
+def test_cluster_multicast_variant(sq, monkeypatch):
+    """SQ_CLUSTER=1: the Cout >= 128 convs run as 2-CTA clusters sharing every weight stage by multicast
+    (lock-step tile loops, odd tile counts -> a zero-filled dummy tile): same logits as the plain launch."""
+    filters = (16, 32, 64, 128, 256)
+    w = synth.unet_weights(filters, 1, 2, bridge='concat', seed=42)
+    x = synth.frames(3, 112, 80, 1, seed=5, n_objects=4)            # 3 frames: odd tile counts at levels 3-4
+    plain = _net(filters, (112, 80), 'concat', 1, 2, w).predict(x)
+    monkeypatch.setenv('SQ_CLUSTER', '1')
+    clustered = _net(filters, (112, 80), 'concat', 1, 2, w).predict(x)
+    np.testing.assert_array_equal(clustered['logits'], plain['logits'])
+    np.testing.assert_array_equal(clustered['mask'], plain['mask'])
