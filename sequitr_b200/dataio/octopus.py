@@ -175,11 +175,18 @@ class OctopusData(object):
     def __len__(self):
         return self.num_frames
 
-    def frames_raw(self, start, count):
+    def frames_raw(self, start, count, out=None):
         """ ``count`` frames from ``start`` as ONE contiguous (count,H,W) array in the stored integer
-        type (crossing file boundaries) -- the batch ``UNet.segment_and_localise`` takes. """
+        type (crossing file boundaries) -- the batch ``UNet.segment_and_localise`` takes.  ``out``: an
+        optional destination, e.g. a page-locked buffer from ``utils.pinned_array`` reused per batch. """
         count = min(int(count), self.num_frames - int(start))
-        out = np.empty((max(count, 0), self.framesize[0], self.framesize[1]), dtype='uint' + str(self.bit_depth))
+        shape = (max(count, 0), self.framesize[0], self.framesize[1])
+        if out is None:
+            out = np.empty(shape, dtype='uint' + str(self.bit_depth))
+        else:
+            out = out[:shape[0]]
+            if out.shape != shape or out.dtype != np.dtype('uint' + str(self.bit_depth)):
+                raise ValueError('frames_raw: out must be a (>=count,H,W) array of the stream dtype')
         done = 0
         while done < count:
             local = self._select_file(start + done)

@@ -261,3 +261,19 @@ def struct_be_tiff(tmp_path, img):
             fh.write(struct.pack('>HHII', tag, typ, cnt, val))
         fh.write(struct.pack('>I', 0))
     return path
+
+
+def test_pinned_array_and_reader_destination(tmp_path):
+    from sequitr_b200.dataio import OctopusData, write_octopus_stream
+    import torch
+    frames = np.arange(5 * 6 * 8, dtype=np.uint16).reshape(5, 6, 8)
+    stem = str(tmp_path / 'S_')
+    write_octopus_stream(stem, frames, frames_per_file=2)
+    buf = np.zeros((4, 6, 8), np.uint16)
+    if torch.cuda.is_available():                      # page-locking needs a CUDA driver
+        buf = utils.pinned_array((4, 6, 8), np.uint16)
+    got = OctopusData(stem).frames_raw(1, 3, out=buf)
+    np.testing.assert_array_equal(got, frames[1:4])
+    assert np.shares_memory(got, buf)
+    with pytest.raises(ValueError):
+        OctopusData(stem).frames_raw(0, 2, out=np.zeros((2, 6, 8), np.uint8))
