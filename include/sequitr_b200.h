@@ -204,6 +204,25 @@ int sq_weighted_ce(sq_handle_t h, const float *logits_dev, const uint8_t *labels
                    const float *weights_dev, long long npix, int K, double *loss_dev,
                    float *grad_dev, void *workspace_dev, size_t workspace_bytes, void *stream);
 
+/* tr_augment of the training input pipeline (reference networks/unet.py:348-401; config 5): random
+ * rotation about the image centre, crop, one-hot label expansion -- fused into one gather kernel, so
+ * only the (ch,cw) crop is computed (the reference rotates four full-size tensors with
+ * tf.contrib.image.rotate :373-383, then crops :391-393).  Per frame i the caller supplies the
+ * projective coefficients transforms_host[6i..6i+5] = (a0,a1,a2,b0,b1,b2) mapping an OUTPUT pixel
+ * (x = column, y = row) to the input sample point (a0*x + a1*y + a2, b0*x + b1*y + b2) -- for a
+ * rotation by theta TensorFlow's angles_to_projective_transforms gives (cos, -sin, x_off, sin, cos,
+ * y_off) -- and the crop origin crop_host[2i..2i+1] = (rh, rw) (:387-388).  image_dev float32
+ * (n,hgt,wid,c) is sampled BILINEAR, label_dev uint8 (n,hgt,wid) NEAREST (std::round), weights_dev
+ * float32 (n,hgt,wid) BILINEAR plus 1 wherever the NEAREST sample point lies outside the frame (the
+ * reference's wgt_mask :380-383); samples outside the frame read 0.  All coordinate arithmetic is
+ * float32 without fused multiply-add (TensorFlow 1.x ImageProjectiveTransform).  Outputs:
+ * image_out (n,ch,cw,c) float32, label_out (n,ch,cw,num_outputs) uint8 one-hot of classes
+ * 0..num_outputs-1 (:396-398, num_outputs <= 5), weights_out (n,ch,cw) float32. */
+int sq_tr_augment(sq_handle_t h, const float *image_dev, const uint8_t *label_dev, const float *weights_dev,
+                  int n, int hgt, int wid, int c, const float *transforms_host, const int *crop_host,
+                  int ch, int cw, int num_outputs, float *image_out_dev, uint8_t *label_out_dev,
+                  float *weights_out_dev, void *stream);
+
 /* The whole data-parallel hot path on HOST frames: H2D -> UNet -> argmax ->
  * label-and-localise -> D2H of the centroid tables (the call a Sequitr job
  * function makes per batch of frames).  frames_host float32 (n,hgt,wid,cin);

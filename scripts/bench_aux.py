@@ -57,4 +57,16 @@ for name, fn, bpp in (
                  'achieved_GBs': gbs, 'frac_of_hbm_peak': gbs / PEAK})
     print('%-38s %8.3f ms  %7.1f us/frame  %2d B/px  %8.1f GB/s  %5.1f%% of %.0f GB/s'
           % (name, ms, 1e3 * ms / N, bpp, gbs, 100 * gbs / PEAK, PEAK))
+# tr_augment: 2048^2 frames -> 1024^2 rotated crops, bytes counted per OUTPUT pixel (9 gathered in, 10 out)
+lab8_d = (lab_d % 5).to(torch.uint8).contiguous()
+wgt_d = ops.weightmap_edt(mask_d, 10., 5., 'float32')
+rs = np.random.RandomState(0)
+tr = np.stack([ops.rotation_transform(2 * np.pi * rs.uniform(), H, W) for _ in range(N)])
+cr = rs.randint(0, 1024, (N, 2)).astype(np.int32)
+ms = timeit(lambda: ops.tr_augment(frames_d, lab8_d, wgt_d, tr, cr, 1024, 1024, 2))
+gbs = N * 1024 * 1024 * 19 / (ms * 1e-3) / 1e9
+rows.append({'kernel': 'tr_augment 2048^2 -> 1024^2 (rotate+crop+one-hot)', 'ms_per_launch': ms, 'us_per_frame': 1e3 * ms / N,
+             'bytes_per_px': 19, 'achieved_GBs': gbs, 'frac_of_hbm_peak': gbs / PEAK})
+print('%-38s %8.3f ms  %7.1f us/frame  %2d B/px  %8.1f GB/s  %5.1f%% of %.0f GB/s'
+      % ('tr_augment (rotate+crop+one-hot)', ms, 1e3 * ms / N, 19, gbs, 100 * gbs / PEAK, PEAK))
 print(json.dumps({'frames_per_launch': N, 'hbm_peak_GBs': PEAK, 'kernels': rows}))

@@ -14,6 +14,9 @@
 * ``prep_ref.npz``       -- inputs + outputs of the REFERENCE's ``ImageNorm`` / ``ImageOutliers`` /
   ``ImageBGSubtract`` pipes (pre-inference clean-up).
 
+* ``augment_kat.npz``    -- a known-answer test of the ``tr_augment`` oracle (TensorFlow's projective
+  resampling restated; the reference's dependency is absent), to detect drift of the contract.
+
 The /root/reference tree does not travel to the GPU box; these files do.
 """
 import os
@@ -65,7 +68,25 @@ def prep_cases():
     return cases
 
 
+def augment_kat():
+    from oracle import augment_oracle as ao
+    rng = np.random.default_rng(31)
+    n, h, w, c, ch, cw, k = 4, 40, 52, 2, 24, 32, 3
+    image = rng.standard_normal((n, h, w, c)).astype(np.float32)
+    label = rng.integers(0, 4, (n, h, w)).astype(np.uint8)
+    weights = rng.uniform(1, 11, (n, h, w)).astype(np.float32)
+    theta = np.array([0.0, 0.4, 2.2, 5.0], dtype=np.float32)
+    crop = np.array([[0, 0], [16, 20], [3, 7], [10, 1]], dtype=np.int32)
+    outs = [ao.tr_augment(image[i], label[i], weights[i], theta[i], crop[i, 0], crop[i, 1], ch, cw, k) for i in range(n)]
+    np.savez_compressed(os.path.join(OUT, 'augment_kat.npz'), image=image, label=label, weights=weights, theta=theta,
+                        crop=crop, ch=ch, cw=cw, k=k, image_out=np.stack([o[0] for o in outs]),
+                        label_out=np.stack([o[1] for o in outs]), weights_out=np.stack([o[2] for o in outs]))
+    print('augment_kat.npz')
+
+
 def main():
+    if sys.argv[1:] == ['augment']:
+        return augment_kat()
     os.makedirs(OUT, exist_ok=True)
     ref = ref_loader.load_reference_pipeline()
 
@@ -125,6 +146,7 @@ def main():
     rb = unet_c.unet_forward(x, w, filters, 'concat', contract='bf16')
     np.savez_compressed(os.path.join(OUT, 'unet_kat.npz'), x=x, logits=r['logits'],
                         mask=r['mask'], logits_bf16=rb['logits'], filters=np.array(filters))
+    augment_kat()
     print('golden vectors written to', OUT)
 
 

@@ -58,6 +58,8 @@ _SIGNATURES = {
     'sq_weighted_ce_workspace_bytes': (c_int, [c_void_p, _P(c_size_t)]),
     'sq_weighted_ce': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_longlong, c_int, c_void_p,
                        c_void_p, c_void_p, c_size_t, c_void_p]),
+    'sq_tr_augment': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
+                              c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     'sq_prep_workspace_bytes': (c_int, [c_void_p, c_int, c_int, _P(c_size_t)]),
     'sq_image_norm': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_size_t,
                               c_void_p]),

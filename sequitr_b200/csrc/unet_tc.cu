@@ -804,8 +804,15 @@ __device__ __forceinline__ void mma_m16n8k16_bf16(float *c, const uint32_t *a, u
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-constexpr int FIRST_ROWS = 8;              // rows per block (one warp per row; a multiple of 8)
 constexpr int FIRST_TW = 128;              // pixels per block row
+// rows per block: one warp per row, several passes (a multiple of 8).  Tall blocks amortise the
+// per-block set-up (weight fragments, tap offsets: ~100 instructions per thread) and shrink the halo
+// share of the staging; the cap keeps the staged tile below ~40 KB of static shared memory.
+__host__ __device__ constexpr int first_rows(int cin, int kz)
+{
+    const int r = (10240 / (kz * ((FIRST_TW + 2) * cin + 2)) - 2) / 8 * 8;
+    return r > 32 ? 32 : (r < 8 ? 8 : r);
+}
 
 template <int CIN, int COUT, int KZ>
 __global__ void __launch_bounds__(256)
@@ -815,6 +822,7 @@ first_conv_kernel(const float *__restrict__ in, const float *__restrict__ wf,
 {
     // KZ = 1: planar 3x3 (D = 1); KZ = 3: 3x3x3 on slice z of a volume, taps ordered (kz, ky, kx)
     constexpr int KTOT = 9 * KZ * CIN, KS = (KTOT + 15) / 16, NT = COUT / 8;
+    constexpr int FIRST_ROWS = first_rows(CIN, KZ);
     constexpr int SROW = (FIRST_TW + 2) * CIN + 2;            // staged row pitch (floats)
     constexpr int SSLICE = (FIRST_ROWS + 2) * SROW;
     __shared__ float tile[KZ * SSLICE];
@@ -823,16 +831,19 @@ first_conv_kernel(const float *__restrict__ in, const float *__restrict__ wf,
     const int np = blockIdx.z, x0 = blockIdx.x * FIRST_TW, y0 = blockIdx.y * FIRST_ROWS;
     const int z = np % D;
 
-    // stage the KZ x (ROWS+2) x (TW+2) input halo tile once (zero outside the image = SAME padding)
+    // stage the KZ x (ROWS+2) x (TW+2) input halo tile once (zero outside the image = SAME padding):
+    // one warp per staged row, lanes along the row
     constexpr int ROWF = (FIRST_TW + 2) * CIN;
-    for (int i = threadIdx.x; i < KZ * (FIRST_ROWS + 2) * ROWF; i += 256) {
-        const int kz = i / ((FIRST_ROWS + 2) * ROWF), r = i % ((FIRST_ROWS + 2) * ROWF);
-        const int ry = r / ROWF, rx = r % ROWF;
-        const int zz = z + kz - (KZ >> 1), yy = y0 + ry - 1, e = (x0 - 1) * CIN + rx;
-        float v = 0.0f;
-        if (zz >= 0 && zz < D && yy >= 0 && yy < H && e >= 0 && e < W * CIN)
-            v = __ldg(in + ((size_t)(np + zz - z) * H + yy) * W * CIN + e);
-        tile[kz * SSLICE + ry * SROW + rx] = v;
+    for (int ri = warp; ri < KZ * (FIRST_ROWS + 2); ri += 8) {
+        const int kz = ri / (FIRST_ROWS + 2), ry = ri % (FIRST_ROWS + 2);
+        const int zz = z + kz - (KZ >> 1), yy = y0 + ry - 1, e0 = (x0 - 1) * CIN;
+        const bool row_ok = zz >= 0 && zz < D && yy >= 0 && yy < H;
+        const float *srow = in + ((size_t)(np + zz - z) * H + (row_ok ? yy : 0)) * W * CIN + e0;
+        float *trow = tile + kz * SSLICE + ry * SROW;
+        for (int rx = lane; rx < ROWF; rx += 32) {
+            const int e = e0 + rx;
+            trow[rx] = (row_ok && e >= 0 && e < W * CIN) ? __ldg(srow + rx) : 0.0f;
+        }
     }
     // B fragments: b0 = (k = 2t, 2t+1 ; n = g), b1 = (k = 2t+8, 2t+9 ; n = g); zero beyond KTOT
     uint32_t bw[KS][NT][2];
@@ -1488,7 +1499,8 @@ int tc_run(sq_unet_s *u, bool dry, const float *in, int n, int dep, int hgt, int
         if (l == 0 && vol) {
             const float *wf = (const float *)c1->w_tc;
             const int key = u->cin * 1000 + c1->cout;
-            const dim3 g3((W + FIRST_TW - 1) / FIRST_TW, (H + FIRST_ROWS - 1) / FIRST_ROWS, n * D);
+            const int fr3 = first_rows(u->cin, 3);
+            const dim3 g3((W + FIRST_TW - 1) / FIRST_TW, (H + fr3 - 1) / fr3, n * D);
             SQ_REQUIRE((long long)n * D <= 65535, SQ_EINVAL, "unet(bf16): more than 65535 slices per call");
 #define SQ_FIRST3M(CI, CO) first_conv_kernel<CI, CO, 3><<<g3, 256, 0, st>>>(in, wf, c1->scale, c1->shift, t1[0], n, D, H, W)
             if (key == 1016) SQ_FIRST3M(1, 16);
@@ -1513,7 +1525,8 @@ int tc_run(sq_unet_s *u, bool dry, const float *in, int n, int dep, int hgt, int
             ++u->last_launches;
             SQ_CHECK_LAUNCH();
         } else if (l == 0) {
-            const dim3 grid((W + FIRST_TW - 1) / FIRST_TW, (H + FIRST_ROWS - 1) / FIRST_ROWS, n);
+            const int fr = first_rows(u->cin, 1);
+            const dim3 grid((W + FIRST_TW - 1) / FIRST_TW, (H + fr - 1) / fr, n);
             const float *wf = (const float *)c1->w_tc;
 #define SQ_FIRST(CI, CO) first_conv_kernel<CI, CO, 1><<<grid, 256, 0, st>>>(in, wf, c1->scale, c1->shift, t1[0], n, 1, H, W)
             const int key = u->cin * 1000 + c1->cout;

@@ -477,3 +477,65 @@ class UNet3D(_ConcreteUNet):
         _ConcreteUNet.__init__(self, p, mode)
         if self.ndim != 3:
             raise ValueError('UNet3D needs a 3-D shape (width, height, slices)')
+
+
+
+def tr_augment(features, params, rng=None):
+    """ Augment the dataset by random cropping, flipping and rotations
+
+    Drop-in for the reference ``tr_augment`` (networks/unet.py:348-401): identical augmentations
+    are applied to the image (bilinear), the labels (nearest) and the weight map (bilinear, plus one
+    outside the rotated frame :380-383), the result is cropped to ``params['shape']`` and the label
+    is expanded to ``params['num_outputs']`` one-hot channels (:396-398).  The four full-size
+    ``tf.contrib.image.rotate`` calls and the crop run as ONE gather kernel (``sq_tr_augment``).
+
+    features: dict with 'image' (N,H,W,C) float32, 'label' (N,H,W[,1]) uint8, 'weights'
+    (N,H,W[,1]) float32, 'shape' = (N,H,W,C) -- NumPy arrays or cuda tensors.  The random draws
+    (theta = 2*pi*U[0,1) :370, crop origin :387-388) come from ``rng`` (``numpy.random.RandomState``,
+    one draw per example); pass ``features['theta']`` / ``features['crop']`` to fix them.
+    Returns ``img, {'label': label, 'weights': weights}`` like the reference (cuda tensors).
+    """
+    import torch
+    rng = rng or np.random
+    dev = 'cuda'
+
+    def to_dev(v, dtype):
+        t = v if torch.is_tensor(v) else torch.from_numpy(np.ascontiguousarray(v))
+        return t.to(device=dev, dtype=dtype).contiguous()
+
+    img = to_dev(features['image'], torch.float32)
+    if img.dim() == 3:
+        img = img[None]
+    n, height, width, _ = (int(v) for v in img.shape)
+    label = to_dev(features['label'], torch.uint8).reshape(n, height, width)
+    weights = to_dev(features['weights'], torch.float32).reshape(n, height, width)
+    if 'shape' in features and tuple(int(v) for v in features['shape'])[1:3] != (height, width):
+        raise ValueError("features['shape'] does not match the image")
+    outputs = params.get('num_outputs', 2)
+    ch, cw = params.get('shape', (512, 512))[0:2]
+    if ch > height or cw > width:
+        raise ValueError('crop (%d,%d) larger than the image (%d,%d)' % (ch, cw, height, width))
+    thetas = features.get('theta')
+    if thetas is None:
+        thetas = [np.float32(2.) * np.float32(rng.uniform()) * np.float32(np.pi) for _ in range(n)]
+    thetas = np.broadcast_to(np.asarray(thetas, dtype=np.float32), (n,))
+    crops = features.get('crop')
+    if crops is None:
+        # the reference's `if (ch,cw != height,width)` is always true (:386); tf.random_uniform needs
+        # maxval > 0, so a crop as large as the image keeps origin 0 here instead of raising
+        crops = [(rng.randint(0, height - ch) if height > ch else 0,
+                  rng.randint(0, width - cw) if width > cw else 0) for _ in range(n)]
+    crops = np.broadcast_to(np.asarray(crops, dtype=np.int32), (n, 2))
+    transforms = np.stack([ops.rotation_transform(t, height, width) for t in thetas])
+    img, label, weights = ops.tr_augment(img, label, weights, transforms, crops, ch, cw, outputs)
+    return img, {'label': label, 'weights': weights[..., None]}
+
+
+def preprocess_norm(features):
+    """ normalise images or volumes to mean 0. and std 1.0
+
+    The reference computes the normalised image and then returns the UN-normalised ``features``
+    (networks/unet.py:405-432: the assignment at :430 is commented out), so this is the identity;
+    use ``pipeline.ImageNorm`` / ``segment_and_localise(normalise=True)`` for the active transform.
+    """
+    return features

@@ -129,6 +129,42 @@ def weighted_cross_entropy(logits, labels, weights, want_grad=True, workspace=No
     return loss, grad
 
 
+def rotation_transform(theta, height, width):
+    """TensorFlow 1.x ``angles_to_projective_transforms`` for one angle (float32 arithmetic):
+    (cos, -sin, x_off, sin, cos, y_off) maps an output pixel (x, y) to its input sample point, a
+    rotation about the image centre as ``tf.contrib.image.rotate`` (reference networks/unet.py:373)."""
+    f32 = np.float32
+    theta = f32(theta)
+    c, s = np.cos(theta, dtype=f32), np.sin(theta, dtype=f32)
+    wm1, hm1 = f32(width) - f32(1), f32(height) - f32(1)
+    x_off = (wm1 - (c * wm1 - s * hm1)) / f32(2)
+    y_off = (hm1 - (s * wm1 + c * hm1)) / f32(2)
+    return np.array([c, -s, x_off, s, c, y_off], dtype=f32)
+
+
+def tr_augment(image, label, weights, transforms, crops, ch, cw, num_outputs=2):
+    """Fused rotate + crop + one-hot of the training pipeline (reference networks/unet.py:348-401)
+    on cuda tensors: image float32 (N,H,W,C), label uint8 (N,H,W), weights float32 (N,H,W);
+    transforms float32 ndarray (N,6) (see ``rotation_transform``), crops int ndarray (N,2) = (rh, rw).
+    Returns (image (N,ch,cw,C) float32, label (N,ch,cw,num_outputs) uint8, weights (N,ch,cw) float32)."""
+    torch = _torch()
+    lib = _lib.load()
+    assert image.is_cuda and image.dtype == torch.float32 and image.is_contiguous() and image.dim() == 4
+    n, h, w, c = (int(v) for v in image.shape)
+    assert label.dtype == torch.uint8 and tuple(label.shape) == (n, h, w) and label.is_contiguous()
+    assert weights.dtype == torch.float32 and tuple(weights.shape) == (n, h, w) and weights.is_contiguous()
+    transforms = np.ascontiguousarray(transforms, dtype=np.float32).reshape(n, 6)
+    crops = np.ascontiguousarray(crops, dtype=np.int32).reshape(n, 2)
+    img_o = torch.empty((n, ch, cw, c), dtype=torch.float32, device=image.device)
+    lab_o = torch.empty((n, ch, cw, num_outputs), dtype=torch.uint8, device=image.device)
+    wgt_o = torch.empty((n, ch, cw), dtype=torch.float32, device=image.device)
+    _lib.check(lib.sq_tr_augment(_lib.handle(image.device.index), image.data_ptr(), label.data_ptr(),
+                                 weights.data_ptr(), n, h, w, c, transforms.ctypes.data, crops.ctypes.data,
+                                 int(ch), int(cw), int(num_outputs), img_o.data_ptr(), lab_o.data_ptr(),
+                                 wgt_o.data_ptr(), _lib.stream_ptr()))
+    return img_o, lab_o, wgt_o
+
+
 def _stack_geometry(x):
     torch = _torch()
     assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 4

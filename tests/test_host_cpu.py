@@ -277,3 +277,62 @@ def test_pinned_array_and_reader_destination(tmp_path):
     assert np.shares_memory(got, buf)
     with pytest.raises(ValueError):
         OctopusData(stem).frames_raw(0, 2, out=np.zeros((2, 6, 8), np.uint8))
+
+
+def test_tracker_formats_round_trip(tmp_path):
+    """dataio/tracker.py (reference :36-260): Track container, JSON (plain and zipped) and XML."""
+    import json
+    import zipfile
+    from sequitr_b200.dataio import tracker
+
+    def mk(i, n):
+        d = {'ID': i, 'x': [10.04 + k for k in range(n)], 'y': [5.55 + 2 * k for k in range(n)],
+             'z': [0.0] * n, 't': list(range(3, 3 + n)), 'length': n, 'label': [0] * n, 'parent': i,
+             'children': [], 'fate': 4}
+        return d
+
+    folder = str(tmp_path)
+    files = []
+    for i, n in ((1, 4), (2, 6)):
+        fn = 'track_%d_GFP.json' % i
+        files.append(fn)
+        with open(os.path.join(folder, fn), 'w') as f:
+            json.dump(mk(i, n), f)
+    with open(os.path.join(folder, 'tracks_GFP.json'), 'w') as f:
+        json.dump({'GFP': {'files': files, 'path': folder, 'zipped': False}}, f)
+    tracks = tracker.read_JSON(folder, 'GFP')
+    assert [t.ID for t in tracks] == [1, 2] and len(tracks[1]) == 6
+    t = tracks[0]
+    assert t.cell_type == 'GFP' and t.filename == files[0] and t.n is t.t
+    assert t.in_frame(4) and not t.in_frame(99) and t.fate_as_string == 'mitosis'
+    c = t.get_copy_at_frame(5)
+    assert c.ref is t and c.x == t.x[2] and c.t == 5 and c.ID == 1 and t.get_copy_at_frame(99) is None
+    assert t['x'] is t.x and t['nonexistent'] is None
+    t.neighborhood = [{'n_total': 3}, {'n_total': 5}]
+    assert t['n_total'] == [3, 5]
+    with pytest.raises(TypeError):
+        t.get_neighborhood_attr(3)
+    t.neighborhood = []
+    # zipped variant
+    with zipfile.ZipFile(os.path.join(folder, 'tracks_RFP.zip'), 'w') as z:
+        z.writestr('track_7_RFP.json', json.dumps(mk(7, 3)))
+    with open(os.path.join(folder, 'tracks_RFP.json'), 'w') as f:
+        json.dump({'RFP': {'files': ['track_7_RFP.json'], 'path': folder, 'zipped': True}}, f)
+    z = tracker.read_JSON(folder, 'RFP')
+    assert len(z) == 1 and z[0].ID == 7 and z[0].cell_type == 'RFP'
+    with pytest.raises(IOError):
+        tracker.read_JSON(folder, 'iRFP')
+    # XML: coordinates are written to one decimal; the frame list comes back as Track.t
+    xml = os.path.join(folder, 'tracks.xml')
+    tracker.write_XML(xml, tracks)
+    back = tracker.read_XML(xml, cell_type='GFP')
+    assert [b.ID for b in back] == [1, 2]
+    assert back[0].x == [10.0, 11.0, 12.0, 13.0]
+    assert back[0].y == [float('%2.1f' % v) for v in tracks[0].y]
+    assert back[0].t == tracks[0].t and back[0].label == tracks[0].label and back[0].fate == 4
+    assert back[0].length == 4 and back[0].parent == 1 and back[0].children == []
+    assert tracker.read_XML(None) == [] and tracker.read_XML(os.path.join(folder, 'missing.xml')) == []
+    with pytest.raises(IOError):
+        tracker.read_XML(os.path.join(folder, 'tracks.json'))
+    with pytest.raises(TypeError):
+        tracker.read_XML(3)
