@@ -51,6 +51,42 @@ def dense_layer_bytes(filters=FILTERS, px=H * W, classes_mask_bytes=1):
         total += p * 2 * (2 * f + f)                                   # conv1 on concat(up, skip)
         total += p * 2 * f + (p * 2 * f if l > 0 else p * classes_mask_bytes)
     return total
+
+
+def dense_layer_traffic(filters=FILTERS, px=H * W, cin=1, classes_mask_bytes=1):
+    """The same compulsory bytes split per layer into (read, written), keyed by TF scope: a B200's HBM
+    takes ~3.9 TB/s of pure writes against ~6.5 TB/s of reads or of a read+write mix
+    (scripts/hbm_probe.py), so a write-heavy layer has a higher floor than its byte count suggests."""
+    nl, t = len(filters), {}
+    for l, f in enumerate(filters):
+        p = px / 4 ** l
+        t['UNet/down%d/conv1' % l] = (p * (4 * cin if l == 0 else 2 * filters[l - 1]), p * 2 * f)
+        t['UNet/down%d/conv2' % l] = (p * 2 * f, p * 2 * f + (p / 4 * 2 * f if l < nl - 1 else 0))
+    for l in range(nl - 2, -1, -1):
+        p, f = px / 4 ** l, filters[l]
+        t['UNet/up%d/upscale' % l] = (p / 4 * 2 * filters[l + 1], p * 2 * f)
+        t['UNet/up%d/conv1' % l] = (p * 2 * 2 * f, p * 2 * f)
+        t['UNet/up%d/conv2' % l] = (p * 2 * f, p * 2 * f if l > 0 else p * classes_mask_bytes)
+    return t
+
+
+def hbm_write_only_gbs(dev):
+    """Pure-write HBM bandwidth measured live (torch fill_ of 1 GiB of float32, best of 5, CUDA events)."""
+    import torch
+    buf = torch.empty(1 << 28, dtype=torch.float32, device=dev)
+    best = None
+    for i in range(6):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        buf.fill_(float(i))
+        e1.record()
+        torch.cuda.synchronize()
+        if i:
+            best = e0.elapsed_time(e1) if best is None else min(best, e0.elapsed_time(e1))
+    del buf
+    return (1 << 30) / (best * 1e-3) / 1e9
+
+
 METRIC = "frames/sec 2048^2 UNet2D seg+localize"
 
 
@@ -286,8 +322,10 @@ def main():
         for _ in range(3):
             rows = net.profile(dev_pool)
         reps = 3
+        layer_ms = {}
         for _ in range(reps):
             for name, lms, fl in net.profile(dev_pool):
+                layer_ms[name] = layer_ms.get(name, 0.0) + lms / reps
                 if fl > 0 and name not in ('UNet/down0/conv1', 'UNet/to_image'):
                     dense_ms += lms
                     dense_fl += fl
@@ -316,6 +354,28 @@ def main():
                         "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes / (n_dense // reps),
                         "kernel": "same 21 launches, compulsory bf16 activation bytes (each layer reads its "
                                   "inputs once, writes its output once)"}
+
+        # Per-layer floor: max(all bytes / copy peak, written bytes / write-only peak, FLOPs / sustained
+        # tensor peak), summed over every UNet launch of a step (first conv included) against the time
+        # those launches took: how far the layer-by-layer design is from ITS OWN limits.
+        try:
+            wr_peak = hbm_write_only_gbs(dev)
+            floor_ms = meas_ms = 0.0
+            traffic_l = dense_layer_traffic()
+            flops_l = {name: fl for name, _, fl in rows}
+            for name, (rd, wr) in traffic_l.items():
+                if name not in layer_ms:
+                    continue
+                fl = flops_l.get(name, 0.0)
+                floor_ms += 1e3 * max((rd + wr) * B / (hbm_peak * 1e9), wr * B / (wr_peak * 1e9), fl / (peak * 1e12))
+                meas_ms += layer_ms[name]
+            roofline_hbm["layer_floor"] = {
+                "hbm_write_only_gbs": wr_peak, "floor_ms_per_step": floor_ms, "measured_ms_per_step": meas_ms,
+                "frac": floor_ms / meas_ms if meas_ms else None,
+                "model": "sum over the UNet launches of max(bytes / copy peak, written bytes / write-only peak, "
+                         "FLOPs / sustained bf16 peak)"}
+        except Exception as e:                       # explanatory only: never fail the bench line on it
+            roofline_hbm["layer_floor"] = {"error": str(e)}
 
     # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same workload
     cpu = None

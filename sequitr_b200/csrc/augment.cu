@@ -25,52 +25,76 @@ __device__ __forceinline__ float aug_coord(float c0, float c1, float c2, float x
     return __fadd_rn(__fadd_rn(__fmul_rn(c0, x), __fmul_rn(c1, y)), c2);
 }
 
-template <typename T>
-__device__ __forceinline__ float aug_read(const T *__restrict__ img, int hgt, int wid, int c, int y, int x, int ch)
-{
-    return (y >= 0 && y < hgt && x >= 0 && x < wid) ? (float)img[((long long)y * wid + x) * c + ch] : 0.0f;
-}
+// the four corner taps of a zero-filled bilinear sample: offsets (or -1 outside) and the float32 weights
+struct AugTaps {
+    long long o00, o01, o10, o11;
+    float wx0, wx1, wy0, wy1;
+};
 
-__device__ __forceinline__ float aug_bilinear(const float *__restrict__ img, int hgt, int wid, int c, float y, float x,
-                                              int ch)
+__device__ __forceinline__ AugTaps aug_taps(int hgt, int wid, float y, float x)
 {
+    AugTaps T;
     const float yf = floorf(y), xf = floorf(x);
     const float yc = __fadd_rn(yf, 1.0f), xc = __fadd_rn(xf, 1.0f);
     // clamp before the int conversion: coordinates far outside the frame read the fill value anyway
     const int y0 = (int)fminf(fmaxf(yf, -2.0f), (float)hgt + 1.0f), x0 = (int)fminf(fmaxf(xf, -2.0f), (float)wid + 1.0f);
-    const float wx1 = __fsub_rn(xc, x), wx0 = __fsub_rn(x, xf);
-    const float v_floor = __fadd_rn(__fmul_rn(wx1, aug_read(img, hgt, wid, c, y0, x0, ch)),
-                                    __fmul_rn(wx0, aug_read(img, hgt, wid, c, y0, x0 + 1, ch)));
-    const float v_ceil = __fadd_rn(__fmul_rn(wx1, aug_read(img, hgt, wid, c, y0 + 1, x0, ch)),
-                                   __fmul_rn(wx0, aug_read(img, hgt, wid, c, y0 + 1, x0 + 1, ch)));
-    return __fadd_rn(__fmul_rn(__fsub_rn(yc, y), v_floor), __fmul_rn(__fsub_rn(y, yf), v_ceil));
+    const bool r0 = y0 >= 0 && y0 < hgt, r1 = y0 + 1 >= 0 && y0 + 1 < hgt;
+    const bool c0 = x0 >= 0 && x0 < wid, c1 = x0 + 1 >= 0 && x0 + 1 < wid;
+    const long long base = (long long)y0 * wid + x0;
+    T.o00 = (r0 && c0) ? base : -1;
+    T.o01 = (r0 && c1) ? base + 1 : -1;
+    T.o10 = (r1 && c0) ? base + wid : -1;
+    T.o11 = (r1 && c1) ? base + wid + 1 : -1;
+    T.wx1 = __fsub_rn(xc, x); T.wx0 = __fsub_rn(x, xf);
+    T.wy1 = __fsub_rn(yc, y); T.wy0 = __fsub_rn(y, yf);
+    return T;
 }
 
-// one thread per cropped pixel; a 32x8 block keeps the rotated footprint compact for L1/L2
+__device__ __forceinline__ float aug_tap(const float *__restrict__ img, long long o, int c, int ch)
+{
+    return o >= 0 ? __ldg(img + o * c + ch) : 0.0f;
+}
+
+// TensorFlow's order: (x_ceil-x)*f(x_floor) + (x-x_floor)*f(x_ceil) per row, then the same over rows
+__device__ __forceinline__ float aug_bilinear(const float *__restrict__ img, const AugTaps &T, int c, int ch)
+{
+    const float v_floor = __fadd_rn(__fmul_rn(T.wx1, aug_tap(img, T.o00, c, ch)), __fmul_rn(T.wx0, aug_tap(img, T.o01, c, ch)));
+    const float v_ceil = __fadd_rn(__fmul_rn(T.wx1, aug_tap(img, T.o10, c, ch)), __fmul_rn(T.wx0, aug_tap(img, T.o11, c, ch)));
+    return __fadd_rn(__fmul_rn(T.wy1, v_floor), __fmul_rn(T.wy0, v_ceil));
+}
+
+// A block owns a 32x32 tile of the crop (one warp per row, four passes): the rotated footprint of a
+// square tile touches ~1.5x its own sectors, a flat 32x8 strip more than 2x.
+constexpr int AUG_TILE = 32;
+
 __global__ void __launch_bounds__(256)
 augment_kernel(const float *__restrict__ image, const uint8_t *__restrict__ label, const float *__restrict__ weights,
                int hgt, int wid, int c, int ch, int cw, int k, AugParams P, float *__restrict__ image_out,
                uint8_t *__restrict__ label_out, float *__restrict__ weights_out)
 {
-    const int ox = blockIdx.x * 32 + (threadIdx.x & 31);
-    const int oy = blockIdx.y * 8 + (threadIdx.x >> 5);
+    const int ox = blockIdx.x * AUG_TILE + (threadIdx.x & 31);
     const int n = blockIdx.z;
-    if (ox >= cw || oy >= ch) return;
+    if (ox >= cw) return;
     const AugFrame F = P.f[n];
-    const float x = (float)(ox + F.rw), y = (float)(oy + F.rh);
-    const float ix = aug_coord(F.a0, F.a1, F.a2, x, y);
-    const float iy = aug_coord(F.b0, F.b1, F.b2, x, y);
     const long long frame = (long long)hgt * wid;
     const float *img = image + (long long)n * frame * c;
-    const long long o = ((long long)n * ch + oy) * cw + ox;
-    for (int q = 0; q < c; ++q) image_out[o * c + q] = aug_bilinear(img, hgt, wid, c, iy, ix, q);
-    // NEAREST: std::round = half away from zero
-    const float ry = roundf(iy), rx = roundf(ix);
-    const bool inside = ry >= 0.0f && ry < (float)hgt && rx >= 0.0f && rx < (float)wid;
-    const int lab = inside ? label[(long long)n * frame + (long long)ry * wid + (long long)rx] : 0;
-    for (int q = 0; q < k; ++q) label_out[o * k + q] = (uint8_t)(lab == q);
-    const float wv = aug_bilinear(weights + (long long)n * frame, hgt, wid, 1, iy, ix, 0);
-    weights_out[o] = __fadd_rn(wv, inside ? 0.0f : 1.0f);
+    const float *wgt = weights + (long long)n * frame;
+    const uint8_t *lab = label + (long long)n * frame;
+    const float x = (float)(ox + F.rw);
+    for (int oy = blockIdx.y * AUG_TILE + (threadIdx.x >> 5); oy < min(ch, (int)(blockIdx.y + 1) * AUG_TILE); oy += 8) {
+        const float y = (float)(oy + F.rh);
+        const float ix = aug_coord(F.a0, F.a1, F.a2, x, y);
+        const float iy = aug_coord(F.b0, F.b1, F.b2, x, y);
+        const AugTaps T = aug_taps(hgt, wid, iy, ix);
+        const long long o = ((long long)n * ch + oy) * cw + ox;
+        for (int q = 0; q < c; ++q) image_out[o * c + q] = aug_bilinear(img, T, c, q);
+        // NEAREST: std::round = half away from zero
+        const float ry = roundf(iy), rx = roundf(ix);
+        const bool inside = ry >= 0.0f && ry < (float)hgt && rx >= 0.0f && rx < (float)wid;
+        const int lv = inside ? lab[(long long)ry * wid + (long long)rx] : 0;
+        for (int q = 0; q < k; ++q) label_out[o * k + q] = (uint8_t)(lv == q);
+        weights_out[o] = __fadd_rn(aug_bilinear(wgt, T, 1, 0), inside ? 0.0f : 1.0f);
+    }
 }
 
 }  // namespace
@@ -100,7 +124,7 @@ extern "C" int sq_tr_augment(sq_handle_t h, const float *image, const uint8_t *l
             P.f[i] = AugFrame{t[0], t[1], t[2], t[3], t[4], t[5], crop_host[2 * (n0 + i)], crop_host[2 * (n0 + i) + 1]};
         }
         for (int i = nb; i < AUG_MAX_BATCH; ++i) P.f[i] = AugFrame{1, 0, 0, 0, 1, 0, 0, 0};
-        dim3 grid((unsigned)sq_div_up(cw, 32), (unsigned)sq_div_up(ch, 8), (unsigned)nb);
+        dim3 grid((unsigned)sq_div_up(cw, AUG_TILE), (unsigned)sq_div_up(ch, AUG_TILE), (unsigned)nb);
         augment_kernel<<<grid, 256, 0, st>>>(image + n0 * in_frame * c, label + n0 * in_frame, weights + n0 * in_frame,
                                              hgt, wid, c, ch, cw, num_outputs, P, image_out + n0 * out_frame * c,
                                              label_out + n0 * out_frame * num_outputs, weights_out + n0 * out_frame);

@@ -69,13 +69,22 @@ norm_partial(const T *__restrict__ in, long long npix, int C, double *__restrict
     if (C == 1 && (npix & 3) == 0) {
         // single channel: 16-byte loads, four independent accumulators per moment
         double s0 = 0, s1 = 0, s2 = 0, s3 = 0, q0 = 0, q1 = 0, q2 = 0, q3 = 0;
-        for (long long p = (long long)blockIdx.x * PREP_THREADS + threadIdx.x; p < (npix >> 2);
-             p += (long long)PREP_BLOCKS * PREP_THREADS) {
-            const float4 f = load4<T>(img + 4 * p);
+        // four 16-byte loads in flight per thread (a frame is only ~8 iterations per thread: without
+        // the batching the pass is latency-bound), accumulated in the same order as a plain loop
+        constexpr long long STRIDE = (long long)PREP_BLOCKS * PREP_THREADS;
+        const long long nv = npix >> 2;
+        long long p = (long long)blockIdx.x * PREP_THREADS + threadIdx.x;
+        auto acc4 = [&](const float4 f) {
             const double a = f.x, b = f.y, cc = f.z, d = f.w;
             s0 += a; s1 += b; s2 += cc; s3 += d;
             q0 = fma(a, a, q0); q1 = fma(b, b, q1); q2 = fma(cc, cc, q2); q3 = fma(d, d, q3);
+        };
+        for (; p + 3 * STRIDE < nv; p += 4 * STRIDE) {
+            const float4 f0 = load4<T>(img + 4 * p), f1 = load4<T>(img + 4 * (p + STRIDE));
+            const float4 f2 = load4<T>(img + 4 * (p + 2 * STRIDE)), f3 = load4<T>(img + 4 * (p + 3 * STRIDE));
+            acc4(f0); acc4(f1); acc4(f2); acc4(f3);
         }
+        for (; p < nv; p += STRIDE) acc4(load4<T>(img + 4 * p));
         v[0] = (s0 + s1) + (s2 + s3);
         v[1] = (q0 + q1) + (q2 + q3);
     } else {
@@ -101,7 +110,12 @@ __global__ void norm_final(const double *__restrict__ part, long long npix, int 
     const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (i >= nc) return;
     double s = 0.0, q = 0.0;
-    for (int b = lane; b < PREP_BLOCKS; b += 32) { s += part[((size_t)i * PREP_BLOCKS + b) * 2]; q += part[((size_t)i * PREP_BLOCKS + b) * 2 + 1]; }
+    double2 v[PREP_BLOCKS / 32];
+#pragma unroll
+    for (int k = 0; k < PREP_BLOCKS / 32; ++k)          // every load in flight before the first add
+        v[k] = reinterpret_cast<const double2 *>(part)[(size_t)i * PREP_BLOCKS + lane + 32 * k];
+#pragma unroll
+    for (int k = 0; k < PREP_BLOCKS / 32; ++k) { s += v[k].x; q += v[k].y; }
     s = warp_sum(s);
     q = warp_sum(q);
     if (lane != 0) return;
@@ -245,13 +259,17 @@ bg_partial(const float *__restrict__ in, int H, int W, BgGram G, double *__restr
         const float *row = img + (size_t)y * W;
         double r0 = 0.0, r1 = 0.0, r2 = 0.0;
         if ((W & 3) == 0 && ((uintptr_t)img & 15) == 0) {
-            for (int x = lane * 4; x < W; x += 128) {
+            // s = (x - cu) / su for this lane's four columns; the next group of columns is 128 further:
+            // x is an exact small integer in fp64, so it is advanced by addition instead of a per-pixel
+            // int -> double conversion (the conversion pipe, not HBM, bounded this pass)
+            double xd = (double)(lane * 4);
+            for (int x = lane * 4; x < W; x += 128, xd += 128.0) {
                 const float4 f = __ldg(reinterpret_cast<const float4 *>(row + x));
                 const float fv[4] = {f.x, f.y, f.z, f.w};
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const double I = (double)fv[j];
-                    const double s = ((double)(x + j) - G.cu) * isu;
+                    const double s = ((xd + (double)j) - G.cu) * isu;
                     const double Is = I * s;
                     r0 += I;
                     r1 += Is;
@@ -283,8 +301,11 @@ __global__ void bg_solve(const double *__restrict__ part, BgGram G, int nimg, do
     // one block of 6 warps per image: warp i reduces moment i, thread 0 solves
     __shared__ double rhs[6];
     const int n = blockIdx.x, i = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double s = 0.0;
-    for (int b = lane; b < PREP_BLOCKS; b += 32) s += part[((size_t)n * PREP_BLOCKS + b) * 6 + i];
+    double s = 0.0, v[PREP_BLOCKS / 32];
+#pragma unroll
+    for (int k = 0; k < PREP_BLOCKS / 32; ++k) v[k] = part[((size_t)n * PREP_BLOCKS + lane + 32 * k) * 6 + i];
+#pragma unroll
+    for (int k = 0; k < PREP_BLOCKS / 32; ++k) s += v[k];
     s = warp_sum(s);
     if (lane == 0) rhs[i] = s;
     __syncthreads();
