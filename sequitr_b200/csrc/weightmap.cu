@@ -416,107 +416,109 @@ __global__ void w1_table_kernel(double *__restrict__ table, int n, double w0e, d
     if (i >= n) return;
     const double d = sqrt((double)i);
     table[i] = w0e * exp(-(d * d) / denom) + 0.0 + 1.0;
+    if (i == n - 1) table[n] = 1.0;                      // one past the cut-off: the class weight alone
 }
 
-// grid (ceil(W/32), ceil(H/64), n), block 256, dyn smem (rows8 + rows8/8) * 32 * 2 bytes with
-// rows8 = 64 + 2R rounded up to 8.  The window is staged as SQUARED row distances (uint16, 0xFFFF =
-// none within R) plus the minimum of every 8-row block, and a pixel scans block by block outwards:
-// a block whose lower bound dy_min^2 + block_min cannot beat the current best is skipped with one
-// load, so a pixel far from every object costs ~2R/8 loads instead of 2R, and one next to an object
-// opens one or two blocks.  Every candidate is a real pixel, so the minimum is exact whenever it is
-// <= R^2; beyond R the weight is exactly 1.
-constexpr unsigned short INF16S = 0xFFFFu;
+// W1 column pass: out(y, x) = min over dy of dy^2 + g(y + dy, x)^2, brute force over |dy| <= RMAX with the
+// packed add-min of the DPX unit: ONE instruction (VIADDMNMX.U16x2: min(a + b, c) per 16-bit half) updates
+// the running minimum of two adjacent columns for one dy, and with the loops fully unrolled dy^2 is an
+// immediate operand.  A thread owns 2 columns x DP_JR consecutive rows; a window row loaded once from
+// shared memory (one LDS.32 = 2 columns) feeds all DP_JR outputs.  (2 RMAX + 1) / 2 instructions per pixel
+// (36.5 at RMAX = 36), no branches, no divergence -- the block-pruned scan it replaces spent ~360.
+// grid (ceil(W/128), ceil(H/32), n), block 256 = 64 column pairs x 4 row groups; static smem:
+// (32 + 2 RMAX) x 128 squared row distances (uint16; 0x7FFF = no seed within R, which cannot wrap:
+// 0x7FFF + RMAX^2 < 65536).  Every candidate is a real pixel, so the minimum is exact whenever it is
+// <= R^2 (rows up to RMAX >= R away are scanned; what they add is > R^2); beyond R the weight is exactly 1.
+constexpr int DP_TW = 128, DP_TH = 32, DP_JR = 8;
+constexpr unsigned DP_INF = 0x7FFFu;
 
-template <typename OutT>
-__global__ void __launch_bounds__(256)
-edt_cols_tile(const unsigned char *__restrict__ g8, const int *__restrict__ anyfg,
-              const double *__restrict__ table, OutT *__restrict__ out, int hgt, int wid, int R,
-              double w0e, double denom)
+// frame without any seed: SciPy's transform then measures to a virtual seed (reference behaviour kept by
+// the general kernel too); cold path, kept out of line
+__device__ __noinline__ double seedless_weight(const double *__restrict__ table, int y, int x, unsigned R2, double w0e,
+                                               double denom)
 {
-    extern __shared__ __align__(16) unsigned short gs2[];
-    __shared__ int tile_min;
-    const int x0 = blockIdx.x * CT_W, y0 = blockIdx.y * CT_H;
+    const unsigned b = (unsigned)(y + 1) * (unsigned)(y + 1) + (unsigned)x * (unsigned)x;
+    if (b <= R2) return __ldg(table + b);
+    const double d = sqrt((double)b);
+    return w0e * exp(-(d * d) / denom) + 0.0 + 1.0;
+}
+
+template <typename OutT, int RMAX>
+__global__ void __launch_bounds__(256)
+edt_cols_dpx(const unsigned char *__restrict__ g8, const int *__restrict__ anyfg,
+             const double *__restrict__ table, OutT *__restrict__ out, int hgt, int wid, int R,
+             double w0e, double denom)
+{
+    constexpr int ROWS = DP_TH + 2 * RMAX;
+    __shared__ __align__(16) unsigned short s2[ROWS * DP_TW];
+    const int x0 = blockIdx.x * DP_TW, y0 = blockIdx.y * DP_TH;
     const long long fo = (long long)blockIdx.z * hgt * wid;
-    const int rows = CT_H + 2 * R, nblk = (rows + 7) >> 3, rows8 = nblk * 8;
-    unsigned short *bm = gs2 + rows8 * CT_W;             // [nblk][32] block minima
-    const int col = threadIdx.x & 31, x = x0 + col, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) tile_min = 0xFFFF;
-    __syncthreads();
-    int mn = 0xFFFF;
-    for (int r = warp; r < rows8; r += 8) {
-        const int yy = y0 - R + r;
-        unsigned short v = INF16S;
-        if (r < rows && yy >= 0 && yy < hgt && x < wid) {
-            const unsigned g = g8[fo + (long long)yy * wid + x];
-            if (g != INF8) v = (unsigned short)(g * g);
-        }
-        gs2[r * CT_W + col] = v;
-        mn = min(mn, (int)v);
-    }
-    if (mn < 0xFFFF) atomicMin(&tile_min, mn);
-    __syncthreads();
-    for (int b = warp; b < nblk; b += 8) {
-        unsigned m = INF16S;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) m = min(m, (unsigned)gs2[(b * 8 + k) * CT_W + col]);
-        bm[b * CT_W + col] = (unsigned short)m;
-    }
-    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bool none = !anyfg[blockIdx.z];
-    const bool empty = (tile_min == 0xFFFF) && !none;    // nothing within reach of this tile
+    // stage: one warp per window row, four columns per lane
+    for (int r = warp; r < ROWS; r += 8) {
+        const int yy = y0 - RMAX + r, xx = x0 + 4 * lane;
+        unsigned v[4] = {DP_INF, DP_INF, DP_INF, DP_INF};
+        if (yy >= 0 && yy < hgt) {
+            const unsigned char *row = g8 + fo + (long long)yy * wid;
+            if (xx + 3 < wid && (wid & 3) == 0) {
+                const unsigned u = __ldg(reinterpret_cast<const unsigned *>(row + xx));
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { const unsigned g = (u >> (8 * k)) & 0xffu; if (g != INF8) v[k] = g * g; }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (xx + k < wid) { const unsigned g = row[xx + k]; if (g != INF8) v[k] = g * g; }
+            }
+        }
+        *reinterpret_cast<uint2 *>(s2 + r * DP_TW + 4 * lane) = make_uint2(v[0] | (v[1] << 16), v[2] | (v[3] << 16));
+    }
+    __syncthreads();
+    const int pair = (warp & 1) * 32 + lane, grp = warp >> 1;          // columns x0 + 2 pair, +1; rows y0 + 8 grp ..
+    const unsigned *w32 = reinterpret_cast<const unsigned *>(s2) + (grp * DP_JR) * (DP_TW / 2) + pair;
+    unsigned best[DP_JR];
+#pragma unroll
+    for (int j = 0; j < DP_JR; ++j) best[j] = DP_INF * 0x10001u;
+#pragma unroll
+    for (int r = 0; r < DP_JR + 2 * RMAX; ++r) {                     // window row y0 + 8 grp - RMAX + r
+        const unsigned g = w32[r * (DP_TW / 2)];
+#pragma unroll
+        for (int j = 0; j < DP_JR; ++j) {
+            const int dy = r - RMAX - j;                                 // a constant after unrolling
+            if (dy >= -RMAX && dy <= RMAX) best[j] = __viaddmin_u16x2(g, (unsigned)(dy * dy) * 0x10001u, best[j]);
+        }
+    }
     const unsigned R2 = (unsigned)R * R;
-    for (int ly = warp; ly < CT_H; ly += 8) {
-        const int y = y0 + ly;
-        if (x >= wid || y >= hgt) continue;
-        const long long idx = fo + (long long)y * wid + x;
-        if (empty) { out[idx] = (OutT)1.0; continue; }
-        const int p = ly + R;                                            // this pixel's window row
-        const unsigned g0 = gs2[p * CT_W + col];
-        if (g0 == 0) { out[idx] = (OutT)2.0; continue; }               // foreground (row distance 0)
-        unsigned best;
-        if (none) {
-            best = (unsigned)(y + 1) * (unsigned)(y + 1) + (unsigned)x * (unsigned)x;   // SciPy, no seed
+    const int x = x0 + 2 * pair;
+    if (x >= wid) return;
+    OutT *o = out + fo + (long long)(y0 + grp * DP_JR) * wid + x;
+    const bool both = x + 1 < wid && (wid & 1) == 0;
+    if (none) {                                                          // cold: frame without any seed
+        for (int j = 0; j < DP_JR && y0 + grp * DP_JR + j < hgt; ++j, o += wid)
+            for (int e = 0; e < 2 && x + e < wid; ++e) {
+                const unsigned b = (best[j] >> (16 * e)) & 0xffffu;
+                o[e] = b == 0 ? (OutT)2.0 : (OutT)seedless_weight(table, y0 + grp * DP_JR + j, x + e, R2, w0e, denom);
+            }
+        return;
+    }
+#pragma unroll
+    for (int j = 0; j < DP_JR; ++j, o += wid) {
+        if (y0 + grp * DP_JR + j >= hgt) break;
+        OutT w[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            // table[d2] for d2 <= R^2, table[R^2 + 1] = 1 (beyond the cut-off); foreground (distance 0) = 2
+            const unsigned b = (best[j] >> (16 * e)) & 0xffffu;
+            const OutT v = (OutT)__ldg(table + min(b, R2 + 1u));
+            w[e] = b == 0 ? (OutT)2.0 : v;
+        }
+        if (both) {
+            if constexpr (sizeof(OutT) == 4) *reinterpret_cast<float2 *>(o) = make_float2((float)w[0], (float)w[1]);
+            else *reinterpret_cast<double2 *>(o) = make_double2((double)w[0], (double)w[1]);
         } else {
-            best = g0;                                                   // 0xFFFF if nothing in this row
-            const int bo = p >> 3, off = p & 7;
-            // own block
-            if (bm[bo * CT_W + col] < best) {
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const int dy = k - off;
-                    best = min(best, (unsigned)(dy * dy) + gs2[(bo * 8 + k) * CT_W + col]);
-                }
-            }
-            // blocks above / below, nearest first
-            for (int k = 1; k < nblk; ++k) {
-                const int du = off + 8 * k - 7, dd = 8 * k - off;        // nearest row of block bo-k / bo+k
-                const unsigned du2 = (unsigned)(du * du), dd2 = (unsigned)(dd * dd);
-                if ((du2 >= best && dd2 >= best) || (du > R && dd > R)) break;   // rows beyond R cannot matter
-                if (bo - k >= 0 && du2 + bm[(bo - k) * CT_W + col] < best) {
-                    const unsigned short *gr = gs2 + ((bo - k) * 8) * CT_W + col;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int dy = du + 7 - j;                       // row j of the block
-                        best = min(best, (unsigned)(dy * dy) + gr[j * CT_W]);
-                    }
-                }
-                if (bo + k < nblk && dd2 + bm[(bo + k) * CT_W + col] < best) {
-                    const unsigned short *gr = gs2 + ((bo + k) * 8) * CT_W + col;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int dy = dd + j;
-                        best = min(best, (unsigned)(dy * dy) + gr[j * CT_W]);
-                    }
-                }
-            }
+            o[0] = w[0];
+            if (x + 1 < wid) o[1] = w[1];
         }
-        double w = 1.0;
-        if (best <= R2) w = __ldg(table + best);
-        else if (none) {          // seedless frame: R was clamped to the image size, evaluate directly
-            const double d = sqrt((double)best);
-            w = w0e * exp(-(d * d) / denom) + 0.0 + 1.0;
-        }
-        out[idx] = (OutT)w;
     }
 }
 
@@ -720,7 +722,7 @@ extern "C" int sq_weightmap_workspace_bytes(sq_handle_t h, int n, int hgt, int w
     } else {
         a.take<unsigned short>(px);
         a.take<int>(n);
-        a.take<double>(WR_MAX * WR_MAX + 1);
+        a.take<double>(WR_MAX * WR_MAX + 2);
     }
     *bytes = a.off;
     return SQ_OK;
@@ -736,7 +738,7 @@ extern "C" int sq_weightmap_edt(sq_handle_t h, const uint8_t *mask, int n, int h
     SqArena a(ws, ws_bytes);
     unsigned short *g = a.take<unsigned short>(px);
     int *anyfg = a.take<int>(n);
-    double *table = a.take<double>(WR_MAX * WR_MAX + 1);
+    double *table = a.take<double>(WR_MAX * WR_MAX + 2);
     SQ_REQUIRE(a.ok(), SQ_ENOMEM, "weightmap_edt: workspace %zu < %zu bytes", ws_bytes, a.off);
     cudaStream_t st = (cudaStream_t)stream_;
     const double denom = 2.0 * sigma * sigma + 1e-99;          // pipeline.py:478
@@ -754,13 +756,14 @@ extern "C" int sq_weightmap_edt(sq_handle_t h, const uint8_t *mask, int n, int h
         } else
             edt_rows_bits<<<dim3(hgt, n), 256, (size_t)((wid + 31) / 32 + 4) * 4, st>>>(mask, g8, anyfg, hgt, wid, rmax);
         w1_table_kernel<<<sq_div_up(rmax * rmax + 1, 256), 256, 0, st>>>(table, rmax * rmax + 1, w0e, denom);
-        const dim3 tgrid(sq_div_up(wid, CT_W), sq_div_up(hgt, CT_H), n);
-        const int rows8 = (CT_H + 2 * rmax + 7) / 8 * 8;
-        const size_t sm = (size_t)(rows8 + rows8 / 8) * CT_W * sizeof(unsigned short);
-        if (out_dtype == SQ_F32)
-            edt_cols_tile<float><<<tgrid, 256, sm, st>>>(g8, anyfg, table, (float *)out, hgt, wid, rmax, w0e, denom);
-        else
-            edt_cols_tile<double><<<tgrid, 256, sm, st>>>(g8, anyfg, table, (double *)out, hgt, wid, rmax, w0e, denom);
+        const dim3 tgrid(sq_div_up(wid, DP_TW), sq_div_up(hgt, DP_TH), n);
+#define SQ_W1_COLS(T, RM) edt_cols_dpx<T, RM><<<tgrid, 256, 0, st>>>(g8, anyfg, table, (T *)out, hgt, wid, rmax, w0e, denom)
+        if (out_dtype == SQ_F32) {
+            if (rmax <= 36) SQ_W1_COLS(float, 36); else if (rmax <= 48) SQ_W1_COLS(float, 48); else SQ_W1_COLS(float, 64);
+        } else {
+            if (rmax <= 36) SQ_W1_COLS(double, 36); else if (rmax <= 48) SQ_W1_COLS(double, 48); else SQ_W1_COLS(double, 64);
+        }
+#undef SQ_W1_COLS
         SQ_CHECK_LAUNCH();
         return SQ_OK;
     }
