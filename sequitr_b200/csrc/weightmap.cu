@@ -522,10 +522,107 @@ edt_cols_dpx(const unsigned char *__restrict__ g8, const int *__restrict__ anyfg
     }
 }
 
+// W3 column pass on the same DPX add-min, 32-bit: a candidate is the key (squared distance << 18 | label), so
+// the minimum carries the label of the nearest instance along.  Sweep 1: k1 = min over rows of keyA + dy^2
+// (keyA = the row's nearest label) -> d1^2 and its label L1.  Sweep 2: the nearest pixel of a row whose label
+// differs from L1 is the row's nearest label if that is not L1, else its second nearest (the row pass keeps the
+// two nearest DISTINCT labels), so k2 = min over rows of (labelA != L1 ? keyA : keyB) + dy^2 -> d2^2: a compare,
+// a select and one VIADDMNMX.U32 per (pixel, dy), no branches, no divergence; ~4 instructions per (pixel, dy)
+// in total against ~16 for the block-pruned two-minimum scan (inst_cols_tile, kept for labels >= 2^18).
+// A thread owns one column and sweeps IP_JR rows at a time; grid (ceil(W/64), ceil(H/64), n), block 256 = 64
+// columns x 4 row groups of 16 rows; dyn smem 2 x (64 + 2 RMAX) x 64 keys.  Rows / labels beyond R hold IP_INF (cannot wrap:
+// IP_INF + RMAX^2 << 18 < 2^32); exact for the same reason as the W1 pass.
+constexpr int IP_TW = 64, IP_TH = 64, IP_JR = 8;
+constexpr unsigned IP_LBITS = 18, IP_LMASK = (1u << IP_LBITS) - 1u, IP_INFC = 12000u, IP_INF = IP_INFC << IP_LBITS;
+
+template <typename OutT, int RMAX>
+__global__ void __launch_bounds__(256, 3)      // three blocks per SM: one stages its window while the others sweep
+inst_cols_dpx(const int *__restrict__ la, const int *__restrict__ lb, const unsigned char *__restrict__ da,
+              const unsigned char *__restrict__ db, const int *__restrict__ big, OutT *__restrict__ out, int hgt,
+              int wid, int R, double w0, double denom, double wc0, double wc1)
+{
+    if (big[blockIdx.z]) return;                       // labels >= 2^18 in this frame: inst_cols_tile does it
+    constexpr int ROWS = IP_TH + 2 * RMAX, GROUPS = 256 / IP_TW, PER_GROUP = IP_TH / GROUPS;
+    extern __shared__ __align__(16) unsigned keys_[];
+    unsigned *kA = keys_, *kB = keys_ + ROWS * IP_TW;
+    const int x0 = blockIdx.x * IP_TW, y0 = blockIdx.y * IP_TH;
+    const long long fo = (long long)blockIdx.z * hgt * wid;
+    const int col = threadIdx.x & (IP_TW - 1), grp = threadIdx.x / IP_TW, x = x0 + col;
+    for (int r = grp; r < ROWS; r += GROUPS) {
+        const int yy = y0 - RMAX + r;
+        unsigned a = IP_INF, b = IP_INF;
+        if (yy >= 0 && yy < hgt && x < wid) {
+            const long long j = fo + (long long)yy * wid + x;
+            const unsigned d1 = da[j], d2 = db[j];
+            if (d1 != INF8) a = ((d1 * d1) << IP_LBITS) | (unsigned)la[j];
+            if (d2 != INF8) b = ((d2 * d2) << IP_LBITS) | (unsigned)lb[j];
+        }
+        kA[r * IP_TW + col] = a;
+        kB[r * IP_TW + col] = b;
+    }
+    __syncthreads();
+    const double reach = (double)(R + 1);
+    const unsigned reach2 = (unsigned)((R + 1) * (R + 1));
+#pragma unroll 1
+    for (int sub = 0; sub < PER_GROUP / IP_JR; ++sub) {                   // IP_JR rows at a time
+        const int ly = grp * PER_GROUP + sub * IP_JR;                    // first output row of this batch (in the tile)
+        const unsigned *pa = kA + ly * IP_TW + col, *pb = kB + ly * IP_TW + col;
+        unsigned k1[IP_JR], k2[IP_JR], l1[IP_JR];
+#pragma unroll
+        for (int j = 0; j < IP_JR; ++j) k1[j] = k2[j] = 0xffffffffu;
+#pragma unroll
+        for (int r = 0; r < IP_JR + 2 * RMAX; ++r) {                     // window row y0 + ly - RMAX + r
+            const unsigned g = pa[r * IP_TW];
+#pragma unroll
+            for (int j = 0; j < IP_JR; ++j) {
+                const int dy = r - RMAX - j;                                 // a constant after unrolling
+                if (dy >= -RMAX && dy <= RMAX) k1[j] = __viaddmin_u32(g, (unsigned)(dy * dy) << IP_LBITS, k1[j]);
+            }
+            if ((r & 7) == 7) asm volatile("" ::: "memory");     // keep the loads of later rows from piling up in registers
+        }
+        // d2 >= d1: a pixel further than reach/2 from its nearest label keeps the class weight whatever d2
+        // is, and so does the foreground; a warp with no other pixel skips the second sweep (75 % of the work)
+        bool need = false;
+#pragma unroll
+        for (int j = 0; j < IP_JR; ++j) {
+            l1[j] = k1[j] & IP_LMASK;
+            const unsigned c1 = k1[j] >> IP_LBITS;
+            need |= c1 != 0 && 4u * c1 <= reach2;
+        }
+        if (__any_sync(0xffffffffu, need)) {
+#pragma unroll
+            for (int r = 0; r < IP_JR + 2 * RMAX; ++r) {
+                const unsigned ga = pa[r * IP_TW], gb = pb[r * IP_TW], lr = ga & IP_LMASK;
+#pragma unroll
+                for (int j = 0; j < IP_JR; ++j) {
+                    const int dy = r - RMAX - j;
+                    if (dy >= -RMAX && dy <= RMAX)
+                        k2[j] = __viaddmin_u32(lr != l1[j] ? ga : gb, (unsigned)(dy * dy) << IP_LBITS, k2[j]);
+                }
+                if ((r & 3) == 3) asm volatile("" ::: "memory");
+            }
+        }
+        if (x >= wid) continue;
+        OutT *o = out + fo + (long long)(y0 + ly) * wid + x;
+#pragma unroll
+        for (int j = 0; j < IP_JR; ++j, o += wid) {
+            if (y0 + ly + j >= hgt) break;
+            const unsigned c1 = k1[j] >> IP_LBITS, c2 = k2[j] >> IP_LBITS;
+            double w = wc0;
+            if (c1 == 0) w = wc1;                                            // foreground: row distance 0
+            else if (c2 < IP_INFC && c1 + c2 <= reach2) {                    // (d1 + d2)^2 >= d1^2 + d2^2: cheap reject
+                const double sum = sqrt((double)c1) + sqrt((double)c2);
+                if (sum <= reach) w = wc0 + w0 * exp(-(sum * sum) / denom);   // beyond: cannot change the result
+            }
+            *o = (OutT)w;
+        }
+    }
+}
+
 // W3 row pass.  grid (hgt, n), block 256, dyn smem: 2 * ceil(wid/32) words (run starts, run ends)
 __global__ void inst_rows_bits(const int *__restrict__ labels, int *__restrict__ la,
                                int *__restrict__ lb, unsigned char *__restrict__ da,
-                               unsigned char *__restrict__ db, int hgt, int wid, int R)
+                               unsigned char *__restrict__ db, int *__restrict__ big, int hgt, int wid, int R)
 {
     extern __shared__ unsigned bits[];
     const long long ro = ((long long)blockIdx.y * hgt + blockIdx.x) * wid;
@@ -540,6 +637,7 @@ __global__ void inst_rows_bits(const int *__restrict__ labels, int *__restrict__
             ln = x + 1 < wid ? lr[x + 1] : 0;
         }
         const bool fg = l > 0;
+        if (l > (int)IP_LMASK) big[blockIdx.y] = 1;          // label too wide for the packed keys (benign race)
         const unsigned s = __ballot_sync(0xffffffffu, fg && lp != l);
         const unsigned e = __ballot_sync(0xffffffffu, fg && ln != l);
         if ((threadIdx.x & 31) == 0) { sbits[x >> 5] = s; ebits[x >> 5] = e; }
@@ -603,8 +701,9 @@ __global__ void __launch_bounds__(256)
 inst_cols_tile(const int *__restrict__ la, const int *__restrict__ lb,
                const unsigned char *__restrict__ da, const unsigned char *__restrict__ db,
                OutT *__restrict__ out, int hgt, int wid, int R, double w0, double denom, double wc0,
-               double wc1)
+               double wc1, const int *__restrict__ only_if)
 {
+    if (only_if && !only_if[blockIdx.z]) return;       // this frame went through inst_cols_dpx
     extern __shared__ __align__(16) unsigned char ws_[];
     const int rows = CT_H + 2 * R, nblk = (rows + 7) >> 3, rows8 = nblk * 8;
     int *sla = reinterpret_cast<int *>(ws_);
@@ -719,6 +818,7 @@ extern "C" int sq_weightmap_workspace_bytes(sq_handle_t h, int n, int hgt, int w
     if (instance_mode) {
         a.take<int>(px); a.take<int>(px);
         a.take<unsigned short>(px); a.take<unsigned short>(px);
+        a.take<int>(n);
     } else {
         a.take<unsigned short>(px);
         a.take<int>(n);
@@ -792,6 +892,7 @@ extern "C" int sq_weightmap_unet(sq_handle_t h, const int32_t *labels, int n, in
     SqArena a(ws, ws_bytes);
     int *la = a.take<int>(px), *lb = a.take<int>(px);
     unsigned short *da = a.take<unsigned short>(px), *db = a.take<unsigned short>(px);
+    int *big = a.take<int>(n);
     SQ_REQUIRE(a.ok(), SQ_ENOMEM, "weightmap_unet: workspace %zu < %zu bytes", ws_bytes, a.off);
     cudaStream_t st = (cudaStream_t)stream_;
     const double denom = 2.0 * sigma * sigma + 1e-99;
@@ -802,18 +903,37 @@ extern "C" int sq_weightmap_unet(sq_handle_t h, const int32_t *labels, int n, in
 
     if (rmax <= WR_MAX) {
         unsigned char *da8 = reinterpret_cast<unsigned char *>(da), *db8 = reinterpret_cast<unsigned char *>(db);
-        inst_rows_bits<<<dim3(hgt, n), 256, (size_t)((wid + 31) / 32) * 8, st>>>(labels, la, lb, da8, db8, hgt, wid, rmax);
+        SQ_CUDA(cudaMemsetAsync(big, 0, n * sizeof(int), st));
+        inst_rows_bits<<<dim3(hgt, n), 256, (size_t)((wid + 31) / 32) * 8, st>>>(labels, la, lb, da8, db8, big, hgt, wid, rmax);
+        {
+            // DPX column pass (labels < 2^18); frames flagged by the row pass fall through to the scan kernel
+            const dim3 dgrid(sq_div_up(wid, IP_TW), sq_div_up(hgt, IP_TH), n);
+#define SQ_W3_COLS(T, RM)                                                                                          \
+    do {                                                                                                           \
+        auto k = inst_cols_dpx<T, RM>;                                                                             \
+        const size_t dsm = (size_t)2 * (IP_TH + 2 * RM) * IP_TW * sizeof(unsigned);                                \
+        SQ_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));                  \
+        k<<<dgrid, 256, dsm, st>>>(la, lb, da8, db8, big, (T *)out, hgt, wid, rmax, w0, denom, wc0, wc1);           \
+    } while (0)
+            if (out_dtype == SQ_F32) {
+                if (rmax <= 36) SQ_W3_COLS(float, 36); else if (rmax <= 48) SQ_W3_COLS(float, 48); else SQ_W3_COLS(float, 64);
+            } else {
+                if (rmax <= 36) SQ_W3_COLS(double, 36); else if (rmax <= 48) SQ_W3_COLS(double, 48); else SQ_W3_COLS(double, 64);
+            }
+#undef SQ_W3_COLS
+            SQ_CHECK_LAUNCH();
+        }
         const dim3 tgrid(sq_div_up(wid, CT_W), sq_div_up(hgt, CT_H), n);
         const int rows8 = (CT_H + 2 * rmax + 7) / 8 * 8;
         const size_t sm = (size_t)rows8 * CT_W * 10 + (size_t)(rows8 / 8) * CT_W;
         if (out_dtype == SQ_F32) {
             auto k = inst_cols_tile<float>;
             if (sm > 48 * 1024) SQ_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-            k<<<tgrid, 256, sm, st>>>(la, lb, da8, db8, (float *)out, hgt, wid, rmax, w0, denom, wc0, wc1);
+            k<<<tgrid, 256, sm, st>>>(la, lb, da8, db8, (float *)out, hgt, wid, rmax, w0, denom, wc0, wc1, big);
         } else {
             auto k = inst_cols_tile<double>;
             if (sm > 48 * 1024) SQ_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-            k<<<tgrid, 256, sm, st>>>(la, lb, da8, db8, (double *)out, hgt, wid, rmax, w0, denom, wc0, wc1);
+            k<<<tgrid, 256, sm, st>>>(la, lb, da8, db8, (double *)out, hgt, wid, rmax, w0, denom, wc0, wc1, big);
         }
         SQ_CHECK_LAUNCH();
         return SQ_OK;

@@ -128,6 +128,30 @@ def test_w3_random_label_images(sq, seed):
         np.testing.assert_allclose(got32, ref.astype(np.float32), rtol=1.2e-7, atol=0)
 
 
+def test_w3_wide_labels_take_the_scan_kernel(sq):
+    """The DPX column pass packs (squared distance, label) into one 32-bit key, labels < 2^18; frames
+    holding wider labels are flagged by the row pass and go through the scan kernel.  Same results, also
+    when one call mixes both kinds of frame."""
+    import torch
+    from sequitr_b200 import ops
+    lab = synth.instance_labels(120, 200, 20, seed=11, rmin=3, rmax=8).astype(np.int32)
+    wide = np.where(lab > 0, lab + 300000, 0).astype(np.int32)          # same geometry, labels >= 2^18
+    huge = np.where(lab > 0, lab * 7 + (1 << 30), 0).astype(np.int32)
+    ref = wo.weightmap_w3(lab, 10., 5.)
+    for variant in (wide, huge):
+        np.testing.assert_allclose(ops.weightmap_unet_host(variant, 10., 5., out_dtype='float64'), ref,
+                                   rtol=RTOL64, atol=0)
+    stack = np.stack([lab, wide, lab[::-1].copy(), huge])
+    got = ops.weightmap_unet(torch.from_numpy(stack).cuda(), 10., 5., None, 'float64').cpu().numpy()
+    for i, r in enumerate((ref, ref, ref[::-1], ref)):
+        np.testing.assert_allclose(got[i], r, rtol=RTOL64, atol=0)
+    # labels just below / at the limit
+    edge = np.where(lab > 0, lab + (1 << 18) - 1 - lab.max(), 0).astype(np.int32)      # max label = 2^18 - 1
+    np.testing.assert_allclose(ops.weightmap_unet_host(edge, 10., 5., out_dtype='float64'), ref, rtol=RTOL64, atol=0)
+    np.testing.assert_allclose(ops.weightmap_unet_host(edge + (edge > 0), 10., 5., out_dtype='float64'), ref,
+                               rtol=RTOL64, atol=0)
+
+
 def test_w3_edge_cases_and_properties(sq):
     from sequitr_b200 import ops, pipeline
     empty = np.zeros((40, 50), np.int32)
