@@ -140,10 +140,14 @@ __global__ void scan_i32(const int *__restrict__ in, int *__restrict__ out, int 
     int *dst = out + (long long)f * pitch;
     if (threadIdx.x == 0) carry_sh = 0;
     __syncthreads();
-    for (int start = 0; start < len; start += 1024) {
-        const int i = start + threadIdx.x;
-        const int v = (i < len) ? src[i] : 0;
-        int s = v;
+    // four consecutive elements per thread: a 2048^2 frame (32768 segments) takes 8 rounds, not 32
+    for (int start = 0; start < len; start += 4096) {
+        const int i = start + 4 * threadIdx.x;
+        int v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = (i + k < len) ? src[i + k] : 0;
+        const int tsum = (v[0] + v[1]) + (v[2] + v[3]);
+        int s = tsum;
         for (int o = 1; o < 32; o <<= 1) {
             int t = __shfl_up_sync(0xffffffffu, s, o);
             if (lane >= o) s += t;
@@ -161,7 +165,12 @@ __global__ void scan_i32(const int *__restrict__ in, int *__restrict__ out, int 
         __syncthreads();
         const int carry = carry_sh;
         const int incl = s + (wid > 0 ? warp_sums[wid - 1] : 0);
-        if (i < len) dst[i] = carry + incl - v;
+        int run = carry + incl - tsum;                         // exclusive prefix of this thread's first element
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (i + k < len) dst[i + k] = run;
+            run += v[k];
+        }
         __syncthreads();
         if (threadIdx.x == 1023) carry_sh = carry + incl;
         __syncthreads();
@@ -207,7 +216,10 @@ __device__ __forceinline__ void merge_with_line(const uint8_t *mk, const int *se
                                                 const int *run_start, const int *run_end, int *parent,
                                                 const Dims &dm, int i, int pl, int x0, int x1, uint8_t c)
 {
-    const int jb = seg_off[pl * dm.nseg], je = seg_off[(pl + 1) * dm.nseg];
+    // runs never cross a segment border, so [x0, x1] lies in ONE segment and only the runs of that segment
+    // of line `pl` can overlap it
+    const int sg = pl * dm.nseg + x0 / SEG;
+    const int jb = seg_off[sg], je = seg_off[sg + 1];
     for (int j = jb; j < je; ++j) {
         const int s = run_start[j];
         const int xs = s - pl * dm.W;
@@ -331,7 +343,7 @@ __global__ void ccl_order(const uint8_t *__restrict__ mask, const int *__restric
                           const int *__restrict__ nroots, int *__restrict__ sorted_root,
                           int *__restrict__ class_base, Dims dm, int max_rows)
 {
-    __shared__ uint8_t cls[ORDER_PAR];
+    __shared__ __align__(4) uint8_t cls[ORDER_PAR];
     __shared__ int cnt_sh[256];
     const int f = blockIdx.x;
     const int c = threadIdx.x;
@@ -360,9 +372,14 @@ __global__ void ccl_order(const uint8_t *__restrict__ mask, const int *__restric
     class_base[f * 256 + c] = cnt_sh[c];
     if (n <= ORDER_PAR) {
         for (int j = c; j < n; j += 256) {
+            // stable rank = earlier roots of the same class, four class bytes per compare
             const uint8_t v = cls[j];
+            const unsigned vv = (unsigned)v * 0x01010101u;
+            const unsigned *cw = reinterpret_cast<const unsigned *>(cls);
+            const int full = j >> 2, rem = j & 3;
             int rank = 0;
-            for (int i = 0; i < j; ++i) rank += (cls[i] == v);
+            for (int i = 0; i < full; ++i) rank += __popc(__vcmpeq4(cw[i], vv) & 0x01010101u);
+            if (rem) rank += __popc(__vcmpeq4(cw[full], vv) & (0x01010101u & ((1u << (8 * rem)) - 1u)));
             const int row = cnt_sh[v] + rank;
             const int r = rl[j];
             pa[r] = -2 - row;
