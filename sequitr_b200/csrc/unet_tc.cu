@@ -78,6 +78,16 @@ __device__ __forceinline__ uint32_t bf162_max(uint32_t a, uint32_t b)
     return *reinterpret_cast<uint32_t *>(&m);
 }
 
+__device__ __forceinline__ void mma_m16n8k16_bf16(float *c, const uint32_t *a, uint32_t b0, uint32_t b1);
+
+// Fused first conv (NBLD > 0): the fp32 single-channel input and the first conv's parameters; the A half of
+// every smem stage is then BUILT by NBLD extra warps (conv1 of the halo patch) instead of fetched by TMA.
+struct FirstArgs {
+    const float *in;           // (n, H, W) fp32
+    const float *wf;           // [9][16] fp32 holding bf16-rounded weights
+    const float *scale, *shift;
+};
+
 // Epilogue variants of the 3x3 conv kernel
 constexpr int EPI_STORE = 0;   // activation -> bf16 blocked tensor
 constexpr int EPI_POOL = 1;    // same + the 2x2 max-pooled tensor (fused max_pool_layer)
@@ -97,14 +107,20 @@ struct HeadArgs {
 // shared memory, halving the L2 -> SM weight traffic that otherwise caps the Cout >= 128 layers (36.8 /
 // 73.7 KB of weights per k-step and 128-256 pixel tile).  A stage is free when the MMAs of BOTH CTAs
 // have retired (tcgen05.commit multicast onto both CTAs' `empty` barriers).
-template <int COUT, int S, bool UP, int NBUF, int MINB, int EPI, int HK, int NMMA, bool CL>
-__global__ void __launch_bounds__(TC_THREADS + 32 * (NMMA - 1), MINB)
+// NBLD > 0 = level-0 fusion: the layer's input is the FIRST conv's output (Cin = 1 -> 16 channels), which
+// never goes to HBM: warps FIRST_BLD.. compute it for each 66 x 10 halo patch (mma.sync.m16n8k16 on the
+// L1-cached fp32 frame, exactly the fragments and epilogue of first_conv_kernel, zeros outside the image =
+// this layer's SAME padding) and write it into the stage in the layout TMA would have produced.
+template <int COUT, int S, bool UP, int NBUF, int MINB, int EPI, int HK, int NMMA, bool CL, int NBLD = 0>
+__global__ void __launch_bounds__(TC_THREADS + 32 * (NMMA - 1) + 32 * NBLD, MINB)
 conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                int ks0, int ks1, const bf16 *__restrict__ wts, const float *__restrict__ scale,
                const float *__restrict__ shift, bf16 *__restrict__ out, bf16 *__restrict__ out_pool,
                HeadArgs head, int nimg, int H, int W, int relu, int nstages, int D, int KZ,
-               int out_mul, int out_off)
+               int out_mul, int out_off, FirstArgs first)
 {
+    static_assert(NBLD == 0 || (!UP && !CL), "fused first conv: plain 3x3 conv launches only");
+    constexpr int FIRST_BLD = 1 + NMMA + 4 * EPI_GROUPS;       // first builder warp
     // Volumes: activations are [n][z][c/8][y][x][8]; a (z-slice, image) pair is one "image" np =
     // n*D + z for tiling and for the epilogue, and a 3x3x3 conv is the same 9-tap stage run for
     // KZ = 3 z-offsets: k-step q = kz*ksteps + ks loads the halo patch of slice z + kz - 1 (TMA
@@ -127,7 +143,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     const int ksteps = ks0 + ks1, qsteps = KZ * ksteps;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < nstages; ++i) { tc::mbar_init(&full_bar[i], 1); tc::mbar_init(&empty_bar[i], NMMA * (CL ? 2 : 1)); }
+        for (int i = 0; i < nstages; ++i) { tc::mbar_init(&full_bar[i], 1 + NBLD); tc::mbar_init(&empty_bar[i], NMMA * (CL ? 2 : 1)); }
         for (int i = 0; i < 2; ++i) { tc::mbar_init(&tfull_bar[i], NMMA); tc::mbar_init(&tempty_bar[i], 4 * EPI_GROUPS); }
         tc::fence_barrier_init();
         tc::tma_prefetch_desc(&mapA0);
@@ -163,9 +179,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                     const int kz = q / ksteps, ks = q - kz * ksteps;
                     const int zc = z + kz - (KZ >> 1);
                     tc::mbar_wait(&empty_bar[stage], phase ^ 1);
-                    tc::mbar_arrive_expect_tx(&full_bar[stage], C::A_BYTES + C::B_BYTES);
+                    tc::mbar_arrive_expect_tx(&full_bar[stage], (NBLD ? 0 : C::A_BYTES) + C::B_BYTES);
                     uint8_t *sA = smem + (size_t)stage * C::STAGE_BYTES;
-                    if (ks < ks0) tc::tma_load_5d(sA, &mapA0, &full_bar[stage], x0 * 8, y0, ks * 2, zc, n);
+                    if (NBLD) { /* the builder warps write the patch */ }
+                    else if (ks < ks0) tc::tma_load_5d(sA, &mapA0, &full_bar[stage], x0 * 8, y0, ks * 2, zc, n);
                     else          tc::tma_load_5d(sA, &mapA1, &full_bar[stage], x0 * 8, y0, (ks - ks0) * 2, zc, n);
                     if (CL)      // my half of the weights, into both CTAs
                         tc::bulk_load_mc(sA + C::A_BYTES + crank * (C::B_BYTES / 2),
@@ -225,6 +242,107 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             }
             if (tc::elect_one()) tc::umma_commit(&tfull_bar[buf]);   // accumulators of this tile complete
             __syncwarp();
+        }
+    } else if (NBLD > 0 && warp >= FIRST_BLD) {
+        // ================================================== first-conv builders
+        if constexpr (NBLD > 0) {
+            const int bw = warp - FIRST_BLD, g = lane >> 2, t = lane & 3;
+            uint32_t bwf[2][2];
+            float sc1[2][2], sh1[2][2];
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int k0 = 2 * t + 8 * h;
+                    const float w0 = k0 < 9 ? first.wf[k0 * 16 + nt * 8 + g] : 0.0f;
+                    const float w1 = k0 + 1 < 9 ? first.wf[(k0 + 1) * 16 + nt * 8 + g] : 0.0f;
+                    bwf[nt][h] = pack_bf16(w0, w1);
+                }
+#pragma unroll
+                for (int e = 0; e < 2; ++e) { sc1[nt][e] = first.scale[nt * 8 + 2 * t + e]; sh1[nt][e] = first.shift[nt * 8 + 2 * t + e]; }
+            }
+            // this lane's taps: k = 2t, 2t+1 (always < 9) and, for t = 0 only, k = 8
+            constexpr int RW = C::PW + 2, RH = 16 * ((C::PH + 15) / 16) + 2, NRAW = RW * RH;   // raw fp32 halo of the patch
+            // (rows rounded up to whole 16-row m-tiles: the short last m-tile of a column reads them, stores nothing)
+            constexpr int RPT = (NRAW + 32 * NBLD - 1) / (32 * NBLD);         // raw values per builder thread
+            __shared__ float raw[2][NRAW];
+            const int ta = 2 * t, tb = 2 * t + 1;
+            const int oa = (ta / 3) * RW + ta % 3, ob = (tb / 3) * RW + tb % 3, oc = 2 * RW + 2;
+            const int bt = threadIdx.x - FIRST_BLD * 32;                      // 0 .. 32 NBLD - 1
+            // global -> registers for one tile's raw halo (zero outside the image): issued one tile ahead so
+            // that the L2 latency hides behind the previous tile's conv1
+            float nxt[RPT];
+            auto fetch = [&](int tl) {
+                const int tx = tl % tiles_x, ty = (tl / tiles_x) % tiles_y, np = tl / (tiles_x * tiles_y);
+                const int xr = tx * 8 - 2, yr = ty * C::TH - 2;
+                const float *img = first.in + (size_t)np * H * W;
+#pragma unroll
+                for (int k = 0; k < RPT; ++k) {
+                    const int i = bt + k * 32 * NBLD;
+                    const int rr = i / RW, cc = i - rr * RW;
+                    const int Y = yr + rr, X = xr + cc;
+                    nxt[k] = (i < NRAW && Y >= 0 && Y < H && X >= 0 && X < W) ? __ldg(img + (size_t)Y * W + X) : 0.0f;
+                }
+            };
+            int stage = 0, buf = 0;
+            uint32_t phase = 0;
+            if ((int)blockIdx.x < ntiles) fetch(blockIdx.x);
+            for (int tl = blockIdx.x; tl < ntiles; tl += gridDim.x) {
+                const int tx = tl % tiles_x, ty = (tl / tiles_x) % tiles_y;
+                const int x0 = tx * 8 - 1, y0 = ty * C::TH - 1;
+#pragma unroll
+                for (int k = 0; k < RPT; ++k) {
+                    const int i = bt + k * 32 * NBLD;
+                    if (i < NRAW) raw[buf][i] = nxt[k];
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * NBLD) : "memory");   // the builders' own barrier
+                if (tl + (int)gridDim.x < ntiles) fetch(tl + gridDim.x);
+                tc::mbar_wait(&empty_bar[stage], phase ^ 1);
+                uint8_t *sA = smem + (size_t)stage * C::STAGE_BYTES;
+                // m-tiles run DOWN the patch columns (16 consecutive rows of one column, CT per column): no
+                // division per pixel, and every lane's offsets are a per-lane constant plus a warp-uniform term
+                constexpr int CT = (C::PH + 15) / 16, MTC = CT * C::PW;
+                const float *rb = raw[buf] + g * RW;                              // row g of the raw halo
+                uint8_t *sl = sA + g * (C::PW * 16) + 4 * t;
+                const bool interior = y0 >= 0 && y0 + C::PH <= H && x0 >= 0 && x0 + C::PW <= W;
+#pragma unroll 2
+                for (int m = bw; m < MTC; m += NBLD) {
+                    const int c = m / CT, r0 = (m - c * CT) * 16;                 // warp-uniform
+                    const float *q0 = rb + r0 * RW + c, *q1 = q0 + 8 * RW;        // tap (0,0) of pixels (r0+g, c), (r0+g+8, c)
+                    uint32_t a[4];
+                    a[0] = pack_bf16(q0[oa], q0[ob]);
+                    a[1] = pack_bf16(q1[oa], q1[ob]);
+                    a[2] = (t == 0) ? pack_bf16(q0[oc], 0.0f) : 0u;               // k = 8: tap (2, 2)
+                    a[3] = (t == 0) ? pack_bf16(q1[oc], 0.0f) : 0u;
+                    bool keep[2], live[2];
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int r = r0 + g + 8 * e;
+                        live[e] = r < C::PH;                                      // the last m-tile of a column is short
+                        const int Y = y0 + r, X = x0 + c;
+                        keep[e] = interior || (Y >= 0 && Y < H && X >= 0 && X < W);   // outside the image: SAME padding
+                    }
+                    uint8_t *d0 = sl + (r0 * C::PW + c) * 16;
+#pragma unroll
+                    for (int nt = 0; nt < 2; ++nt) {
+                        float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+                        mma_m16n8k16_bf16(acc, a, bwf[nt][0], bwf[nt][1]);
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const float v0 = fmaxf(fmaf(acc[2 * e], sc1[nt][0], sh1[nt][0]), 0.0f);
+                            const float v1 = fmaxf(fmaf(acc[2 * e + 1], sc1[nt][1], sh1[nt][1]), 0.0f);
+                            if (live[e])
+                                *reinterpret_cast<uint32_t *>(d0 + nt * (C::PH * C::PW * 16) + e * (8 * C::PW * 16)) =
+                                    keep[e] ? pack_bf16(v0, v1) : 0u;
+                        }
+                    }
+                }
+                tc::fence_proxy_async();                    // generic-proxy writes -> visible to the UMMA reads
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&full_bar[stage]);
+                if (++stage == nstages) { stage = 0; phase ^= 1; }
+                buf ^= 1;
+            }
         }
     } else {
         // ========================================================= epilogue
@@ -1170,16 +1288,55 @@ int launch_tc(sq_unet_s *u, const SqLayer &L, const bf16 *in0, int cb0, const bf
         cfg.gridDim = dim3((unsigned)grid);
         SQ_CUDA(cudaLaunchKernelEx(&cfg, kern, m0, m1, cb0 / 2, in1 ? cb1 / 2 : 0, (const bf16 *)L.w_tc + g.w_off,
                                    (const float *)L.scale, (const float *)L.shift, out, out_pool, head, nimg, H, W,
-                                   relu, nstages, g.D, g.KZ, g.out_mul, g.out_off));
+                                   relu, nstages, g.D, g.KZ, g.out_mul, g.out_off, FirstArgs{}));
     } else {
         const int grid = std::min(tiles, MINB * u->h->sm_count);
         kern<<<grid, threads, smem, st>>>(m0, m1, cb0 / 2, in1 ? cb1 / 2 : 0, (const bf16 *)L.w_tc + g.w_off, L.scale,
                                          L.shift, out, out_pool, head, nimg, H, W, relu, nstages, g.D, g.KZ,
-                                         g.out_mul, g.out_off);
+                                         g.out_mul, g.out_off, FirstArgs{});
     }
     ++u->last_launches;
     SQ_CHECK_LAUNCH();
     return SQ_OK;
+}
+
+// Level-0 fusion: down0/conv1 (Cin = 1 -> 16) computed inside down0/conv2's producer (NBLD builder warps), the
+// 16-channel intermediate never touches HBM.  Planar stacks, 16 -> 16 channels, fused 2x2 max-pool epilogue.
+template <int NBLD>
+int launch_tc_first_n(sq_unet_s *u, const SqLayer &L1, const SqLayer &L2, const float *in, bf16 *out, bf16 *out_pool,
+                      const TcGeo &g, cudaStream_t st)
+{
+    constexpr int COUT = 16, S = 4, NBUF = 2, MINB = 2;
+    using C = Cfg<COUT, S, false>;
+    const int nimg = g.nimg, H = g.H, W = g.W;
+    CUtensorMap m0;
+    SQ_TRY(make_map(&m0, out, nimg, 1, 2, H, W, C::PW, C::PH));      // unused by the kernel (no TMA patch loads)
+    int nstages = std::min(MAX_STAGES, ((216 / MINB) * 1024 - 2048) / C::STAGE_BYTES);
+    nstages = std::max(nstages, 2);
+    const size_t smem = (size_t)nstages * C::STAGE_BYTES + 1024;
+    auto kern = conv_tc_kernel<COUT, S, false, NBUF, MINB, EPI_POOL, 0, 1, false, NBLD>;
+    static size_t attr_smem[64] = {0};
+    size_t &have = attr_smem[u->h->device & 63];
+    const int threads = TC_THREADS + 32 * NBLD;
+    if (smem > have) {
+        SQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        have = smem;
+    }
+    const int tiles = nimg * ((W + 7) / 8) * ((H + C::TH - 1) / C::TH);
+    const int grid = std::min(tiles, MINB * u->h->sm_count);
+    HeadArgs none = {};
+    const FirstArgs fa = {in, (const float *)L1.w_tc, (const float *)L1.scale, (const float *)L1.shift};
+    kern<<<grid, threads, smem, st>>>(m0, m0, 1, 0, (const bf16 *)L2.w_tc + g.w_off, L2.scale, L2.shift, out, out_pool,
+                                     none, nimg, H, W, 1, nstages, 1, 1, g.out_mul, g.out_off, fa);
+    ++u->last_launches;
+    SQ_CHECK_LAUNCH();
+    return SQ_OK;
+}
+
+int launch_tc_first(sq_unet_s *u, const SqLayer &L1, const SqLayer &L2, const float *in, bf16 *out, bf16 *out_pool,
+                    const TcGeo &g, cudaStream_t st)
+{
+    return launch_tc_first_n<4>(u, L1, L2, in, out, out_pool, g, st);
 }
 
 template <int COUT, int S, int MINB, int NMMA = 1, bool CL = false>
@@ -1312,6 +1469,15 @@ int xc_variant()
     // SQ_XC=0 disables the x-combined kernels, SQ_XC=2 forces them (A/B measurements, tests)
     const char *e = getenv("SQ_XC");
     return e ? atoi(e) : 1;
+}
+
+bool first_fusion_enabled()
+{
+    // SQ_FUSE_FIRST=1 opts in.  Bit-identical to the two-launch path but slower on B200 (0.60 vs 0.147 + 0.225 ms
+    // per 4 frames of 2048^2): at N = 16 the tensor core's A-operand reads already use most of the 128 B/clk of
+    // shared-memory bandwidth, and the builders' reads and writes queue behind them.
+    const char *e = getenv("SQ_FUSE_FIRST");
+    return e && atoi(e) != 0;
 }
 
 bool use_clusters()
@@ -1496,6 +1662,9 @@ int tc_run(sq_unet_s *u, bool dry, const float *in, int n, int dep, int hgt, int
         SqLayer *c1 = layer_by_scope(u, scope);
         snprintf(scope, sizeof scope, "UNet/down%d/conv2", l);
         SqLayer *c2 = layer_by_scope(u, scope);
+        // level-0 fusion: Cin = 1 -> 16 -> 16 channels on planar stacks with the pooled copy fused (SQ_FUSE_FIRST=0: off)
+        const bool fuse_first = l == 0 && !vol && u->cin == 1 && c1->cout == 16 && c2->cout == 16 && nl > 1 &&
+                                first_fusion_enabled();
         if (l == 0 && vol) {
             const float *wf = (const float *)c1->w_tc;
             const int key = u->cin * 1000 + c1->cout;
@@ -1524,6 +1693,8 @@ int tc_run(sq_unet_s *u, bool dry, const float *in, int n, int dep, int hgt, int
 #undef SQ_FIRST3M
             ++u->last_launches;
             SQ_CHECK_LAUNCH();
+        } else if (l == 0 && fuse_first) {
+            // down0/conv1 runs inside down0/conv2's producer warps (launch_tc_first below)
         } else if (l == 0) {
             const int fr = first_rows(u->cin, 1);
             const dim3 grid((W + FIRST_TW - 1) / FIRST_TW, (H + fr - 1) / fr, n);
@@ -1573,7 +1744,8 @@ int tc_run(sq_unet_s *u, bool dry, const float *in, int n, int dep, int hgt, int
         const bool fuse_pool = (l < nl - 1) && c2->cout <= 128;
         if (l < nl - 1) pool_fused[l + 1] = fuse_pool;
         bf16 *pool_dst = !fuse_pool ? nullptr : (vol ? xyp[l + 1] : pooled[l + 1]);
-        SQ_TRY(conv3x3_tc(u, *c2, t1[l], c2->cin0, nullptr, 0, skip[l], pool_dst, nullptr, geo, st));
+        if (fuse_first && pool_dst) SQ_TRY(launch_tc_first(u, *c1, *c2, in, skip[l], pool_dst, geo, st));
+        else SQ_TRY(conv3x3_tc(u, *c2, t1[l], c2->cin0, nullptr, 0, skip[l], pool_dst, nullptr, geo, st));
         sq_timer_mark(u, st, c2->scope.c_str(), c2->flops_per_px * px);
     }
     SqLayer *head = layer_by_scope(u, "UNet/to_image");

@@ -245,3 +245,21 @@ def test_cluster_multicast_variant(sq, monkeypatch):
     clustered = _net(filters, (112, 80), 'concat', 1, 2, w).predict(x)
     np.testing.assert_array_equal(clustered['logits'], plain['logits'])
     np.testing.assert_array_equal(clustered['mask'], plain['mask'])
+
+
+@pytest.mark.parametrize('shape,n', [((112, 80), 3), ((64, 200), 1), ((512, 512), 2)])
+def test_first_conv_fused_into_the_second(sq, monkeypatch, shape, n):
+    """SQ_FUSE_FIRST=1: down0/conv1 is computed by builder warps inside down0/conv2's producer (the
+    16-channel intermediate never goes to HBM): one launch fewer, logits bit-identical to the two-launch
+    path (same mma.sync fragments, same bf16 rounding of the intermediate, zeros outside the image)."""
+    filters = (16, 32, 64)
+    w = synth.unet_weights(filters, 1, 2, bridge='concat', seed=7)
+    x = synth.frames(n, shape[0], shape[1], 1, seed=11, n_objects=5)
+    net = _net(filters, shape, 'concat', 1, 2, w)
+    plain = net.predict(x)
+    launches = net.launches()
+    monkeypatch.setenv('SQ_FUSE_FIRST', '1')
+    fused = net.predict(x)
+    assert net.launches() == launches - 1
+    np.testing.assert_array_equal(fused['logits'], plain['logits'])
+    np.testing.assert_array_equal(fused['mask'], plain['mask'])
