@@ -25,6 +25,9 @@
 //                   taps folded into N = 3*Cout (3 MMAs per k-step), combined by lane shuffles in the
 //                   epilogue; weights resident in shared memory
 // Epilogue variants: plain store, store + fused 2x2 max-pool, fused 1x1 head + softmax + argmax.
+// Run-time switches (A/B measurements and tests; defaults are the measured optimum): SQ_XC=0/2 disables /
+// forces the x-combined kernel, SQ_CLUSTER=1 runs the Cout >= 128 convs as weight-multicasting CTA pairs,
+// SQ_FUSE_FIRST=1 computes down0/conv1 with builder warps inside down0/conv2's producer (NBLD > 0 below).
 // The first conv (Cin <= 4: K = 9..108 -- warp-level mma.sync on a staged halo tile), the depth
 // half of the 2x2x2 pool, the element-wise bridges and the stand-alone head are bandwidth-bound
 // CUDA-core kernels on the same layout.
