@@ -450,7 +450,11 @@ edt_cols_dpx(const unsigned char *__restrict__ g8, const int *__restrict__ anyfg
              double w0e, double denom)
 {
     constexpr int ROWS = DP_TH + 2 * RMAX;
+    constexpr bool TAB = RMAX <= 36;                     // the look-up table fits next to the window
     __shared__ __align__(16) unsigned short s2[ROWS * DP_TW];
+    __shared__ OutT tab[TAB ? RMAX * RMAX + 2 : 1];
+    if constexpr (TAB)
+        for (int i = threadIdx.x; i < R * R + 2; i += 256) tab[i] = (OutT)__ldg(table + i);
     const int x0 = blockIdx.x * DP_TW, y0 = blockIdx.y * DP_TH;
     const long long fo = (long long)blockIdx.z * hgt * wid;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -509,7 +513,9 @@ edt_cols_dpx(const unsigned char *__restrict__ g8, const int *__restrict__ anyfg
         for (int e = 0; e < 2; ++e) {
             // table[d2] for d2 <= R^2, table[R^2 + 1] = 1 (beyond the cut-off); foreground (distance 0) = 2
             const unsigned b = (best[j] >> (16 * e)) & 0xffffu;
-            const OutT v = (OutT)__ldg(table + min(b, R2 + 1u));
+            OutT v;
+            if constexpr (TAB) v = tab[min(b, R2 + 1u)];
+            else v = (OutT)__ldg(table + min(b, R2 + 1u));
             w[e] = b == 0 ? (OutT)2.0 : v;
         }
         if (both) {
@@ -529,10 +535,12 @@ edt_cols_dpx(const unsigned char *__restrict__ g8, const int *__restrict__ anyfg
 // two nearest DISTINCT labels), so k2 = min over rows of (labelA != L1 ? keyA : keyB) + dy^2 -> d2^2: a compare,
 // a select and one VIADDMNMX.U32 per (pixel, dy), no branches, no divergence; ~4 instructions per (pixel, dy)
 // in total against ~16 for the block-pruned two-minimum scan (inst_cols_tile, kept for labels >= 2^18).
-// A thread owns one column and sweeps IP_JR rows at a time; grid (ceil(W/64), ceil(H/64), n), block 256 = 64
-// columns x 4 row groups of 16 rows; dyn smem 2 x (64 + 2 RMAX) x 64 keys.  Rows / labels beyond R hold IP_INF (cannot wrap:
+// A thread owns one column and sweeps IP_JR = 4 rows at a time (longer batches double the unrolled code, which
+// already misses the instruction cache -- ncu: 70 % hits -- and made ptxas hoist the window loads until registers
+// spilled; the loads are volatile for the same reason); grid (ceil(W/64), ceil(H/64), n), block 256 = 64 columns
+// x 4 row groups of 16 rows; dyn smem 2 x (64 + 2 RMAX) x 64 keys.  Rows / labels beyond R hold IP_INF (cannot wrap:
 // IP_INF + RMAX^2 << 18 < 2^32); exact for the same reason as the W1 pass.
-constexpr int IP_TW = 64, IP_TH = 64, IP_JR = 8;
+constexpr int IP_TW = 64, IP_TH = 64, IP_JR = 4;
 constexpr unsigned IP_LBITS = 18, IP_LMASK = (1u << IP_LBITS) - 1u, IP_INFC = 12000u, IP_INF = IP_INFC << IP_LBITS;
 
 template <typename OutT, int RMAX>
@@ -566,7 +574,8 @@ inst_cols_dpx(const int *__restrict__ la, const int *__restrict__ lb, const unsi
 #pragma unroll 1
     for (int sub = 0; sub < PER_GROUP / IP_JR; ++sub) {                   // IP_JR rows at a time
         const int ly = grp * PER_GROUP + sub * IP_JR;                    // first output row of this batch (in the tile)
-        const unsigned *pa = kA + ly * IP_TW + col, *pb = kB + ly * IP_TW + col;
+        // volatile: keeps ptxas from hoisting dozens of window loads ahead of the sweep (which spilled registers)
+        const volatile unsigned *pa = kA + ly * IP_TW + col, *pb = kB + ly * IP_TW + col;
         unsigned k1[IP_JR], k2[IP_JR], l1[IP_JR];
 #pragma unroll
         for (int j = 0; j < IP_JR; ++j) k1[j] = k2[j] = 0xffffffffu;
