@@ -391,20 +391,30 @@ __global__ void edt_rows_bits16(const uint8_t *__restrict__ mask, unsigned char 
     if (__any_sync(0xffffffffu, any != 0) && (threadIdx.x & 31) == 0) anyfg[blockIdx.y] = 1;
     __syncthreads();
     for (int c = threadIdx.x; c < nchunk; c += blockDim.x) {
-        const int x0 = c << 4, wi = x0 >> 5;
+        const int x0 = c << 4, wi = x0 >> 5, sh = x0 & 31;                 // sh = 0 or 16: a chunk never straddles a word
         const unsigned wm2 = bits[wi - 2], wm1 = bits[wi - 1], w0 = bits[wi], wp1 = bits[wi + 1], wp2 = bits[wi + 2];
-        unsigned o[4] = {0, 0, 0, 0};
+        // distance of pixel x0-1 to the nearest seed at or left of it, of pixel x0+16 to the nearest at or right of
+        // it (64-pixel windows; R <= WR_MAX = 64), then one sweep in each direction over the chunk's 16 bits:
+        // ~10 instructions per pixel instead of two 64-bit window extractions + clz/ffs per pixel
+        const unsigned lhi = sh ? __funnelshift_l(wm1, w0, 16) : wm1, llo = sh ? __funnelshift_l(wm2, wm1, 16) : wm2;
+        const unsigned rlo = sh ? wp1 : __funnelshift_r(w0, wp1, 16), rhi = sh ? wp2 : __funnelshift_r(wp1, wp2, 16);
+        const unsigned long long L = ((unsigned long long)lhi << 32) | llo;      // bit 63 = pixel x0-1
+        const unsigned long long Rw = ((unsigned long long)rhi << 32) | rlo;     // bit 0  = pixel x0+16
+        const unsigned b16 = (w0 >> sh) & 0xffffu;
+        unsigned dl = L ? (unsigned)__clzll((long long)L) : 1000u;               // 0 if pixel x0-1 is a seed
+        unsigned dlv[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-            const int sh = (x0 & 31) + j;                                // 0..31: the chunk never straddles a word
-            const unsigned lhi = __funnelshift_l(wm1, w0, 31 - sh), llo = __funnelshift_l(wm2, wm1, 31 - sh);
-            const unsigned rlo = __funnelshift_r(w0, wp1, sh), rhi = __funnelshift_r(wp1, wp2, sh);
-            const unsigned long long L = ((unsigned long long)lhi << 32) | llo;
-            const unsigned long long Rw = ((unsigned long long)rhi << 32) | rlo;
-            int d = 1 << 20;
-            if (L) d = __clzll((long long)L);
-            if (Rw) d = min(d, __ffsll((long long)Rw) - 1);
-            o[j >> 2] |= (unsigned)(d <= R ? d : INF8) << (8 * (j & 3));
+            dl = (b16 & (1u << j)) ? 0u : dl + 1u;
+            dlv[j] = dl;
+        }
+        unsigned dr = Rw ? (unsigned)(__ffsll((long long)Rw) - 1) : 1000u;       // 0 if pixel x0+16 is a seed
+        unsigned o[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int j = 15; j >= 0; --j) {
+            dr = (b16 & (1u << j)) ? 0u : dr + 1u;
+            const unsigned d = min(dlv[j], dr);
+            o[j >> 2] |= (d <= (unsigned)R ? d : (unsigned)INF8) << (8 * (j & 3));
         }
         reinterpret_cast<uint4 *>(g8 + ro)[c] = make_uint4(o[0], o[1], o[2], o[3]);
     }
