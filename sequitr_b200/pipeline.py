@@ -1,19 +1,29 @@
-"""Drop-in for the weight-map pipes of the reference ``sequitr/pipeline.py``:
-``ImagePipe`` (:162-189), ``ImagePipeline`` (:42-98, chaining only),
-``ImageWeightMap`` (:455-479, GPU) and ``ImageWeightMap2`` (:482-571).
+"""Drop-in for the image pipes of the reference ``sequitr/pipeline.py`` that sit on the hot path:
+``ImagePipe`` (:162-189), ``ImagePipeline`` (:42-98) with its JSON round trip
+(``save_image_pipeline`` :104-133, ``load_image_pipeline`` :137-154), the pre-inference pipes
+``ImageOutliers`` / ``ImageNorm`` / ``ImageBGSubtract`` (GPU), ``ImageWeightMap`` (:455-479, GPU),
+``ImageWeightMap2`` (:482-571, host) and the index-only pipes ``ImageFlip`` (:226-240) and
+``ImageSample`` (:408-452).  ``ImageResize`` / ``ImageRotate`` / ``ImageBlur`` (scikit-image /
+SciPy augmentation filters) are not part of this path; ``networks.unet.tr_augment`` is the GPU
+augmentation.
 
 ``ImageWeightMapUNet`` is the north-star ``w_c + w0*exp(-(d1+d2)^2/2 sigma^2)`` map
 on instance labels (GPU); it is what ``weightmap.create_weightmaps`` uses by
 default in this package.
 """
+import inspect
+import json
+import sys
+from collections import OrderedDict
+
 import numpy as np
 
 from . import ops
 
 
 class ImagePipeline(object):
-    """ ImagePipeline: chain ImagePipe objects (pipeline.py:42-98; JSON save/load of
-    the augmentation pipes is outside the hot path and not provided). """
+    """ ImagePipeline: chain ImagePipe objects (pipeline.py:42-98), save / load the chain's
+    parameters as JSON. """
 
     def __init__(self, pipeline=[]):
         self.pipeline = pipeline
@@ -42,6 +52,48 @@ class ImagePipeline(object):
         for pipe in self.pipeline:
             pipe.update()
 
+    def save(self, filename):
+        """ Write out the pipeline as a JSON file """
+        save_image_pipeline(filename, self)
+
+    @staticmethod
+    def load(filename):
+        """ Read in the pipeline from a JSON file """
+        return load_image_pipeline(filename)
+
+
+def save_image_pipeline(filename, pipeline_object):
+    """ Save out the parameters of an ImagePipeline as a JSON file (reference :104-133): one
+    entry per pipe, class name -> constructor arguments read back from the attributes of the same
+    name (like the reference, pipes of the same class overwrite each other). """
+    if not isinstance(pipeline_object, ImagePipeline):
+        raise TypeError('Pipeline must be of type ImagePipeline')
+    if not filename.endswith('.json'):
+        filename += '.json'
+    pipes = []
+    for pipe in pipeline_object.pipeline:
+        pipe_args = [a for a in inspect.signature(pipe.__init__).parameters]
+        vals = {}
+        for a in pipe_args:
+            v = getattr(pipe, a)
+            vals[a] = list(v) if isinstance(v, tuple) else v
+        pipes.append((pipe.__class__.__name__, vals))
+    with open(filename, 'w') as json_file:
+        json.dump({'ImagePipeline': OrderedDict(pipes)}, json_file, indent=2, separators=(',', ': '))
+
+
+def load_image_pipeline(filename):
+    """ Load and create an ImagePipeline object from a file (reference :137-154). """
+    with open(filename, 'r') as json_file:
+        pipes = json.load(json_file, object_pairs_hook=OrderedDict)
+    pipeline = []
+    for name, kwargs in pipes['ImagePipeline'].items():
+        Pipe = getattr(sys.modules[__name__], name)
+        if not (isinstance(Pipe, type) and issubclass(Pipe, ImagePipe)):
+            raise TypeError('%s is not an image pipe' % name)
+        pipeline.append(Pipe(**kwargs))
+    return ImagePipeline(pipeline)
+
 
 class ImagePipe(object):
     """ ImagePipe: primitive image pipe (pipeline.py:162-189). """
@@ -63,6 +115,54 @@ class ImagePipe(object):
 
     def update(self):
         self.iter = (self.iter + 1) % len(self)
+
+
+class ImageFlip(ImagePipe):
+    """ ImageFlip: mirror flips in sequence, for data augmentation (reference :226-240). """
+
+    def __init__(self):
+        ImagePipe.__init__(self)
+        self.flips = [[], [np.fliplr], [np.flipud], [np.fliplr, np.flipud]]
+
+    def pipe(self, image):
+        for flip in self.flips[self.iter]:
+            image = flip(image)
+        return image
+
+    def __len__(self):
+        return len(self.flips)
+
+
+class ImageSample(ImagePipe):
+    """ ImageSample: randomly placed regions of interest; the positions are kept so that the same
+    regions of corresponding labels or weights can be taken (reference :408-452). """
+
+    def __init__(self, samples=16, ROI_size=(512, 512)):
+        ImagePipe.__init__(self)
+        self.samples = samples
+        self.ROI_size = ROI_size
+        self.im_size = None
+        self.boundary = int(ROI_size[0] / 2.)
+        self.coords = None
+
+    def pipe(self, image):
+        sampled = np.zeros((self.samples, self.ROI_size[0], self.ROI_size[1], image.shape[-1]))
+        self.im_size = image.shape
+        if not self.coords:
+            self.update()
+        b = self.boundary
+        for sample, (x, y) in enumerate(self.coords):
+            sampled[sample, ...] = image[x - b:x + b, y - b:y + b, ...]
+        return sampled
+
+    def update(self):
+        b = self.boundary
+        x = np.random.randint(b, high=self.im_size[0] - b, size=(self.samples,))
+        y = np.random.randint(b, high=self.im_size[1] - b, size=(self.samples,))
+        self.coords = list(zip(x, y))
+
+    def __len__(self):
+        return self.samples
 
 
 def _binary_plane(image, who):

@@ -336,3 +336,41 @@ def test_tracker_formats_round_trip(tmp_path):
         tracker.read_XML(os.path.join(folder, 'tracks.json'))
     with pytest.raises(TypeError):
         tracker.read_XML(3)
+
+
+def test_image_pipeline_json_round_trip(tmp_path):
+    """pipeline.py:104-154: constructor arguments are read back from attributes of the same name, the
+    file maps class names to them, loading rebuilds the chain.  No compute call is made here."""
+    import json
+    p = pipeline.ImagePipeline([pipeline.ImageOutliers(sigma=3, threshold=4.5), pipeline.ImageNorm(),
+                                pipeline.ImageWeightMap(w0=8., sigma=2.5), pipeline.ImageSample(samples=4, ROI_size=(64, 64)),
+                                pipeline.ImageFlip()])
+    fn = str(tmp_path / 'pipe')
+    p.save(fn)
+    with open(fn + '.json') as f:
+        d = json.load(f)
+    assert list(d['ImagePipeline']) == ['ImageOutliers', 'ImageNorm', 'ImageWeightMap', 'ImageSample', 'ImageFlip']
+    assert d['ImagePipeline']['ImageWeightMap'] == {'w0': 8.0, 'sigma': 2.5}
+    q = pipeline.ImagePipeline.load(fn + '.json')
+    assert [type(a) for a in q.pipeline] == [type(a) for a in p.pipeline]
+    assert q.pipeline[0].sigma == 3 and q.pipeline[0].threshold == 4.5 and q.pipeline[2].w0 == 8.0
+    assert q.pipeline[3].samples == 4 and tuple(q.pipeline[3].ROI_size) == (64, 64)
+    assert len(q) == 1 * 1 * 1 * 4 * 4
+    with pytest.raises(TypeError):
+        pipeline.save_image_pipeline(fn, [1, 2])
+    # the index-only pipes: flips cycle with update(), samples reuse their coordinates
+    img = np.arange(12, dtype=np.float32).reshape(3, 4)
+    flip = pipeline.ImageFlip()
+    outs = []
+    for _ in range(4):
+        outs.append(flip(img)[..., 0].copy())
+        flip.update()
+    assert np.array_equal(outs[0], img) and np.array_equal(outs[1], img[:, ::-1])
+    assert np.array_equal(outs[2], img[::-1]) and np.array_equal(outs[3], img[::-1, ::-1])
+    big = np.random.default_rng(0).random((100, 120)).astype(np.float32)
+    smp = pipeline.ImageSample(samples=3, ROI_size=(16, 16))
+    a = smp(big)
+    b = smp(big * 2)
+    assert a.shape == (3, 16, 16, 1) and np.allclose(b, 2 * a)
+    (x, y) = smp.coords[0]
+    assert np.allclose(a[0, ..., 0], big[x - 8:x + 8, y - 8:y + 8])
