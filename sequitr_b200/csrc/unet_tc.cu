@@ -955,15 +955,26 @@ first_conv_kernel(const float *__restrict__ in, const float *__restrict__ wf,
     // stage the KZ x (ROWS+2) x (TW+2) input halo tile once (zero outside the image = SAME padding):
     // one warp per staged row, lanes along the row
     constexpr int ROWF = (FIRST_TW + 2) * CIN;
+#pragma unroll 2
     for (int ri = warp; ri < KZ * (FIRST_ROWS + 2); ri += 8) {
         const int kz = ri / (FIRST_ROWS + 2), ry = ri % (FIRST_ROWS + 2);
         const int zz = z + kz - (KZ >> 1), yy = y0 + ry - 1, e0 = (x0 - 1) * CIN;
         const bool row_ok = zz >= 0 && zz < D && yy >= 0 && yy < H;
         const float *srow = in + ((size_t)(np + zz - z) * H + (row_ok ? yy : 0)) * W * CIN + e0;
         float *trow = tile + kz * SSLICE + ry * SROW;
-        for (int rx = lane; rx < ROWF; rx += 32) {
-            const int e = e0 + rx;
-            trow[rx] = (row_ok && e >= 0 && e < W * CIN) ? __ldg(srow + rx) : 0.0f;
+        // every load of the row in flight before the first store (ncu: this kernel's top stall was the
+        // L2 latency of the staging loads, issued one per iteration)
+        constexpr int NLD = (ROWF + 31) / 32;
+        float v[NLD];
+#pragma unroll
+        for (int k = 0; k < NLD; ++k) {
+            const int rx = lane + 32 * k, e = e0 + rx;
+            v[k] = (row_ok && rx < ROWF && e >= 0 && e < W * CIN) ? __ldg(srow + rx) : 0.0f;
+        }
+#pragma unroll
+        for (int k = 0; k < NLD; ++k) {
+            const int rx = lane + 32 * k;
+            if (rx < ROWF) trow[rx] = v[k];
         }
     }
     // B fragments: b0 = (k = 2t, 2t+1 ; n = g), b1 = (k = 2t+8, 2t+9 ; n = g); zero beyond KTOT
