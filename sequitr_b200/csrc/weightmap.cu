@@ -469,7 +469,8 @@ edt_cols_dpx(const unsigned char *__restrict__ g8, const int *__restrict__ anyfg
     const long long fo = (long long)blockIdx.z * hgt * wid;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bool none = !anyfg[blockIdx.z];
-    // stage: one warp per window row, four columns per lane
+    // stage: one warp per window row, four columns per lane (unrolled: several rows' loads in flight)
+#pragma unroll 4
     for (int r = warp; r < ROWS; r += 8) {
         const int yy = y0 - RMAX + r, xx = x0 + 4 * lane;
         unsigned v[4] = {DP_INF, DP_INF, DP_INF, DP_INF};
@@ -566,17 +567,28 @@ inst_cols_dpx(const int *__restrict__ la, const int *__restrict__ lb, const unsi
     const int x0 = blockIdx.x * IP_TW, y0 = blockIdx.y * IP_TH;
     const long long fo = (long long)blockIdx.z * hgt * wid;
     const int col = threadIdx.x & (IP_TW - 1), grp = threadIdx.x / IP_TW, x = x0 + col;
-    for (int r = grp; r < ROWS; r += GROUPS) {
-        const int yy = y0 - RMAX + r;
-        unsigned a = IP_INF, b = IP_INF;
-        if (yy >= 0 && yy < hgt && x < wid) {
-            const long long j = fo + (long long)yy * wid + x;
-            const unsigned d1 = da[j], d2 = db[j];
-            if (d1 != INF8) a = ((d1 * d1) << IP_LBITS) | (unsigned)la[j];
-            if (d2 != INF8) b = ((d2 * d2) << IP_LBITS) | (unsigned)lb[j];
+    // ROWS / GROUPS rows per thread, four rows (16 loads) in flight at a time: issued one row per
+    // iteration the staging was a chain of L2 round trips
+    for (int rb = grp; rb < ROWS; rb += 4 * GROUPS) {
+        unsigned d1[4], d2[4], l1v[4], l2v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int r = rb + k * GROUPS, yy = y0 - RMAX + r;
+            const bool ok = r < ROWS && yy >= 0 && yy < hgt && x < wid;
+            const long long j = ok ? fo + (long long)yy * wid + x : 0;
+            d1[k] = ok ? (unsigned)__ldg(da + j) : (unsigned)INF8;
+            d2[k] = ok ? (unsigned)__ldg(db + j) : (unsigned)INF8;
+            l1v[k] = ok ? (unsigned)__ldg(la + j) : 0u;
+            l2v[k] = ok ? (unsigned)__ldg(lb + j) : 0u;
         }
-        kA[r * IP_TW + col] = a;
-        kB[r * IP_TW + col] = b;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int r = rb + k * GROUPS;
+            if (r < ROWS) {
+                kA[r * IP_TW + col] = d1[k] != INF8 ? ((d1[k] * d1[k]) << IP_LBITS) | l1v[k] : IP_INF;
+                kB[r * IP_TW + col] = d2[k] != INF8 ? ((d2[k] * d2[k]) << IP_LBITS) | l2v[k] : IP_INF;
+            }
+        }
     }
     __syncthreads();
     const double reach = (double)(R + 1);
