@@ -14,7 +14,7 @@
 // component's first voxel in raster order = SciPy's numbering order.
 //
 // Kernels (HBM-bound; algorithmic traffic 1 B/voxel in, rows out):
-//   run_count     runs per 128-voxel row segment (4 voxels per lane + shuffles)
+//   run_count     runs per 512-voxel row segment (16 voxels per lane, byte-wise SIMD compares + shuffles)
 //   scan_i32      per-frame exclusive scan (segment counts, then root counts)
 //   run_emit      run start / end lists in raster order, parent[i] = i
 //   run_merge     unions with overlapping runs of the previous row / previous plane
@@ -28,7 +28,8 @@
 
 namespace {
 
-constexpr int SEG = 128;             // voxels per warp segment (4 per lane)
+constexpr int PPL = 16;              // voxels per lane (one 16-byte load)
+constexpr int SEG = 32 * PPL;        // voxels per warp segment
 constexpr int CHUNK = 2048;          // runs per compress/emit block
 constexpr int CHUNK_THREADS = 256;
 
@@ -40,7 +41,7 @@ struct Dims {
     int nsegs;                        // rows*nseg segments per frame
     int maxruns;                      // run capacity per frame
     int nchunks;                      // ceil(maxruns / CHUNK)
-    int vec;                          // 1: 32-bit mask loads are aligned
+    int vec;                          // 1: 16-byte mask loads are aligned
 };
 
 __device__ __forceinline__ int find_root(const int *P, int i)
@@ -74,31 +75,35 @@ __device__ __forceinline__ void unite(int *P, int a, int b)
     }
 }
 
-// start / end bits of the 4 voxels this lane owns in its segment; returns popc(start) | popc(end)<<16
+// start / end bits of the PPL = 16 voxels this lane owns in its segment; returns popc(start) | popc(end)<<16.
+// Byte-wise SIMD: a voxel starts a run when it is non-zero and differs from its left neighbour, ends one
+// when it differs from its right neighbour (four voxels per compare).
 __device__ __forceinline__ unsigned segment_bits(const uint8_t *__restrict__ line, int x, int W, int vec,
                                                  int lane, unsigned &sb, unsigned &eb)
 {
-    unsigned w = 0;
-    if (vec && x + 3 < W) {
-        w = *reinterpret_cast<const unsigned *>(line + x);
+    unsigned w[4] = {0u, 0u, 0u, 0u};
+    if (vec && x + PPL - 1 < W) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(line + x);
+        w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
     } else {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-            if (x + k < W) w |= (unsigned)line[x + k] << (8 * k);
+        for (int k = 0; k < PPL; ++k)
+            if (x + k < W) w[k >> 2] |= (unsigned)line[x + k] << (8 * (k & 3));
     }
-    unsigned prev = __shfl_up_sync(0xffffffffu, w >> 24, 1);
-    unsigned next = __shfl_down_sync(0xffffffffu, w & 0xffu, 1);
+    unsigned prev = __shfl_up_sync(0xffffffffu, w[3] >> 24, 1);
+    unsigned next = __shfl_down_sync(0xffffffffu, w[0] & 0xffu, 1);
     if (lane == 0) prev = 0;                       // segment borders always cut a run
     if (lane == 31) next = 0;
     sb = 0;
     eb = 0;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const unsigned p = (w >> (8 * k)) & 0xffu;
-        const unsigned l = k ? (w >> (8 * (k - 1))) & 0xffu : prev;
-        const unsigned r = k < 3 ? (w >> (8 * (k + 1))) & 0xffu : next;
-        if (p && p != l) sb |= 1u << k;
-        if (p && p != r) eb |= 1u << k;
+    for (int i = 0; i < 4; ++i) {
+        const unsigned lw = (w[i] << 8) | (i ? w[i - 1] >> 24 : prev);
+        const unsigned rw = (w[i] >> 8) | ((i < 3 ? w[i + 1] & 0xffu : next) << 24);
+        const unsigned nz = __vcmpne4(w[i], 0u);
+        const unsigned s4 = nz & __vcmpne4(w[i], lw) & 0x01010101u, e4 = nz & __vcmpne4(w[i], rw) & 0x01010101u;
+        sb |= ((s4 * 0x10204080u) >> 28) << (4 * i);           // bytes 0..3 -> bits 0..3
+        eb |= ((e4 * 0x10204080u) >> 28) << (4 * i);
     }
     return (unsigned)__popc(sb) | ((unsigned)__popc(eb) << 16);
 }
@@ -122,7 +127,7 @@ __global__ void run_count(const uint8_t *__restrict__ mask, int *__restrict__ se
     const int line = s / dm.nseg, seg = s % dm.nseg;
     const uint8_t *lp = mask + (long long)blockIdx.y * dm.vox + (long long)line * dm.W;
     unsigned sb, eb;
-    const unsigned c = segment_bits(lp, seg * SEG + lane * 4, dm.W, dm.vec, lane, sb, eb);
+    const unsigned c = segment_bits(lp, seg * SEG + lane * PPL, dm.W, dm.vec, lane, sb, eb);
     const unsigned tot = warp_inclusive_scan(c & 0xffffu, lane);
     if (lane == 31) seg_count[(long long)blockIdx.y * (dm.nsegs + 1) + s] = (int)tot;
 }
@@ -192,7 +197,7 @@ __global__ void run_emit(const uint8_t *__restrict__ mask, const int *__restrict
     const int f = blockIdx.y;
     const int line = s / dm.nseg, seg = s % dm.nseg;
     const uint8_t *lp = mask + (long long)f * dm.vox + (long long)line * dm.W;
-    const int x = seg * SEG + lane * 4;
+    const int x = seg * SEG + lane * PPL;
     unsigned sb, eb;
     const unsigned c = segment_bits(lp, x, dm.W, dm.vec, lane, sb, eb);
     const unsigned incl = warp_inclusive_scan(c, lane);
@@ -200,14 +205,17 @@ __global__ void run_emit(const uint8_t *__restrict__ mask, const int *__restrict
     const long long rb = (long long)f * dm.maxruns;
     const int base = seg_off[(long long)f * (dm.nsegs + 1) + s];
     int is = base + (int)((incl - c) & 0xffffu), ie = base + (int)((incl - c) >> 16);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        if (sb & (1u << k)) {
-            run_start[rb + is] = line * dm.W + x + k;
-            parent[rb + is] = is;
-            ++is;
-        }
-        if (eb & (1u << k)) run_end[rb + ie++] = x + k;
+    while (sb) {                                   // set bits in ascending order = raster order
+        const int k = __ffs(sb) - 1;
+        sb &= sb - 1;
+        run_start[rb + is] = line * dm.W + x + k;
+        parent[rb + is] = is;
+        ++is;
+    }
+    while (eb) {
+        const int k = __ffs(eb) - 1;
+        eb &= eb - 1;
+        run_end[rb + ie++] = x + k;
     }
 }
 
@@ -504,7 +512,7 @@ int make_dims(int n, int d, int hgt, int wid, int max_rows, const void *mask, Di
     SQ_REQUIRE(mr < (1ll << 31) - CHUNK, SQ_EINVAL, "label: frame too large");
     dm->maxruns = (int)mr;
     dm->nchunks = sq_div_up(mr, CHUNK);
-    dm->vec = (wid % 4 == 0) && (((uintptr_t)mask & 3u) == 0);
+    dm->vec = (wid % PPL == 0) && (((uintptr_t)mask & (PPL - 1)) == 0);     // 16-byte mask loads are aligned
     return SQ_OK;
 }
 
