@@ -155,6 +155,8 @@ def ptr(t):
     return t.data_ptr()
 
 
-def stream_ptr():
+def stream_ptr(device=None):
+    """Raw handle of torch's current stream ON `device` (a tensor's device / index / None = the
+    current device): kernels must run on a stream of the GPU that owns their buffers."""
     import torch
-    return torch.cuda.current_stream().cuda_stream
+    return torch.cuda.current_stream(device).cuda_stream

@@ -15,6 +15,8 @@ extern "C" const char *sq_version(void) { return "sequitr_b200 0.1 (sm_100a)"; }
 
 extern "C" const char *sq_last_error(void) { return g_err; }
 
+extern "C" int sq_destroy(sq_handle_t h);
+
 extern "C" int sq_create(int device, sq_handle_t *out)
 {
     SQ_REQUIRE(out, SQ_EINVAL, "sq_create: null pointer");
@@ -34,12 +36,18 @@ extern "C" int sq_create(int device, sq_handle_t *out)
     h->cc_major = prop.major;
     h->cc_minor = prop.minor;
     h->total_mem = prop.totalGlobalMem;
-    SQ_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-    SQ_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; ++i) {
-        SQ_CUDA(cudaEventCreateWithFlags(&h->ev_h2d[i], cudaEventDisableTiming));
-        SQ_CUDA(cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
-    }
+    // a failure below must not leak the half-built handle (sq_destroy frees whatever exists)
+    auto build = [&]() -> int {
+        SQ_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        SQ_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            SQ_CUDA(cudaEventCreateWithFlags(&h->ev_h2d[i], cudaEventDisableTiming));
+            SQ_CUDA(cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
+        }
+        return SQ_OK;
+    };
+    const int st = build();
+    if (st != SQ_OK) { sq_destroy(h); return st; }
     *out = h;
     return SQ_OK;
 }

@@ -571,6 +571,7 @@ extern "C" int sq_label_centroids_host(sq_handle_t h, const uint8_t *mask_host, 
                                        float *table_host, int32_t *counts_host, int max_rows)
 {
     SQ_REQUIRE(h && mask_host && table_host && counts_host, SQ_EINVAL, "label_host: null pointer");
+    SqHostCall call(h);
     Dims dm;
     SQ_TRY(make_dims(n, d, hgt, wid, max_rows, nullptr, &dm));
     SQ_CUDA(cudaSetDevice(h->device));

@@ -522,6 +522,7 @@ extern "C" int sq_image_pipe_host(sq_handle_t h, int which, const float *in_host
 {
     SQ_TRY(check_stack(h, n, hgt, wid, c));
     SQ_REQUIRE(in_host && out_host, SQ_EINVAL, "image_pipe_host: null pointer");
+    SqHostCall call(h);
     SQ_REQUIRE(which >= 0 && which <= 2, SQ_EINVAL, "image_pipe_host: unknown pipe %d", which);
     SQ_REQUIRE(which != 2 || c == 1, SQ_EINVAL, "image_pipe_host: background subtraction takes one channel");
     SQ_CUDA(cudaSetDevice(h->device));

@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -55,6 +56,23 @@ struct sq_handle_s {
     cudaStream_t stream = nullptr;      // library-owned stream for *_host calls
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+    // the *_host entry points share the staging arena, the two streams and the events above: they
+    // serialise on this mutex (device-pointer entry points own nothing in the handle and need no lock)
+    std::mutex host_mu;
+};
+
+// Scope of one *_host call: serialises the calls of a handle and, on EVERY exit path (also the early
+// error returns), drains both library streams so that no asynchronous copy still reads or writes the
+// caller's host buffers after the call has returned.
+struct SqHostCall {
+    sq_handle_s *h;
+    std::lock_guard<std::mutex> lock;
+    explicit SqHostCall(sq_handle_s *hh) : h(hh), lock(hh->host_mu) {}
+    ~SqHostCall()
+    {
+        cudaStreamSynchronize(h->copy_stream);
+        cudaStreamSynchronize(h->stream);
+    }
 };
 
 int sq_reserve_pinned(sq_handle_s *h, size_t bytes);

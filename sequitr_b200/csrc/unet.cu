@@ -525,9 +525,23 @@ extern "C" int sq_unet_profile(sq_unet_t u, const float *in, int n, int d, int h
     return SQ_OK;
 }
 
+static int segment_localise_impl(sq_unet_t u, const void *frames_host, int in_dtype, int normalise,
+                                 int n, int hgt, int wid, int frame0, float *table_host,
+                                 int32_t *counts_host, int max_rows, uint8_t *mask_host);
+
 extern "C" int sq_segment_localise_raw_host(sq_unet_t u, const void *frames_host, int in_dtype, int normalise,
                                             int n, int hgt, int wid, int frame0, float *table_host,
                                             int32_t *counts_host, int max_rows, uint8_t *mask_host)
+{
+    SQ_REQUIRE(u && u->h, SQ_EINVAL, "segment_localise_host: null plan");
+    SqHostCall call(u->h);          // one host call per handle at a time; streams drained on every exit path
+    return segment_localise_impl(u, frames_host, in_dtype, normalise, n, hgt, wid, frame0, table_host,
+                                 counts_host, max_rows, mask_host);
+}
+
+static int segment_localise_impl(sq_unet_t u, const void *frames_host, int in_dtype, int normalise,
+                                 int n, int hgt, int wid, int frame0, float *table_host,
+                                 int32_t *counts_host, int max_rows, uint8_t *mask_host)
 {
     SQ_TRY(check_geometry(u, n, 1, hgt, wid));
     SQ_REQUIRE(u->ndim == 2, SQ_EUNSUPPORTED, "segment_localise_host: planar stacks only");

@@ -987,6 +987,7 @@ extern "C" int sq_weightmap_edt_host(sq_handle_t h, const uint8_t *mask_host, in
 {
     SQ_TRY(check_common(h, n, hgt, wid, out_dtype));
     SQ_REQUIRE(mask_host && out_host, SQ_EINVAL, "weightmap_edt_host: null pointer");
+    SqHostCall call(h);
     SQ_CUDA(cudaSetDevice(h->device));
     const size_t px = (size_t)n * hgt * wid;
     const size_t esz = out_dtype == SQ_F32 ? 4 : 8;
@@ -1014,6 +1015,7 @@ extern "C" int sq_weightmap_unet_host(sq_handle_t h, const int32_t *labels_host,
 {
     SQ_TRY(check_common(h, n, hgt, wid, out_dtype));
     SQ_REQUIRE(labels_host && out_host, SQ_EINVAL, "weightmap_unet_host: null pointer");
+    SqHostCall call(h);
     SQ_CUDA(cudaSetDevice(h->device));
     const size_t px = (size_t)n * hgt * wid;
     const size_t esz = out_dtype == SQ_F32 ? 4 : 8;

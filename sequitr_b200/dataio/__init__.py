@@ -2,4 +2,3 @@
 from .octopus import OctopusData, write_octopus_stream   # noqa: F401
 from .micromanager import (MicromanagerMetadataParser, MicromanagerReader, read_tiff, write_tiff,   # noqa: F401
                            write_micromanager_position)
-from .tracker import FATE_LABELS, Track, read_JSON, read_XML, write_XML   # noqa: F401

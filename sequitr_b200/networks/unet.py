@@ -79,7 +79,8 @@ class UNet(object):
         self._trace = []
         self._weights = None
         self._plan = None
-        self._ws = ops.Workspace()
+        self._device = params.get('device', None)   # CUDA device index; None = the current device at first use
+        self._ws = None
 
     # ------------------------------------------------------------ properties
     @property
@@ -265,8 +266,18 @@ class UNet(object):
         except Exception:
             pass
 
-    def _ensure_plan(self):
+    def _ensure_plan(self, device=None):
+        """The CUDA plan lives on ONE device: the first one it is used on (default: the current
+        device).  Buffers of another GPU are refused instead of being handed to the wrong stream."""
+        import torch
+        if device is not None:
+            device = torch.device(device).index
+            if device is None:
+                device = torch.cuda.current_device()
         if self._plan is not None:
+            if device is not None and device != self._device:
+                raise ValueError('this network is bound to cuda:%d, the features live on cuda:%d '
+                                 '(build one network per GPU)' % (self._device, device))
             return self._plan
         if any(k != 3 for k in self.kernel):
             raise NotImplementedError('only 3x3(x3) kernels are implemented')
@@ -278,7 +289,15 @@ class UNet(object):
         filt = (ctypes.c_int * len(self.filters))(*self.filters)
         plan = ctypes.c_void_p()
         mode = _lib.MODE_BF16_TC if self.compute == 'bf16' else _lib.MODE_FP32_EXACT
-        _lib.check(lib.sq_unet_create(_lib.handle(), self.ndim, self.n_inputs, self.n_outputs, filt,
+        if device is None:
+            device = self._device
+        if device is None:
+            _lib.handle()                       # raises without a CUDA device
+            device = torch.cuda.current_device()
+        self._device = int(device)
+        device = self._device
+        self._ws = ops.Workspace(device='cuda:%d' % device)
+        _lib.check(lib.sq_unet_create(_lib.handle(device), self.ndim, self.n_inputs, self.n_outputs, filt,
                                       len(self.filters), _lib.BRIDGE_CODES[self.bridge_type], mode,
                                       ctypes.byref(plan)))
         try:
@@ -320,15 +339,16 @@ class UNet(object):
     # ------------------------------------------------------------ execution
     def _execute(self, input_layer, want=('logits', 'probs', 'mask')):
         import torch
-        plan = self._ensure_plan()
         lib = _lib.load()
         is_numpy = isinstance(input_layer, np.ndarray)
         if is_numpy:
-            x = torch.from_numpy(np.ascontiguousarray(input_layer, dtype=np.float32)).cuda()
+            plan = self._ensure_plan()
+            x = torch.from_numpy(np.ascontiguousarray(input_layer, dtype=np.float32)).to('cuda:%d' % self._device)
         else:
             x = input_layer.contiguous().float()
             if not x.is_cuda:
                 raise ValueError('features must be a numpy array or a cuda tensor')
+            plan = self._ensure_plan(x.device)
         if x.dim() != self.ndim + 2 or x.shape[-1] != self.n_inputs:
             raise ValueError('features have shape %s, expected (N,%s%d)' %
                              (tuple(x.shape), 'D,H,W,' if self.ndim == 3 else 'H,W,', self.n_inputs))
@@ -347,7 +367,7 @@ class UNet(object):
             out['mask'] = torch.empty(sp, dtype=torch.uint8, device=x.device)
         _lib.check(lib.sq_unet_forward(plan, x.data_ptr(), n, d, h, w, _lib.ptr(out.get('probs')),
                                        _lib.ptr(out.get('mask')), _lib.ptr(out.get('logits')),
-                                       ws.data_ptr(), ws.numel(), _lib.stream_ptr()))
+                                       ws.data_ptr(), ws.numel(), _lib.stream_ptr(x.device)))
         if is_numpy:
             out = {k: v.cpu().numpy() for k, v in out.items()}
         return out
@@ -366,9 +386,9 @@ class UNet(object):
     def profile(self, features):
         """Per-layer device times of one instrumented forward pass:
         list of (scope, milliseconds, algorithmic FLOPs).  ``features`` must be a cuda tensor."""
-        plan = self._ensure_plan()
         lib = _lib.load()
         x = self._as_input(features).contiguous().float()
+        plan = self._ensure_plan(x.device)
         n = x.shape[0]
         d, h, w = (1,) + tuple(x.shape[1:3]) if self.ndim == 2 else tuple(x.shape[1:4])
         need = ctypes.c_size_t()
@@ -380,7 +400,7 @@ class UNet(object):
         flops = (ctypes.c_double * cap)()
         nl = ctypes.c_int()
         _lib.check(lib.sq_unet_profile(plan, x.data_ptr(), n, d, h, w, ws.data_ptr(), ws.numel(),
-                                       _lib.stream_ptr(), names, ms, flops, cap, ctypes.byref(nl)))
+                                       _lib.stream_ptr(x.device), names, ms, flops, cap, ctypes.byref(nl)))
         return [(names[i].decode(), float(ms[i]), float(flops[i])) for i in range(min(nl.value, cap))]
 
     def launches(self):

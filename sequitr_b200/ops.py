@@ -36,8 +36,10 @@ _default_ws = {}
 
 
 def _ws(key):
+    """Default scratch buffer of (purpose, device index): allocated ON that device, whatever the
+    current device is."""
     if key not in _default_ws:
-        _default_ws[key] = Workspace()
+        _default_ws[key] = Workspace(device='cuda:%d' % key[1])
     return _default_ws[key]
 
 
@@ -62,7 +64,7 @@ def label_centroids(mask, max_rows=4096, frame0=0, want_labels=False, workspace=
     labels = torch.empty(mask.shape, dtype=torch.int32, device=mask.device) if want_labels else None
     _lib.check(lib.sq_label_centroids(hd, mask.data_ptr(), n, d, h, w, frame0, _lib.ptr(labels),
                                       table.data_ptr(), counts.data_ptr(), max_rows,
-                                      ws.data_ptr(), ws.numel(), _lib.stream_ptr()))
+                                      ws.data_ptr(), ws.numel(), _lib.stream_ptr(mask.device)))
     return (table, counts, labels) if want_labels else (table, counts)
 
 
@@ -82,7 +84,7 @@ def weightmap_edt(mask, w0=10., sigma=5., out_dtype='float32', want_d2=False, wo
     _lib.check(lib.sq_weightmap_edt(hd, mask.data_ptr(), n, h, w, float(w0), float(sigma),
                                     _lib.F32 if out_dtype == 'float32' else _lib.F64,
                                     out.data_ptr(), _lib.ptr(d2), ws.data_ptr(), ws.numel(),
-                                    _lib.stream_ptr()))
+                                    _lib.stream_ptr(mask.device)))
     return (out, d2) if want_d2 else out
 
 
@@ -102,7 +104,7 @@ def weightmap_unet(labels, w0=10., sigma=5., wc=None, out_dtype='float32', works
     _lib.check(lib.sq_weightmap_unet(hd, labels.data_ptr(), n, h, w, float(w0), float(sigma),
                                      None if wc_arr is None else ctypes.cast(wc_arr, ctypes.c_void_p),
                                      _lib.F32 if out_dtype == 'float32' else _lib.F64,
-                                     out.data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream_ptr()))
+                                     out.data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream_ptr(labels.device)))
     return out
 
 
@@ -125,7 +127,7 @@ def weighted_cross_entropy(logits, labels, weights, want_grad=True, workspace=No
     grad = torch.empty_like(logits) if want_grad else None
     _lib.check(lib.sq_weighted_ce(hd, logits.data_ptr(), labels.data_ptr(), weights.data_ptr(), npix, k,
                                   loss.data_ptr(), _lib.ptr(grad), ws.data_ptr(), ws.numel(),
-                                  _lib.stream_ptr()))
+                                  _lib.stream_ptr(logits.device)))
     return loss, grad
 
 
@@ -161,7 +163,7 @@ def tr_augment(image, label, weights, transforms, crops, ch, cw, num_outputs=2):
     _lib.check(lib.sq_tr_augment(_lib.handle(image.device.index), image.data_ptr(), label.data_ptr(),
                                  weights.data_ptr(), n, h, w, c, transforms.ctypes.data, crops.ctypes.data,
                                  int(ch), int(cw), int(num_outputs), img_o.data_ptr(), lab_o.data_ptr(),
-                                 wgt_o.data_ptr(), _lib.stream_ptr()))
+                                 wgt_o.data_ptr(), _lib.stream_ptr(image.device)))
     return img_o, lab_o, wgt_o
 
 
@@ -182,7 +184,7 @@ def image_norm(x, out=None, workspace=None):
     ws = (workspace or _ws(('prep', x.device.index))).get(need.value)
     out = torch.empty_like(x) if out is None else out
     _lib.check(lib.sq_image_norm(hd, x.data_ptr(), out.data_ptr(), n, h, w, c, ws.data_ptr(), ws.numel(),
-                                 _lib.stream_ptr()))
+                                 _lib.stream_ptr(x.device)))
     return out
 
 
@@ -193,7 +195,7 @@ def image_outliers(x, size=2, threshold=5.):
     n, h, w, c = _stack_geometry(x)
     out = torch.empty_like(x)
     _lib.check(lib.sq_image_outliers(_lib.handle(x.device.index), x.data_ptr(), out.data_ptr(), n, h, w, c,
-                                     int(size), float(threshold), _lib.stream_ptr()))
+                                     int(size), float(threshold), _lib.stream_ptr(x.device)))
     return out
 
 
@@ -211,7 +213,7 @@ def image_bgsubtract(x, out_dtype='float32', workspace=None):
     out = torch.empty(x.shape, dtype=torch.float32 if out_dtype == 'float32' else torch.float64, device=x.device)
     _lib.check(lib.sq_image_bgsubtract(hd, x.data_ptr(), out.data_ptr(),
                                        _lib.F32 if out_dtype == 'float32' else _lib.F64, n, h, w,
-                                       ws.data_ptr(), ws.numel(), _lib.stream_ptr()))
+                                       ws.data_ptr(), ws.numel(), _lib.stream_ptr(x.device)))
     return out
 
 

@@ -8,8 +8,8 @@ SciPy augmentation filters) are not part of this path; ``networks.unet.tr_augmen
 augmentation.
 
 ``ImageWeightMapUNet`` is the north-star ``w_c + w0*exp(-(d1+d2)^2/2 sigma^2)`` map
-on instance labels (GPU); it is what ``weightmap.create_weightmaps`` uses by
-default in this package.
+on instance labels (GPU); ``weightmap.create_weightmaps(method='unet')`` selects it (the
+default there stays the reference's ``ImageWeightMap2``).
 """
 import inspect
 import json

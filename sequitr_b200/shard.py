@@ -19,6 +19,33 @@ def merge_tables(per_rank_tables):
     return out
 
 
+def tables_digest(tables):
+    """sha256 over the per-frame centroid tables in frame order (row count + float32 bytes of every
+    frame): two runs of the same stack -- whatever the number of ranks, the shard boundaries or the
+    chunking -- must produce the same digest."""
+    import hashlib
+    import numpy as np
+    h = hashlib.sha256()
+    for t in tables:
+        t = np.ascontiguousarray(t, dtype=np.float32)
+        h.update(np.int64(len(t)).tobytes())
+        h.update(t.tobytes())
+    return h.hexdigest()
+
+
+def segment_stack(net, frames, frame0=0, frames_per_call=250, max_rows=4096, normalise=True):
+    """Run this rank's contiguous frame range ``frames`` (host array (n,H,W[,C]); camera-native
+    uint8 / uint16 or float32) through ``net.segment_and_localise`` call by call and return the list of
+    per-frame tables, rows carrying GLOBAL frame indices (``frame0`` = global index of ``frames[0]``):
+    the loop a Sequitr job runs over a time-lapse (reference utils.py:531-578), one rank's share of it."""
+    out = []
+    n = len(frames)
+    for s in range(0, n, frames_per_call):
+        out.extend(net.segment_and_localise(frames[s:s + frames_per_call], frame0=frame0 + s,
+                                            max_rows=max_rows, normalise=normalise))
+    return out
+
+
 def bind_to_gpu_numa(device_index):
     """Pin the calling worker process to the CPUs NVML reports as closest to GPU ``device_index`` (one
     worker per GPU, the reference's model: core.py:41-42), so that the pinned frame buffers it allocates

@@ -108,6 +108,54 @@ def frames(n, h, w, cin=1, seed=1234, n_objects=None, first_frame=0):
     return out
 
 
+def to_camera_counts(frames_f32, gain=400.0, offset=3000.0):
+    """float32 synthetic frames -> uint16 camera counts (what dataio.OctopusData.frames_raw delivers)."""
+    return np.clip(np.asarray(frames_f32, dtype=np.float32) * np.float32(gain) + np.float32(offset),
+                   0, 65535).astype(np.uint16)
+
+
+def _camera_chunk(args):
+    buf, lo, t0, n, h, w, seed = args
+    out = np.frombuffer(buf, dtype=np.uint16).reshape(-1, h, w)
+    out[t0 - lo:t0 - lo + n] = to_camera_counts(frames(n, h, w, 1, seed=seed, first_frame=t0)[..., 0])
+    return n
+
+
+def camera_stack(lo, hi, h, w, seed=1234, workers=None, chunk=4):
+    """uint16 (hi-lo, H, W) time-lapse of GLOBAL frames [lo, hi): frame t depends on (seed, t) only, so
+    every rank of a sharded run generates exactly its own slice of the same stack.  Rendered by a pool
+    of forked worker processes into one anonymous shared mapping (call this BEFORE initialising CUDA:
+    the children must not inherit a CUDA context).  Returns an ndarray backed by that mapping."""
+    import mmap
+    import os
+    n = hi - lo
+    nbytes = max(n * h * w * 2, mmap.PAGESIZE)
+    buf = mmap.mmap(-1, nbytes)                       # MAP_SHARED | MAP_ANONYMOUS: visible to the children
+    workers = max(1, min(workers or (os.cpu_count() or 1), (n + chunk - 1) // chunk or 1))
+    jobs = [(buf, lo, t0, min(chunk, hi - t0), h, w, seed) for t0 in range(lo, hi, chunk)]
+    if workers == 1 or len(jobs) <= 1:
+        for j in jobs:
+            _camera_chunk(j)
+    else:
+        procs = []
+        for k in range(workers):                      # static round-robin split, no pickling of the buffer
+            pid = os.fork()
+            if pid == 0:
+                code = 0
+                try:
+                    for j in jobs[k::workers]:
+                        _camera_chunk(j)
+                except BaseException:
+                    code = 1
+                os._exit(code)
+            procs.append(pid)
+        for pid in procs:
+            _, status = os.waitpid(pid, 0)
+            if status != 0:
+                raise RuntimeError('camera_stack: a worker process failed (status %d)' % status)
+    return np.frombuffer(buf, dtype=np.uint16)[:n * h * w].reshape(n, h, w)
+
+
 def volumes(n, d, h, w, cin=1, seed=4321):
     """float32 (N,D,H,W,Cin) synthetic z-stacks: noise + a few soft balls."""
     rng = np.random.default_rng(seed)

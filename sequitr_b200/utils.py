@@ -150,9 +150,4 @@ def pinned_array(shape, dtype=np.float32):
     tdt = {np.dtype(np.float32): torch.float32, np.dtype(np.uint16): torch.uint16,
            np.dtype(np.uint8): torch.uint8, np.dtype(np.int32): torch.int32}[np.dtype(dtype)]
     t = torch.empty(tuple(int(v) for v in shape), dtype=tdt).pin_memory()
-    a = t.numpy()
-    _PINNED_KEEPALIVE[id(a)] = t            # the tensor owns the memory
-    return a
-
-
-_PINNED_KEEPALIVE = {}
+    return t.numpy()                        # the array's .base keeps the pinned tensor alive

@@ -2,11 +2,14 @@
 ``create_weightmaps`` (:171-205) and the CLI (:210-233).
 
 ``create_weightmaps(method=...)`` selects the weight pipe:
-  'unet'     (default) GPU north-star map w_c + w0*exp(-(d1+d2)^2/2 sigma^2); the bool
+  'delaunay' (default) the reference's own choice, ``pipeline.ImageWeightMap2``
+             (weightmap.py:181; host, SciPy/Qhull) -- the same call writes the same files;
+  'edt'      opt-in: GPU ``pipeline.ImageWeightMap`` (exact EDT, single distance);
+  'unet'     opt-in: GPU north-star map w_c + w0*exp(-(d1+d2)^2/2 sigma^2); the bool
              mask the reference passes (weightmap.py:203) is split into instances
-             by the GPU connected-component kernel first;
-  'edt'      GPU ``pipeline.ImageWeightMap``;
-  'delaunay' the reference's own choice, ``pipeline.ImageWeightMap2`` (host, SciPy/Qhull).
+             by the GPU connected-component kernel first.
+The two GPU methods write numerically DIFFERENT maps than the reference's Delaunay
+approximation, which is why they are never the default.
 """
 import os
 import re
@@ -78,7 +81,7 @@ _METHODS = {'unet': ImageWeightMapUNet, 'edt': ImageWeightMap, 'delaunay': Image
 
 
 def create_weightmaps(path, folders, w0=10., sigma=3., thresh_fn=lambda x: x > 0,
-                      name_weights_folder=True, method='unet'):
+                      name_weights_folder=True, method='delaunay'):
     """ Generate weightmaps for the images using the binary masks (weightmap.py:171-205) """
     if method not in _METHODS:
         raise ValueError('method must be one of %s' % sorted(_METHODS))
@@ -111,7 +114,8 @@ def main(argv=None):
                    help='Specify the sub-folders of image data')
     p.add_argument('--w0', type=float, default=30., help='Specify the amplitude')
     p.add_argument('--sigma', type=float, default=3., help='Specify the sigma')
-    p.add_argument('--method', default='unet', choices=sorted(_METHODS))
+    p.add_argument('--method', default='delaunay', choices=sorted(_METHODS),
+                   help="'delaunay' = the reference's ImageWeightMap2 (host); 'edt' / 'unet' = GPU maps (opt-in)")
     args = p.parse_args(argv)
     create_weightmaps(args.workdir, args.folders, w0=args.w0, sigma=args.sigma, method=args.method)
 

@@ -7,7 +7,16 @@ can flip a bf16 rounding (2^-9 relative) of an individual activation, and such f
 propagate through the 23 layers.  We therefore accept |logit - oracle| <= 2% of the logit
 range (mean error <= 0.2%), |prob - oracle| <= half that logit tolerance (softmax is
 1/2-Lipschitz in the max-norm) and require masks to agree everywhere the oracle's top-2
-logit margin exceeds twice the logit tolerance.
+logit margin exceeds twice the logit tolerance (the margin rule: only near-ties may flip), with
+at most 1e-3 of the pixels (or 4 pixels of a tiny test image) differing at all.
+
+Against the fp32 evaluation of the same network (the reference's arithmetic: TF float32; oracle
+contract 'fp32') the benchmarked bf16 path is checked at BASELINE's full frame size on the bench's
+own weights and frames (`test_benchmarked_path_against_the_fp32_oracle_2048`): every differing mask
+pixel must be a near-tie of the fp32 logits (margin <= 1% of the logit range), at most 1e-3 of the
+pixels may differ, and the centroid tables the consumer sees (utils.py:540-564) are compared row
+by row (same object count up to 2 rows, every matched row within 0.5 px).  The numbers measured
+there are the ones `bench.py` prints (`parity` key).
 """
 import numpy as np
 import pytest
@@ -30,7 +39,7 @@ def _compare(out, ref, name=''):
     margin = srt[..., -1] - srt[..., -2]
     differ = out['mask'] != ref['mask']
     assert margin[differ].max(initial=0.0) <= 2 * tol, '%s: mask differs at a decided pixel' % name
-    assert differ.mean() < 0.01
+    assert differ.sum() <= max(4, 1e-3 * differ.size), '%s: %d of %d mask pixels differ' % (name, differ.sum(), differ.size)
     return err.max(), differ.mean()
 
 
@@ -99,21 +108,76 @@ def test_blob_detector_masks_and_centroids_1024(sq):
     assert (mask != ref['mask']).mean() < 2e-4
     assert 100 <= len(tables[0]) <= 220                       # ~150 discs at 1024^2
     np.testing.assert_array_equal(tables[0], centroid_oracle.centroid_tables(mask)[0])
+    ref32 = unet_c.unet_forward(x, w, filters, 'concat', contract='fp32')
+    _fp32_parity('1024^2', mask, tables, ref32['mask'], ref32['logits'])
+
+
+def _fp32_parity(name, mask, tables, ref_mask, ref_logits, ref_tables=None):
+    """The benchmarked-path contract against an fp32 evaluation: near-tie-only mask flips, at most
+    1e-3 of the pixels, and the consumer's centroid rows matched one to one within half a pixel."""
+    from oracle import centroid_oracle
+    from sequitr_b200 import parity
+    mp = parity.mask_parity(mask, ref_mask, ref_logits)
+    assert mp['mismatch_frac'] <= 1e-3, '%s: %r' % (name, mp)
+    assert mp['max_margin_of_mismatch'] <= 0.01 * mp['logit_range'], \
+        '%s: a mask pixel flipped where the fp32 evaluation was decided: %r' % (name, mp)
+    if ref_tables is None:
+        ref_tables = centroid_oracle.centroid_tables(ref_mask)
+    cd = parity.centroid_set_diff(tables, ref_tables, tol_px=0.5)
+    assert abs(cd['rows'] - cd['ref_rows']) <= 2, '%s: %r' % (name, cd)
+    assert cd['unmatched'] + cd['ref_unmatched'] <= 4, '%s: %r' % (name, cd)
+    assert cd['max_shift_px'] <= 0.5
+    print('%s: mask %r centroids %r' % (name, mp, cd))
+    return mp, cd
+
+
+def test_benchmarked_path_against_the_fp32_oracle_2048(sq):
+    """BASELINE configs[2] on the bench's own weights and frames, one 2048^2 frame: the C oracle in
+    its fp32 contract (the reference's arithmetic) is the judge.  (1) The fp32 exact GPU mode is
+    bit-identical to it at this size too (logits and mask), which is what lets `bench.py` use that
+    mode as the on-device stand-in for the oracle.  (2) The bf16 tensor-core path -- the one whose
+    speed is reported -- differs from it only at near-ties, and its centroid tables match row by row."""
+    from sequitr_b200.networks import UNet2D
+    filters = (16, 32, 64, 128, 256)
+    w = synth.blob_detector_weights(filters, 1, 2, seed=1)
+    x = synth.frames(1, 2048, 2048, 1, seed=1234)               # bench.py's first frame
+    ref = unet_c.unet_forward(x, w, filters, 'concat', contract='fp32')
+    net32 = UNet2D({'filters': filters, 'shape': (2048, 2048), 'bridge': 'concat', 'compute': 'fp32'})
+    net32.load_weights(w)
+    b = net32.predict(x, want=('logits', 'mask'))
+    np.testing.assert_array_equal(b['logits'], ref['logits'])
+    np.testing.assert_array_equal(b['mask'], ref['mask'])
+    del net32
+    net = _net(filters, (2048, 2048), 'concat', 1, 2, w)
+    tables, mask = net.segment_and_localise(x, return_mask=True)
+    np.testing.assert_array_equal(mask, net.predict(x, want=('mask',))['mask'])
+    assert 450 <= len(tables[0]) <= 700                         # ~600 discs at 2048^2
+    mp, cd = _fp32_parity('2048^2 bench frame', mask, tables, ref['mask'], ref['logits'])
+    # same frame as RAW uint16 camera counts, widened + normalised on the device (the bench's headline
+    # end-to-end input): compared with the fp32 evaluation of the identically normalised frame
+    from oracle import prep_oracle
+    raw = np.clip(x[..., 0] * 400.0 + 3000.0, 0, 65535).astype(np.uint16)
+    xn = prep_oracle.image_norm(raw[0].astype(np.float32))[None, ..., None].astype(np.float32)
+    refn = unet_c.unet_forward(xn, w, filters, 'concat', contract='fp32')
+    tables_u16, mask_u16 = net.segment_and_localise(raw, return_mask=True, normalise=True)
+    _fp32_parity('2048^2 uint16 frame', mask_u16, tables_u16, refn['mask'], refn['logits'])
 
 
 def test_full_size_2048_against_fp32_exact_mode(sq):
-    """At BASELINE's frame size the CPU oracle is too slow for a unit test; the fp32 exact
-    GPU mode (bit-verified against the oracle above) stands in for it."""
+    """A second 2048^2 frame, judged by the fp32 exact GPU mode (bit-identical to the oracle: test
+    above and tests/test_gpu_unet_fp32.py): margin rule on the mask, centroid rows matched."""
     from sequitr_b200.networks import UNet2D
     filters = (16, 32, 64, 128, 256)
     w = synth.blob_detector_weights(filters, 1, 2, seed=1)
     x = synth.frames(1, 2048, 2048, 1, seed=77)
-    a = _net(filters, (2048, 2048), 'concat', 1, 2, w).predict(x, want=('probs', 'mask'))
+    net = _net(filters, (2048, 2048), 'concat', 1, 2, w)
+    a = net.predict(x, want=('probs', 'mask'))
     net32 = UNet2D({'filters': filters, 'shape': (2048, 2048), 'bridge': 'concat', 'compute': 'fp32'})
     net32.load_weights(w)
-    b = net32.predict(x, want=('probs', 'mask'))
-    assert (a['mask'] != b['mask']).mean() < 5e-4
+    b = net32.predict(x, want=('probs', 'logits', 'mask'))
     assert np.abs(a['probs'] - b['probs']).mean() < 2e-3
+    tables = net.segment_and_localise(x)
+    _fp32_parity('2048^2 seed 77', a['mask'], tables, b['mask'], b['logits'])
 
 
 def test_unsupported_configs_fail_loudly(sq):
@@ -188,14 +252,14 @@ def test_baseline_config_sizes_against_fp32_exact_mode(sq, name, n, shape, cin, 
     net32 = UNet2D({'filters': filters, 'shape': shape, 'bridge': 'concat', 'num_inputs': cin,
                     'num_outputs': k, 'compute': 'fp32'})
     net32.load_weights(w)
-    b = net32.predict(x, want=('probs', 'mask'))
-    assert (a['mask'] != b['mask']).mean() < 5e-4, name
+    b = net32.predict(x, want=('probs', 'logits', 'mask'))
     assert np.abs(a['probs'] - b['probs']).mean() < 2e-3, name
     tables, mask = net.segment_and_localise(x, return_mask=True)
     np.testing.assert_array_equal(mask, a['mask'])
     assert sum(len(t) for t in tables) >= 20, name
     for t, want in zip(tables, centroid_oracle.centroid_tables(mask)):
         np.testing.assert_array_equal(t, want)
+    _fp32_parity(name, mask, tables, b['mask'], b['logits'])
 
 
 @pytest.mark.parametrize('seed', range(12))

@@ -201,7 +201,11 @@ def test_create_weightmaps_gpu_methods(sq, tmp_path):
     out = weightmap.create_weightmaps(str(tmp_path), ['setA'], w0=10., sigma=5., method='edt')
     w = cv2.imread(out[0], cv2.IMREAD_UNCHANGED)
     np.testing.assert_allclose(w, wo.weightmap_w1(mask, 10., 5.)[..., 0].astype(np.float32), rtol=1.2e-7)
-    out = weightmap.create_weightmaps(str(tmp_path), ['setA'], w0=10., sigma=5.)
+    out = weightmap.create_weightmaps(str(tmp_path), ['setA'], w0=10., sigma=5., method='unet')
     from scipy.ndimage import label
     w = cv2.imread(out[0], cv2.IMREAD_UNCHANGED)
     np.testing.assert_allclose(w, wo.weightmap_w3(label(mask)[0], 10., 5.).astype(np.float32), rtol=1.2e-7)
+    # the default stays the reference's own pipe (weightmap.py:181: ImageWeightMap2, host-side Delaunay)
+    out = weightmap.create_weightmaps(str(tmp_path), ['setA'], w0=10., sigma=5.)
+    w = cv2.imread(out[0], cv2.IMREAD_UNCHANGED)
+    np.testing.assert_allclose(w, wo.weightmap_w2(mask, 10., 5.)[..., 0].astype(np.float32), rtol=1e-6)

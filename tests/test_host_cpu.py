@@ -279,65 +279,6 @@ def test_pinned_array_and_reader_destination(tmp_path):
         OctopusData(stem).frames_raw(0, 2, out=np.zeros((2, 6, 8), np.uint8))
 
 
-def test_tracker_formats_round_trip(tmp_path):
-    """dataio/tracker.py (reference :36-260): Track container, JSON (plain and zipped) and XML."""
-    import json
-    import zipfile
-    from sequitr_b200.dataio import tracker
-
-    def mk(i, n):
-        d = {'ID': i, 'x': [10.04 + k for k in range(n)], 'y': [5.55 + 2 * k for k in range(n)],
-             'z': [0.0] * n, 't': list(range(3, 3 + n)), 'length': n, 'label': [0] * n, 'parent': i,
-             'children': [], 'fate': 4}
-        return d
-
-    folder = str(tmp_path)
-    files = []
-    for i, n in ((1, 4), (2, 6)):
-        fn = 'track_%d_GFP.json' % i
-        files.append(fn)
-        with open(os.path.join(folder, fn), 'w') as f:
-            json.dump(mk(i, n), f)
-    with open(os.path.join(folder, 'tracks_GFP.json'), 'w') as f:
-        json.dump({'GFP': {'files': files, 'path': folder, 'zipped': False}}, f)
-    tracks = tracker.read_JSON(folder, 'GFP')
-    assert [t.ID for t in tracks] == [1, 2] and len(tracks[1]) == 6
-    t = tracks[0]
-    assert t.cell_type == 'GFP' and t.filename == files[0] and t.n is t.t
-    assert t.in_frame(4) and not t.in_frame(99) and t.fate_as_string == 'mitosis'
-    c = t.get_copy_at_frame(5)
-    assert c.ref is t and c.x == t.x[2] and c.t == 5 and c.ID == 1 and t.get_copy_at_frame(99) is None
-    assert t['x'] is t.x and t['nonexistent'] is None
-    t.neighborhood = [{'n_total': 3}, {'n_total': 5}]
-    assert t['n_total'] == [3, 5]
-    with pytest.raises(TypeError):
-        t.get_neighborhood_attr(3)
-    t.neighborhood = []
-    # zipped variant
-    with zipfile.ZipFile(os.path.join(folder, 'tracks_RFP.zip'), 'w') as z:
-        z.writestr('track_7_RFP.json', json.dumps(mk(7, 3)))
-    with open(os.path.join(folder, 'tracks_RFP.json'), 'w') as f:
-        json.dump({'RFP': {'files': ['track_7_RFP.json'], 'path': folder, 'zipped': True}}, f)
-    z = tracker.read_JSON(folder, 'RFP')
-    assert len(z) == 1 and z[0].ID == 7 and z[0].cell_type == 'RFP'
-    with pytest.raises(IOError):
-        tracker.read_JSON(folder, 'iRFP')
-    # XML: coordinates are written to one decimal; the frame list comes back as Track.t
-    xml = os.path.join(folder, 'tracks.xml')
-    tracker.write_XML(xml, tracks)
-    back = tracker.read_XML(xml, cell_type='GFP')
-    assert [b.ID for b in back] == [1, 2]
-    assert back[0].x == [10.0, 11.0, 12.0, 13.0]
-    assert back[0].y == [float('%2.1f' % v) for v in tracks[0].y]
-    assert back[0].t == tracks[0].t and back[0].label == tracks[0].label and back[0].fate == 4
-    assert back[0].length == 4 and back[0].parent == 1 and back[0].children == []
-    assert tracker.read_XML(None) == [] and tracker.read_XML(os.path.join(folder, 'missing.xml')) == []
-    with pytest.raises(IOError):
-        tracker.read_XML(os.path.join(folder, 'tracks.json'))
-    with pytest.raises(TypeError):
-        tracker.read_XML(3)
-
-
 def test_image_pipeline_json_round_trip(tmp_path):
     """pipeline.py:104-154: constructor arguments are read back from attributes of the same name, the
     file maps class names to them, loading rebuilds the chain.  No compute call is made here."""
@@ -374,3 +315,77 @@ def test_image_pipeline_json_round_trip(tmp_path):
     assert a.shape == (3, 16, 16, 1) and np.allclose(b, 2 * a)
     (x, y) = smp.coords[0]
     assert np.allclose(a[0, ..., 0], big[x - 8:x + 8, y - 8:y + 8])
+
+
+def test_parity_helpers_on_the_two_oracle_contracts():
+    """sequitr_b200.parity on real data without a GPU: the oracle's bf16 contract stands in for the
+    tensor-core path, its fp32 contract is the reference arithmetic.  Mask flips are near-ties only and
+    the centroid rows pair up one to one."""
+    from oracle import unet_c, centroid_oracle
+    from sequitr_b200 import parity
+    filters = (16, 32, 64)
+    x = synth.frames(2, 96, 128, 1, seed=3, n_objects=6)
+    w = synth.blob_detector_weights(filters, 1, 2, seed=1)
+    a = unet_c.unet_forward(x, w, filters, 'concat', contract='bf16')
+    b = unet_c.unet_forward(x, w, filters, 'concat', contract='fp32')
+    mp = parity.mask_parity(a['mask'], b['mask'], b['logits'])
+    assert mp['pixels'] == 2 * 96 * 128 and mp['mismatch'] == int((a['mask'] != b['mask']).sum())
+    assert mp['mismatch_frac'] <= 1e-3 and mp['max_margin_of_mismatch'] <= 0.01 * mp['logit_range']
+    same = parity.mask_parity(b['mask'], b['mask'], b['logits'])
+    assert same['mismatch'] == 0 and same['max_margin_of_mismatch'] == 0.0
+    ta, tb = centroid_oracle.centroid_tables(a['mask']), centroid_oracle.centroid_tables(b['mask'])
+    cd = parity.centroid_set_diff(ta, tb)
+    assert cd['rows'] == cd['ref_rows'] == sum(len(t) for t in tb) and cd['unmatched'] == cd['ref_unmatched'] == 0
+    assert cd['identical'] + cd['moved'] == cd['rows'] and cd['max_shift_px'] <= 0.5
+    assert parity.centroid_set_diff(tb, tb)['rows_changed'] == 0
+    # an object that vanishes and one that moves by more than the tolerance
+    broken = [t.copy() for t in tb]
+    broken[0] = broken[0][1:]
+    broken[1][0, 1] += 3.0
+    cd = parity.centroid_set_diff(broken, tb)
+    assert cd['ref_unmatched'] == 2 and cd['unmatched'] == 1 and cd['rows_changed'] == 3
+    with pytest.raises(ValueError):
+        parity.mask_parity(a['mask'][:1], b['mask'], b['logits'])
+    # K > 2 margins
+    lg = np.array([[[0.0, 2.0, 1.5]]], np.float32)
+    assert abs(parity.top2_margin(lg)[0, 0] - 0.5) < 1e-7
+
+
+def test_camera_stack_is_a_function_of_the_global_frame_index():
+    """synth.camera_stack: forked renderers write one shared mapping; any shard of the stack equals the
+    same frames rendered alone (what makes the per-rank slices of bench.py's 2000-frame stack consistent)."""
+    whole = synth.camera_stack(0, 11, 48, 64, seed=5, workers=3, chunk=2)
+    assert whole.shape == (11, 48, 64) and whole.dtype == np.uint16
+    part = synth.camera_stack(4, 9, 48, 64, seed=5, workers=1)
+    np.testing.assert_array_equal(part, whole[4:9])
+    one = synth.to_camera_counts(synth.frames(1, 48, 64, 1, seed=5, first_frame=7)[..., 0])
+    np.testing.assert_array_equal(one[0], whole[7])
+    assert len(synth.camera_stack(3, 3, 48, 64)) == 0
+
+
+def test_segment_stack_and_digest_with_a_stub_network():
+    """shard.segment_stack walks a rank's range call by call with GLOBAL frame indices; tables_digest is
+    independent of how the stack was split into calls / ranks."""
+    from sequitr_b200 import shard
+
+    class Stub(object):
+        def __init__(self):
+            self.calls = []
+
+        def segment_and_localise(self, frames, frame0=0, max_rows=4096, normalise=False):
+            self.calls.append((len(frames), frame0, normalise))
+            return [np.full((int(f[0, 0]) % 3, 5), frame0 + i, np.float32) for i, f in enumerate(frames)]
+
+    stack = np.arange(23, dtype=np.uint16)[:, None, None] * np.ones((1, 2, 2), np.uint16)
+    s1 = Stub()
+    whole = shard.segment_stack(s1, stack, frame0=0, frames_per_call=10)
+    assert s1.calls == [(10, 0, True), (10, 10, True), (3, 20, True)]
+    parts = []
+    for r in range(4):
+        lo, hi = shard.frame_range(r, 4, 23)
+        parts.append(shard.segment_stack(Stub(), stack[lo:hi], frame0=lo, frames_per_call=4))
+    merged = shard.merge_tables(parts)
+    assert len(merged) == 23 and all((t[:, 0] == i).all() for i, t in enumerate(merged))
+    assert shard.tables_digest(merged) == shard.tables_digest(whole)
+    merged[5] = merged[5] + 1
+    assert shard.tables_digest(merged) != shard.tables_digest(whole)
