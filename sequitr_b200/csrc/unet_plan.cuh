@@ -41,6 +41,7 @@ struct sq_unet_s {
     std::vector<void *> dev_allocs;             // freed in sq_unet_destroy
     void *tc_state = nullptr;                   // owned by unet_tc.cu
     SqLayerTimer timer;
+    std::map<std::string, std::string> aux_names;   // stable storage for timer names of fused launches
 };
 
 // ---- tensor-core path (unet_tc.cu)

@@ -908,6 +908,357 @@ conv_xc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     }
 }
 
+// ------------------------------------- fused PAIR of x-combined 3x3 convs (conv1 -> conv2 on chip)
+// conv_block of the reference (networks/unet.py:265-277) as ONE launch for Cout <= 32 planar layers: the
+// intermediate activation (conv1's output) never goes to HBM.  Per tile:
+//     TMA: (8S+2) x 16 input patch(es) -> stage 1 (x-combined MMAs, as conv_xc_kernel) -> TMEM
+//     epilogue 1: TMEM -> combine / scale / shift / ReLU / bf16 -> shared-memory patch P1 (zeros outside the
+//                 image = conv2's SAME padding), laid out exactly like a TMA-fetched patch
+//     stage 2: x-combined MMAs reading P1 -> the SAME TMEM columns -> epilogue 2 (store / pool / fused head)
+// Geometry: 16 input columns -> 14 columns of P1 -> 12 output columns; 8S+2 input rows -> 8S rows of P1 ->
+// 8S-2 output rows (S = 2: a 14 x 12 output tile from an 18 x 16 input patch).  The MMA warp issues
+// stage 1 of tile i+1 BEFORE stage 2 of tile i and the epilogue warps mirror that order, so the tensor pipe
+// works on the next tile while P1 of the current one is being written; two accumulator buffers, two CTAs
+// per SM.  Weights of both convs stay resident in shared memory.
+template <int COUT, int S>
+struct PCfg {
+    static constexpr int N = 3 * COUT;
+    static constexpr int TW = 12, TH = 8 * S - 2;        // output tile
+    static constexpr int PW = 16, PH = 8 * S + 2;        // input patch of stage 1 == allocated P1 patch
+    static constexpr int A_BYTES = 2 * PH * PW * 16;     // 16 channels of a patch
+    static constexpr int P1_BYTES = (COUT / 16) * A_BYTES;
+    static constexpr int B_BYTES = 3 * 2 * N * 16;       // one k-step of x-combined weights
+    static constexpr int ACC_STRIDE = (N <= 64) ? 64 : 128;
+    static constexpr int ACC_COLS = S * ACC_STRIDE;
+    static constexpr uint32_t LBO_A = PH * PW * 16, SBO_A = 128, LBO_B = N * 16, SBO_B = 128;
+};
+
+template <int COUT, int S, int EPI, int HK>
+__global__ void __launch_bounds__(TC_THREADS, 2)
+conv_xc_pair_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
+                    int ks0, int ks1, const bf16 *__restrict__ w1, const float *__restrict__ scale1,
+                    const float *__restrict__ shift1, const bf16 *__restrict__ w2,
+                    const float *__restrict__ scale2, const float *__restrict__ shift2,
+                    bf16 *__restrict__ out, bf16 *__restrict__ out_pool, HeadArgs head, int nimg, int H, int W,
+                    int nstages)
+{
+    using C = PCfg<COUT, S>;
+    constexpr int K2 = COUT / 16, NC16 = COUT / 16, CBo = COUT / 8;
+    constexpr int TMEM_COLS = (2 * C::ACC_COLS <= 64) ? 64 : (2 * C::ACC_COLS <= 128) ? 128
+                            : (2 * C::ACC_COLS <= 256) ? 256 : 512;
+    static_assert(2 * 2 * C::ACC_COLS <= 512, "two CTAs per SM must fit in TMEM");
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+    __shared__ uint64_t full_bar[XC_MAX_STAGES], empty_bar[XC_MAX_STAGES], w_bar;
+    __shared__ uint64_t acc1_full[2], p1_full[2], acc2_full[2], acc_free[2];
+    __shared__ uint32_t tmem_base_sh;
+    __shared__ __align__(16) float s_scale1[COUT], s_shift1[COUT], s_scale2[COUT], s_shift2[COUT];
+    __shared__ __align__(16) float s_head[EPI == EPI_HEAD ? COUT * HK + HK : 4];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_x = (W + C::TW - 1) / C::TW, tiles_y = (H + C::TH - 1) / C::TH;
+    const int tpi = tiles_x * tiles_y, ntiles = nimg * tpi;
+    const int ksteps1 = ks0 + ks1;
+    const int w1_bytes = ksteps1 * C::B_BYTES, w2_bytes = K2 * C::B_BYTES;
+    const int stage_bytes = ksteps1 * C::A_BYTES;
+    uint8_t *sW1 = smem, *sW2 = smem + w1_bytes;
+    uint8_t *sP1 = smem + ((w1_bytes + w2_bytes + 127) & ~127);
+    uint8_t *ring = sP1 + 2 * C::P1_BYTES;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < nstages; ++i) { tc::mbar_init(&full_bar[i], 1); tc::mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < 2; ++i) {
+            tc::mbar_init(&acc1_full[i], 1);
+            tc::mbar_init(&p1_full[i], 4 * EPI_GROUPS);
+            tc::mbar_init(&acc2_full[i], 1);
+            tc::mbar_init(&acc_free[i], 4 * EPI_GROUPS);
+        }
+        tc::mbar_init(&w_bar, 1);
+        tc::fence_barrier_init();
+        tc::tma_prefetch_desc(&mapA0);
+        tc::tma_prefetch_desc(&mapA1);
+    }
+    if (warp == 1) { tc::tmem_alloc(&tmem_base_sh, TMEM_COLS); tc::tmem_relinquish(); }
+    for (int i = threadIdx.x; i < COUT; i += TC_THREADS) {
+        s_scale1[i] = scale1[i]; s_shift1[i] = shift1[i]; s_scale2[i] = scale2[i]; s_shift2[i] = shift2[i];
+    }
+    if constexpr (EPI == EPI_HEAD) {
+        for (int i = threadIdx.x; i < COUT * HK; i += TC_THREADS) s_head[(i % HK) * COUT + i / HK] = head.w[i];
+        for (int i = threadIdx.x; i < HK; i += TC_THREADS) s_head[COUT * HK + i] = head.w[COUT * HK + i];
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = tmem_base_sh;
+    const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+    if (warp == 0) {
+        // ===================================================== TMA producer
+        if (lane == 0) {
+            tc::mbar_arrive_expect_tx(&w_bar, (uint32_t)(w1_bytes + w2_bytes));
+            for (int q = 0; q < ksteps1; ++q)
+                tc::bulk_load(sW1 + (size_t)q * C::B_BYTES, w1 + (size_t)q * (C::B_BYTES / 2), C::B_BYTES, &w_bar);
+            for (int q = 0; q < K2; ++q)
+                tc::bulk_load(sW2 + (size_t)q * C::B_BYTES, w2 + (size_t)q * (C::B_BYTES / 2), C::B_BYTES, &w_bar);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+                const int tx = t % tiles_x, ty = (t / tiles_x) % tiles_y, n = t / tpi;
+                const int x0 = tx * C::TW - 2, y0 = ty * C::TH - 2;
+                tc::mbar_wait(&empty_bar[stage], phase ^ 1);
+                tc::mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
+                uint8_t *sA = ring + (size_t)stage * stage_bytes;
+                tc::tma_load_5d(sA, &mapA0, &full_bar[stage], x0 * 8, y0, 0, 0, n);        // all ks0 k-steps, one box
+                if (ks1) tc::tma_load_5d(sA + (size_t)ks0 * C::A_BYTES, &mapA1, &full_bar[stage], x0 * 8, y0, 0, 0, n);
+                if (++stage == nstages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // ======================================================= MMA issuer
+        const uint32_t idesc = tc::instr_desc_bf16(128, C::N);
+        const uint32_t a_hi = ((C::SBO_A >> 4) & 0x3FFFu) | (1u << 14);
+        const uint32_t b_hi = ((C::SBO_B >> 4) & 0x3FFFu) | (1u << 14);
+        const uint32_t lbo_a = ((C::LBO_A >> 4) & 0x3FFFu) << 16, lbo_b = ((C::LBO_B >> 4) & 0x3FFFu) << 16;
+        int stage = 0;
+        uint32_t phase = 0;
+        tc::mbar_wait(&w_bar, 0);
+        // stage 2 of this CTA's tile number i: P1[i & 1] x W2 -> accumulator buffer i & 1
+        auto stage2 = [&](int i) {
+            const int b = i & 1;
+            tc::mbar_wait(&p1_full[b], (i >> 1) & 1);
+            tc::tc_fence_after();
+            if (tc::elect_one()) {
+                const uint32_t a_lo = ((tc::smem_u32(sP1 + (size_t)b * C::P1_BYTES) >> 4) & 0x3FFFu) | lbo_a;
+                const uint32_t b_lo = ((tc::smem_u32(sW2) >> 4) & 0x3FFFu) | lbo_b;
+                const uint32_t d0 = tmem_base + b * C::ACC_COLS;
+#pragma unroll
+                for (int k = 0; k < K2; ++k)
+#pragma unroll
+                    for (int j = 0; j < S; ++j)
+#pragma unroll
+                        for (int ky = 0; ky < 3; ++ky)
+                            tc::umma_bf16_parts(d0 + j * C::ACC_STRIDE,
+                                                a_lo + (uint32_t)(k * (C::A_BYTES >> 4) + (j * 8 + ky) * C::PW), a_hi,
+                                                b_lo + (uint32_t)(k * (C::B_BYTES >> 4) + ky * 2 * C::N), b_hi, idesc,
+                                                (k == 0 && ky == 0) ? 0u : 1u);
+                tc::umma_commit(&acc2_full[b]);
+            }
+            __syncwarp();
+        };
+        for (int it = 0; it < my_tiles; ++it) {
+            const int b = it & 1;
+            tc::mbar_wait(&acc_free[b], ((it >> 1) & 1) ^ 1);
+            tc::mbar_wait(&full_bar[stage], phase);
+            tc::tc_fence_after();
+            if (tc::elect_one()) {
+                const uint32_t a_lo = ((tc::smem_u32(ring + (size_t)stage * stage_bytes) >> 4) & 0x3FFFu) | lbo_a;
+                const uint32_t b_lo = ((tc::smem_u32(sW1) >> 4) & 0x3FFFu) | lbo_b;
+                const uint32_t d0 = tmem_base + b * C::ACC_COLS;
+                for (int k = 0; k < ksteps1; ++k)
+#pragma unroll
+                    for (int j = 0; j < S; ++j)
+#pragma unroll
+                        for (int ky = 0; ky < 3; ++ky)
+                            tc::umma_bf16_parts(d0 + j * C::ACC_STRIDE,
+                                                a_lo + (uint32_t)(k * (C::A_BYTES >> 4) + (j * 8 + ky) * C::PW), a_hi,
+                                                b_lo + (uint32_t)(k * (C::B_BYTES >> 4) + ky * 2 * C::N), b_hi, idesc,
+                                                (k == 0 && ky == 0) ? 0u : 1u);
+                tc::umma_commit(&empty_bar[stage]);
+                tc::umma_commit(&acc1_full[b]);
+            }
+            __syncwarp();
+            if (++stage == nstages) { stage = 0; phase ^= 1; }
+            if (it > 0) stage2(it - 1);
+        }
+        stage2(my_tiles - 1);
+    } else {
+        // ========================================================= epilogue
+        const int q4 = warp & 3;
+        const int half = (warp - 2) >> 2;
+        const int ph = q4 * 2 + (lane >> 4), pw = lane & 15;
+        const uint32_t lane_addr = (uint32_t)(q4 * 32) << 16;
+        const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.0f, 0.0f);
+        // x-combination of one 16-channel chunk of sub-tile j: v[e] = D'[x-1][0] + D'[x][1] + D'[x+1][2]
+        auto combine = [&](uint32_t col, float *v) {
+            uint32_t a0[16], a1[16], a2[16];
+            tc::tmem_ld16(col, a0);
+            tc::tmem_ld16(col + COUT, a1);
+            tc::tmem_ld16(col + 2 * COUT, a2);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 16; ++e)
+                v[e] = __shfl_up_sync(0xffffffffu, __uint_as_float(a0[e]), 1) + __uint_as_float(a1[e]) +
+                       __shfl_down_sync(0xffffffffu, __uint_as_float(a2[e]), 1);
+        };
+        // epilogue 1 of this CTA's tile number i: accumulators -> P1[i & 1]
+        auto epi1 = [&](int i) {
+            const int b = i & 1;
+            const int t = (int)blockIdx.x + i * (int)gridDim.x;
+            const int tx = t % tiles_x, ty = (t / tiles_x) % tiles_y;
+            tc::mbar_wait(&acc1_full[b], (i >> 1) & 1);
+            tc::tc_fence_after();
+            const uint32_t tbase = tmem_base + lane_addr + b * C::ACC_COLS;
+            uint8_t *p1 = sP1 + (size_t)b * C::P1_BYTES;
+#pragma unroll
+            for (int ii = 0; ii < (S * NC16 + EPI_GROUPS - 1) / EPI_GROUPS; ++ii) {
+                const int item = ii * EPI_GROUPS + half;
+                if (item >= S * NC16) break;
+                const int j = item / NC16, c16 = item % NC16;
+                const int r = j * 8 + ph;                                   // P1 row
+                const int Y = ty * C::TH - 1 + r, X = tx * C::TW - 2 + pw;   // image position of this lane's value
+                const bool inside = (Y >= 0) && (Y < H) && (X >= 0) && (X < W);
+                float v[16];
+                combine(tbase + j * C::ACC_STRIDE + c16 * 16, v);
+                uint32_t o[8];
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const float4 sc = *reinterpret_cast<const float4 *>(s_scale1 + c16 * 16 + 4 * g);
+                    const float4 sh = *reinterpret_cast<const float4 *>(s_shift1 + c16 * 16 + 4 * g);
+                    __nv_bfloat162 p0 = __hmax2(__floats2bfloat162_rn(fmaf(v[4 * g], sc.x, sh.x), fmaf(v[4 * g + 1], sc.y, sh.y)), zero2);
+                    __nv_bfloat162 p1v = __hmax2(__floats2bfloat162_rn(fmaf(v[4 * g + 2], sc.z, sh.z), fmaf(v[4 * g + 3], sc.w, sh.w)), zero2);
+                    o[2 * g] = inside ? *reinterpret_cast<uint32_t *>(&p0) : 0u;      // conv2's SAME padding
+                    o[2 * g + 1] = inside ? *reinterpret_cast<uint32_t *>(&p1v) : 0u;
+                }
+                if (pw >= 1 && pw <= 14) {
+                    uint8_t *d = p1 + ((size_t)(c16 * 2) * C::PH + r) * (C::PW * 16) + (pw - 1) * 16;
+                    *reinterpret_cast<uint4 *>(d) = make_uint4(o[0], o[1], o[2], o[3]);
+                    *reinterpret_cast<uint4 *>(d + C::PH * C::PW * 16) = make_uint4(o[4], o[5], o[6], o[7]);
+                }
+            }
+            tc::tc_fence_before();
+            tc::fence_proxy_async();                  // generic-proxy writes of P1 -> visible to the UMMA reads
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&p1_full[b]);
+        };
+        // epilogue 2 of tile number i: accumulators -> output
+        auto epi2 = [&](int i) {
+            const int b = i & 1;
+            const int t = (int)blockIdx.x + i * (int)gridDim.x;
+            const int tx = t % tiles_x, ty = (t / tiles_x) % tiles_y, n = t / tpi;
+            tc::mbar_wait(&acc2_full[b], (i >> 1) & 1);
+            tc::tc_fence_after();
+            const uint32_t tbase = tmem_base + lane_addr + b * C::ACC_COLS;
+            const int x = tx * C::TW + pw - 1;
+            const bool xok = (pw >= 1) && (pw <= C::TW) && (x < W);
+            if constexpr (EPI != EPI_HEAD) {
+                const size_t plane = (size_t)H * W * 8;
+#pragma unroll
+                for (int ii = 0; ii < (S * NC16 + EPI_GROUPS - 1) / EPI_GROUPS; ++ii) {
+                    const int item = ii * EPI_GROUPS + half;
+                    if (item >= S * NC16) break;
+                    const int j = item / NC16, c16 = item % NC16;
+                    const int r = j * 8 + ph, y = ty * C::TH + r;
+                    const bool valid = xok && (r < C::TH) && (y < H);
+                    float v[16];
+                    combine(tbase + j * C::ACC_STRIDE + c16 * 16, v);
+                    uint32_t o[8];
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        const float4 sc = *reinterpret_cast<const float4 *>(s_scale2 + c16 * 16 + 4 * g);
+                        const float4 sh = *reinterpret_cast<const float4 *>(s_shift2 + c16 * 16 + 4 * g);
+                        __nv_bfloat162 p0 = __hmax2(__floats2bfloat162_rn(fmaf(v[4 * g], sc.x, sh.x), fmaf(v[4 * g + 1], sc.y, sh.y)), zero2);
+                        __nv_bfloat162 p1v = __hmax2(__floats2bfloat162_rn(fmaf(v[4 * g + 2], sc.z, sh.z), fmaf(v[4 * g + 3], sc.w, sh.w)), zero2);
+                        o[2 * g] = *reinterpret_cast<uint32_t *>(&p0);
+                        o[2 * g + 1] = *reinterpret_cast<uint32_t *>(&p1v);
+                    }
+                    if (valid) {
+                        bf16 *p = out + ((((size_t)n * CBo + c16 * 2) * H + y) * W + x) * 8;
+                        *reinterpret_cast<uint4 *>(p) = make_uint4(o[0], o[1], o[2], o[3]);
+                        *reinterpret_cast<uint4 *>(p + plane) = make_uint4(o[4], o[5], o[6], o[7]);
+                    }
+                    if (EPI == EPI_POOL) {
+                        // rows (y, y+1) sit 16 lanes apart (TH and the tile origin are even), columns (x, x+1) in
+                        // lanes (pw, pw+1) with pw odd
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const uint32_t m = bf162_max(o[e], __shfl_xor_sync(0xffffffffu, o[e], 16));
+                            o[e] = bf162_max(m, __shfl_down_sync(0xffffffffu, m, 1));
+                        }
+                        if (valid && lane < 16 && (pw & 1)) {
+                            const int Hp = H >> 1, Wp = W >> 1;
+                            bf16 *p = out_pool + ((((size_t)n * CBo + c16 * 2) * Hp + (y >> 1)) * Wp + (x >> 1)) * 8;
+                            *reinterpret_cast<uint4 *>(p) = make_uint4(o[0], o[1], o[2], o[3]);
+                            *reinterpret_cast<uint4 *>(p + (size_t)Hp * Wp * 8) = make_uint4(o[4], o[5], o[6], o[7]);
+                        }
+                    }
+                }
+            } else {
+#pragma unroll 1
+                for (int j = half; j < S; j += EPI_GROUPS) {
+                    const int r = j * 8 + ph, y = ty * C::TH + r;
+                    const bool valid = xok && (r < C::TH) && (y < H);
+                    float hl[HK > 0 ? HK : 1];
+#pragma unroll
+                    for (int k = 0; k < HK; ++k) hl[k] = 0.0f;
+#pragma unroll 1
+                    for (int c16 = 0; c16 < NC16; ++c16) {
+                        float v[16], f[16];
+                        combine(tbase + j * C::ACC_STRIDE + c16 * 16, v);
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            const float4 sc = *reinterpret_cast<const float4 *>(s_scale2 + c16 * 16 + 4 * g);
+                            const float4 sh = *reinterpret_cast<const float4 *>(s_shift2 + c16 * 16 + 4 * g);
+                            // the head consumes the activation as it would have been stored (bf16)
+                            const float2 t0 = __bfloat1622float2(__floats2bfloat162_rn(
+                                fmaxf(fmaf(v[4 * g], sc.x, sh.x), 0.0f), fmaxf(fmaf(v[4 * g + 1], sc.y, sh.y), 0.0f)));
+                            const float2 t1 = __bfloat1622float2(__floats2bfloat162_rn(
+                                fmaxf(fmaf(v[4 * g + 2], sc.z, sh.z), 0.0f), fmaxf(fmaf(v[4 * g + 3], sc.w, sh.w), 0.0f)));
+                            f[4 * g] = t0.x; f[4 * g + 1] = t0.y; f[4 * g + 2] = t1.x; f[4 * g + 3] = t1.y;
+                        }
+#pragma unroll
+                        for (int k = 0; k < HK; ++k) {
+                            const float4 *wk = reinterpret_cast<const float4 *>(s_head + k * COUT + c16 * 16);
+#pragma unroll
+                            for (int g = 0; g < 4; ++g) {
+                                const float4 w4 = wk[g];
+                                hl[k] = fmaf(f[4 * g], w4.x, hl[k]);
+                                hl[k] = fmaf(f[4 * g + 1], w4.y, hl[k]);
+                                hl[k] = fmaf(f[4 * g + 2], w4.z, hl[k]);
+                                hl[k] = fmaf(f[4 * g + 3], w4.w, hl[k]);
+                            }
+                        }
+                    }
+                    const size_t p = ((size_t)n * H + y) * W + x;
+                    int best = 0;
+                    float m = -INFINITY;
+#pragma unroll
+                    for (int k = 0; k < HK; ++k) {
+                        hl[k] += s_head[COUT * HK + k];
+                        if (hl[k] > m) { m = hl[k]; best = k; }
+                    }
+                    if (valid && head.mask) head.mask[p] = (uint8_t)best;
+                    if (valid && head.logits) {
+#pragma unroll
+                        for (int k = 0; k < HK; ++k) head.logits[p * HK + k] = hl[k];
+                    }
+                    if (valid && head.probs) {
+                        float sum = 0.0f;
+#pragma unroll
+                        for (int k = 0; k < HK; ++k) { hl[k] = expf(hl[k] - m); sum += hl[k]; }
+#pragma unroll
+                        for (int k = 0; k < HK; ++k) head.probs[p * HK + k] = hl[k] / sum;
+                    }
+                }
+            }
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&acc_free[b]);
+        };
+        // same order as the MMA warp: stage 1 of tile i+1 is drained before stage 2 of tile i
+        for (int it = 0; it < my_tiles; ++it) {
+            epi1(it);
+            if (it > 0) epi2(it - 1);
+        }
+        epi2(my_tiles - 1);
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tc::tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
 // ------------------------------------------------------- bandwidth-bound kernels
 // First conv: fp32 NHWC input with few channels -> bf16 blocked.  K = 9*CIN (9 or 27) is far
 // too small for a tcgen05 tile, and on CUDA cores the layer is instruction-bound (144 FMA per
@@ -1220,6 +1571,15 @@ struct TcState {
     int sm_count = 148;
 };
 
+// SQ_GRID_DIV=d (experiments only): persistent grids of the tcgen05 kernels shrink to 1/d of the resident
+// CTA slots, so that launches of two streams can be co-resident on every SM.
+int grid_div()
+{
+    static int d = 0;
+    if (d == 0) { const char *e = getenv("SQ_GRID_DIV"); d = e ? std::max(1, atoi(e)) : 1; }
+    return d;
+}
+
 int dev_upload(sq_unet_s *u, const void *src, size_t bytes, void **dst)
 {
     SQ_CUDA(cudaMalloc(dst, std::max<size_t>(bytes, 16)));
@@ -1304,7 +1664,7 @@ int launch_tc(sq_unet_s *u, const SqLayer &L, const bf16 *in0, int cb0, const bf
                                    (const float *)L.scale, (const float *)L.shift, out, out_pool, head, nimg, H, W,
                                    relu, nstages, g.D, g.KZ, g.out_mul, g.out_off, FirstArgs{}));
     } else {
-        const int grid = std::min(tiles, MINB * u->h->sm_count);
+        const int grid = std::min(tiles, MINB * u->h->sm_count / grid_div());
         kern<<<grid, threads, smem, st>>>(m0, m1, cb0 / 2, in1 ? cb1 / 2 : 0, (const bf16 *)L.w_tc + g.w_off, L.scale,
                                          L.shift, out, out_pool, head, nimg, H, W, relu, nstages, g.D, g.KZ,
                                          g.out_mul, g.out_off, FirstArgs{});
@@ -1406,7 +1766,7 @@ int launch_xc_k(sq_unet_s *u, const SqLayer &L, const bf16 *in0, int cb0, const 
         have = smem;
     }
     const int tiles = nimg * g.D * ((W + C::TW - 1) / C::TW) * ((H + C::TH - 1) / C::TH);
-    const int grid = std::min(tiles, MINB * u->h->sm_count);
+    const int grid = std::min(tiles, MINB * u->h->sm_count / grid_div());
     long long *phase_dbg = nullptr;
 #ifdef SQ_XC_PHASE_DIAG
     if (getenv("SQ_XC_PHASE")) {
@@ -1476,6 +1836,75 @@ int conv3x3_xc(sq_unet_s *u, const SqLayer &L, const bf16 *in0, int c0, const bf
     if (out_pool)
         return launch_xc<COUT, S, NBUF, MINB, EPI_POOL, 0, PADACC>(u, L, in0, c0 / 8, in1, c1 / 8, out, out_pool, none, g, st);
     return launch_xc<COUT, S, NBUF, MINB, EPI_STORE, 0, PADACC>(u, L, in0, c0 / 8, in1, c1 / 8, out, nullptr, none, g, st);
+}
+
+// Fused conv_block (conv1 -> conv2 in one launch, the intermediate stays on chip): planar layers with
+// Cout = 16 whose stage-1 input fits one ring stage.  Opt-in (SQ_PAIR=1): parity-green but SLOWER than the two
+// launches on B200 (up0: 0.92 ms against 0.296 + 0.230 ms per 4 frames of 2048^2) -- the x-combined epilogue
+// costs ~260 clk per 128-lane x 16-channel item per SM (half of it the 32 shuffles at one warp-shuffle per
+// clock), a tile needs four of them, and with two accumulator buffers the chain MMA1 -> epilogue 1 -> MMA2 ->
+// epilogue 2 of a tile serialises.
+bool pair_enabled()
+{
+    const char *e = getenv("SQ_PAIR");
+    return e && atoi(e) != 0;
+}
+
+template <int COUT, int S, int EPI, int HK>
+int launch_pair_k(sq_unet_s *u, const SqLayer &L1, const SqLayer &L2, const bf16 *in0, int cb0, const bf16 *in1,
+                  int cb1, bf16 *out, bf16 *out_pool, const HeadArgs &head, const TcGeo &g, cudaStream_t st)
+{
+    using C = PCfg<COUT, S>;
+    const int nimg = g.nimg, H = g.H, W = g.W;
+    const int ks0 = cb0 / 2, ks1 = in1 ? cb1 / 2 : 0, ksteps1 = ks0 + ks1;
+    CUtensorMap m0, m1;
+    SQ_TRY(make_map(&m0, in0, nimg, 1, cb0, H, W, C::PW, C::PH, cb0, 1));
+    if (in1) SQ_TRY(make_map(&m1, in1, nimg, 1, cb1, H, W, C::PW, C::PH, cb1, 1));
+    else m1 = m0;
+    const int budget = (216 / 2) * 1024 - 2048;
+    const int fixed = ((ksteps1 + COUT / 16) * C::B_BYTES + 127) / 128 * 128 + 2 * C::P1_BYTES;
+    const int stage_bytes = ksteps1 * C::A_BYTES;
+    const int nstages = std::min(XC_MAX_STAGES, (budget - fixed) / stage_bytes);
+    if (nstages < 2) return SQ_NOT_APPLICABLE;
+    const size_t smem = (size_t)fixed + (size_t)nstages * stage_bytes + 1024;
+    auto kern = conv_xc_pair_kernel<COUT, S, EPI, HK>;
+    static size_t attr_smem[64] = {0};
+    size_t &have = attr_smem[u->h->device & 63];
+    if (smem > have) {
+        SQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        have = smem;
+    }
+    const int tiles = nimg * ((W + C::TW - 1) / C::TW) * ((H + C::TH - 1) / C::TH);
+    const int grid = std::min(tiles, 2 * u->h->sm_count / grid_div());
+    kern<<<grid, TC_THREADS, smem, st>>>(m0, m1, ks0, ks1, (const bf16 *)L1.w_xc, L1.scale, L1.shift,
+                                         (const bf16 *)L2.w_xc, L2.scale, L2.shift, out, out_pool, head, nimg, H, W,
+                                         nstages);
+    ++u->last_launches;
+    SQ_CHECK_LAUNCH();
+    return SQ_OK;
+}
+
+// SQ_NOT_APPLICABLE: the caller runs the two layers separately
+int conv_pair_tc(sq_unet_s *u, const SqLayer &L1, const SqLayer &L2, const bf16 *in0, int c0, const bf16 *in1, int c1,
+                 bf16 *out, bf16 *out_pool, const HeadArgs *head, const TcGeo &g, cudaStream_t st)
+{
+    if (!pair_enabled() || g.D != 1 || g.KZ != 1 || !L1.w_xc || !L2.w_xc || L1.cout != L2.cout ||
+        L2.cin0 != L1.cout || L2.cin1 != 0 || c0 % 16 || c1 % 16 || (g.H & 1) || (g.W & 1))
+        return SQ_NOT_APPLICABLE;
+    const HeadArgs none = {nullptr, 0, nullptr, nullptr, nullptr};
+    if (L1.cout == 16) {
+        if (head) {
+            switch (head->K) {
+            case 2: return launch_pair_k<16, 2, EPI_HEAD, 2>(u, L1, L2, in0, c0 / 8, in1, c1 / 8, nullptr, nullptr, *head, g, st);
+            case 3: return launch_pair_k<16, 2, EPI_HEAD, 3>(u, L1, L2, in0, c0 / 8, in1, c1 / 8, nullptr, nullptr, *head, g, st);
+            case 4: return launch_pair_k<16, 2, EPI_HEAD, 4>(u, L1, L2, in0, c0 / 8, in1, c1 / 8, nullptr, nullptr, *head, g, st);
+            }
+            return SQ_NOT_APPLICABLE;
+        }
+        if (out_pool) return launch_pair_k<16, 2, EPI_POOL, 0>(u, L1, L2, in0, c0 / 8, in1, c1 / 8, out, out_pool, none, g, st);
+        return launch_pair_k<16, 2, EPI_STORE, 0>(u, L1, L2, in0, c0 / 8, in1, c1 / 8, out, nullptr, none, g, st);
+    }
+    return SQ_NOT_APPLICABLE;
 }
 
 int xc_variant()
@@ -1800,11 +2229,27 @@ int tc_run(sq_unet_s *u, bool dry, const float *in, int n, int dep, int hgt, int
             sq_timer_mark(u, st, "bridge", 0);
             in0 = merged[l];
         }
+        const bool last = (l == 0 && head_fused);
+        const HeadArgs ha = {(const float *)head->w_tc, head->cout, logits, probs, mask};
+        // conv_block as one launch where the fused pair kernel applies (the intermediate `ut` stays on chip)
+        {
+            const int r = vol ? SQ_NOT_APPLICABLE
+                              : conv_pair_tc(u, *c1, *c2, in0, c1->cin0, in1, c1->cin1, last ? nullptr : uo[l], nullptr,
+                                             last ? &ha : nullptr, geo, st);
+            if (r != SQ_NOT_APPLICABLE) {
+                SQ_TRY(r);
+                const char *pname = u->aux_names.emplace(c1->scope, c1->scope + "+conv2").first->second.c_str();
+                sq_timer_mark(u, st, pname,
+                              (c1->flops_per_px + c2->flops_per_px + (last ? head->flops_per_px : 0.0)) * px);
+                if (last) return SQ_OK;
+                cur = uo[l];
+                continue;
+            }
+        }
         SQ_TRY(conv3x3_tc(u, *c1, in0, c1->cin0, in1, c1->cin1, ut[l], nullptr, nullptr, geo, st));
         sq_timer_mark(u, st, c1->scope.c_str(), c1->flops_per_px * px);
-        if (l == 0 && head_fused) {
+        if (last) {
             // last conv of the net: 1x1 head + softmax + argmax run in its epilogue
-            const HeadArgs ha = {(const float *)head->w_tc, head->cout, logits, probs, mask};
             SQ_TRY(conv3x3_tc(u, *c2, ut[l], c2->cin0, nullptr, 0, nullptr, nullptr, &ha, geo, st));
             sq_timer_mark(u, st, c2->scope.c_str(), (c2->flops_per_px + head->flops_per_px) * px);
             return SQ_OK;
