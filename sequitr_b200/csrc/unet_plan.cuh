@@ -21,6 +21,10 @@ struct SqLayer {
     // tensor-core device weights (bf16, re-laid-out; see unet_tc.cu)
     void *w_tc = nullptr;
     void *w_xc = nullptr;         // x-combined layout for Cout <= 32 convs (conv_xc_kernel)
+    // level-0 layers on the quad (space-to-depth) layout (conv_qd_kernel): weights re-laid-out as a 64-wide
+    // half-resolution conv, scale / shift repeated for the four output parities
+    void *w_qd = nullptr;
+    float *scale_q = nullptr, *shift_q = nullptr;
 };
 
 struct SqLayerTimer {

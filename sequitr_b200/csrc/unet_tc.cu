@@ -1259,6 +1259,303 @@ conv_xc_pair_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
     }
 }
 
+// ------------------------------------ level-0 layers on the QUAD (space-to-depth) layout
+// At Cout = 16 a 128 x 16 x 16 MMA is bound by its A-operand fetch (4 KB of shared memory, ~39 clk) and does
+// 1/4 of the math a 64-wide instruction does in ~48 clk.  The level-0 tensors (16 channels at full
+// resolution) are therefore kept as QUAD tensors: a 2x2 block of pixels becomes ONE pixel of a half-resolution
+// image with 4 x 16 = 64 channels, channel = q*16 + c with q = 2*(y & 1) + (x & 1):
+//     quad[n][(q*16 + c) / 8][y / 2][x / 2][c % 8]
+// On that layout
+//   * a 3x3 conv 16 -> 16 is a 3x3 conv 64 -> 64 at half resolution whose weight blocks are zero for most
+//     (tap, input-parity) pairs: input parity (iy, ix) only reaches the taps ty in {iy ? -1,0 : 0,+1},
+//     tx likewise -- FOUR 128 x 64 x 16 MMAs per 16 input channels (one k-step = one input parity of one
+//     source) instead of 4 x 9 = 36 MMAs 128 x 16 x 16 for the same 512 output pixels;
+//   * the 2x2 stride-2 up-conv 32 -> 16 is a plain 1x1 conv 32 -> 64 (output parity = kernel tap), no
+//     scattered store;
+//   * the fused 2x2 max-pool is a max over the four 16-column groups of ONE accumulator row (no shuffles);
+//   * the fused head runs once per 16-column group.
+// Same persistent warp-specialised structure as conv_tc_kernel (TMA producer / MMA issuer / 8 epilogue
+// warps, smem ring + double-buffered TMEM); the weights of all k-steps stay resident in shared memory and a
+// ring stage holds KPS k-steps fetched by one TMA box.  NTAP = 4: quad 3x3 conv; NTAP = 1: 1x1 conv.
+template <int S, int NTAP>
+struct QCfg {
+    static constexpr int COUT = 64;
+    static constexpr int TH = 16 * S;
+    static constexpr int PW = NTAP == 4 ? 10 : 8, PH = NTAP == 4 ? TH + 2 : TH;
+    static constexpr int A_BYTES = 2 * PH * PW * 16;            // one k-step (16 channels) of the patch
+    static constexpr int W_BYTES = NTAP * 2 * COUT * 16;        // one k-step of the weights
+    static constexpr int ACC_COLS = S * COUT;
+    static constexpr uint32_t LBO_A = PH * PW * 16, SBO_A = PW * 16;
+    static constexpr uint32_t LBO_B = COUT * 16, SBO_B = 128;
+    static_assert(A_BYTES % 128 == 0, "TMA destination alignment");
+};
+
+constexpr int QD_MAX_STAGES = 8;
+
+template <int S, int NTAP, int KPS, int EPI, int HK>
+__global__ void __launch_bounds__(TC_THREADS, 2)
+conv_qd_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
+               int ks0, int ks1, const bf16 *__restrict__ wts, const float *__restrict__ scale,
+               const float *__restrict__ shift, bf16 *__restrict__ out, bf16 *__restrict__ out_pool,
+               HeadArgs head, int nimg, int H, int W, int relu, int nstages, int wres, long long *phase_dbg)
+{
+#ifdef SQ_XC_PHASE_DIAG
+#define QD_T0() const long long t_ = phase_dbg ? clock64() : 0
+#define QD_ACC(var) if (phase_dbg) var += clock64() - t_
+    long long d_wait0 = 0, d_wait1 = 0, d_work = 0;
+#else
+#define QD_T0() do { } while (0)
+#define QD_ACC(var) do { } while (0)
+#endif
+    // H, W: the quad image (half the level-0 frame).  scale / shift: 64 entries (the layer's 16, four times).
+    using C = QCfg<S, NTAP>;
+    constexpr int COUT = C::COUT, NBUF = 2, A_STAGE = KPS * C::A_BYTES;
+    constexpr int TMEM_COLS = (NBUF * C::ACC_COLS <= 128) ? 128 : (NBUF * C::ACC_COLS <= 256) ? 256 : 512;
+    static_assert(2 * NBUF * C::ACC_COLS <= 512, "two co-resident CTAs must fit in TMEM");
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+    __shared__ uint64_t full_bar[QD_MAX_STAGES], empty_bar[QD_MAX_STAGES], tfull_bar[2], tempty_bar[2], w_bar;
+    __shared__ uint32_t tmem_base_sh;
+    __shared__ __align__(16) float s_scale[COUT], s_shift[COUT];
+    __shared__ __align__(16) float s_head[EPI == EPI_HEAD ? 16 * HK + HK : 4];      // [k][c] then bias[k]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_x = (W + 7) >> 3, tiles_y = (H + C::TH - 1) / C::TH;
+    const int ntiles = nimg * tiles_x * tiles_y;
+    const int ksteps = ks0 + ks1;
+    uint8_t *ring = smem + ((wres + 127) & ~127);
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < nstages; ++i) { tc::mbar_init(&full_bar[i], 1); tc::mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < 2; ++i) { tc::mbar_init(&tfull_bar[i], 1); tc::mbar_init(&tempty_bar[i], 4 * EPI_GROUPS); }
+        tc::mbar_init(&w_bar, 1);
+        tc::fence_barrier_init();
+        tc::tma_prefetch_desc(&mapA0);
+        tc::tma_prefetch_desc(&mapA1);
+    }
+    if (warp == 1) { tc::tmem_alloc(&tmem_base_sh, TMEM_COLS); tc::tmem_relinquish(); }
+    for (int i = threadIdx.x; i < COUT; i += TC_THREADS) { s_scale[i] = scale[i]; s_shift[i] = shift[i]; }
+    if constexpr (EPI == EPI_HEAD) {
+        for (int i = threadIdx.x; i < 16 * HK; i += TC_THREADS) s_head[(i % HK) * 16 + i / HK] = head.w[i];
+        for (int i = threadIdx.x; i < HK; i += TC_THREADS) s_head[16 * HK + i] = head.w[16 * HK + i];
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = tmem_base_sh;
+
+    if (warp == 0) {
+        // ===================================================== TMA producer
+        if (lane == 0) {
+            tc::mbar_arrive_expect_tx(&w_bar, (uint32_t)wres);
+            for (int q = 0; q < ksteps; ++q)
+                tc::bulk_load(smem + (size_t)q * C::W_BYTES, wts + (size_t)q * (C::W_BYTES / 2), C::W_BYTES, &w_bar);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+                const int tx = t % tiles_x, ty = (t / tiles_x) % tiles_y, n = t / (tiles_x * tiles_y);
+                const int x0 = tx * 8 - (NTAP == 4 ? 1 : 0), y0 = ty * C::TH - (NTAP == 4 ? 1 : 0);
+                for (int ks = 0; ks < ksteps; ks += KPS) {
+                    { QD_T0(); tc::mbar_wait(&empty_bar[stage], phase ^ 1); QD_ACC(d_wait0); }
+                    QD_T0();
+                    tc::mbar_arrive_expect_tx(&full_bar[stage], A_STAGE);
+                    uint8_t *sA = ring + (size_t)stage * A_STAGE;
+                    if (ks < ks0) tc::tma_load_5d(sA, &mapA0, &full_bar[stage], x0 * 8, y0, ks * 2, 0, n);
+                    else          tc::tma_load_5d(sA, &mapA1, &full_bar[stage], x0 * 8, y0, (ks - ks0) * 2, 0, n);
+                    QD_ACC(d_work);
+                    if (++stage == nstages) { stage = 0; phase ^= 1; }
+                }
+            }
+#ifdef SQ_XC_PHASE_DIAG
+            if (phase_dbg) { phase_dbg[blockIdx.x * 8 + 0] = d_wait0; phase_dbg[blockIdx.x * 8 + 1] = d_work; }
+#endif
+        }
+    } else if (warp == 1) {
+        // ======================================================= MMA issuer
+        const uint32_t idesc = tc::instr_desc_bf16(128, COUT);
+        const uint32_t a_hi = ((C::SBO_A >> 4) & 0x3FFFu) | (1u << 14);
+        const uint32_t b_hi = ((C::SBO_B >> 4) & 0x3FFFu) | (1u << 14);
+        const uint32_t w_lo = ((tc::smem_u32(smem) >> 4) & 0x3FFFu) | (((C::LBO_B >> 4) & 0x3FFFu) << 16);
+        int stage = 0;
+        uint32_t phase = 0;
+        int it = 0;
+        tc::mbar_wait(&w_bar, 0);
+        for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+            const int buf = it % NBUF;
+            { QD_T0(); tc::mbar_wait(&tempty_bar[buf], ((it / NBUF) & 1) ^ 1); QD_ACC(d_wait0); }
+            tc::tc_fence_after();
+            for (int ks = 0; ks < ksteps; ks += KPS) {
+                { QD_T0(); tc::mbar_wait(&full_bar[stage], phase); QD_ACC(d_wait1); }
+                tc::tc_fence_after();
+                QD_T0();
+                if (tc::elect_one()) {
+                    const uint32_t a_base = tc::smem_u32(ring + (size_t)stage * A_STAGE);
+                    const uint32_t a_lo = ((a_base >> 4) & 0x3FFFu) | (((C::LBO_A >> 4) & 0x3FFFu) << 16);
+                    const uint32_t d0 = tmem_base + buf * C::ACC_COLS;
+#pragma unroll
+                    for (int kk = 0; kk < KPS; ++kk) {
+                        const int k = ks + kk;
+                        // input parity of this k-step: the first patch row / column its two taps start from
+                        const int iy = (k >> 1) & 1, ix = k & 1;
+                        const uint32_t b_k = w_lo + (uint32_t)(k * (C::W_BYTES >> 4));
+#pragma unroll
+                        for (int j = 0; j < S; ++j) {
+                            if (NTAP == 4) {
+#pragma unroll
+                                for (int tp = 0; tp < 4; ++tp) {
+                                    const uint32_t a_off = (uint32_t)(kk * (C::A_BYTES >> 4) +
+                                                                      (j * 16 + (tp >> 1) + 1 - iy) * C::PW + (tp & 1) + 1 - ix);
+                                    tc::umma_bf16_parts(d0 + j * COUT, a_lo + a_off, a_hi, b_k + tp * 2 * COUT, b_hi, idesc,
+                                                        (k > 0 || tp > 0) ? 1u : 0u);
+                                }
+                            } else {
+                                tc::umma_bf16_parts(d0 + j * COUT, a_lo + (uint32_t)(kk * (C::A_BYTES >> 4) + j * 16 * C::PW), a_hi,
+                                                    b_k, b_hi, idesc, k > 0 ? 1u : 0u);
+                            }
+                        }
+                    }
+                    tc::umma_commit(&empty_bar[stage]);
+                }
+                __syncwarp();
+                QD_ACC(d_work);
+                if (++stage == nstages) { stage = 0; phase ^= 1; }
+            }
+            if (tc::elect_one()) tc::umma_commit(&tfull_bar[buf]);
+            __syncwarp();
+        }
+#ifdef SQ_XC_PHASE_DIAG
+        if (phase_dbg && lane == 0) {
+            phase_dbg[blockIdx.x * 8 + 2] = d_wait0; phase_dbg[blockIdx.x * 8 + 3] = d_wait1; phase_dbg[blockIdx.x * 8 + 4] = d_work;
+        }
+#endif
+    } else {
+        // ========================================================= epilogue
+        const int q4 = warp & 3, half = (warp - 2) >> 2;
+        const int r = q4 * 32 + lane, ph = r >> 3, pw = r & 7;
+        const uint32_t lane_addr = (uint32_t)(q4 * 32) << 16;
+        const size_t plane = (size_t)H * W * 8;
+        int it = 0;
+        for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+            const int buf = it % NBUF;
+            const int tx = t % tiles_x, ty = (t / tiles_x) % tiles_y, n = t / (tiles_x * tiles_y);
+            const int x = tx * 8 + pw;
+            { QD_T0(); tc::mbar_wait(&tfull_bar[buf], (it / NBUF) & 1); QD_ACC(d_wait0); }
+            tc::tc_fence_after();
+            QD_T0();
+            const uint32_t tbase = tmem_base + lane_addr + buf * C::ACC_COLS;
+#pragma unroll 1
+            for (int j = 0; j < S; ++j) {
+                const int y = ty * C::TH + j * 16 + ph;
+                const bool valid = (y < H) && (x < W);
+                if (EPI == EPI_POOL && (j % EPI_GROUPS) != half) continue;
+                uint32_t mx[8];
+#pragma unroll 1
+                for (int c16 = 0; c16 < 4; ++c16) {
+                    if (EPI == EPI_STORE && ((j * 4 + c16) % EPI_GROUPS) != half) continue;
+                    if (EPI == EPI_HEAD && (c16 >> 1) != half) continue;
+                    uint32_t v[16];
+                    tc::tmem_ld16(tbase + j * COUT + c16 * 16, v);
+                    tc::tmem_ld_wait();
+                    uint32_t o[8];
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        const float4 sc = *reinterpret_cast<const float4 *>(s_scale + c16 * 16 + 4 * g);
+                        const float4 sh = *reinterpret_cast<const float4 *>(s_shift + c16 * 16 + 4 * g);
+                        float a = fmaf(__uint_as_float(v[4 * g]), sc.x, sh.x);
+                        float b = fmaf(__uint_as_float(v[4 * g + 1]), sc.y, sh.y);
+                        float c = fmaf(__uint_as_float(v[4 * g + 2]), sc.z, sh.z);
+                        float d = fmaf(__uint_as_float(v[4 * g + 3]), sc.w, sh.w);
+                        if (relu) { a = fmaxf(a, 0.0f); b = fmaxf(b, 0.0f); c = fmaxf(c, 0.0f); d = fmaxf(d, 0.0f); }
+                        o[2 * g] = pack_bf16(a, b);
+                        o[2 * g + 1] = pack_bf16(c, d);
+                    }
+                    if constexpr (EPI == EPI_HEAD) {
+                        // the head consumes the activation as it would have been stored (bf16); this 16-column
+                        // group is level-0 pixel (2y + oy, 2x + ox), (oy, ox) = (c16 >> 1, c16 & 1)
+                        float hl[HK > 0 ? HK : 1];
+#pragma unroll
+                        for (int k = 0; k < HK; ++k) hl[k] = 0.0f;
+                        float f[16];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const float2 t2 = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162 *>(&o[e]));
+                            f[2 * e] = t2.x;
+                            f[2 * e + 1] = t2.y;
+                        }
+#pragma unroll
+                        for (int k = 0; k < HK; ++k) {
+                            const float4 *wk = reinterpret_cast<const float4 *>(s_head + k * 16);
+#pragma unroll
+                            for (int g = 0; g < 4; ++g) {
+                                const float4 w4 = wk[g];
+                                hl[k] = fmaf(f[4 * g], w4.x, hl[k]);
+                                hl[k] = fmaf(f[4 * g + 1], w4.y, hl[k]);
+                                hl[k] = fmaf(f[4 * g + 2], w4.z, hl[k]);
+                                hl[k] = fmaf(f[4 * g + 3], w4.w, hl[k]);
+                            }
+                        }
+                        int best = 0;
+                        float m = -INFINITY;
+#pragma unroll
+                        for (int k = 0; k < HK; ++k) {
+                            hl[k] += s_head[16 * HK + k];
+                            if (hl[k] > m) { m = hl[k]; best = k; }
+                        }
+                        const size_t p = ((size_t)n * (2 * H) + 2 * y + (c16 >> 1)) * (size_t)(2 * W) + 2 * x + (c16 & 1);
+                        if (head.mask) {
+                            // both pixels of this lane's row pair (ox = 0, 1) leave in one 2-byte store
+                            if ((c16 & 1) == 0) mx[0] = (uint32_t)best;
+                            else if (valid) *reinterpret_cast<uint16_t *>(head.mask + p - 1) = (uint16_t)(mx[0] | ((uint32_t)best << 8));
+                        }
+                        if (valid && head.logits) {
+#pragma unroll
+                            for (int k = 0; k < HK; ++k) head.logits[p * HK + k] = hl[k];
+                        }
+                        if (valid && head.probs) {
+                            float sum = 0.0f;
+#pragma unroll
+                            for (int k = 0; k < HK; ++k) { hl[k] = expf(hl[k] - m); sum += hl[k]; }
+#pragma unroll
+                            for (int k = 0; k < HK; ++k) head.probs[p * HK + k] = hl[k] / sum;
+                        }
+                    } else {
+                        if (valid) {
+                            bf16 *p = out + ((((size_t)n * 8 + c16 * 2) * H + y) * W + x) * 8;
+                            *reinterpret_cast<uint4 *>(p) = make_uint4(o[0], o[1], o[2], o[3]);
+                            *reinterpret_cast<uint4 *>(p + plane) = make_uint4(o[4], o[5], o[6], o[7]);
+                        }
+                        if constexpr (EPI == EPI_POOL) {
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) mx[e] = (c16 == 0) ? o[e] : bf162_max(mx[e], o[e]);
+                        }
+                    }
+                }
+                if (EPI == EPI_POOL && valid) {
+                    // the 2x2 max-pooled tensor of the level-0 activation: 16 channels at quad resolution
+                    bf16 *p = out_pool + ((((size_t)n * 2) * H + y) * W + x) * 8;
+                    *reinterpret_cast<uint4 *>(p) = make_uint4(mx[0], mx[1], mx[2], mx[3]);
+                    *reinterpret_cast<uint4 *>(p + plane) = make_uint4(mx[4], mx[5], mx[6], mx[7]);
+                }
+            }
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&tempty_bar[buf]);
+            QD_ACC(d_work);
+        }
+#ifdef SQ_XC_PHASE_DIAG
+        if (phase_dbg && warp == 2 && lane == 0) { phase_dbg[blockIdx.x * 8 + 5] = d_wait0; phase_dbg[blockIdx.x * 8 + 6] = d_work; }
+#endif
+    }
+#undef QD_T0
+#undef QD_ACC
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tc::tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
 // ------------------------------------------------------- bandwidth-bound kernels
 // First conv: fp32 NHWC input with few channels -> bf16 blocked.  K = 9*CIN (9 or 27) is far
 // too small for a tcgen05 tile, and on CUDA cores the layer is instruction-bound (144 FMA per
@@ -1286,7 +1583,8 @@ __host__ __device__ constexpr int first_rows(int cin, int kz)
     return r > 32 ? 32 : (r < 8 ? 8 : r);
 }
 
-template <int CIN, int COUT, int KZ>
+// QOUT: the output is written as a quad tensor (conv_qd_kernel's layout; planar frames with even H and W).
+template <int CIN, int COUT, int KZ, bool QOUT = false>
 __global__ void __launch_bounds__(256)
 first_conv_kernel(const float *__restrict__ in, const float *__restrict__ wf,
                   const float *__restrict__ scale, const float *__restrict__ shift,
@@ -1360,13 +1658,17 @@ first_conv_kernel(const float *__restrict__ in, const float *__restrict__ wf,
             src[ks][j] = tz * SSLICE + (warp + tr / 3) * SROW + (g + tr % 3) * CIN + c;
         }
     __syncthreads();
-    const size_t plane = (size_t)H * W * 8;
+    // quad output: pixel (y, x) -> channel blocks (2*(y&1) + (x&1))*NT + nt of the half-resolution image; x0, 16q
+    // and 8r are even, so the column parity is g's and one fragment row spans 8 pixels = 4 quad columns
+    const size_t plane = QOUT ? (size_t)(H >> 1) * (W >> 1) * 8 : (size_t)H * W * 8;
 #pragma unroll 1
     for (int rr = 0; rr < FIRST_ROWS; rr += 8) {
         const int y = y0 + warp + rr;
         if (y >= H) return;
         const int roff = rr * SROW;                      // this row's offset in the staged tile
-        bf16 *orow = out + (((size_t)np * NT * H + y) * W + x0 + g) * 8 + 2 * t;
+        bf16 *orow = QOUT ? out + ((((size_t)np * 4 + 2 * (y & 1) + (g & 1)) * NT * (H >> 1) + (y >> 1)) * (W >> 1) +
+                                   ((x0 + g) >> 1)) * 8 + 2 * t
+                          : out + (((size_t)np * NT * H + y) * W + x0 + g) * 8 + 2 * t;
 #pragma unroll 2
         for (int q = 0; q < FIRST_TW / 16; ++q) {
             if (x0 + 16 * q >= W) break;
@@ -1394,7 +1696,7 @@ first_conv_kernel(const float *__restrict__ in, const float *__restrict__ wf,
                     const float v0 = fmaxf(fmaf(acc[nt][2 * r], sc[nt][0], sh[nt][0]), 0.0f);
                     const float v1 = fmaxf(fmaf(acc[nt][2 * r + 1], sc[nt][1], sh[nt][1]), 0.0f);
                     if (x0 + 16 * q + g + 8 * r < W)
-                        *reinterpret_cast<uint32_t *>(orow + nt * plane + (size_t)(16 * q + 8 * r) * 8) = pack_bf16(v0, v1);
+                        *reinterpret_cast<uint32_t *>(orow + nt * plane + (size_t)((16 * q + 8 * r) >> (QOUT ? 1 : 0)) * 8) = pack_bf16(v0, v1);
                 }
         }
     }
@@ -1972,6 +2274,89 @@ int upconv_tc(sq_unet_s *u, const SqLayer &L, const bf16 *in, bf16 *out, const T
     SQ_REQUIRE(false, SQ_EUNSUPPORTED, "bf16 mode: unsupported up-conv filter count %d", L.cout);
 }
 
+// ---- quad (space-to-depth) level-0 launches.  g.H, g.W: the quad image (half the frame).
+bool quad_enabled()
+{
+    // SQ_QUAD=0 keeps level 0 on the full-resolution kernels (A/B measurements, tests)
+    const char *e = getenv("SQ_QUAD");
+    return !e || atoi(e) != 0;
+}
+
+template <int NTAP, int KPS, int EPI, int HK>
+int launch_qd(sq_unet_s *u, const SqLayer &L, const bf16 *in0, int cb0, const bf16 *in1, int cb1, bf16 *out,
+              bf16 *out_pool, const HeadArgs &head, const TcGeo &g, int relu, cudaStream_t st)
+{
+    constexpr int S = 2;
+    using C = QCfg<S, NTAP>;
+    const int nimg = g.nimg, H = g.H, W = g.W;
+    CUtensorMap m0, m1;
+    SQ_TRY(make_map(&m0, in0, nimg, 1, cb0, H, W, C::PW, C::PH, 2 * KPS, 1));
+    if (in1) SQ_TRY(make_map(&m1, in1, nimg, 1, cb1, H, W, C::PW, C::PH, 2 * KPS, 1));
+    else m1 = m0;
+    const int ks0 = cb0 / 2, ks1 = in1 ? cb1 / 2 : 0, ksteps = ks0 + ks1;
+    SQ_REQUIRE(ks0 % KPS == 0 && ks1 % KPS == 0 && (NTAP == 1 || (ks0 % 4 == 0 && ks1 % 4 == 0)), SQ_ESTATE,
+               "conv_qd: %d + %d k-steps do not fit the stage layout", ks0, ks1);
+    const int budget = (216 / 2) * 1024 - 2048;
+    const int wres = ksteps * C::W_BYTES, stage_bytes = KPS * C::A_BYTES;
+    const int nstages = std::min(QD_MAX_STAGES, (budget - wres) / stage_bytes);
+    SQ_REQUIRE(nstages >= 2, SQ_ESTATE, "conv_qd: configuration does not fit in shared memory");
+    const size_t smem = (size_t)((wres + 127) & ~127) + (size_t)nstages * stage_bytes + 1024;
+    auto kern = conv_qd_kernel<S, NTAP, KPS, EPI, HK>;
+    static size_t attr_smem[64] = {0};
+    size_t &have = attr_smem[u->h->device & 63];
+    if (smem > have) {
+        SQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        have = smem;
+    }
+    const int tiles = nimg * ((W + 7) / 8) * ((H + C::TH - 1) / C::TH);
+    const int grid = std::min(tiles, 2 * u->h->sm_count / grid_div());
+    long long *phase_dbg = nullptr;
+#ifdef SQ_XC_PHASE_DIAG
+    if (getenv("SQ_XC_PHASE")) {
+        SQ_CUDA(cudaMalloc(&phase_dbg, (size_t)grid * 8 * sizeof(long long)));
+        SQ_CUDA(cudaMemset(phase_dbg, 0, (size_t)grid * 8 * sizeof(long long)));
+    }
+#endif
+    kern<<<grid, TC_THREADS, smem, st>>>(m0, m1, ks0, ks1, (const bf16 *)L.w_qd, L.scale_q, L.shift_q, out, out_pool,
+                                         head, nimg, H, W, relu, nstages, wres, phase_dbg);
+    ++u->last_launches;
+    SQ_CHECK_LAUNCH();
+    if (phase_dbg) {
+        // diagnostics (-DSQ_XC_PHASE_DIAG builds only): average clocks per tile each role spent waiting / working
+        SQ_CUDA(cudaStreamSynchronize(st));
+        std::vector<long long> h((size_t)grid * 8);
+        SQ_CUDA(cudaMemcpy(h.data(), phase_dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+        SQ_CUDA(cudaFree(phase_dbg));
+        double a[8] = {0};
+        for (int b2 = 0; b2 < grid; ++b2) for (int i = 0; i < 8; ++i) a[i] += (double)h[(size_t)b2 * 8 + i] / grid;
+        const double tpc = (double)tiles / grid;
+        fprintf(stderr, "qd_phase %s NTAP=%d KPS=%d EPI=%d stages=%d tiles/CTA=%.0f | per tile clk: producer wait_empty %.0f issue %.0f | "
+                "mma wait_tempty %.0f wait_full %.0f issue %.0f | epilogue wait_tfull %.0f work %.0f\n", L.scope.c_str(), NTAP, KPS, EPI,
+                nstages, tpc, a[0] / tpc, a[1] / tpc, a[2] / tpc, a[3] / tpc, a[4] / tpc, a[5] / tpc, a[6] / tpc);
+    }
+    return SQ_OK;
+}
+
+// quad 3x3 conv; c0 / c1: level-0 channels of the two sources (16 each) -> 4*c/8 channel blocks of the quad image
+int conv3x3_qd(sq_unet_s *u, const SqLayer &L, const bf16 *in0, int c0, const bf16 *in1, int c1, bf16 *out,
+               bf16 *out_pool, const HeadArgs *head, const TcGeo &g, cudaStream_t st)
+{
+    const HeadArgs none = {nullptr, 0, nullptr, nullptr, nullptr};
+    const int cb0 = 4 * c0 / 8, cb1 = 4 * c1 / 8;
+    if (head) {
+        switch (head->K) {
+        case 2: return launch_qd<4, 2, EPI_HEAD, 2>(u, L, in0, cb0, in1, cb1, nullptr, nullptr, *head, g, 1, st);
+        case 3: return launch_qd<4, 2, EPI_HEAD, 3>(u, L, in0, cb0, in1, cb1, nullptr, nullptr, *head, g, 1, st);
+        case 4: return launch_qd<4, 2, EPI_HEAD, 4>(u, L, in0, cb0, in1, cb1, nullptr, nullptr, *head, g, 1, st);
+        }
+        SQ_REQUIRE(false, SQ_EUNSUPPORTED, "fused head supports 2..4 classes");
+    }
+    if (out_pool) return launch_qd<4, 2, EPI_POOL, 0>(u, L, in0, cb0, in1, cb1, out, out_pool, none, g, 1, st);
+    // two sources: 8 k-steps of resident weights (64 KB) leave room for single-k-step stages only
+    if (in1) return launch_qd<4, 1, EPI_STORE, 0>(u, L, in0, cb0, in1, cb1, out, nullptr, none, g, 1, st);
+    return launch_qd<4, 2, EPI_STORE, 0>(u, L, in0, cb0, in1, cb1, out, nullptr, none, g, 1, st);
+}
+
 SqLayer *layer_by_scope(sq_unet_s *u, const std::string &scope)
 {
     for (SqLayer &l : u->layers)
@@ -2056,6 +2441,53 @@ int sq_tc_finalize(sq_unet_s *u)
             SQ_TRY(dev_upload(u, w.data(), w.size() * 4, &L.w_tc));
         }
     }
+    // Level-0 layers of planar nets with filters[0] = 16 also get the quad (space-to-depth) form used by
+    // conv_qd_kernel: [k-step = (source, input parity)][tap (a, b)][ci%16/8][(output parity, co)][8]
+    if (u->ndim == 2 && u->nlev >= 2 && u->filters[0] == 16) {
+        for (SqLayer &L : u->layers) {
+            if (L.level != 0 || L.cout != 16) continue;
+            const std::vector<float> &k = u->host[L.scope + "/kernel"].data;
+            const int C = L.cin0 + L.cin1;
+            std::vector<uint16_t> w;
+            if (L.kind == SqLayer::CONV && C % 16 == 0) {
+                w.assign((size_t)(C / 16) * 4 * 4 * 2 * 64 * 8, 0);
+                for (int src = 0; src < C / 16; ++src)
+                    for (int qi = 0; qi < 4; ++qi)                     // input parity (iy, ix)
+                        for (int tp = 0; tp < 4; ++tp)                 // half-resolution tap (a, b): ty = a - iy, tx = b - ix
+                            for (int kb = 0; kb < 2; ++kb)
+                                for (int qo = 0; qo < 4; ++qo)         // output parity (oy, ox)
+                                    for (int co = 0; co < 16; ++co)
+                                        for (int e = 0; e < 8; ++e) {
+                                            const int iy = qi >> 1, ix = qi & 1, oy = qo >> 1, ox = qo & 1;
+                                            const int ky = 2 * ((tp >> 1) - iy) + iy - oy + 1, kx = 2 * ((tp & 1) - ix) + ix - ox + 1;
+                                            if (ky < 0 || ky > 2 || kx < 0 || kx > 2) continue;
+                                            const int ci = src * 16 + kb * 8 + e;
+                                            w[((((((size_t)src * 4 + qi) * 4 + tp) * 2 + kb) * 64) + qo * 16 + co) * 8 + e] =
+                                                host_bf16(k[((size_t)(ky * 3 + kx) * C + ci) * 16 + co]);
+                                        }
+            } else if (L.kind == SqLayer::UPCONV && C % 16 == 0) {
+                // 1x1 conv C -> 64: [k-step][ci%16/8][(tap = output parity, co)][8]
+                w.assign((size_t)C * 64, 0);
+                for (int ks = 0; ks < C / 16; ++ks)
+                    for (int kb = 0; kb < 2; ++kb)
+                        for (int qo = 0; qo < 4; ++qo)
+                            for (int co = 0; co < 16; ++co)
+                                for (int e = 0; e < 8; ++e) {
+                                    const int ci = ks * 16 + kb * 8 + e;
+                                    w[((((size_t)ks * 2 + kb) * 64) + qo * 16 + co) * 8 + e] =
+                                        host_bf16(k[((size_t)qo * 16 + co) * C + ci]);
+                                }
+            } else {
+                continue;
+            }
+            SQ_TRY(dev_upload(u, w.data(), w.size() * 2, &L.w_qd));
+            std::vector<float> sc(64), sh(64);
+            const std::vector<float> &s0 = u->host[L.scope + "/_scale"].data, &t0 = u->host[L.scope + "/_shift"].data;
+            for (int i = 0; i < 64; ++i) { sc[i] = s0[i % 16]; sh[i] = t0[i % 16]; }
+            SQ_TRY(dev_upload(u, sc.data(), 64 * 4, (void **)&L.scale_q));
+            SQ_TRY(dev_upload(u, sh.data(), 64 * 4, (void **)&L.shift_q));
+        }
+    }
     TcState *s = new TcState();
     s->sm_count = u->h->sm_count;
     u->tc_state = s;
@@ -2097,6 +2529,16 @@ int tc_run(sq_unet_s *u, bool dry, const float *in, int n, int dep, int hgt, int
     const int threads = 256;
     char scope[64];
     std::vector<char> pool_fused(nl + 1, 0);
+    // level 0 on the quad (space-to-depth) layout: planar nets with 16 filters at level 0, even frame sizes and
+    // a fused head; t1[0], skip[0], up[0], merged[0], ut[0] are then quad tensors (same sizes)
+    bool quad = !vol && nl >= 2 && u->filters[0] == 16 && (hgt % 2 == 0) && (wid % 2 == 0) && u->cin <= 4 &&
+                u->nout >= 2 && u->nout <= 4 && ((uintptr_t)mask % 2 == 0) && quad_enabled() &&
+                !first_fusion_enabled() && !pair_enabled();
+    for (const SqLayer &L : u->layers)
+        if (L.level == 0 && L.kind != SqLayer::HEAD && !(L.kind == SqLayer::CONV && L.cin0 == u->cin && L.scope == "UNet/down0/conv1") &&
+            !L.w_qd)
+            quad = false;
+    const TcGeo geoq = {n, 1, hgt / 2, wid / 2, 1, 1, 0, 0};
     for (int l = 0; l < nl; ++l) {
         const int D = depth(l), H = hgt >> l, W = wid >> l;
         const long long px = (long long)n * D * H * W;
@@ -2143,8 +2585,13 @@ int tc_run(sq_unet_s *u, bool dry, const float *in, int n, int dep, int hgt, int
             const dim3 grid((W + FIRST_TW - 1) / FIRST_TW, (H + fr - 1) / fr, n);
             const float *wf = (const float *)c1->w_tc;
 #define SQ_FIRST(CI, CO) first_conv_kernel<CI, CO, 1><<<grid, 256, 0, st>>>(in, wf, c1->scale, c1->shift, t1[0], n, 1, H, W)
-            const int key = u->cin * 1000 + c1->cout;
+#define SQ_FIRSTQ(CI) first_conv_kernel<CI, 16, 1, true><<<grid, 256, 0, st>>>(in, wf, c1->scale, c1->shift, t1[0], n, 1, H, W)
+            const int key = quad ? u->cin : u->cin * 1000 + c1->cout;
             switch (key) {
+            case 1: SQ_FIRSTQ(1); break;
+            case 2: SQ_FIRSTQ(2); break;
+            case 3: SQ_FIRSTQ(3); break;
+            case 4: SQ_FIRSTQ(4); break;
             case 1016: SQ_FIRST(1, 16); break;
             case 1032: SQ_FIRST(1, 32); break;
             case 1064: SQ_FIRST(1, 64); break;
@@ -2160,6 +2607,7 @@ int tc_run(sq_unet_s *u, bool dry, const float *in, int n, int dep, int hgt, int
                            u->cin, c1->cout);
             }
 #undef SQ_FIRST
+#undef SQ_FIRSTQ
             ++u->last_launches;
             SQ_CHECK_LAUNCH();
         } else {
@@ -2187,7 +2635,8 @@ int tc_run(sq_unet_s *u, bool dry, const float *in, int n, int dep, int hgt, int
         const bool fuse_pool = (l < nl - 1) && c2->cout <= 128;
         if (l < nl - 1) pool_fused[l + 1] = fuse_pool;
         bf16 *pool_dst = !fuse_pool ? nullptr : (vol ? xyp[l + 1] : pooled[l + 1]);
-        if (fuse_first && pool_dst) SQ_TRY(launch_tc_first(u, *c1, *c2, in, skip[l], pool_dst, geo, st));
+        if (l == 0 && quad) SQ_TRY(conv3x3_qd(u, *c2, t1[0], c2->cin0, nullptr, 0, skip[0], pool_dst, nullptr, geoq, st));
+        else if (fuse_first && pool_dst) SQ_TRY(launch_tc_first(u, *c1, *c2, in, skip[l], pool_dst, geo, st));
         else SQ_TRY(conv3x3_tc(u, *c2, t1[l], c2->cin0, nullptr, 0, skip[l], pool_dst, nullptr, geo, st));
         sq_timer_mark(u, st, c2->scope.c_str(), c2->flops_per_px * px);
     }
@@ -2212,6 +2661,13 @@ int tc_run(sq_unet_s *u, bool dry, const float *in, int n, int dep, int hgt, int
                 const TcGeo gu = {n * (D / 2), 1, H / 2, W / 2, 1, 2, kz, kz * wslice};
                 SQ_TRY(upconv_tc(u, *us, cur, up[l], gu, st));
             }
+        } else if (l == 0 && quad) {
+            // 2x2 stride-2 up-conv onto the quad layout = 1x1 conv cin -> 4 x 16 at half resolution
+            const HeadArgs none = {nullptr, 0, nullptr, nullptr, nullptr};
+            if ((us->cin0 / 16) % 2 == 0)
+                SQ_TRY((launch_qd<1, 2, EPI_STORE, 0>(u, *us, cur, us->cin0 / 8, nullptr, 0, up[0], nullptr, none, geoq, 0, st)));
+            else
+                SQ_TRY((launch_qd<1, 1, EPI_STORE, 0>(u, *us, cur, us->cin0 / 8, nullptr, 0, up[0], nullptr, none, geoq, 0, st)));
         } else {
             const TcGeo gu = {n, 1, H / 2, W / 2, 1, 1, 0, 0};
             SQ_TRY(upconv_tc(u, *us, cur, up[l], gu, st));
@@ -2232,6 +2688,13 @@ int tc_run(sq_unet_s *u, bool dry, const float *in, int n, int dep, int hgt, int
         const bool last = (l == 0 && head_fused);
         const HeadArgs ha = {(const float *)head->w_tc, head->cout, logits, probs, mask};
         // conv_block as one launch where the fused pair kernel applies (the intermediate `ut` stays on chip)
+        if (l == 0 && quad) {
+            SQ_TRY(conv3x3_qd(u, *c1, in0, c1->cin0, in1, c1->cin1, ut[0], nullptr, nullptr, geoq, st));
+            sq_timer_mark(u, st, c1->scope.c_str(), c1->flops_per_px * px);
+            SQ_TRY(conv3x3_qd(u, *c2, ut[0], c2->cin0, nullptr, 0, nullptr, nullptr, &ha, geoq, st));
+            sq_timer_mark(u, st, c2->scope.c_str(), (c2->flops_per_px + head->flops_per_px) * px);
+            return SQ_OK;
+        }
         {
             const int r = vol ? SQ_NOT_APPLICABLE
                               : conv_pair_tc(u, *c1, *c2, in0, c1->cin0, in1, c1->cin1, last ? nullptr : uo[l], nullptr,

@@ -224,6 +224,7 @@ def test_both_conv_kernels_cover_every_layer(sq, monkeypatch, xc):
     """Cout <= 32 convs have two tcgen05 kernels (9-tap and x-combined, picked by k-steps per tile);
     SQ_XC=0 / SQ_XC=2 force one or the other on every such layer, incl. fused pool and fused head."""
     monkeypatch.setenv('SQ_XC', xc)
+    monkeypatch.setenv('SQ_QUAD', '0')        # level 0 on the full-resolution kernels (see test_quad_level0)
     filters = (16, 32, 64)
     for bridge, cin, k, shape in (('concat', 1, 2, (64, 88)), ('eltwise_add', 3, 3, (48, 80))):
         w = synth.unet_weights(filters, cin, k, bridge=bridge, seed=21)
@@ -300,6 +301,35 @@ def test_random_geometries(sq, seed):
     ref = unet_c.unet_forward(x, weights, filters, bridge, contract='bf16')
     _compare(out, ref, 'seed %d: %s filters=%s bridge=%s cin=%d k=%d shape=%s' %
              (seed, '3d' if vol else '2d', filters, bridge, cin, k, x.shape))
+
+
+@pytest.mark.parametrize('quad', ['1', '0'])
+@pytest.mark.parametrize('bridge,cin,k,filters,shape,n', [
+    ('concat', 1, 2, (16, 32), (70, 122), 2),            # quad image 35 x 61: ragged tiles both ways
+    ('concat', 3, 3, (16, 32, 64), (96, 72), 1),
+    ('eltwise_mul', 2, 4, (16, 32, 64), (136, 48), 2),   # three 32-row tiles down the quad image
+    (None, 4, 2, (16, 16), (64, 80), 1),                 # one k-step up-conv
+    ('concat', 1, 2, (16, 64), (40, 200), 1),            # four k-steps into the up-conv
+])
+def test_quad_level0(sq, monkeypatch, quad, bridge, cin, k, filters, shape, n):
+    """Level 0 of planar nets with filters[0] = 16 runs on the quad (space-to-depth) layout by default
+    (conv_qd_kernel: first conv writes quads, 64-wide half-resolution MMAs, pool / head per accumulator
+    row); SQ_QUAD=0 keeps the full-resolution kernels.  Both against the bf16-contract oracle, and the two
+    against each other (same products, another accumulation order)."""
+    w = synth.unet_weights(filters, cin, k, bridge=bridge, affine=True, seed=31)
+    x = synth.frames(n, shape[0], shape[1], cin, seed=9, n_objects=4)
+    monkeypatch.setenv('SQ_QUAD', quad)
+    net = _net(filters, shape, bridge, cin, k, w)
+    out = net.predict(x)
+    ref = unet_c.unet_forward(x, w, filters, bridge, contract='bf16')
+    _compare(out, ref, 'SQ_QUAD=%s %s' % (quad, bridge))
+    assert net.launches() == 5 * len(filters) - 3 + (0 if bridge in ('concat', None) else len(filters) - 1)
+    if quad == '1':
+        monkeypatch.setenv('SQ_QUAD', '0')
+        other = net.predict(x)
+        tol = 0.02 * float(ref['logits'].max() - ref['logits'].min())
+        assert np.abs(out['logits'] - other['logits']).max() <= tol
+        assert (out['mask'] != other['mask']).mean() <= 5e-3
 
 
 def test_cluster_multicast_variant(sq, monkeypatch):
