@@ -63,6 +63,21 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint64_t *bar, uint32_t parity
     return ok;
 }
 // Bounded wait: a pipeline bug must fail loudly (trap -> CUDA error), never hang the GPU.
+// -DSQ_MBAR_DEBUG builds (diagnostics only): a wait that times out reports its source line and lets the
+// kernel run to completion with garbage results, so the message reaches the host.
+#ifdef SQ_MBAR_DEBUG
+__device__ int sq_mbar_abort = 0;
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, int line = __builtin_LINE())
+{
+    for (uint32_t i = 0; i < (1u << 22); ++i) {
+        if (mbar_try_wait(bar, parity)) return;
+        if ((i & 1023) == 1023 && *(volatile int *)&sq_mbar_abort) return;
+    }
+    if (atomicExch(&sq_mbar_abort, 1) == 0 || (threadIdx.x & 31) == 0)
+        printf("sequitr_b200: mbarrier wait timed out at line %d (block %d warp %d lane %d parity %u)\n", line,
+               (int)blockIdx.x, (int)(threadIdx.x >> 5), (int)(threadIdx.x & 31), parity);
+}
+#else
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
     for (uint32_t i = 0; i < (1u << 26); ++i)
@@ -71,6 +86,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
            (int)threadIdx.x);
     __trap();
 }
+#endif
 
 // ----------------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *m)
@@ -93,6 +109,15 @@ __device__ __forceinline__ void tma_load_5d(void *dst, const CUtensorMap *m, uin
         "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes"
         " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(smem_u32(dst)),
         "l"((uint64_t)m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *m, uint64_t *bar, int c0,
+                                            int c1, int c2)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)),
+        "l"((uint64_t)m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
 __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *m, uint64_t *bar, int c0,
@@ -216,6 +241,21 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t *v)
         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
           "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
           "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+// 32 consecutive columns
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t *v)
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+          "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+          "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+          "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
         : "r"(taddr)
         : "memory");
 }

@@ -1556,6 +1556,281 @@ conv_qd_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     }
 }
 
+// --------------------- down0/conv1 -> down0/conv2 (+ 2x2 max-pool) as ONE launch on the quad layout
+// The 16-channel output of the first conv (64 of the 108 B/px the two layers move) never goes to HBM.
+// Per tile of 8 x 32 quad pixels (16 x 64 frame pixels), one CTA per SM, 22 warps:
+//   warp 0       TMA: the fp32 halo of the tile (24 x 70 frame pixels, zero fill outside the frame)
+//   warps 2-5    builders: im2col of the first conv for the 10 x 34 quad pixels of conv2's halo patch --
+//                row p = the 4 x 4 frame-pixel window around quad pixel p, 16 bf16 = ONE k-step (A1)
+//   warp 1       MMA: conv1 = 3 MMAs 128 x 64 x 16 (A1 x B1, B1 = the 3x3 kernel scattered over
+//                (output parity, window position)) -> acc1; conv2 = 32 quad MMAs on the patch P -> acc2
+//   warps 6-21   epilogue 1: acc1 -> scale/shift/ReLU -> bf16 -> P in shared memory, laid out exactly like a
+//                TMA-fetched quad patch (zeros outside the frame = conv2's SAME padding);
+//                epilogue 2: acc2 -> scale/shift/ReLU -> bf16 -> quad tensor + in-thread 2x2 max-pool
+// The MMA warp issues conv1 of tile i+1 before conv2 of tile i and the epilogue warps mirror that order, so
+// the tensor pipe runs conv2 of a tile while its successor's patch is being written (A1, the fp32 halo, P and
+// acc2 are double-buffered).  conv2's output columns are ordered (co / 8, parity, co % 8): one 32-column
+// TMEM load holds all four parities of 8 channels, i.e. four 16-byte stores and the pooled vector.
+struct QF {
+    static constexpr int TH = 32, PW = 10, PH = 34, PROWS = PW * PH;      // conv2's halo patch (quad pixels)
+    static constexpr int MT1 = 3, A1_ROWS = 128 * MT1;
+    static constexpr int A1_BYTES = A1_ROWS * 32;                         // [2][384][8] bf16
+    static constexpr int RAW_W = 32, RAW_H = 2 * PH + 2;       // 128-byte rows; the box starts one column early (16-byte aligned)
+    static constexpr int RAW_BYTES = (RAW_W * RAW_H * 4 + 127) / 128 * 128;
+    static constexpr int P_BYTES = 8 * PROWS * 16;
+    static constexpr int W2_BYTES = 4 * 4 * 2 * 64 * 16, B1_BYTES = 2 * 64 * 16;
+    static constexpr int OFF_B1 = 0, OFF_W2 = B1_BYTES, OFF_A1 = OFF_W2 + W2_BYTES, OFF_RAW = OFF_A1 + 2 * A1_BYTES,
+                         OFF_P = OFF_RAW + 2 * RAW_BYTES, SMEM = OFF_P + 2 * P_BYTES;
+    static constexpr int EPI_WARPS = 16, BLD_WARPS = 4, THREADS = 32 * (2 + BLD_WARPS + EPI_WARPS);
+    static_assert(OFF_A1 % 128 == 0 && OFF_RAW % 128 == 0 && OFF_P % 128 == 0 && P_BYTES % 128 == 0, "alignment");
+};
+
+__global__ void __launch_bounds__(QF::THREADS, 1)
+conv_qf_kernel(const __grid_constant__ CUtensorMap mapIn, const bf16 *__restrict__ wts,
+               const float *__restrict__ scale1, const float *__restrict__ shift1,
+               const float *__restrict__ scale2, const float *__restrict__ shift2,
+               bf16 *__restrict__ out, bf16 *__restrict__ out_pool, int nimg, int H, int W)
+{
+    // H, W: the quad image.  wts: B1 then W2 (QF::B1_BYTES + QF::W2_BYTES), scale / shift: the layers' own 16.
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+    __shared__ uint64_t w_bar, raw_full[2], raw_empty[2], a1_full[2], a1_empty[2], acc1_full, acc1_empty,
+        p_full[2], p_empty[2], acc2_full[2], acc2_empty[2];
+    __shared__ uint32_t tmem_base_sh;
+    __shared__ __align__(16) float s_sc1[16], s_sh1[16];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_x = (W + 7) >> 3, tiles_y = (H + QF::TH - 1) / QF::TH;
+    const int ntiles = nimg * tiles_x * tiles_y;
+    const int nt = ((int)blockIdx.x < ntiles) ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+
+    if (threadIdx.x == 0) {
+        tc::mbar_init(&w_bar, 1);
+        for (int i = 0; i < 2; ++i) {
+            tc::mbar_init(&raw_full[i], 1); tc::mbar_init(&raw_empty[i], QF::BLD_WARPS);
+            tc::mbar_init(&a1_full[i], QF::BLD_WARPS); tc::mbar_init(&a1_empty[i], 1);
+            tc::mbar_init(&p_full[i], QF::EPI_WARPS); tc::mbar_init(&p_empty[i], 1);
+            tc::mbar_init(&acc2_full[i], 1); tc::mbar_init(&acc2_empty[i], QF::EPI_WARPS);
+        }
+        tc::mbar_init(&acc1_full, 1); tc::mbar_init(&acc1_empty, QF::EPI_WARPS);
+        tc::fence_barrier_init();
+        tc::tma_prefetch_desc(&mapIn);
+    }
+    if (warp == 1) { tc::tmem_alloc(&tmem_base_sh, 512); tc::tmem_relinquish(); }
+    if (threadIdx.x < 16) { s_sc1[threadIdx.x] = scale1[threadIdx.x]; s_sh1[threadIdx.x] = shift1[threadIdx.x]; }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = tmem_base_sh;
+    constexpr uint32_t ACC1 = 0, ACC2 = 256;                 // TMEM columns: acc1 3 x 64, acc2 2 x (2 x 64)
+
+    if (warp == 0) {
+        // ===================================================== TMA producer
+        if (lane == 0) {
+            tc::mbar_arrive_expect_tx(&w_bar, QF::B1_BYTES + QF::W2_BYTES);
+            tc::bulk_load(smem + QF::OFF_B1, wts, QF::B1_BYTES, &w_bar);
+            for (int q = 0; q < 4; ++q)
+                tc::bulk_load(smem + QF::OFF_W2 + q * (QF::W2_BYTES / 4), wts + (QF::B1_BYTES + q * (QF::W2_BYTES / 4)) / 2,
+                              QF::W2_BYTES / 4, &w_bar);
+            for (int it = 0; it < nt; ++it) {
+                const int t = blockIdx.x + it * gridDim.x, b = it & 1;
+                const int tx = t % tiles_x, ty = (t / tiles_x) % tiles_y, n = t / (tiles_x * tiles_y);
+                tc::mbar_wait(&raw_empty[b], ((it >> 1) & 1) ^ 1);
+                tc::mbar_arrive_expect_tx(&raw_full[b], QF::RAW_W * QF::RAW_H * 4);
+                // frame pixels (16 tx - 3 ..., 64 ty - 3 ...): the 4 x 4 windows of quad pixels (8 tx - 1 ..., 32 ty - 1 ...);
+                // the box starts at column 16 tx - 4 so that every row of it is 16-byte aligned in global memory
+                tc::tma_load_3d(smem + QF::OFF_RAW + b * QF::RAW_BYTES, &mapIn, &raw_full[b], 16 * tx - 4, 64 * ty - 3, n);
+            }
+        }
+    } else if (warp == 1) {
+        // ======================================================= MMA issuer
+        const uint32_t idesc = tc::instr_desc_bf16(128, 64);
+        const uint32_t sbase = tc::smem_u32(smem);
+        const uint32_t hi128 = ((128u >> 4) & 0x3FFFu) | (1u << 14);                 // SBO = 128 (A1, B1, W2)
+        const uint32_t hiP = (((uint32_t)(QF::PW * 16) >> 4) & 0x3FFFu) | (1u << 14);   // SBO of the patch = one row
+        const uint32_t b1_lo = (((sbase + QF::OFF_B1) >> 4) & 0x3FFFu) | (((64u * 16u) >> 4) << 16);
+        const uint32_t w2_lo = (((sbase + QF::OFF_W2) >> 4) & 0x3FFFu) | (((64u * 16u) >> 4) << 16);
+        tc::mbar_wait(&w_bar, 0);
+        for (int it = 0; it <= nt; ++it) {
+            if (it < nt) {
+                const int b = it & 1;
+                tc::mbar_wait(&a1_full[b], (it >> 1) & 1);
+                tc::mbar_wait(&acc1_empty, (it & 1) ^ 1);
+                tc::tc_fence_after();
+                if (tc::elect_one()) {
+                    const uint32_t a1_lo = (((sbase + QF::OFF_A1 + b * QF::A1_BYTES) >> 4) & 0x3FFFu) |
+                                           ((((uint32_t)QF::A1_ROWS * 16u) >> 4) << 16);
+#pragma unroll
+                    for (int m = 0; m < QF::MT1; ++m)
+                        tc::umma_bf16_parts(tmem_base + ACC1 + m * 64, a1_lo + m * (2048 >> 4), hi128, b1_lo, hi128, idesc, 0u);
+                    tc::umma_commit(&a1_empty[b]);
+                    tc::umma_commit(&acc1_full);
+                }
+                __syncwarp();
+            }
+            if (it >= 1) {
+                const int j2 = it - 1, b = j2 & 1;
+                tc::mbar_wait(&p_full[b], (j2 >> 1) & 1);
+                tc::mbar_wait(&acc2_empty[b], ((j2 >> 1) & 1) ^ 1);
+                tc::tc_fence_after();
+                if (tc::elect_one()) {
+                    const uint32_t p_lo = (((sbase + QF::OFF_P + b * QF::P_BYTES) >> 4) & 0x3FFFu) |
+                                          ((((uint32_t)QF::PROWS * 16u) >> 4) << 16);
+                    const uint32_t d0 = tmem_base + ACC2 + b * 128;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int iy = k >> 1, ix = k & 1;
+#pragma unroll
+                        for (int j = 0; j < 2; ++j)
+#pragma unroll
+                            for (int tp = 0; tp < 4; ++tp) {
+                                const uint32_t a_off = (uint32_t)(k * (2 * QF::PROWS) + (j * 16 + (tp >> 1) + 1 - iy) * QF::PW +
+                                                                  (tp & 1) + 1 - ix);
+                                tc::umma_bf16_parts(d0 + j * 64, p_lo + a_off, hiP, w2_lo + (uint32_t)((k * 4 + tp) * (2048 >> 4)),
+                                                    hi128, idesc, (k > 0 || tp > 0) ? 1u : 0u);
+                            }
+                    }
+                    tc::umma_commit(&p_empty[b]);
+                    tc::umma_commit(&acc2_full[b]);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp < 2 + QF::BLD_WARPS) {
+        // ===================================================== im2col builders
+        const int bt = threadIdx.x - 64;                     // 0 .. 127
+        int roff[3];                                         // this thread's rows p = bt + 128 k: window origin in the halo
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int p = bt + 128 * k, py = p / QF::PW, px = p - py * QF::PW;
+            roff[k] = (2 * py) * QF::RAW_W + 2 * px;
+        }
+        for (int it = 0; it < nt; ++it) {
+            const int b = it & 1;
+            tc::mbar_wait(&raw_full[b], (it >> 1) & 1);
+            tc::mbar_wait(&a1_empty[b], ((it >> 1) & 1) ^ 1);
+            const float *raw = reinterpret_cast<const float *>(smem + QF::OFF_RAW + b * QF::RAW_BYTES);
+            uint8_t *a1 = smem + QF::OFF_A1 + b * QF::A1_BYTES;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const int p = bt + 128 * k;
+                if (p < QF::PROWS) {
+                    uint32_t o[8];
+#pragma unroll
+                    for (int wy = 0; wy < 4; ++wy) {
+                        // window columns 2 px + 1 .. 2 px + 4 of the staged row (the box starts one column early)
+                        const float2 c0 = *reinterpret_cast<const float2 *>(raw + roff[k] + wy * QF::RAW_W);
+                        const float2 c1 = *reinterpret_cast<const float2 *>(raw + roff[k] + wy * QF::RAW_W + 2);
+                        const float2 c2 = *reinterpret_cast<const float2 *>(raw + roff[k] + wy * QF::RAW_W + 4);
+                        o[2 * wy] = pack_bf16(c0.y, c1.x);
+                        o[2 * wy + 1] = pack_bf16(c1.y, c2.x);
+                    }
+                    *reinterpret_cast<uint4 *>(a1 + p * 16) = make_uint4(o[0], o[1], o[2], o[3]);
+                    *reinterpret_cast<uint4 *>(a1 + QF::A1_ROWS * 16 + p * 16) = make_uint4(o[4], o[5], o[6], o[7]);
+                }
+            }
+            tc::fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) { tc::mbar_arrive(&a1_full[b]); tc::mbar_arrive(&raw_empty[b]); }
+        }
+    } else {
+        // ========================================================= epilogue
+        const int g = (warp - 2 - QF::BLD_WARPS) >> 2, q4 = warp & 3;
+        const int r = q4 * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(q4 * 32) << 16;
+        int ppy[3], ppx[3];
+#pragma unroll
+        for (int m = 0; m < 3; ++m) { const int p = m * 128 + r; ppy[m] = p / QF::PW; ppx[m] = p - ppy[m] * QF::PW; }
+        // epilogue 2: this group owns sub-tile j2 and channels c8*8 .. c8*8+7 (all four parities)
+        const int j2 = g >> 1, c8 = g & 1;
+        float sc2[8], sh2[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { sc2[e] = scale2[c8 * 8 + e]; sh2[e] = shift2[c8 * 8 + e]; }
+        const size_t plane = (size_t)H * W * 8;
+        for (int it = 0; it <= nt; ++it) {
+            if (it < nt) {
+                // ---- epilogue 1: conv1's accumulators -> the bf16 halo patch of conv2
+                const int t = blockIdx.x + it * gridDim.x, b = it & 1;
+                const int tx = t % tiles_x, ty = (t / tiles_x) % tiles_y;
+                const int x0 = tx * 8 - 1, y0 = ty * QF::TH - 1;
+                tc::mbar_wait(&acc1_full, it & 1);
+                tc::mbar_wait(&p_empty[b], ((it >> 1) & 1) ^ 1);
+                tc::tc_fence_after();
+                uint8_t *P = smem + QF::OFF_P + b * QF::P_BYTES + (2 * g) * (QF::PROWS * 16);
+#pragma unroll
+                for (int m = 0; m < 3; ++m) {
+                    if (m == 2 && q4 == 3) continue;         // rows 352.. lie beyond the patch (warp-uniform)
+                    uint32_t v[16];
+                    tc::tmem_ld16(tmem_base + lane_addr + ACC1 + m * 64 + g * 16, v);
+                    tc::tmem_ld_wait();
+                    const int Y = y0 + ppy[m], X = x0 + ppx[m];
+                    const bool inside = Y >= 0 && Y < H && X >= 0 && X < W;
+                    uint32_t o[8];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float4 sc = *reinterpret_cast<const float4 *>(s_sc1 + 4 * q);
+                        const float4 sh = *reinterpret_cast<const float4 *>(s_sh1 + 4 * q);
+                        o[2 * q] = pack_bf16(fmaxf(fmaf(__uint_as_float(v[4 * q]), sc.x, sh.x), 0.0f),
+                                             fmaxf(fmaf(__uint_as_float(v[4 * q + 1]), sc.y, sh.y), 0.0f));
+                        o[2 * q + 1] = pack_bf16(fmaxf(fmaf(__uint_as_float(v[4 * q + 2]), sc.z, sh.z), 0.0f),
+                                                 fmaxf(fmaf(__uint_as_float(v[4 * q + 3]), sc.w, sh.w), 0.0f));
+                    }
+                    if (!inside) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) o[e] = 0u;
+                    }
+                    const int p = m * 128 + r;
+                    if (p < QF::PROWS) {
+                        *reinterpret_cast<uint4 *>(P + p * 16) = make_uint4(o[0], o[1], o[2], o[3]);
+                        *reinterpret_cast<uint4 *>(P + QF::PROWS * 16 + p * 16) = make_uint4(o[4], o[5], o[6], o[7]);
+                    }
+                }
+                tc::fence_proxy_async();                     // generic-proxy writes -> visible to the UMMA reads
+                tc::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) { tc::mbar_arrive(&p_full[b]); tc::mbar_arrive(&acc1_empty); }
+            }
+            if (it >= 1) {
+                // ---- epilogue 2: conv2's accumulators -> quad tensor + pooled tensor
+                const int i2 = it - 1, t = blockIdx.x + i2 * gridDim.x, b = i2 & 1;
+                const int tx = t % tiles_x, ty = (t / tiles_x) % tiles_y, n = t / (tiles_x * tiles_y);
+                const int y = ty * QF::TH + j2 * 16 + (r >> 3), x = tx * 8 + (r & 7);
+                const bool valid = (y < H) && (x < W);
+                tc::mbar_wait(&acc2_full[b], (i2 >> 1) & 1);
+                tc::tc_fence_after();
+                uint32_t v[32];
+                tc::tmem_ld32(tmem_base + lane_addr + ACC2 + b * 128 + j2 * 64 + c8 * 32, v);
+                tc::tmem_ld_wait();
+                tc::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&acc2_empty[b]);          // the accumulators are in registers
+                uint32_t mx[4];
+                bf16 *po = out + ((((size_t)n * 8 + c8) * H + y) * W + x) * 8;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    uint32_t o[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        o[e] = pack_bf16(fmaxf(fmaf(__uint_as_float(v[q * 8 + 2 * e]), sc2[2 * e], sh2[2 * e]), 0.0f),
+                                         fmaxf(fmaf(__uint_as_float(v[q * 8 + 2 * e + 1]), sc2[2 * e + 1], sh2[2 * e + 1]), 0.0f));
+                    if (valid) *reinterpret_cast<uint4 *>(po + (size_t)(2 * q) * plane) = make_uint4(o[0], o[1], o[2], o[3]);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) mx[e] = (q == 0) ? o[e] : bf162_max(mx[e], o[e]);
+                }
+                if (valid)
+                    *reinterpret_cast<uint4 *>(out_pool + ((((size_t)n * 2 + c8) * H + y) * W + x) * 8) =
+                        make_uint4(mx[0], mx[1], mx[2], mx[3]);
+            }
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tc::tmem_dealloc(tmem_base, 512);
+    }
+}
+
 // ------------------------------------------------------- bandwidth-bound kernels
 // First conv: fp32 NHWC input with few channels -> bf16 blocked.  K = 9*CIN (9 or 27) is far
 // too small for a tcgen05 tile, and on CUDA cores the layer is instruction-bound (144 FMA per
@@ -2337,6 +2612,46 @@ int launch_qd(sq_unet_s *u, const SqLayer &L, const bf16 *in0, int cb0, const bf
     return SQ_OK;
 }
 
+bool qfuse_enabled()
+{
+    // SQ_QFUSE=0: down0/conv1 and down0/conv2 as two launches (A/B measurements, tests)
+    const char *e = getenv("SQ_QFUSE");
+    return !e || atoi(e) != 0;
+}
+
+// down0/conv1 + down0/conv2 + pool in one launch (conv_qf_kernel); g.H, g.W: the quad image
+int launch_qf(sq_unet_s *u, const SqLayer &L1, const SqLayer &L2, const float *in, bf16 *out, bf16 *out_pool,
+              const TcGeo &g, cudaStream_t st)
+{
+    sq_encode_tiled_fn enc = sq_get_encode_tiled();
+    SQ_REQUIRE(enc, SQ_ECUDA, "cuTensorMapEncodeTiled entry point not available");
+    const int H0 = 2 * g.H, W0 = 2 * g.W;
+    CUtensorMap m;
+    cuuint64_t dims[3] = {(cuuint64_t)W0, (cuuint64_t)H0, (cuuint64_t)g.nimg};
+    cuuint64_t strides[2] = {(cuuint64_t)W0 * 4, (cuuint64_t)H0 * W0 * 4};
+    cuuint32_t box[3] = {(cuuint32_t)QF::RAW_W, (cuuint32_t)QF::RAW_H, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)in, dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    SQ_REQUIRE(r == CUDA_SUCCESS, SQ_ECUDA, "cuTensorMapEncodeTiled failed (%d) for the fp32 frames (%d,%d,%d)", (int)r,
+               g.nimg, H0, W0);
+    const size_t smem = (size_t)QF::SMEM + 1024;
+    static size_t attr_smem[64] = {0};
+    size_t &have = attr_smem[u->h->device & 63];
+    if (smem > have) {
+        SQ_CUDA(cudaFuncSetAttribute(conv_qf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        have = smem;
+    }
+    const int tiles = g.nimg * ((g.W + 7) / 8) * ((g.H + QF::TH - 1) / QF::TH);
+    const int grid = std::min(tiles, u->h->sm_count / grid_div());
+    conv_qf_kernel<<<grid, QF::THREADS, smem, st>>>(m, (const bf16 *)L2.w_qf, L1.scale, L1.shift, L2.scale, L2.shift, out,
+                                                   out_pool, g.nimg, g.H, g.W);
+    ++u->last_launches;
+    SQ_CHECK_LAUNCH();
+    return SQ_OK;
+}
+
 // quad 3x3 conv; c0 / c1: level-0 channels of the two sources (16 each) -> 4*c/8 channel blocks of the quad image
 int conv3x3_qd(sq_unet_s *u, const SqLayer &L, const bf16 *in0, int c0, const bf16 *in1, int c1, bf16 *out,
                bf16 *out_pool, const HeadArgs *head, const TcGeo &g, cudaStream_t st)
@@ -2481,6 +2796,30 @@ int sq_tc_finalize(sq_unet_s *u)
                 continue;
             }
             SQ_TRY(dev_upload(u, w.data(), w.size() * 2, &L.w_qd));
+            if (L.scope == "UNet/down0/conv2" && u->cin == 1 && C == 16) {
+                // conv_qf_kernel: B1[(parity, co)][window position wy*4 + wx] of the first conv (one k-step), then this
+                // layer's quad weights with the output columns reordered to (co / 8, parity, co % 8)
+                const std::vector<float> &k1 = u->host["UNet/down0/conv1/kernel"].data;
+                std::vector<uint16_t> f((size_t)(QF::B1_BYTES + QF::W2_BYTES) / 2, 0);
+                for (int kb = 0; kb < 2; ++kb)
+                    for (int qo = 0; qo < 4; ++qo)
+                        for (int co = 0; co < 16; ++co)
+                            for (int e = 0; e < 8; ++e) {
+                                const int kk = kb * 8 + e, wy = kk >> 2, wx = kk & 3, ky = wy - (qo >> 1), kx = wx - (qo & 1);
+                                if (ky < 0 || ky > 2 || kx < 0 || kx > 2) continue;
+                                f[(((size_t)kb * 64) + qo * 16 + co) * 8 + e] = host_bf16(k1[(size_t)(ky * 3 + kx) * 16 + co]);
+                            }
+                const size_t base = QF::B1_BYTES / 2;
+                for (int qi = 0; qi < 4; ++qi)
+                    for (int tp = 0; tp < 4; ++tp)
+                        for (int kb = 0; kb < 2; ++kb)
+                            for (int qo = 0; qo < 4; ++qo)
+                                for (int co = 0; co < 16; ++co)
+                                    for (int e = 0; e < 8; ++e)
+                                        f[base + (((((size_t)qi * 4 + tp) * 2 + kb) * 64) + (co / 8) * 32 + qo * 8 + co % 8) * 8 + e] =
+                                            w[(((((size_t)qi * 4 + tp) * 2 + kb) * 64) + qo * 16 + co) * 8 + e];
+                SQ_TRY(dev_upload(u, f.data(), f.size() * 2, &L.w_qf));
+            }
             std::vector<float> sc(64), sh(64);
             const std::vector<float> &s0 = u->host[L.scope + "/_scale"].data, &t0 = u->host[L.scope + "/_shift"].data;
             for (int i = 0; i < 64; ++i) { sc[i] = s0[i % 16]; sh[i] = t0[i % 16]; }
@@ -2550,6 +2889,8 @@ int tc_run(sq_unet_s *u, bool dry, const float *in, int n, int dep, int hgt, int
         // level-0 fusion: Cin = 1 -> 16 -> 16 channels on planar stacks with the pooled copy fused (SQ_FUSE_FIRST=0: off)
         const bool fuse_first = l == 0 && !vol && u->cin == 1 && c1->cout == 16 && c2->cout == 16 && nl > 1 &&
                                 first_fusion_enabled();
+        // quad layout: both convs of level 0 in one launch (the first conv's output stays on chip)
+        const bool qfuse = l == 0 && quad && c2->w_qf && (wid % 4 == 0) && ((uintptr_t)in % 16 == 0) && qfuse_enabled();
         if (l == 0 && vol) {
             const float *wf = (const float *)c1->w_tc;
             const int key = u->cin * 1000 + c1->cout;
@@ -2578,8 +2919,8 @@ int tc_run(sq_unet_s *u, bool dry, const float *in, int n, int dep, int hgt, int
 #undef SQ_FIRST3M
             ++u->last_launches;
             SQ_CHECK_LAUNCH();
-        } else if (l == 0 && fuse_first) {
-            // down0/conv1 runs inside down0/conv2's producer warps (launch_tc_first below)
+        } else if (l == 0 && (fuse_first || qfuse)) {
+            // down0/conv1 runs inside down0/conv2's launch (launch_qf / launch_tc_first below)
         } else if (l == 0) {
             const int fr = first_rows(u->cin, 1);
             const dim3 grid((W + FIRST_TW - 1) / FIRST_TW, (H + fr - 1) / fr, n);
@@ -2630,11 +2971,17 @@ int tc_run(sq_unet_s *u, bool dry, const float *in, int n, int dep, int hgt, int
             if (vol || !pool_fused[l]) sq_timer_mark(u, st, "maxpool", 0);
             SQ_TRY(conv3x3_tc(u, *c1, pooled[l], c1->cin0, nullptr, 0, t1[l], nullptr, nullptr, geo, st));
         }
-        sq_timer_mark(u, st, c1->scope.c_str(), c1->flops_per_px * px);
+        if (!qfuse) sq_timer_mark(u, st, c1->scope.c_str(), c1->flops_per_px * px);
         // the level's second conv also emits the (xy-)pooled tensor the next level starts from
         const bool fuse_pool = (l < nl - 1) && c2->cout <= 128;
         if (l < nl - 1) pool_fused[l + 1] = fuse_pool;
         bf16 *pool_dst = !fuse_pool ? nullptr : (vol ? xyp[l + 1] : pooled[l + 1]);
+        if (qfuse) {
+            SQ_TRY(launch_qf(u, *c1, *c2, in, skip[0], pool_dst, geoq, st));
+            const char *pname = u->aux_names.emplace(c1->scope, c1->scope + "+conv2").first->second.c_str();
+            sq_timer_mark(u, st, pname, (c1->flops_per_px + c2->flops_per_px) * px);
+            continue;
+        }
         if (l == 0 && quad) SQ_TRY(conv3x3_qd(u, *c2, t1[0], c2->cin0, nullptr, 0, skip[0], pool_dst, nullptr, geoq, st));
         else if (fuse_first && pool_dst) SQ_TRY(launch_tc_first(u, *c1, *c2, in, skip[l], pool_dst, geo, st));
         else SQ_TRY(conv3x3_tc(u, *c2, t1[l], c2->cin0, nullptr, 0, skip[l], pool_dst, nullptr, geo, st));

@@ -303,33 +303,41 @@ def test_random_geometries(sq, seed):
              (seed, '3d' if vol else '2d', filters, bridge, cin, k, x.shape))
 
 
-@pytest.mark.parametrize('quad', ['1', '0'])
+@pytest.mark.parametrize('mode', ['fused', 'quad', 'full'])
 @pytest.mark.parametrize('bridge,cin,k,filters,shape,n', [
-    ('concat', 1, 2, (16, 32), (70, 122), 2),            # quad image 35 x 61: ragged tiles both ways
+    ('concat', 1, 2, (16, 32), (70, 122), 2),            # quad image 35 x 61: ragged tiles both ways; W % 4 != 0
+    ('concat', 1, 2, (16, 32), (70, 124), 3),            # same, W % 4 == 0: the fused first pair applies
     ('concat', 3, 3, (16, 32, 64), (96, 72), 1),
     ('eltwise_mul', 2, 4, (16, 32, 64), (136, 48), 2),   # three 32-row tiles down the quad image
     (None, 4, 2, (16, 16), (64, 80), 1),                 # one k-step up-conv
     ('concat', 1, 2, (16, 64), (40, 200), 1),            # four k-steps into the up-conv
+    ('eltwise_add', 1, 3, (16, 32, 64), (264, 144), 2),  # several tiles per CTA column, 9 x 5 tiles per frame
 ])
-def test_quad_level0(sq, monkeypatch, quad, bridge, cin, k, filters, shape, n):
+def test_quad_level0(sq, monkeypatch, mode, bridge, cin, k, filters, shape, n):
     """Level 0 of planar nets with filters[0] = 16 runs on the quad (space-to-depth) layout by default
-    (conv_qd_kernel: first conv writes quads, 64-wide half-resolution MMAs, pool / head per accumulator
-    row); SQ_QUAD=0 keeps the full-resolution kernels.  Both against the bf16-contract oracle, and the two
-    against each other (same products, another accumulation order)."""
+    (conv_qd_kernel: 64-wide half-resolution MMAs, pool / head per accumulator row), and with one input
+    channel down0/conv1 + down0/conv2 + pool are ONE launch (conv_qf_kernel: the first conv's output stays in
+    shared memory).  SQ_QFUSE=0 keeps the two launches, SQ_QUAD=0 the full-resolution kernels.  Each against
+    the bf16-contract oracle, and against the full-resolution path (same products, another accumulation order)."""
     w = synth.unet_weights(filters, cin, k, bridge=bridge, affine=True, seed=31)
     x = synth.frames(n, shape[0], shape[1], cin, seed=9, n_objects=4)
-    monkeypatch.setenv('SQ_QUAD', quad)
+    monkeypatch.setenv('SQ_QUAD', '0' if mode == 'full' else '1')
+    monkeypatch.setenv('SQ_QFUSE', '1' if mode == 'fused' else '0')
     net = _net(filters, shape, bridge, cin, k, w)
     out = net.predict(x)
     ref = unet_c.unet_forward(x, w, filters, bridge, contract='bf16')
-    _compare(out, ref, 'SQ_QUAD=%s %s' % (quad, bridge))
-    assert net.launches() == 5 * len(filters) - 3 + (0 if bridge in ('concat', None) else len(filters) - 1)
-    if quad == '1':
+    _compare(out, ref, '%s %s' % (mode, bridge))
+    fused = mode == 'fused' and cin == 1 and shape[1] % 4 == 0
+    assert net.launches() == 5 * len(filters) - 3 + (0 if bridge in ('concat', None) else len(filters) - 1) - (1 if fused else 0)
+    if mode != 'full':
         monkeypatch.setenv('SQ_QUAD', '0')
         other = net.predict(x)
         tol = 0.02 * float(ref['logits'].max() - ref['logits'].min())
         assert np.abs(out['logits'] - other['logits']).max() <= tol
         assert (out['mask'] != other['mask']).mean() <= 5e-3
+        again = net.predict(x[:1])                                     # batch-independent, deterministic
+        monkeypatch.setenv('SQ_QUAD', '1')
+        np.testing.assert_array_equal(net.predict(x[:1])['logits'], out['logits'][:1])
 
 
 def test_cluster_multicast_variant(sq, monkeypatch):
