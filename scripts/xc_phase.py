@@ -1,6 +1,6 @@
 """Diagnostics: per-role wait/work clocks of the x-combined conv kernels (SQ_XC_PHASE=1)."""
 import os, sys
-os.environ['SQ_XC_PHASE'] = '1'
+os.environ.setdefault('SQ_XC_PHASE', '1')
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from sequitr_b200 import synth

@@ -1585,19 +1585,32 @@ struct QF {
     static_assert(OFF_A1 % 128 == 0 && OFF_RAW % 128 == 0 && OFF_P % 128 == 0 && P_BYTES % 128 == 0, "alignment");
 };
 
+// the two layers' folded epilogues, passed BY VALUE: the epilogue warps read them as constant-bank operands of
+// their FFMAs (shared-memory loads queue behind the tensor core's operand fetches while MMAs are running)
+struct QfEpi {
+    float sc1[16], sh1[16], sc2[16], sh2[16];
+};
+
 __global__ void __launch_bounds__(QF::THREADS, 1)
-conv_qf_kernel(const __grid_constant__ CUtensorMap mapIn, const bf16 *__restrict__ wts,
-               const float *__restrict__ scale1, const float *__restrict__ shift1,
-               const float *__restrict__ scale2, const float *__restrict__ shift2,
-               bf16 *__restrict__ out, bf16 *__restrict__ out_pool, int nimg, int H, int W)
+conv_qf_kernel(const __grid_constant__ CUtensorMap mapIn, const bf16 *__restrict__ wts, const QfEpi ep,
+               bf16 *__restrict__ out, bf16 *__restrict__ out_pool, int nimg, int H, int W, long long *phase_dbg)
 {
+#ifdef SQ_XC_PHASE_DIAG
+#define QF_W(i, stmt) do { const long long t_ = phase_dbg ? clock64() : 0; stmt; if (phase_dbg) dacc[i] += clock64() - t_; } while (0)
+#define QF_T0() const long long t0_ = phase_dbg ? clock64() : 0
+#define QF_T1(i) if (phase_dbg) dacc[i] += clock64() - t0_
+    long long dacc[6] = {0, 0, 0, 0, 0, 0};
+#else
+#define QF_W(i, stmt) do { stmt; } while (0)
+#define QF_T0() do { } while (0)
+#define QF_T1(i) do { } while (0)
+#endif
     // H, W: the quad image.  wts: B1 then W2 (QF::B1_BYTES + QF::W2_BYTES), scale / shift: the layers' own 16.
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
     __shared__ uint64_t w_bar, raw_full[2], raw_empty[2], a1_full[2], a1_empty[2], acc1_full, acc1_empty,
         p_full[2], p_empty[2], acc2_full[2], acc2_empty[2];
     __shared__ uint32_t tmem_base_sh;
-    __shared__ __align__(16) float s_sc1[16], s_sh1[16];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_x = (W + 7) >> 3, tiles_y = (H + QF::TH - 1) / QF::TH;
@@ -1617,7 +1630,6 @@ conv_qf_kernel(const __grid_constant__ CUtensorMap mapIn, const bf16 *__restrict
         tc::tma_prefetch_desc(&mapIn);
     }
     if (warp == 1) { tc::tmem_alloc(&tmem_base_sh, 512); tc::tmem_relinquish(); }
-    if (threadIdx.x < 16) { s_sc1[threadIdx.x] = scale1[threadIdx.x]; s_sh1[threadIdx.x] = shift1[threadIdx.x]; }
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
@@ -1635,7 +1647,7 @@ conv_qf_kernel(const __grid_constant__ CUtensorMap mapIn, const bf16 *__restrict
             for (int it = 0; it < nt; ++it) {
                 const int t = blockIdx.x + it * gridDim.x, b = it & 1;
                 const int tx = t % tiles_x, ty = (t / tiles_x) % tiles_y, n = t / (tiles_x * tiles_y);
-                tc::mbar_wait(&raw_empty[b], ((it >> 1) & 1) ^ 1);
+                QF_W(0, tc::mbar_wait(&raw_empty[b], ((it >> 1) & 1) ^ 1));
                 tc::mbar_arrive_expect_tx(&raw_full[b], QF::RAW_W * QF::RAW_H * 4);
                 // frame pixels (16 tx - 3 ..., 64 ty - 3 ...): the 4 x 4 windows of quad pixels (8 tx - 1 ..., 32 ty - 1 ...);
                 // the box starts at column 16 tx - 4 so that every row of it is 16-byte aligned in global memory
@@ -1654,8 +1666,8 @@ conv_qf_kernel(const __grid_constant__ CUtensorMap mapIn, const bf16 *__restrict
         for (int it = 0; it <= nt; ++it) {
             if (it < nt) {
                 const int b = it & 1;
-                tc::mbar_wait(&a1_full[b], (it >> 1) & 1);
-                tc::mbar_wait(&acc1_empty, (it & 1) ^ 1);
+                QF_W(0, tc::mbar_wait(&a1_full[b], (it >> 1) & 1));
+                QF_W(1, tc::mbar_wait(&acc1_empty, (it & 1) ^ 1));
                 tc::tc_fence_after();
                 if (tc::elect_one()) {
                     const uint32_t a1_lo = (((sbase + QF::OFF_A1 + b * QF::A1_BYTES) >> 4) & 0x3FFFu) |
@@ -1670,8 +1682,8 @@ conv_qf_kernel(const __grid_constant__ CUtensorMap mapIn, const bf16 *__restrict
             }
             if (it >= 1) {
                 const int j2 = it - 1, b = j2 & 1;
-                tc::mbar_wait(&p_full[b], (j2 >> 1) & 1);
-                tc::mbar_wait(&acc2_empty[b], ((j2 >> 1) & 1) ^ 1);
+                QF_W(2, tc::mbar_wait(&p_full[b], (j2 >> 1) & 1));
+                QF_W(3, tc::mbar_wait(&acc2_empty[b], ((j2 >> 1) & 1) ^ 1));
                 tc::tc_fence_after();
                 if (tc::elect_one()) {
                     const uint32_t p_lo = (((sbase + QF::OFF_P + b * QF::P_BYTES) >> 4) & 0x3FFFu) |
@@ -1707,8 +1719,8 @@ conv_qf_kernel(const __grid_constant__ CUtensorMap mapIn, const bf16 *__restrict
         }
         for (int it = 0; it < nt; ++it) {
             const int b = it & 1;
-            tc::mbar_wait(&raw_full[b], (it >> 1) & 1);
-            tc::mbar_wait(&a1_empty[b], ((it >> 1) & 1) ^ 1);
+            QF_W(0, tc::mbar_wait(&raw_full[b], (it >> 1) & 1));
+            QF_W(1, tc::mbar_wait(&a1_empty[b], ((it >> 1) & 1) ^ 1));
             const float *raw = reinterpret_cast<const float *>(smem + QF::OFF_RAW + b * QF::RAW_BYTES);
             uint8_t *a1 = smem + QF::OFF_A1 + b * QF::A1_BYTES;
 #pragma unroll
@@ -1745,59 +1757,73 @@ conv_qf_kernel(const __grid_constant__ CUtensorMap mapIn, const bf16 *__restrict
         const int j2 = g >> 1, c8 = g & 1;
         float sc2[8], sh2[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) { sc2[e] = scale2[c8 * 8 + e]; sh2[e] = shift2[c8 * 8 + e]; }
+        for (int e = 0; e < 8; ++e) { sc2[e] = c8 ? ep.sc2[8 + e] : ep.sc2[e]; sh2[e] = c8 ? ep.sh2[8 + e] : ep.sh2[e]; }
         const size_t plane = (size_t)H * W * 8;
+        const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.0f, 0.0f);
+        // tile coordinates advance incrementally (no division in the loop); (tx, ty, n): the tile of epilogue 1,
+        // (tx2, ty2, n2): the tile of epilogue 2 (one iteration behind)
+        const int tpi = tiles_x * tiles_y, gstep = (int)gridDim.x;
+        int tx = (int)blockIdx.x % tiles_x, ty = ((int)blockIdx.x / tiles_x) % tiles_y, n = (int)blockIdx.x / tpi;
+        const int dtx = gstep % tiles_x, dty = (gstep / tiles_x) % tiles_y, dn = gstep / tpi;
+        int tx2 = 0, ty2 = 0, n2 = 0;
         for (int it = 0; it <= nt; ++it) {
             if (it < nt) {
                 // ---- epilogue 1: conv1's accumulators -> the bf16 halo patch of conv2
-                const int t = blockIdx.x + it * gridDim.x, b = it & 1;
-                const int tx = t % tiles_x, ty = (t / tiles_x) % tiles_y;
+                const int b = it & 1;
                 const int x0 = tx * 8 - 1, y0 = ty * QF::TH - 1;
-                tc::mbar_wait(&acc1_full, it & 1);
-                tc::mbar_wait(&p_empty[b], ((it >> 1) & 1) ^ 1);
+                QF_W(0, tc::mbar_wait(&acc1_full, it & 1));
+                QF_W(1, tc::mbar_wait(&p_empty[b], ((it >> 1) & 1) ^ 1));
                 tc::tc_fence_after();
-                uint8_t *P = smem + QF::OFF_P + b * QF::P_BYTES + (2 * g) * (QF::PROWS * 16);
+                QF_T0();
+                uint8_t *P = smem + QF::OFF_P + b * QF::P_BYTES + (2 * g) * (QF::PROWS * 16) + r * 16;
+                // tiles that touch the frame border zero the patch pixels outside the frame (warp-uniform test)
+                const bool border = x0 < 0 || y0 < 0 || x0 + QF::PW > W || y0 + QF::PH > H;
+                uint32_t v[3][16];
+                tc::tmem_ld16(tmem_base + lane_addr + ACC1 + g * 16, v[0]);
+                tc::tmem_ld16(tmem_base + lane_addr + ACC1 + 64 + g * 16, v[1]);
+                if (q4 != 3) tc::tmem_ld16(tmem_base + lane_addr + ACC1 + 128 + g * 16, v[2]);   // rows 352.. lie beyond the patch
+                tc::tmem_ld_wait();
 #pragma unroll
                 for (int m = 0; m < 3; ++m) {
-                    if (m == 2 && q4 == 3) continue;         // rows 352.. lie beyond the patch (warp-uniform)
-                    uint32_t v[16];
-                    tc::tmem_ld16(tmem_base + lane_addr + ACC1 + m * 64 + g * 16, v);
-                    tc::tmem_ld_wait();
-                    const int Y = y0 + ppy[m], X = x0 + ppx[m];
-                    const bool inside = Y >= 0 && Y < H && X >= 0 && X < W;
+                    if (m == 2 && q4 == 3) continue;
                     uint32_t o[8];
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const float4 sc = *reinterpret_cast<const float4 *>(s_sc1 + 4 * q);
-                        const float4 sh = *reinterpret_cast<const float4 *>(s_sh1 + 4 * q);
-                        o[2 * q] = pack_bf16(fmaxf(fmaf(__uint_as_float(v[4 * q]), sc.x, sh.x), 0.0f),
-                                             fmaxf(fmaf(__uint_as_float(v[4 * q + 1]), sc.y, sh.y), 0.0f));
-                        o[2 * q + 1] = pack_bf16(fmaxf(fmaf(__uint_as_float(v[4 * q + 2]), sc.z, sh.z), 0.0f),
-                                                 fmaxf(fmaf(__uint_as_float(v[4 * q + 3]), sc.w, sh.w), 0.0f));
+                    for (int q = 0; q < 8; ++q) {        // scale / shift: constant-bank operands (kernel parameters), no LDS
+                        __nv_bfloat162 h = __hmax2(__floats2bfloat162_rn(fmaf(__uint_as_float(v[m][2 * q]), ep.sc1[2 * q], ep.sh1[2 * q]),
+                                                                         fmaf(__uint_as_float(v[m][2 * q + 1]), ep.sc1[2 * q + 1], ep.sh1[2 * q + 1])),
+                                                   zero2);      // ReLU after the rounding (max commutes with it)
+                        o[q] = *reinterpret_cast<uint32_t *>(&h);
                     }
-                    if (!inside) {
+                    if (border) {
+                        const int Y = y0 + ppy[m], X = x0 + ppx[m];
+                        if (!(Y >= 0 && Y < H && X >= 0 && X < W)) {
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) o[e] = 0u;
+                            for (int e = 0; e < 8; ++e) o[e] = 0u;
+                        }
                     }
-                    const int p = m * 128 + r;
-                    if (p < QF::PROWS) {
-                        *reinterpret_cast<uint4 *>(P + p * 16) = make_uint4(o[0], o[1], o[2], o[3]);
-                        *reinterpret_cast<uint4 *>(P + QF::PROWS * 16 + p * 16) = make_uint4(o[4], o[5], o[6], o[7]);
+                    if (m < 2 || r < QF::PROWS - 256) {
+                        *reinterpret_cast<uint4 *>(P + m * 2048) = make_uint4(o[0], o[1], o[2], o[3]);
+                        *reinterpret_cast<uint4 *>(P + QF::PROWS * 16 + m * 2048) = make_uint4(o[4], o[5], o[6], o[7]);
                     }
                 }
                 tc::fence_proxy_async();                     // generic-proxy writes -> visible to the UMMA reads
                 tc::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) { tc::mbar_arrive(&p_full[b]); tc::mbar_arrive(&acc1_empty); }
+                QF_T1(3);
             }
             if (it >= 1) {
                 // ---- epilogue 2: conv2's accumulators -> quad tensor + pooled tensor
-                const int i2 = it - 1, t = blockIdx.x + i2 * gridDim.x, b = i2 & 1;
-                const int tx = t % tiles_x, ty = (t / tiles_x) % tiles_y, n = t / (tiles_x * tiles_y);
-                const int y = ty * QF::TH + j2 * 16 + (r >> 3), x = tx * 8 + (r & 7);
+                const int i2 = it - 1, b = i2 & 1;
+                const int y = ty2 * QF::TH + j2 * 16 + (r >> 3), x = tx2 * 8 + (r & 7);
+#ifdef SQ_XC_PHASE_DIAG
+                const bool valid = (y < H) && (x < W) && !(phase_dbg && phase_dbg[gridDim.x * 32] == 2);   // experiment: no stores
+#else
                 const bool valid = (y < H) && (x < W);
-                tc::mbar_wait(&acc2_full[b], (i2 >> 1) & 1);
+#endif
+                QF_W(2, tc::mbar_wait(&acc2_full[b], (i2 >> 1) & 1));
                 tc::tc_fence_after();
+                QF_T0();
                 uint32_t v[32];
                 tc::tmem_ld32(tmem_base + lane_addr + ACC2 + b * 128 + j2 * 64 + c8 * 32, v);
                 tc::tmem_ld_wait();
@@ -1805,24 +1831,44 @@ conv_qf_kernel(const __grid_constant__ CUtensorMap mapIn, const bf16 *__restrict
                 __syncwarp();
                 if (lane == 0) tc::mbar_arrive(&acc2_empty[b]);          // the accumulators are in registers
                 uint32_t mx[4];
-                bf16 *po = out + ((((size_t)n * 8 + c8) * H + y) * W + x) * 8;
+                bf16 *po = out + ((((size_t)n2 * 8 + c8) * H + y) * W + x) * 8;
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     uint32_t o[4];
 #pragma unroll
-                    for (int e = 0; e < 4; ++e)
-                        o[e] = pack_bf16(fmaxf(fmaf(__uint_as_float(v[q * 8 + 2 * e]), sc2[2 * e], sh2[2 * e]), 0.0f),
-                                         fmaxf(fmaf(__uint_as_float(v[q * 8 + 2 * e + 1]), sc2[2 * e + 1], sh2[2 * e + 1]), 0.0f));
+                    for (int e = 0; e < 4; ++e) {
+                        __nv_bfloat162 h = __hmax2(__floats2bfloat162_rn(fmaf(__uint_as_float(v[q * 8 + 2 * e]), sc2[2 * e], sh2[2 * e]),
+                                                                         fmaf(__uint_as_float(v[q * 8 + 2 * e + 1]), sc2[2 * e + 1], sh2[2 * e + 1])),
+                                                   zero2);
+                        o[e] = *reinterpret_cast<uint32_t *>(&h);
+                    }
                     if (valid) *reinterpret_cast<uint4 *>(po + (size_t)(2 * q) * plane) = make_uint4(o[0], o[1], o[2], o[3]);
 #pragma unroll
                     for (int e = 0; e < 4; ++e) mx[e] = (q == 0) ? o[e] : bf162_max(mx[e], o[e]);
                 }
                 if (valid)
-                    *reinterpret_cast<uint4 *>(out_pool + ((((size_t)n * 2 + c8) * H + y) * W + x) * 8) =
+                    *reinterpret_cast<uint4 *>(out_pool + ((((size_t)n2 * 2 + c8) * H + y) * W + x) * 8) =
                         make_uint4(mx[0], mx[1], mx[2], mx[3]);
+                QF_T1(4);
             }
+            tx2 = tx; ty2 = ty; n2 = n;
+            tx += dtx;
+            if (tx >= tiles_x) { tx -= tiles_x; ++ty; }
+            ty += dty;
+            if (ty >= tiles_y) { ty -= tiles_y; ++n; }
+            n += dn;
         }
     }
+#ifdef SQ_XC_PHASE_DIAG
+    // per role (producer, MMA, first builder warp, first epilogue warp): clocks spent in each wait
+    if (phase_dbg && lane == 0 && (warp <= 2 || warp == 2 + QF::BLD_WARPS)) {
+        const int role = warp <= 2 ? warp : 3;
+        for (int i = 0; i < 6; ++i) phase_dbg[(blockIdx.x * 4 + role) * 8 + i] = dacc[i];
+    }
+#endif
+#undef QF_W
+#undef QF_T0
+#undef QF_T1
     tc::tc_fence_before();
     __syncthreads();
     if (warp == 1) {
@@ -2645,10 +2691,43 @@ int launch_qf(sq_unet_s *u, const SqLayer &L1, const SqLayer &L2, const float *i
     }
     const int tiles = g.nimg * ((g.W + 7) / 8) * ((g.H + QF::TH - 1) / QF::TH);
     const int grid = std::min(tiles, u->h->sm_count / grid_div());
-    conv_qf_kernel<<<grid, QF::THREADS, smem, st>>>(m, (const bf16 *)L2.w_qf, L1.scale, L1.shift, L2.scale, L2.shift, out,
-                                                   out_pool, g.nimg, g.H, g.W);
+    long long *phase_dbg = nullptr;
+#ifdef SQ_XC_PHASE_DIAG
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (getenv("SQ_XC_PHASE")) {
+        SQ_CUDA(cudaMalloc(&phase_dbg, ((size_t)grid * 32 + 1) * sizeof(long long)));
+        SQ_CUDA(cudaMemset(phase_dbg, 0, ((size_t)grid * 32 + 1) * sizeof(long long)));
+        const long long flag = atoi(getenv("SQ_XC_PHASE"));            // 2: experiment without the epilogue-2 stores
+        SQ_CUDA(cudaMemcpy(phase_dbg + (size_t)grid * 32, &flag, sizeof flag, cudaMemcpyHostToDevice));
+        cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, st);
+    }
+#endif
+    QfEpi ep;
+    {
+        const std::vector<float> &s1 = u->host[L1.scope + "/_scale"].data, &t1 = u->host[L1.scope + "/_shift"].data;
+        const std::vector<float> &s2 = u->host[L2.scope + "/_scale"].data, &t2 = u->host[L2.scope + "/_shift"].data;
+        for (int i = 0; i < 16; ++i) { ep.sc1[i] = s1[i]; ep.sh1[i] = t1[i]; ep.sc2[i] = s2[i]; ep.sh2[i] = t2[i]; }
+    }
+    conv_qf_kernel<<<grid, QF::THREADS, smem, st>>>(m, (const bf16 *)L2.w_qf, ep, out, out_pool, g.nimg, g.H, g.W, phase_dbg);
     ++u->last_launches;
     SQ_CHECK_LAUNCH();
+#ifdef SQ_XC_PHASE_DIAG
+    if (phase_dbg) {
+        cudaEventRecord(e1, st);
+        SQ_CUDA(cudaStreamSynchronize(st));
+        float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+        std::vector<long long> h((size_t)grid * 32);
+        SQ_CUDA(cudaMemcpy(h.data(), phase_dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+        SQ_CUDA(cudaFree(phase_dbg));
+        double a[32] = {0};
+        for (int b2 = 0; b2 < grid; ++b2) for (int i = 0; i < 32; ++i) a[i] += (double)h[(size_t)b2 * 32 + i] / grid;
+        const double tpc = (double)tiles / grid;
+        fprintf(stderr, "qf_phase %.3f ms, tiles/CTA=%.0f (%.0f clk/tile at 1.965 GHz) | per tile clk: producer wait raw_empty %.0f | mma wait a1_full %.0f "
+                "acc1_empty %.0f p_full %.0f acc2_empty %.0f | builders wait raw_full %.0f a1_empty %.0f | epilogue wait acc1_full %.0f "
+                "p_empty %.0f acc2_full %.0f; work: epilogue 1 %.0f, epilogue 2 %.0f\n", ms, tpc, ms * 1.965e6 / tpc, a[0] / tpc, a[8] / tpc, a[9] / tpc, a[10] / tpc, a[11] / tpc,
+                a[16] / tpc, a[17] / tpc, a[24] / tpc, a[25] / tpc, a[26] / tpc, a[27] / tpc, a[28] / tpc);
+    }
+#endif
     return SQ_OK;
 }
 
