@@ -24,6 +24,7 @@ struct SqLayer {
     // level-0 layers on the quad (space-to-depth) layout (conv_qd_kernel): weights re-laid-out as a 64-wide
     // half-resolution conv, scale / shift repeated for the four output parities
     void *w_qd = nullptr;
+    void *w_qu = nullptr;         // up0/conv1 only: quad weights with permuted output columns (conv_qu_kernel)
     void *w_qf = nullptr;         // down0/conv2 only: first conv's B matrix + conv2 with permuted output columns (conv_qf_kernel)
     float *scale_q = nullptr, *shift_q = nullptr;
 };

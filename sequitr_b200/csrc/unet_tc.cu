@@ -355,12 +355,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         const int ph = r >> 3, pw = r & 7;
         const uint32_t lane_addr = (uint32_t)(q4 * 32) << 16;
         const int CBo = COUT / 8;
+        const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.0f, 0.0f);
+        // tile coordinates advance incrementally (no division in the loop)
+        const int tpi = tiles_x * tiles_y, gstep = (int)gridDim.x;
+        int tx = (int)blockIdx.x % tiles_x, ty = ((int)blockIdx.x / tiles_x) % tiles_y, np = (int)blockIdx.x / tpi;
+        const int dtx = gstep % tiles_x, dty = (gstep / tiles_x) % tiles_y, dnp = gstep / tpi;
         int it = 0;
-        for (int t = blockIdx.x; CL ? (it < iters) : (t < ntiles); t += gridDim.x, ++it) {
+        for (int t = blockIdx.x; CL ? (it < iters) : (t < ntiles); t += gridDim.x, ++it,
+                 tx += dtx, ty += dty + (tx >= tiles_x ? 1 : 0), tx -= (tx >= tiles_x ? tiles_x : 0),
+                 np += dnp + (ty >= tiles_y ? 1 : 0), ty -= (ty >= tiles_y ? tiles_y : 0)) {
             const int buf = it % NBUF;
             const bool live = !CL || t < ntiles;
-            const int tx = t % tiles_x, ty = (t / tiles_x) % tiles_y;
-            const int n = (t / (tiles_x * tiles_y)) * out_mul + out_off;   // output "image" (n*D + z)
+            const int n = np * out_mul + out_off;                          // output "image" (n*D + z)
             tc::mbar_wait(&tfull_bar[buf], (it / NBUF) & 1);
             tc::tc_fence_after();
             if (EPI == EPI_POOL) {
@@ -415,6 +421,46 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                         }
                     }
                 }
+            } else if (!UP && EPI == EPI_STORE) {
+                // work items (sub-tile j, 16-channel chunk c16), two per round trip: both TMEM loads in flight
+                // before the single wait; ReLU on the packed bf16 pair (max commutes with the monotone rounding)
+                constexpr int NC16 = COUT / 16, NI = S * NC16;
+                static_assert(UP || EPI != EPI_STORE || NI % (2 * EPI_GROUPS) == 0, "items come in pairs per group");
+                const int x = tx * 8 + pw;
+                const size_t plane = (size_t)H * W * 8;
+#pragma unroll 1
+                for (int i0 = half; i0 < NI; i0 += 2 * EPI_GROUPS) {
+                    uint32_t v[2][16];
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const int i = i0 + u * EPI_GROUPS, j = i / NC16, c16 = i % NC16;
+                        tc::tmem_ld16(tmem_base + lane_addr + buf * C::ACC_COLS + j * COUT + c16 * 16, v[u]);
+                    }
+                    tc::tmem_ld_wait();
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const int i = i0 + u * EPI_GROUPS, j = i / NC16, c16 = i % NC16;
+                        const int y = ty * C::TH + (C::ILV ? 32 * (j / 2) + 2 * ph + (j & 1) : j * 16 + ph);
+                        uint32_t o[8];
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            const float4 sc = *reinterpret_cast<const float4 *>(s_scale + c16 * 16 + 4 * g);
+                            const float4 sh = *reinterpret_cast<const float4 *>(s_shift + c16 * 16 + 4 * g);
+                            __nv_bfloat162 p0 = __floats2bfloat162_rn(fmaf(__uint_as_float(v[u][4 * g]), sc.x, sh.x),
+                                                                      fmaf(__uint_as_float(v[u][4 * g + 1]), sc.y, sh.y));
+                            __nv_bfloat162 p1 = __floats2bfloat162_rn(fmaf(__uint_as_float(v[u][4 * g + 2]), sc.z, sh.z),
+                                                                      fmaf(__uint_as_float(v[u][4 * g + 3]), sc.w, sh.w));
+                            if (relu) { p0 = __hmax2(p0, zero2); p1 = __hmax2(p1, zero2); }
+                            o[2 * g] = *reinterpret_cast<uint32_t *>(&p0);
+                            o[2 * g + 1] = *reinterpret_cast<uint32_t *>(&p1);
+                        }
+                        if (live && (y < H) && (x < W)) {
+                            bf16 *p = out + ((((size_t)n * CBo + c16 * 2) * H + y) * W + x) * 8;
+                            *reinterpret_cast<uint4 *>(p) = make_uint4(o[0], o[1], o[2], o[3]);
+                            *reinterpret_cast<uint4 *>(p + plane) = make_uint4(o[4], o[5], o[6], o[7]);
+                        }
+                    }
+                }
             } else
 #pragma unroll 1
             for (int j = 0; j < S; ++j) {
@@ -422,60 +468,46 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 const int x = tx * 8 + pw;
                 const bool valid = live && (y < H) && (x < W);
                 if (!UP) {
-                    float hl[HK > 0 ? HK : 1];                     // fused head: running logits
+                    // fused head (EPI_HEAD): the activation is consumed as it would have been stored (bf16)
+                    if ((j % EPI_GROUPS) != half) continue;
+                    constexpr int NC16 = COUT / 16;
+                    float hl[HK > 0 ? HK : 1];                     // running logits
 #pragma unroll
                     for (int k = 0; k < HK; ++k) hl[k] = 0.0f;
-#pragma unroll 1
-                    for (int c16 = 0; c16 < COUT / 16; ++c16) {
-                        if (EPI == EPI_HEAD ? ((j % EPI_GROUPS) != half)
-                                            : (((j * (COUT / 16) + c16) % EPI_GROUPS) != half)) continue;
-                        uint32_t v[16];
-                        tc::tmem_ld16(tmem_base + lane_addr + buf * C::ACC_COLS + j * COUT + c16 * 16, v);
-                        tc::tmem_ld_wait();
-                        uint32_t o[8];
+                    uint32_t v[NC16][16];
+#pragma unroll
+                    for (int c16 = 0; c16 < NC16; ++c16)
+                        tc::tmem_ld16(tmem_base + lane_addr + buf * C::ACC_COLS + j * COUT + c16 * 16, v[c16]);
+                    tc::tmem_ld_wait();
+#pragma unroll
+                    for (int c16 = 0; c16 < NC16; ++c16) {
+                        float f[16];
 #pragma unroll
                         for (int g = 0; g < 4; ++g) {
                             const float4 sc = *reinterpret_cast<const float4 *>(s_scale + c16 * 16 + 4 * g);
                             const float4 sh = *reinterpret_cast<const float4 *>(s_shift + c16 * 16 + 4 * g);
-                            float a = fmaf(__uint_as_float(v[4 * g]), sc.x, sh.x);
-                            float b = fmaf(__uint_as_float(v[4 * g + 1]), sc.y, sh.y);
-                            float c = fmaf(__uint_as_float(v[4 * g + 2]), sc.z, sh.z);
-                            float d = fmaf(__uint_as_float(v[4 * g + 3]), sc.w, sh.w);
-                            if (relu) { a = fmaxf(a, 0.0f); b = fmaxf(b, 0.0f); c = fmaxf(c, 0.0f); d = fmaxf(d, 0.0f); }
-                            o[2 * g] = pack_bf16(a, b);
-                            o[2 * g + 1] = pack_bf16(c, d);
+                            __nv_bfloat162 p0 = __floats2bfloat162_rn(fmaf(__uint_as_float(v[c16][4 * g]), sc.x, sh.x),
+                                                                      fmaf(__uint_as_float(v[c16][4 * g + 1]), sc.y, sh.y));
+                            __nv_bfloat162 p1 = __floats2bfloat162_rn(fmaf(__uint_as_float(v[c16][4 * g + 2]), sc.z, sh.z),
+                                                                      fmaf(__uint_as_float(v[c16][4 * g + 3]), sc.w, sh.w));
+                            if (relu) { p0 = __hmax2(p0, zero2); p1 = __hmax2(p1, zero2); }
+                            const float2 t0 = __bfloat1622float2(p0), t1 = __bfloat1622float2(p1);
+                            f[4 * g] = t0.x; f[4 * g + 1] = t0.y; f[4 * g + 2] = t1.x; f[4 * g + 3] = t1.y;
                         }
-                        if constexpr (EPI == EPI_HEAD) {
-                            // the head consumes the activation as it would have been stored (bf16)
-                            float f[16];
 #pragma unroll
-                            for (int e = 0; e < 8; ++e) {
-                                const float2 t2 = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162 *>(&o[e]));
-                                f[2 * e] = t2.x;
-                                f[2 * e + 1] = t2.y;
-                            }
+                        for (int k = 0; k < HK; ++k) {
+                            const float4 *wk = reinterpret_cast<const float4 *>(s_head + k * COUT + c16 * 16);
 #pragma unroll
-                            for (int k = 0; k < HK; ++k) {
-                                const float4 *wk = reinterpret_cast<const float4 *>(s_head + k * COUT + c16 * 16);
-#pragma unroll
-                                for (int g = 0; g < 4; ++g) {
-                                    const float4 w4 = wk[g];
-                                    hl[k] = fmaf(f[4 * g], w4.x, hl[k]);
-                                    hl[k] = fmaf(f[4 * g + 1], w4.y, hl[k]);
-                                    hl[k] = fmaf(f[4 * g + 2], w4.z, hl[k]);
-                                    hl[k] = fmaf(f[4 * g + 3], w4.w, hl[k]);
-                                }
+                            for (int g = 0; g < 4; ++g) {
+                                const float4 w4 = wk[g];
+                                hl[k] = fmaf(f[4 * g], w4.x, hl[k]);
+                                hl[k] = fmaf(f[4 * g + 1], w4.y, hl[k]);
+                                hl[k] = fmaf(f[4 * g + 2], w4.z, hl[k]);
+                                hl[k] = fmaf(f[4 * g + 3], w4.w, hl[k]);
                             }
-                        } else {
-                            if (valid) {
-                                bf16 *p = out + ((((size_t)n * CBo + c16 * 2) * H + y) * W + x) * 8;
-                                *reinterpret_cast<uint4 *>(p) = make_uint4(o[0], o[1], o[2], o[3]);
-                                *reinterpret_cast<uint4 *>(p + (size_t)H * W * 8) = make_uint4(o[4], o[5], o[6], o[7]);
-                            }
-
                         }
                     }
-                    if (EPI == EPI_HEAD && (j % EPI_GROUPS) == half) {
+                    {
                         const size_t p = ((size_t)n * H + y) * W + x;
                         int best = 0;
                         float m = -INFINITY;
@@ -1430,55 +1462,72 @@ conv_qd_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
 #endif
     } else {
         // ========================================================= epilogue
+        // Work items are (sub-tile j, 16-column group c16), taken two at a time: both TMEM loads in flight before the
+        // single wait; ReLU on the packed bf16 pairs; tile coordinates advance incrementally (no division).
         const int q4 = warp & 3, half = (warp - 2) >> 2;
         const int r = q4 * 32 + lane, ph = r >> 3, pw = r & 7;
         const uint32_t lane_addr = (uint32_t)(q4 * 32) << 16;
         const size_t plane = (size_t)H * W * 8;
+        const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.0f, 0.0f);
+        const int tpi = tiles_x * tiles_y, gstep = (int)gridDim.x;
+        int tx = (int)blockIdx.x % tiles_x, ty = ((int)blockIdx.x / tiles_x) % tiles_y, n = (int)blockIdx.x / tpi;
+        const int dtx = gstep % tiles_x, dty = (gstep / tiles_x) % tiles_y, dn = gstep / tpi;
+        // convert one 16-column group: scale / shift (+ ReLU) -> 8 packed bf16 pairs
+        auto convert = [&](const uint32_t *v, int c16, uint32_t *o) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const float4 sc = *reinterpret_cast<const float4 *>(s_scale + c16 * 16 + 4 * g);
+                const float4 sh = *reinterpret_cast<const float4 *>(s_shift + c16 * 16 + 4 * g);
+                __nv_bfloat162 p0 = __floats2bfloat162_rn(fmaf(__uint_as_float(v[4 * g]), sc.x, sh.x),
+                                                          fmaf(__uint_as_float(v[4 * g + 1]), sc.y, sh.y));
+                __nv_bfloat162 p1 = __floats2bfloat162_rn(fmaf(__uint_as_float(v[4 * g + 2]), sc.z, sh.z),
+                                                          fmaf(__uint_as_float(v[4 * g + 3]), sc.w, sh.w));
+                if (relu) { p0 = __hmax2(p0, zero2); p1 = __hmax2(p1, zero2); }
+                o[2 * g] = *reinterpret_cast<uint32_t *>(&p0);
+                o[2 * g + 1] = *reinterpret_cast<uint32_t *>(&p1);
+            }
+        };
         int it = 0;
         for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
             const int buf = it % NBUF;
-            const int tx = t % tiles_x, ty = (t / tiles_x) % tiles_y, n = t / (tiles_x * tiles_y);
             const int x = tx * 8 + pw;
             { QD_T0(); tc::mbar_wait(&tfull_bar[buf], (it / NBUF) & 1); QD_ACC(d_wait0); }
             tc::tc_fence_after();
             QD_T0();
             const uint32_t tbase = tmem_base + lane_addr + buf * C::ACC_COLS;
+            uint32_t mx[8];                          // POOL: running max over the four parities
+            // this group's pairs of items: STORE (j, c16) with (4j + c16) % 2 == half in order; POOL all four groups
+            // of sub-tile j (j % 2 == half); HEAD the two column parities of row parity `half`, every sub-tile
 #pragma unroll 1
-            for (int j = 0; j < S; ++j) {
+            for (int i = 0; i < S; ++i) {
+                int j, ca, cb;
+                if (EPI == EPI_STORE) { j = i; ca = half; cb = half + 2; }
+                else if (EPI == EPI_POOL) { j = 2 * (i >> 1) + half; ca = 2 * (i & 1); cb = ca + 1; }
+                else { j = i; ca = 2 * half; cb = ca + 1; }
                 const int y = ty * C::TH + j * 16 + ph;
                 const bool valid = (y < H) && (x < W);
-                if (EPI == EPI_POOL && (j % EPI_GROUPS) != half) continue;
-                uint32_t mx[8];
-#pragma unroll 1
-                for (int c16 = 0; c16 < 4; ++c16) {
-                    if (EPI == EPI_STORE && ((j * 4 + c16) % EPI_GROUPS) != half) continue;
-                    if (EPI == EPI_HEAD && (c16 >> 1) != half) continue;
-                    uint32_t v[16];
-                    tc::tmem_ld16(tbase + j * COUT + c16 * 16, v);
-                    tc::tmem_ld_wait();
-                    uint32_t o[8];
+                uint32_t va[16], vb[16];
+                tc::tmem_ld16(tbase + j * COUT + ca * 16, va);
+                tc::tmem_ld16(tbase + j * COUT + cb * 16, vb);
+                tc::tmem_ld_wait();
+                uint32_t oa[8], ob[8];
+                convert(va, ca, oa);
+                convert(vb, cb, ob);
+                if constexpr (EPI == EPI_HEAD) {
+                    // the head consumes the activation as it would have been stored (bf16); 16-column group c16 is
+                    // level-0 pixel (2y + oy, 2x + ox), (oy, ox) = (c16 >> 1, c16 & 1): ca / cb are ox = 0 / 1 of row `half`
+                    int best[2];
+                    const size_t p0 = ((size_t)n * (2 * H) + 2 * y + half) * (size_t)(2 * W) + 2 * x;
 #pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        const float4 sc = *reinterpret_cast<const float4 *>(s_scale + c16 * 16 + 4 * g);
-                        const float4 sh = *reinterpret_cast<const float4 *>(s_shift + c16 * 16 + 4 * g);
-                        float a = fmaf(__uint_as_float(v[4 * g]), sc.x, sh.x);
-                        float b = fmaf(__uint_as_float(v[4 * g + 1]), sc.y, sh.y);
-                        float c = fmaf(__uint_as_float(v[4 * g + 2]), sc.z, sh.z);
-                        float d = fmaf(__uint_as_float(v[4 * g + 3]), sc.w, sh.w);
-                        if (relu) { a = fmaxf(a, 0.0f); b = fmaxf(b, 0.0f); c = fmaxf(c, 0.0f); d = fmaxf(d, 0.0f); }
-                        o[2 * g] = pack_bf16(a, b);
-                        o[2 * g + 1] = pack_bf16(c, d);
-                    }
-                    if constexpr (EPI == EPI_HEAD) {
-                        // the head consumes the activation as it would have been stored (bf16); this 16-column
-                        // group is level-0 pixel (2y + oy, 2x + ox), (oy, ox) = (c16 >> 1, c16 & 1)
+                    for (int u = 0; u < 2; ++u) {
+                        const uint32_t *o = u ? ob : oa;
                         float hl[HK > 0 ? HK : 1];
 #pragma unroll
                         for (int k = 0; k < HK; ++k) hl[k] = 0.0f;
                         float f[16];
 #pragma unroll
                         for (int e = 0; e < 8; ++e) {
-                            const float2 t2 = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162 *>(&o[e]));
+                            const float2 t2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&o[e]));
                             f[2 * e] = t2.x;
                             f[2 * e + 1] = t2.y;
                         }
@@ -1494,49 +1543,57 @@ conv_qd_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                                 hl[k] = fmaf(f[4 * g + 3], w4.w, hl[k]);
                             }
                         }
-                        int best = 0;
+                        int bk = 0;
                         float m = -INFINITY;
 #pragma unroll
                         for (int k = 0; k < HK; ++k) {
                             hl[k] += s_head[16 * HK + k];
-                            if (hl[k] > m) { m = hl[k]; best = k; }
+                            if (hl[k] > m) { m = hl[k]; bk = k; }
                         }
-                        const size_t p = ((size_t)n * (2 * H) + 2 * y + (c16 >> 1)) * (size_t)(2 * W) + 2 * x + (c16 & 1);
-                        if (head.mask) {
-                            // both pixels of this lane's row pair (ox = 0, 1) leave in one 2-byte store
-                            if ((c16 & 1) == 0) mx[0] = (uint32_t)best;
-                            else if (valid) *reinterpret_cast<uint16_t *>(head.mask + p - 1) = (uint16_t)(mx[0] | ((uint32_t)best << 8));
-                        }
+                        best[u] = bk;
                         if (valid && head.logits) {
 #pragma unroll
-                            for (int k = 0; k < HK; ++k) head.logits[p * HK + k] = hl[k];
+                            for (int k = 0; k < HK; ++k) head.logits[(p0 + u) * HK + k] = hl[k];
                         }
                         if (valid && head.probs) {
                             float sum = 0.0f;
 #pragma unroll
                             for (int k = 0; k < HK; ++k) { hl[k] = expf(hl[k] - m); sum += hl[k]; }
 #pragma unroll
-                            for (int k = 0; k < HK; ++k) head.probs[p * HK + k] = hl[k] / sum;
+                            for (int k = 0; k < HK; ++k) head.probs[(p0 + u) * HK + k] = hl[k] / sum;
                         }
-                    } else {
-                        if (valid) {
-                            bf16 *p = out + ((((size_t)n * 8 + c16 * 2) * H + y) * W + x) * 8;
-                            *reinterpret_cast<uint4 *>(p) = make_uint4(o[0], o[1], o[2], o[3]);
-                            *reinterpret_cast<uint4 *>(p + plane) = make_uint4(o[4], o[5], o[6], o[7]);
-                        }
-                        if constexpr (EPI == EPI_POOL) {
+                    }
+                    // both pixels of this lane's row (ox = 0, 1) leave in one 2-byte store
+                    if (valid && head.mask) *reinterpret_cast<uint16_t *>(head.mask + p0) = (uint16_t)(best[0] | (best[1] << 8));
+                } else {
+                    if (valid) {
+                        bf16 *p = out + ((((size_t)n * 8) * H + y) * W + x) * 8;
+                        *reinterpret_cast<uint4 *>(p + (2 * ca) * plane) = make_uint4(oa[0], oa[1], oa[2], oa[3]);
+                        *reinterpret_cast<uint4 *>(p + (2 * ca + 1) * plane) = make_uint4(oa[4], oa[5], oa[6], oa[7]);
+                        *reinterpret_cast<uint4 *>(p + (2 * cb) * plane) = make_uint4(ob[0], ob[1], ob[2], ob[3]);
+                        *reinterpret_cast<uint4 *>(p + (2 * cb + 1) * plane) = make_uint4(ob[4], ob[5], ob[6], ob[7]);
+                    }
+                    if constexpr (EPI == EPI_POOL) {
+                        // the 2x2 max-pooled tensor of the level-0 activation (16 channels at quad resolution): the max
+                        // over the four 16-column groups of the accumulator row, two per pass
 #pragma unroll
-                            for (int e = 0; e < 8; ++e) mx[e] = (c16 == 0) ? o[e] : bf162_max(mx[e], o[e]);
+                        for (int e = 0; e < 8; ++e) {
+                            const uint32_t m2 = bf162_max(oa[e], ob[e]);
+                            mx[e] = (i & 1) ? bf162_max(mx[e], m2) : m2;
+                        }
+                        if ((i & 1) && valid) {
+                            bf16 *pp = out_pool + ((((size_t)n * 2) * H + y) * W + x) * 8;
+                            *reinterpret_cast<uint4 *>(pp) = make_uint4(mx[0], mx[1], mx[2], mx[3]);
+                            *reinterpret_cast<uint4 *>(pp + plane) = make_uint4(mx[4], mx[5], mx[6], mx[7]);
                         }
                     }
                 }
-                if (EPI == EPI_POOL && valid) {
-                    // the 2x2 max-pooled tensor of the level-0 activation: 16 channels at quad resolution
-                    bf16 *p = out_pool + ((((size_t)n * 2) * H + y) * W + x) * 8;
-                    *reinterpret_cast<uint4 *>(p) = make_uint4(mx[0], mx[1], mx[2], mx[3]);
-                    *reinterpret_cast<uint4 *>(p + plane) = make_uint4(mx[4], mx[5], mx[6], mx[7]);
-                }
             }
+            tx += dtx;
+            if (tx >= tiles_x) { tx -= tiles_x; ++ty; }
+            ty += dty;
+            if (ty >= tiles_y) { ty -= tiles_y; ++n; }
+            n += dn;
             tc::tc_fence_before();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&tempty_bar[buf]);
@@ -1869,6 +1926,268 @@ conv_qf_kernel(const __grid_constant__ CUtensorMap mapIn, const bf16 *__restrict
 #undef QF_W
 #undef QF_T0
 #undef QF_T1
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tc::tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// ------------- up0/upscale -> up0/conv1 (concat bridge) as ONE launch on the quad layout
+// The up-sampled tensor (32 of the 80 + 64 B/px the two layers move) never goes to HBM, and the result is
+// bit-identical to the two-launch quad path (same MMAs, same bf16 rounding of the intermediate).  Structure of
+// conv_qf_kernel with two differences: "conv1" is the 2x2 stride-2 up-conv = a 1x1 conv (cin -> 4 x 16) over the
+// 10 x 34 half-resolution pixels of conv's halo patch, whose A operand is the TMA-fetched patch of the level-1
+// tensor itself (no builders); and the conv reads a second source, the skip tensor, through a 4-stage ring of
+// one-k-step TMA boxes that is consumed BEFORE the on-chip patch P (it is ready earlier).  One CTA per SM:
+//   warp 0       TMA: level-1 patch (A1) + 4 skip k-steps per tile
+//   warp 1       MMA: up-conv 3 M-tiles x ksu k-steps -> acc1; conv: 4 skip k-steps + 4 P k-steps, 64 MMAs -> acc2
+//   warps 2-17   epilogue 1: acc1 + bias -> bf16 -> P (zeros outside the frame); epilogue 2: acc2 -> ReLU -> quad tensor
+struct QU {
+    static constexpr int TH = 32, PW = 10, PH = 34, PROWS = PW * PH;
+    static constexpr int KSTEP_BYTES = 2 * PROWS * 16;                    // 16 channels of a patch
+    static constexpr int A1_BYTES = (2 * KSTEP_BYTES + 1024 + 127) / 128 * 128;   // up to 32 input channels (+ M-tile over-read)
+    static constexpr int P_BYTES = 4 * KSTEP_BYTES;
+    static constexpr int WU_BYTES = 2 * 2 * 64 * 16, W_BYTES = 8 * 4 * 2 * 64 * 16;
+    static constexpr int NRING = 4;
+    static constexpr int OFF_WU = 0, OFF_W = WU_BYTES, OFF_A1 = OFF_W + W_BYTES, OFF_P = OFF_A1 + A1_BYTES,
+                         OFF_RING = OFF_P + 2 * P_BYTES, SMEM = OFF_RING + NRING * KSTEP_BYTES;
+    static constexpr int EPI_WARPS = 16, THREADS = 32 * (2 + EPI_WARPS);
+    static_assert(OFF_A1 % 128 == 0 && OFF_P % 128 == 0 && OFF_RING % 128 == 0 && KSTEP_BYTES % 128 == 0, "alignment");
+    static_assert(SMEM + 1024 <= 232448, "shared memory");
+};
+
+__global__ void __launch_bounds__(QU::THREADS, 1)
+conv_qu_kernel(const __grid_constant__ CUtensorMap mapCur, const __grid_constant__ CUtensorMap mapSkip,
+               const bf16 *__restrict__ wup, const bf16 *__restrict__ wts, const QfEpi ep, int ksu,
+               bf16 *__restrict__ out, int nimg, int H, int W)
+{
+    // H, W: the quad image.  wup: the up-conv as a 1x1 conv (ksu k-steps x 2 KB), wts: conv1's quad weights with
+    // permuted output columns (8 k-steps: up-sampled source parities 0-3, skip parities 0-3).  ep.sc1 / sh1: the
+    // up-conv's epilogue, ep.sc2 / sh2: the conv's.
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+    __shared__ uint64_t w_bar, a1_full, a1_empty, acc1_full, acc1_empty, p_full[2], p_empty[2],
+        ring_full[QU::NRING], ring_empty[QU::NRING], acc2_full[2], acc2_empty[2];
+    __shared__ uint32_t tmem_base_sh;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_x = (W + 7) >> 3, tiles_y = (H + QU::TH - 1) / QU::TH;
+    const int ntiles = nimg * tiles_x * tiles_y;
+    const int nt = ((int)blockIdx.x < ntiles) ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+
+    if (threadIdx.x == 0) {
+        tc::mbar_init(&w_bar, 1);
+        tc::mbar_init(&a1_full, 1); tc::mbar_init(&a1_empty, 1);
+        tc::mbar_init(&acc1_full, 1); tc::mbar_init(&acc1_empty, QU::EPI_WARPS);
+        for (int i = 0; i < 2; ++i) {
+            tc::mbar_init(&p_full[i], QU::EPI_WARPS); tc::mbar_init(&p_empty[i], 1);
+            tc::mbar_init(&acc2_full[i], 1); tc::mbar_init(&acc2_empty[i], QU::EPI_WARPS);
+        }
+        for (int i = 0; i < QU::NRING; ++i) { tc::mbar_init(&ring_full[i], 1); tc::mbar_init(&ring_empty[i], 1); }
+        tc::fence_barrier_init();
+        tc::tma_prefetch_desc(&mapCur);
+        tc::tma_prefetch_desc(&mapSkip);
+    }
+    if (warp == 1) { tc::tmem_alloc(&tmem_base_sh, 512); tc::tmem_relinquish(); }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = tmem_base_sh;
+    constexpr uint32_t ACC1 = 0, ACC2 = 256;                 // TMEM columns: acc1 3 x 64, acc2 2 x (2 x 64)
+
+    if (warp == 0) {
+        // ===================================================== TMA producer
+        if (lane == 0) {
+            tc::mbar_arrive_expect_tx(&w_bar, (uint32_t)(ksu * 2048 + QU::W_BYTES));
+            tc::bulk_load(smem + QU::OFF_WU, wup, (uint32_t)(ksu * 2048), &w_bar);
+            for (int q = 0; q < 8; ++q)
+                tc::bulk_load(smem + QU::OFF_W + q * 8192, wts + q * 4096, 8192, &w_bar);
+            int rs = 0;
+            uint32_t rphase = 0;
+            for (int it = 0; it < nt; ++it) {
+                const int t = blockIdx.x + it * gridDim.x;
+                const int tx = t % tiles_x, ty = (t / tiles_x) % tiles_y, n = t / (tiles_x * tiles_y);
+                const int x0 = tx * 8 - 1, y0 = ty * QU::TH - 1;
+                tc::mbar_wait(&a1_empty, (it & 1) ^ 1);
+                tc::mbar_arrive_expect_tx(&a1_full, (uint32_t)(ksu * QU::KSTEP_BYTES));
+                tc::tma_load_5d(smem + QU::OFF_A1, &mapCur, &a1_full, x0 * 8, y0, 0, 0, n);
+                for (int ks = 0; ks < 4; ++ks) {
+                    tc::mbar_wait(&ring_empty[rs], rphase ^ 1);
+                    tc::mbar_arrive_expect_tx(&ring_full[rs], QU::KSTEP_BYTES);
+                    tc::tma_load_5d(smem + QU::OFF_RING + rs * QU::KSTEP_BYTES, &mapSkip, &ring_full[rs], x0 * 8, y0, ks * 2, 0, n);
+                    if (++rs == QU::NRING) { rs = 0; rphase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ======================================================= MMA issuer
+        const uint32_t idesc = tc::instr_desc_bf16(128, 64);
+        const uint32_t sbase = tc::smem_u32(smem);
+        const uint32_t hi128 = ((128u >> 4) & 0x3FFFu) | (1u << 14);
+        const uint32_t hiP = (((uint32_t)(QU::PW * 16) >> 4) & 0x3FFFu) | (1u << 14);
+        const uint32_t lboP = (((uint32_t)QU::PROWS * 16u) >> 4) << 16;
+        const uint32_t wu_lo = (((sbase + QU::OFF_WU) >> 4) & 0x3FFFu) | (((64u * 16u) >> 4) << 16);
+        const uint32_t w_lo = (((sbase + QU::OFF_W) >> 4) & 0x3FFFu) | (((64u * 16u) >> 4) << 16);
+        const uint32_t a1_lo = (((sbase + QU::OFF_A1) >> 4) & 0x3FFFu) | lboP;
+        int rs = 0;
+        uint32_t rphase = 0;
+        tc::mbar_wait(&w_bar, 0);
+        for (int it = 0; it <= nt; ++it) {
+            if (it < nt) {
+                tc::mbar_wait(&a1_full, it & 1);
+                tc::mbar_wait(&acc1_empty, (it & 1) ^ 1);
+                tc::tc_fence_after();
+                if (tc::elect_one()) {
+                    for (int k = 0; k < ksu; ++k)
+#pragma unroll
+                        for (int m = 0; m < 3; ++m)
+                            tc::umma_bf16_parts(tmem_base + ACC1 + m * 64, a1_lo + (uint32_t)(k * (QU::KSTEP_BYTES >> 4) + m * 128), hi128,
+                                                wu_lo + (uint32_t)(k * 128), hi128, idesc, k > 0 ? 1u : 0u);
+                    tc::umma_commit(&a1_empty);
+                    tc::umma_commit(&acc1_full);
+                }
+                __syncwarp();
+            }
+            if (it >= 1) {
+                const int i2 = it - 1, b = i2 & 1;
+                tc::mbar_wait(&acc2_empty[b], ((i2 >> 1) & 1) ^ 1);
+                tc::tc_fence_after();
+                const uint32_t d0 = tmem_base + ACC2 + b * 128;
+                // the skip tensor's four k-steps first (prefetched through the ring) ...
+                for (int ks = 0; ks < 4; ++ks) {
+                    tc::mbar_wait(&ring_full[rs], rphase);
+                    tc::tc_fence_after();
+                    if (tc::elect_one()) {
+                        const uint32_t s_lo = (((sbase + QU::OFF_RING + rs * QU::KSTEP_BYTES) >> 4) & 0x3FFFu) | lboP;
+                        const int iy = ks >> 1, ix = ks & 1;
+#pragma unroll
+                        for (int j = 0; j < 2; ++j)
+#pragma unroll
+                            for (int tp = 0; tp < 4; ++tp)
+                                tc::umma_bf16_parts(d0 + j * 64, s_lo + (uint32_t)((j * 16 + (tp >> 1) + 1 - iy) * QU::PW + (tp & 1) + 1 - ix), hiP,
+                                                    w_lo + (uint32_t)(((4 + ks) * 4 + tp) * 128), hi128, idesc, (ks > 0 || tp > 0) ? 1u : 0u);
+                        tc::umma_commit(&ring_empty[rs]);
+                    }
+                    __syncwarp();
+                    if (++rs == QU::NRING) { rs = 0; rphase ^= 1; }
+                }
+                // ... then the up-sampled patch written by epilogue 1
+                tc::mbar_wait(&p_full[b], (i2 >> 1) & 1);
+                tc::tc_fence_after();
+                if (tc::elect_one()) {
+                    const uint32_t p_lo = (((sbase + QU::OFF_P + b * QU::P_BYTES) >> 4) & 0x3FFFu) | lboP;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int iy = k >> 1, ix = k & 1;
+#pragma unroll
+                        for (int j = 0; j < 2; ++j)
+#pragma unroll
+                            for (int tp = 0; tp < 4; ++tp)
+                                tc::umma_bf16_parts(d0 + j * 64,
+                                                    p_lo + (uint32_t)(k * (QU::KSTEP_BYTES >> 4) + (j * 16 + (tp >> 1) + 1 - iy) * QU::PW + (tp & 1) + 1 - ix),
+                                                    hiP, w_lo + (uint32_t)((k * 4 + tp) * 128), hi128, idesc, 1u);
+                    }
+                    tc::umma_commit(&p_empty[b]);
+                    tc::umma_commit(&acc2_full[b]);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ========================================================= epilogue
+        const int g = (warp - 2) >> 2, q4 = warp & 3;
+        const int r = q4 * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(q4 * 32) << 16;
+        int ppy[3], ppx[3];
+#pragma unroll
+        for (int m = 0; m < 3; ++m) { const int p = m * 128 + r; ppy[m] = p / QU::PW; ppx[m] = p - ppy[m] * QU::PW; }
+        const int j2 = g >> 1, c8 = g & 1;
+        float sc2[8], sh2[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { sc2[e] = c8 ? ep.sc2[8 + e] : ep.sc2[e]; sh2[e] = c8 ? ep.sh2[8 + e] : ep.sh2[e]; }
+        const size_t plane = (size_t)H * W * 8;
+        const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.0f, 0.0f);
+        const int tpi = tiles_x * tiles_y, gstep = (int)gridDim.x;
+        int tx = (int)blockIdx.x % tiles_x, ty = ((int)blockIdx.x / tiles_x) % tiles_y, n = (int)blockIdx.x / tpi;
+        const int dtx = gstep % tiles_x, dty = (gstep / tiles_x) % tiles_y, dn = gstep / tpi;
+        int tx2 = 0, ty2 = 0, n2 = 0;
+        for (int it = 0; it <= nt; ++it) {
+            if (it < nt) {
+                // ---- epilogue 1: the up-conv's accumulators (+ bias, no ReLU) -> the bf16 halo patch of the conv
+                const int b = it & 1;
+                const int x0 = tx * 8 - 1, y0 = ty * QU::TH - 1;
+                tc::mbar_wait(&acc1_full, it & 1);
+                tc::mbar_wait(&p_empty[b], ((it >> 1) & 1) ^ 1);
+                tc::tc_fence_after();
+                uint8_t *P = smem + QU::OFF_P + b * QU::P_BYTES + (2 * g) * (QU::PROWS * 16) + r * 16;
+                const bool border = x0 < 0 || y0 < 0 || x0 + QU::PW > W || y0 + QU::PH > H;
+                uint32_t v[3][16];
+                tc::tmem_ld16(tmem_base + lane_addr + ACC1 + g * 16, v[0]);
+                tc::tmem_ld16(tmem_base + lane_addr + ACC1 + 64 + g * 16, v[1]);
+                if (q4 != 3) tc::tmem_ld16(tmem_base + lane_addr + ACC1 + 128 + g * 16, v[2]);   // rows 352.. lie beyond the patch
+                tc::tmem_ld_wait();
+#pragma unroll
+                for (int m = 0; m < 3; ++m) {
+                    if (m == 2 && q4 == 3) continue;
+                    uint32_t o[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        o[q] = pack_bf16(fmaf(__uint_as_float(v[m][2 * q]), ep.sc1[2 * q], ep.sh1[2 * q]),
+                                         fmaf(__uint_as_float(v[m][2 * q + 1]), ep.sc1[2 * q + 1], ep.sh1[2 * q + 1]));
+                    if (border) {
+                        const int Y = y0 + ppy[m], X = x0 + ppx[m];
+                        if (!(Y >= 0 && Y < H && X >= 0 && X < W)) {
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) o[e] = 0u;
+                        }
+                    }
+                    if (m < 2 || r < QU::PROWS - 256) {
+                        *reinterpret_cast<uint4 *>(P + m * 2048) = make_uint4(o[0], o[1], o[2], o[3]);
+                        *reinterpret_cast<uint4 *>(P + QU::PROWS * 16 + m * 2048) = make_uint4(o[4], o[5], o[6], o[7]);
+                    }
+                }
+                tc::fence_proxy_async();
+                tc::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) { tc::mbar_arrive(&p_full[b]); tc::mbar_arrive(&acc1_empty); }
+            }
+            if (it >= 1) {
+                // ---- epilogue 2: the conv's accumulators -> ReLU -> quad tensor
+                const int i2 = it - 1, b = i2 & 1;
+                const int y = ty2 * QU::TH + j2 * 16 + (r >> 3), x = tx2 * 8 + (r & 7);
+                const bool valid = (y < H) && (x < W);
+                tc::mbar_wait(&acc2_full[b], (i2 >> 1) & 1);
+                tc::tc_fence_after();
+                uint32_t v[32];
+                tc::tmem_ld32(tmem_base + lane_addr + ACC2 + b * 128 + j2 * 64 + c8 * 32, v);
+                tc::tmem_ld_wait();
+                tc::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&acc2_empty[b]);
+                bf16 *po = out + ((((size_t)n2 * 8 + c8) * H + y) * W + x) * 8;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    uint32_t o[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        __nv_bfloat162 h = __hmax2(__floats2bfloat162_rn(fmaf(__uint_as_float(v[q * 8 + 2 * e]), sc2[2 * e], sh2[2 * e]),
+                                                                         fmaf(__uint_as_float(v[q * 8 + 2 * e + 1]), sc2[2 * e + 1], sh2[2 * e + 1])),
+                                                   zero2);
+                        o[e] = *reinterpret_cast<uint32_t *>(&h);
+                    }
+                    if (valid) *reinterpret_cast<uint4 *>(po + (size_t)(2 * q) * plane) = make_uint4(o[0], o[1], o[2], o[3]);
+                }
+            }
+            tx2 = tx; ty2 = ty; n2 = n;
+            tx += dtx;
+            if (tx >= tiles_x) { tx -= tiles_x; ++ty; }
+            ty += dty;
+            if (ty >= tiles_y) { ty -= tiles_y; ++n; }
+            n += dn;
+        }
+    }
     tc::tc_fence_before();
     __syncthreads();
     if (warp == 1) {
@@ -2731,6 +3050,43 @@ int launch_qf(sq_unet_s *u, const SqLayer &L1, const SqLayer &L2, const float *i
     return SQ_OK;
 }
 
+bool qup_enabled()
+{
+    // SQ_QUP=0: up0/upscale and up0/conv1 as two launches (A/B measurements, tests)
+    const char *e = getenv("SQ_QUP");
+    return !e || atoi(e) != 0;
+}
+
+// up0/upscale + up0/conv1 (concat bridge) in one launch (conv_qu_kernel); g.H, g.W: the quad image
+int launch_qu(sq_unet_s *u, const SqLayer &Lu, const SqLayer &L1, const bf16 *cur, const bf16 *skip, bf16 *out,
+              const TcGeo &g, cudaStream_t st)
+{
+    const int cbu = Lu.cin0 / 8, ksu = Lu.cin0 / 16;
+    CUtensorMap mc, ms;
+    SQ_TRY(make_map(&mc, cur, g.nimg, 1, cbu, g.H, g.W, QU::PW, QU::PH, cbu, 1));
+    SQ_TRY(make_map(&ms, skip, g.nimg, 1, 8, g.H, g.W, QU::PW, QU::PH, 2, 1));
+    const size_t smem = (size_t)QU::SMEM + 1024;
+    static size_t attr_smem[64] = {0};
+    size_t &have = attr_smem[u->h->device & 63];
+    if (smem > have) {
+        SQ_CUDA(cudaFuncSetAttribute(conv_qu_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        have = smem;
+    }
+    QfEpi ep;
+    {
+        const std::vector<float> &s1 = u->host[Lu.scope + "/_scale"].data, &t1 = u->host[Lu.scope + "/_shift"].data;
+        const std::vector<float> &s2 = u->host[L1.scope + "/_scale"].data, &t2 = u->host[L1.scope + "/_shift"].data;
+        for (int i = 0; i < 16; ++i) { ep.sc1[i] = s1[i]; ep.sh1[i] = t1[i]; ep.sc2[i] = s2[i]; ep.sh2[i] = t2[i]; }
+    }
+    const int tiles = g.nimg * ((g.W + 7) / 8) * ((g.H + QU::TH - 1) / QU::TH);
+    const int grid = std::min(tiles, u->h->sm_count / grid_div());
+    conv_qu_kernel<<<grid, QU::THREADS, smem, st>>>(mc, ms, (const bf16 *)Lu.w_qd, (const bf16 *)L1.w_qu, ep, ksu, out, g.nimg,
+                                                   g.H, g.W);
+    ++u->last_launches;
+    SQ_CHECK_LAUNCH();
+    return SQ_OK;
+}
+
 // quad 3x3 conv; c0 / c1: level-0 channels of the two sources (16 each) -> 4*c/8 channel blocks of the quad image
 int conv3x3_qd(sq_unet_s *u, const SqLayer &L, const bf16 *in0, int c0, const bf16 *in1, int c1, bf16 *out,
                bf16 *out_pool, const HeadArgs *head, const TcGeo &g, cudaStream_t st)
@@ -2898,6 +3254,16 @@ int sq_tc_finalize(sq_unet_s *u)
                                         f[base + (((((size_t)qi * 4 + tp) * 2 + kb) * 64) + (co / 8) * 32 + qo * 8 + co % 8) * 8 + e] =
                                             w[(((((size_t)qi * 4 + tp) * 2 + kb) * 64) + qo * 16 + co) * 8 + e];
                 SQ_TRY(dev_upload(u, f.data(), f.size() * 2, &L.w_qf));
+            }
+            if (L.scope == "UNet/up0/conv1" && C == 32) {
+                // conv_qu_kernel: the same weights with the output columns reordered to (co / 8, parity, co % 8)
+                std::vector<uint16_t> f(w.size(), 0);
+                for (size_t blk = 0; blk < w.size() / (64 * 8); ++blk)       // (k-step, tap, kb) blocks of [64][8]
+                    for (int qo = 0; qo < 4; ++qo)
+                        for (int co = 0; co < 16; ++co)
+                            for (int e = 0; e < 8; ++e)
+                                f[(blk * 64 + (co / 8) * 32 + qo * 8 + co % 8) * 8 + e] = w[(blk * 64 + qo * 16 + co) * 8 + e];
+                SQ_TRY(dev_upload(u, f.data(), f.size() * 2, &L.w_qu));
             }
             std::vector<float> sc(64), sh(64);
             const std::vector<float> &s0 = u->host[L.scope + "/_scale"].data, &t0 = u->host[L.scope + "/_shift"].data;
@@ -3087,6 +3453,16 @@ int tc_run(sq_unet_s *u, bool dry, const float *in, int n, int dep, int hgt, int
                 const TcGeo gu = {n * (D / 2), 1, H / 2, W / 2, 1, 2, kz, kz * wslice};
                 SQ_TRY(upconv_tc(u, *us, cur, up[l], gu, st));
             }
+        } else if (l == 0 && quad && u->bridge == SQ_BRIDGE_CONCAT && c1->w_qu && (us->cin0 == 16 || us->cin0 == 32) &&
+                   qup_enabled()) {
+            // up-conv + conv1 in one launch: the up-sampled tensor stays on chip
+            const HeadArgs hq = {(const float *)head->w_tc, head->cout, logits, probs, mask};
+            SQ_TRY(launch_qu(u, *us, *c1, cur, skip[0], ut[0], geoq, st));
+            const char *pname = u->aux_names.emplace(us->scope, us->scope + "+conv1").first->second.c_str();
+            sq_timer_mark(u, st, pname, (us->flops_per_px + c1->flops_per_px) * px);
+            SQ_TRY(conv3x3_qd(u, *c2, ut[0], c2->cin0, nullptr, 0, nullptr, nullptr, &hq, geoq, st));
+            sq_timer_mark(u, st, c2->scope.c_str(), (c2->flops_per_px + head->flops_per_px) * px);
+            return SQ_OK;
         } else if (l == 0 && quad) {
             // 2x2 stride-2 up-conv onto the quad layout = 1x1 conv cin -> 4 x 16 at half resolution
             const HeadArgs none = {nullptr, 0, nullptr, nullptr, nullptr};

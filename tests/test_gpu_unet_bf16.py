@@ -311,24 +311,29 @@ def test_random_geometries(sq, seed):
     ('eltwise_mul', 2, 4, (16, 32, 64), (136, 48), 2),   # three 32-row tiles down the quad image
     (None, 4, 2, (16, 16), (64, 80), 1),                 # one k-step up-conv
     ('concat', 1, 2, (16, 64), (40, 200), 1),            # four k-steps into the up-conv
+    ('concat', 2, 2, (16, 16, 32), (72, 104), 2),        # one-k-step up-conv inside the fused up pair
     ('eltwise_add', 1, 3, (16, 32, 64), (264, 144), 2),  # several tiles per CTA column, 9 x 5 tiles per frame
 ])
 def test_quad_level0(sq, monkeypatch, mode, bridge, cin, k, filters, shape, n):
     """Level 0 of planar nets with filters[0] = 16 runs on the quad (space-to-depth) layout by default
     (conv_qd_kernel: 64-wide half-resolution MMAs, pool / head per accumulator row), and with one input
     channel down0/conv1 + down0/conv2 + pool are ONE launch (conv_qf_kernel: the first conv's output stays in
-    shared memory).  SQ_QFUSE=0 keeps the two launches, SQ_QUAD=0 the full-resolution kernels.  Each against
+    shared memory); with the concat bridge up0/upscale + up0/conv1 are one launch too (conv_qu_kernel: the
+    up-sampled tensor stays in shared memory).  SQ_QFUSE=0 / SQ_QUP=0 keep the two launches, SQ_QUAD=0 the
+    full-resolution kernels.  Each against
     the bf16-contract oracle, and against the full-resolution path (same products, another accumulation order)."""
     w = synth.unet_weights(filters, cin, k, bridge=bridge, affine=True, seed=31)
     x = synth.frames(n, shape[0], shape[1], cin, seed=9, n_objects=4)
     monkeypatch.setenv('SQ_QUAD', '0' if mode == 'full' else '1')
     monkeypatch.setenv('SQ_QFUSE', '1' if mode == 'fused' else '0')
+    monkeypatch.setenv('SQ_QUP', '1' if mode == 'fused' else '0')
     net = _net(filters, shape, bridge, cin, k, w)
     out = net.predict(x)
     ref = unet_c.unet_forward(x, w, filters, bridge, contract='bf16')
     _compare(out, ref, '%s %s' % (mode, bridge))
-    fused = mode == 'fused' and cin == 1 and shape[1] % 4 == 0
-    assert net.launches() == 5 * len(filters) - 3 + (0 if bridge in ('concat', None) else len(filters) - 1) - (1 if fused else 0)
+    fused = int(mode == 'fused' and cin == 1 and shape[1] % 4 == 0)            # conv_qf_kernel: down0/conv1 + conv2
+    fused += int(mode == 'fused' and bridge == 'concat' and filters[1] in (16, 32))   # conv_qu_kernel: up0/upscale + conv1
+    assert net.launches() == 5 * len(filters) - 3 + (0 if bridge in ('concat', None) else len(filters) - 1) - fused
     if mode != 'full':
         monkeypatch.setenv('SQ_QUAD', '0')
         other = net.predict(x)
@@ -358,6 +363,7 @@ def test_first_conv_fused_into_the_second(sq, monkeypatch, shape, n):
     """SQ_FUSE_FIRST=1: down0/conv1 is computed by builder warps inside down0/conv2's producer (the
     16-channel intermediate never goes to HBM): one launch fewer, logits bit-identical to the two-launch
     path (same mma.sync fragments, same bf16 rounding of the intermediate, zeros outside the image)."""
+    monkeypatch.setenv('SQ_QUAD', '0')        # the experiment lives on the full-resolution level-0 kernels
     filters = (16, 32, 64)
     w = synth.unet_weights(filters, 1, 2, bridge='concat', seed=7)
     x = synth.frames(n, shape[0], shape[1], 1, seed=11, n_objects=5)
@@ -386,6 +392,7 @@ def test_conv_block_fused_into_one_launch(sq, monkeypatch, bridge, cin, k, shape
     filters = (16, 32, 64)
     w = synth.unet_weights(filters, cin, k, bridge=bridge, seed=13)
     x = synth.frames(n, shape[0], shape[1], cin, seed=17, n_objects=5)
+    monkeypatch.setenv('SQ_QUAD', '0')
     monkeypatch.setenv('SQ_XC', '2')
     monkeypatch.setenv('SQ_PAIR', '0')
     net = _net(filters, shape, bridge, cin, k, w)
