@@ -8,7 +8,7 @@ import os
 
 import numpy as np
 
-from . import ops
+from . import hdf5min, ops
 
 logger = logging.getLogger('worker_process')
 
@@ -30,30 +30,12 @@ def divisible_by_two_n_times(x, n):
     return x % 1 == 0
 
 
-class _NpzGroup(object):
-    """Minimal stand-in for an h5py group when h5py is absent: datasets are kept
-    in memory under their HDF5 path and written as one ``.npz`` on close()."""
-
-    def __init__(self, store, prefix):
-        self._store, self._prefix = store, prefix
-
-    def create_group(self, name):
-        return _NpzGroup(self._store, self._prefix + name + '/')
-
-    def __getitem__(self, name):
-        return _NpzGroup(self._store, self._prefix + name + '/')
-
-    def create_dataset(self, name, data=None, dtype=None):
-        arr = np.asarray(data, dtype=dtype)
-        self._store[self._prefix + name] = arr
-        return arr
-
-
 class HDF5FileHandler(object):
     """ Base class for handling HDF files (utils.py:431-474).
 
-    With h5py installed this writes real HDF5; otherwise the same
-    ``frames/frame_<i>/coords`` datasets go to ``<name>.hdf5.npz``.
+    With h5py installed the file goes through it; otherwise through ``hdf5min``, this package's own
+    writer / reader of the HDF5 subset the ``frames/frame_<i>/coords`` layout needs (version-0
+    superblock, symbol-table groups, contiguous datasets).  Either way the result is a real HDF5 file.
     """
 
     def __init__(self, filename=None, read_only=False):
@@ -71,10 +53,8 @@ class HDF5FileHandler(object):
         logger.info('Opening HDF file: {0:s}'.format(filename))
         if h5py is not None:
             self._hdf = h5py.File(filename, 'r+' if read_only else 'w')
-            self._store = None
         else:
-            self._store = {}
-            self._hdf = _NpzGroup(self._store, '')
+            self._hdf = hdf5min.File(filename, 'r+' if read_only else 'w')
 
     @property
     def hdf(self):
@@ -89,10 +69,7 @@ class HDF5FileHandler(object):
         if self._hdf is None:
             return
         logger.info('Closing HDF file.')
-        if self._store is None:
-            self._hdf.close()
-        else:
-            np.savez(self.filename + '.npz', **self._store)
+        self._hdf.close()
         self._hdf = None
 
 
@@ -138,6 +115,8 @@ class CentroidWriter(HDF5FileHandler):
             tables = self.centroids(segmented[start:start + chunk], self.max_rows, frame0=start)
             for j, this_frame in enumerate(tables):
                 grp = self._hdf['frames'].create_group('frame_' + str(start + j))
+                if len(this_frame) == 0:
+                    this_frame = []                  # the reference writes shape (0,) for a frame without objects (utils.py:570-578)
                 grp.create_dataset('coords', data=this_frame, dtype='float32')
 
 
