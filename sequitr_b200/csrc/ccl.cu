@@ -6,20 +6,19 @@
 // One pass handles ALL classes: two voxels are connected when they share a face and carry
 // the same non-zero value, so label(out == c) for every c falls out of a single union-find.
 // The mask is read as horizontal RUNS of equal non-zero value (a segmentation mask of a few
-// hundred cells has ~10^4 runs against 4*10^6 pixels): only the two run-extraction kernels
-// touch every voxel (1 B/voxel each, the second pass hits L2); everything else -- unions
+// hundred cells has ~10^4 runs against 4*10^6 pixels): only the run-extraction kernel
+// touches every voxel (1 B/voxel, once); everything else -- unions
 // between vertically (and, in 3-D, depth-) adjacent runs, path compression, ordering,
 // 64-bit centroid sums -- is O(runs).  Run slots are allocated in raster order by a prefix
 // sum, so the root of a component (minimum slot, atomicMin union) is the run holding the
 // component's first voxel in raster order = SciPy's numbering order.
 //
 // Kernels (HBM-bound; algorithmic traffic 1 B/voxel in, rows out):
-//   run_count     runs per 512-voxel row segment (16 voxels per lane, byte-wise SIMD compares + shuffles)
-//   scan_i32      per-frame exclusive scan (segment counts, then root counts)
-//   run_emit      run start / end lists in raster order, parent[i] = i
+//   run_scan_emit runs per 512-voxel row segment (16 voxels per lane, byte-wise SIMD compares + shuffles), their
+//                 raster-order slots by a single-pass decoupled look-back scan, run start / end lists, parent[i] = i
 //   run_merge     unions with overlapping runs of the previous row / previous plane
-//   run_compress  full path compression + root count per 2048-run chunk
-//   root_emit     raster-ordered root list
+//   run_compress  full path compression + root count per 2048-run chunk (only chunks that hold runs)
+//   root_emit     raster-ordered root list (chunk offsets summed in the block: no scan launch)
 //   ccl_order     stable counting sort of the roots by class -> table row index
 //   run_accum     64-bit sums (count, sum z, sum y, sum x) per row from run endpoints
 //   ccl_finalize  fp64 divide exactly as center_of_mass does, float32 rows
@@ -118,104 +117,103 @@ __device__ __forceinline__ unsigned warp_inclusive_scan(unsigned v, int lane)
     return v;
 }
 
-// grid (ceil(nsegs/8), n), block 256: one warp per segment
-__global__ void run_count(const uint8_t *__restrict__ mask, int *__restrict__ seg_count, Dims dm)
-{
-    const int lane = threadIdx.x & 31;
-    const int s = blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (s >= dm.nsegs) return;
-    const int line = s / dm.nseg, seg = s % dm.nseg;
-    const uint8_t *lp = mask + (long long)blockIdx.y * dm.vox + (long long)line * dm.W;
-    unsigned sb, eb;
-    const unsigned c = segment_bits(lp, seg * SEG + lane * PPL, dm.W, dm.vec, lane, sb, eb);
-    const unsigned tot = warp_inclusive_scan(c & 0xffffu, lane);
-    if (lane == 31) seg_count[(long long)blockIdx.y * (dm.nsegs + 1) + s] = (int)tot;
-}
+// Single-pass front end: runs per segment, their raster-order slots (an exclusive prefix sum over the
+// frame's segments) and the run lists, in ONE kernel that reads the mask once.  A block owns SPB = 32
+// consecutive segments (warp w: segments 4w .. 4w+3); the prefix across blocks is a decoupled look-back
+// (Merrill & Garland): every block publishes its aggregate, then its inclusive prefix, in one 64-bit status
+// word (flag << 32 | value) and warp 0 walks back over its predecessors' words, 32 at a time.  Blocks take
+// their index from a per-frame ticket counter, so a block only ever waits for blocks that are already running.
+// grid (ceil(nsegs / SPB), n), block 256.  status / ticket are zeroed by the caller.
+constexpr int SPB = 32;
+constexpr unsigned long long ST_AGG = 1ull << 32, ST_PREFIX = 2ull << 32;
 
-// grid (n), block 1024: exclusive scan of `len` ints of one frame (stride `pitch`); the grand
-// total goes to out[len] (if sentinel) and totals[f]
-__global__ void scan_i32(const int *__restrict__ in, int *__restrict__ out, int *__restrict__ totals,
-                         int len, int pitch, int sentinel)
+__global__ void __launch_bounds__(256)
+run_scan_emit(const uint8_t *__restrict__ mask, unsigned long long *__restrict__ status, int *__restrict__ ticket,
+              int *__restrict__ seg_off, int *__restrict__ totals, int *__restrict__ run_start,
+              int *__restrict__ run_end, int *__restrict__ parent, Dims dm, int nblk)
 {
-    __shared__ int warp_sums[32];
-    __shared__ int carry_sh;
-    const int f = blockIdx.x;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int *src = in + (long long)f * pitch;
-    int *dst = out + (long long)f * pitch;
-    if (threadIdx.x == 0) carry_sh = 0;
+    __shared__ int s_bid, s_excl, s_tot[SPB];
+    const int f = blockIdx.y, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_bid = atomicAdd(ticket + f, 1);
     __syncthreads();
-    // four consecutive elements per thread: a 2048^2 frame (32768 segments) takes 8 rounds, not 32
-    for (int start = 0; start < len; start += 4096) {
-        const int i = start + 4 * threadIdx.x;
-        int v[4];
+    const int bid = s_bid;
+    const uint8_t *fm = mask + (long long)f * dm.vox;
+    unsigned sb[4], eb[4], pre[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) v[k] = (i + k < len) ? src[i + k] : 0;
-        const int tsum = (v[0] + v[1]) + (v[2] + v[3]);
-        int s = tsum;
-        for (int o = 1; o < 32; o <<= 1) {
-            int t = __shfl_up_sync(0xffffffffu, s, o);
-            if (lane >= o) s += t;
+    for (int k = 0; k < 4; ++k) {
+        const int s = bid * SPB + wid * 4 + k;
+        sb[k] = eb[k] = pre[k] = 0;
+        unsigned tot = 0;
+        if (s < dm.nsegs) {
+            const int line = s / dm.nseg, seg = s - line * dm.nseg;
+            const unsigned c = segment_bits(fm + (long long)line * dm.W, seg * SEG + lane * PPL, dm.W, dm.vec, lane, sb[k], eb[k]);
+            const unsigned incl = warp_inclusive_scan(c, lane);
+            pre[k] = incl - c;                                  // exclusive (starts | ends << 16) within the segment
+            tot = __shfl_sync(0xffffffffu, incl, 31) & 0xffffu;
         }
-        if (lane == 31) warp_sums[wid] = s;
-        __syncthreads();
-        if (wid == 0) {
-            int w = warp_sums[lane];
-            for (int o = 1; o < 32; o <<= 1) {
-                int t = __shfl_up_sync(0xffffffffu, w, o);
-                if (lane >= o) w += t;
+        if (lane == 0) s_tot[wid * 4 + k] = (int)tot;
+    }
+    __syncthreads();
+    if (wid == 0) {
+        const int v = s_tot[lane];
+        const int incl = (int)warp_inclusive_scan((unsigned)v, lane);
+        const int agg = __shfl_sync(0xffffffffu, incl, 31);
+        s_tot[lane] = incl - v;                                 // exclusive prefix of the segment within the block
+        volatile unsigned long long *st = status + (long long)f * nblk;
+        int excl = 0;
+        if (bid > 0) {
+            if (lane == 0) st[bid] = ST_AGG | (unsigned)agg;
+            int j = bid - 1;
+            while (true) {
+                const int idx = j - lane;
+                unsigned long long w = ST_PREFIX;               // before the first block: prefix 0
+                if (idx >= 0) {
+                    do { w = st[idx]; } while ((w >> 32) == 0);
+                }
+                const unsigned pm = __ballot_sync(0xffffffffu, (w >> 32) == 2);
+                // sum the aggregates up to (and including) the nearest predecessor that already has its prefix
+                const int first = pm ? __ffs(pm) - 1 : 31;
+                int val = (lane <= first) ? (int)(unsigned)w : 0;
+                for (int o = 16; o > 0; o >>= 1) val += __shfl_down_sync(0xffffffffu, val, o);
+                excl += __shfl_sync(0xffffffffu, val, 0);
+                if (pm) break;
+                j -= 32;
             }
-            warp_sums[lane] = w;                               // inclusive over warps
         }
-        __syncthreads();
-        const int carry = carry_sh;
-        const int incl = s + (wid > 0 ? warp_sums[wid - 1] : 0);
-        int run = carry + incl - tsum;                         // exclusive prefix of this thread's first element
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (i + k < len) dst[i + k] = run;
-            run += v[k];
+        if (lane == 0) {
+            __threadfence();
+            st[bid] = ST_PREFIX | (unsigned)(excl + agg);
+            s_excl = excl;
+            if (bid == nblk - 1) {
+                totals[f] = excl + agg;
+                seg_off[(long long)f * (dm.nsegs + 1) + dm.nsegs] = excl + agg;
+            }
         }
-        __syncthreads();
-        if (threadIdx.x == 1023) carry_sh = carry + incl;
-        __syncthreads();
     }
-    if (threadIdx.x == 0) {
-        if (sentinel) dst[len] = carry_sh;
-        totals[f] = carry_sh;
-    }
-}
-
-// same launch shape as run_count: writes the runs of every segment at their raster-order slots
-__global__ void run_emit(const uint8_t *__restrict__ mask, const int *__restrict__ seg_off,
-                         int *__restrict__ run_start, int *__restrict__ run_end,
-                         int *__restrict__ parent, Dims dm)
-{
-    const int lane = threadIdx.x & 31;
-    const int s = blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (s >= dm.nsegs) return;
-    const int f = blockIdx.y;
-    const int line = s / dm.nseg, seg = s % dm.nseg;
-    const uint8_t *lp = mask + (long long)f * dm.vox + (long long)line * dm.W;
-    const int x = seg * SEG + lane * PPL;
-    unsigned sb, eb;
-    const unsigned c = segment_bits(lp, x, dm.W, dm.vec, lane, sb, eb);
-    const unsigned incl = warp_inclusive_scan(c, lane);
-    if (!(sb | eb)) return;
+    __syncthreads();
     const long long rb = (long long)f * dm.maxruns;
-    const int base = seg_off[(long long)f * (dm.nsegs + 1) + s];
-    int is = base + (int)((incl - c) & 0xffffu), ie = base + (int)((incl - c) >> 16);
-    while (sb) {                                   // set bits in ascending order = raster order
-        const int k = __ffs(sb) - 1;
-        sb &= sb - 1;
-        run_start[rb + is] = line * dm.W + x + k;
-        parent[rb + is] = is;
-        ++is;
-    }
-    while (eb) {
-        const int k = __ffs(eb) - 1;
-        eb &= eb - 1;
-        run_end[rb + ie++] = x + k;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int s = bid * SPB + wid * 4 + k;
+        if (s >= dm.nsegs) break;
+        const int base = s_excl + s_tot[wid * 4 + k];
+        if (lane == 0) seg_off[(long long)f * (dm.nsegs + 1) + s] = base;
+        unsigned a = sb[k], e = eb[k];
+        if (!(a | e)) continue;
+        const int line = s / dm.nseg, x = (s - line * dm.nseg) * SEG + lane * PPL;
+        int is = base + (int)(pre[k] & 0xffffu), ie = base + (int)(pre[k] >> 16);
+        while (a) {                                             // set bits in ascending order = raster order
+            const int b = __ffs(a) - 1;
+            a &= a - 1;
+            run_start[rb + is] = line * dm.W + x + b;
+            parent[rb + is] = is;
+            ++is;
+        }
+        while (e) {
+            const int b = __ffs(e) - 1;
+            e &= e - 1;
+            run_end[rb + ie++] = x + b;
+        }
     }
 }
 
@@ -276,7 +274,8 @@ __device__ __forceinline__ int block_sum_256(int v, int *sh)
     return r;                                                  // valid in thread 0
 }
 
-// grid (nchunks, n), block 256
+// grid (blocks, n), block 256: full path compression and the root count of every 2048-run chunk that holds
+// runs (chunks past the frame's last run are never touched: root_emit only reads the first ceil(R / CHUNK))
 __global__ void run_compress(int *__restrict__ parent, const int *__restrict__ totals,
                              int *__restrict__ chunk_count, Dims dm)
 {
@@ -284,58 +283,102 @@ __global__ void run_compress(int *__restrict__ parent, const int *__restrict__ t
     const int f = blockIdx.y;
     const int R = totals[f];
     int *pa = parent + (long long)f * dm.maxruns;
-    const int base = blockIdx.x * CHUNK;
-    int cnt = 0;
-    if (base < R) {
+    for (int chunk = blockIdx.x; chunk * CHUNK < R; chunk += gridDim.x) {
+        const int base = chunk * CHUNK;
+        int cnt = 0;
+        // the thread's 8 runs walk to their roots in LOCK-STEP: 8 independent pointer chases in flight per
+        // thread instead of one after the other (the walk is L2-latency bound: tall components leave chains
+        // as deep as their height)
+        constexpr int NW = CHUNK / CHUNK_THREADS;
+        int x[NW], first[NW];
 #pragma unroll
-        for (int k = 0; k < CHUNK / CHUNK_THREADS; ++k) {
+        for (int k = 0; k < NW; ++k) {
+            const int i = base + k * CHUNK_THREADS + threadIdx.x;
+            first[k] = (i < R) ? __ldcg(pa + i) : -1;
+            x[k] = first[k];
+        }
+        bool moving = true;
+        while (moving) {
+            moving = false;
+            int p[NW];
+#pragma unroll
+            for (int k = 0; k < NW; ++k) p[k] = (x[k] >= 0) ? __ldcg(pa + x[k]) : -1;
+#pragma unroll
+            for (int k = 0; k < NW; ++k)
+                if (p[k] != x[k]) { x[k] = p[k]; moving = true; }
+        }
+#pragma unroll
+        for (int k = 0; k < NW; ++k) {
             const int i = base + k * CHUNK_THREADS + threadIdx.x;
             if (i < R) {
-                const int l = pa[i];
-                const int r = find_root(pa, i);
-                if (r != l) pa[i] = r;
-                cnt += (r == i);
+                if (x[k] != first[k]) pa[i] = x[k];
+                cnt += (x[k] == i);
             }
         }
+        __syncthreads();                                       // sh is reused across chunks
+        const int tot = block_sum_256(cnt, sh);
+        if (threadIdx.x == 0) chunk_count[(long long)f * (dm.nchunks + 1) + chunk] = tot;
     }
-    const int tot = block_sum_256(cnt, sh);
-    if (threadIdx.x == 0) chunk_count[(long long)f * (dm.nchunks + 1) + blockIdx.x] = tot;
 }
 
-// grid (nchunks, n), block 256: thread t owns 8 consecutive runs (keeps raster order)
+// grid (blocks, n), block 256: raster-ordered root list; thread t owns 8 consecutive runs of a chunk.  The
+// chunk's offset is the sum of the counts of the chunks before it (a handful for a real frame), added up by
+// the block itself; the block of chunk 0 also publishes the frame's root count.
 __global__ void root_emit(const int *__restrict__ parent, const int *__restrict__ totals,
-                          const int *__restrict__ chunk_count, const int *__restrict__ chunk_off,
+                          const int *__restrict__ chunk_count, int *__restrict__ nroots,
                           int *__restrict__ rootlist, Dims dm, int max_rows)
 {
-    __shared__ int warp_sums[8];
+    __shared__ int warp_sums[8], sh[8], s_off;
     const int f = blockIdx.y;
-    if (chunk_count[(long long)f * (dm.nchunks + 1) + blockIdx.x] == 0) return;
     const int R = totals[f];
+    const int nact = (R + CHUNK - 1) / CHUNK;
+    const int *cc = chunk_count + (long long)f * (dm.nchunks + 1);
     const int *pa = parent + (long long)f * dm.maxruns;
-    const int base = blockIdx.x * CHUNK + threadIdx.x * 8;
-    int flags = 0, cnt = 0;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const int i = base + k;
-        if (i < R && pa[i] == i) { flags |= 1 << k; ++cnt; }
-    }
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    int s = cnt;
-    for (int o = 1; o < 32; o <<= 1) {
-        int t = __shfl_up_sync(0xffffffffu, s, o);
-        if (lane >= o) s += t;
-    }
-    if (lane == 31) warp_sums[wid] = s;
-    __syncthreads();
-    int pre = 0;
-    for (int w = 0; w < wid; ++w) pre += warp_sums[w];
-    int pos = chunk_off[(long long)f * (dm.nchunks + 1) + blockIdx.x] + pre + s - cnt;
-#pragma unroll
-    for (int k = 0; k < 8; ++k)
-        if (flags & (1 << k)) {
-            if (pos < max_rows) rootlist[(long long)f * max_rows + pos] = base + k;
-            ++pos;
+    if (blockIdx.x == 0 && nact == 0 && threadIdx.x == 0) nroots[f] = 0;
+    for (int chunk = blockIdx.x; chunk < nact; chunk += gridDim.x) {
+        int before = 0, all = 0;
+        for (int i = threadIdx.x; i < nact; i += blockDim.x) {
+            const int c = cc[i];
+            all += c;
+            if (i < chunk) before += c;
         }
+        __syncthreads();
+        const int off = block_sum_256(before, sh);
+        if (threadIdx.x == 0) s_off = off;
+        __syncthreads();
+        if (chunk == 0) {
+            const int tot = block_sum_256(all, sh);
+            if (threadIdx.x == 0) nroots[f] = tot;
+            __syncthreads();
+        }
+        if (cc[chunk] != 0) {
+            const int base = chunk * CHUNK + threadIdx.x * 8;
+            int flags = 0, cnt = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int i = base + k;
+                if (i < R && pa[i] == i) { flags |= 1 << k; ++cnt; }
+            }
+            const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+            int s2 = cnt;
+            for (int o = 1; o < 32; o <<= 1) {
+                int t = __shfl_up_sync(0xffffffffu, s2, o);
+                if (lane >= o) s2 += t;
+            }
+            if (lane == 31) warp_sums[wid] = s2;
+            __syncthreads();
+            int pre = 0;
+            for (int w = 0; w < wid; ++w) pre += warp_sums[w];
+            int pos = s_off + pre + s2 - cnt;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (flags & (1 << k)) {
+                    if (pos < max_rows) rootlist[(long long)f * max_rows + pos] = base + k;
+                    ++pos;
+                }
+        }
+        __syncthreads();
+    }
 }
 
 // grid (n), block 256: stable counting sort of the frame's root runs by class value.
@@ -364,10 +407,21 @@ __global__ void ccl_order(const uint8_t *__restrict__ mask, const int *__restric
 
     cnt_sh[c] = 0;
     __syncthreads();
-    for (int j = c; j < n; j += 256) {
-        const uint8_t v = mk[rs[rl[j]]];
-        if (j < ORDER_PAR) cls[j] = v;
-        atomicAdd(&cnt_sh[v], 1);
+    // class of every root: three dependent loads (root slot -> first voxel -> class), four roots per thread in flight
+    for (int j0 = 0; j0 < n; j0 += 1024) {
+        int r[4], sv[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { const int j = j0 + q * 256 + c; r[q] = j < n ? rl[j] : -1; }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) sv[q] = r[q] >= 0 ? rs[r[q]] : 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (r[q] < 0) continue;
+            const int j = j0 + q * 256 + c;
+            const uint8_t v = mk[sv[q]];
+            if (j < ORDER_PAR) cls[j] = v;
+            atomicAdd(&cnt_sh[v], 1);
+        }
     }
     __syncthreads();
     const int mine = cnt_sh[c];
@@ -467,9 +521,13 @@ __global__ void ccl_finalize(const uint8_t *__restrict__ mask, const int *__rest
 }
 
 struct Workspace {
-    int *seg_count, *seg_off, *totals, *run_start, *run_end, *parent;
-    int *chunk_count, *chunk_off, *nroots, *rootlist, *sorted_root, *class_base;
-    unsigned long long *acc;
+    int *seg_off, *totals, *run_start, *run_end, *parent;
+    int *chunk_count, *nroots, *rootlist, *sorted_root, *class_base;
+    // zeroed before every call, contiguous: look-back status words, centroid accumulators, block tickets
+    unsigned long long *status, *acc;
+    int *ticket;
+    size_t zero_bytes;
+    int nblk;
     size_t bytes;
 };
 
@@ -477,19 +535,22 @@ Workspace carve(void *p, size_t avail, const Dims &dm, int max_rows)
 {
     SqArena a(p, avail);
     Workspace w;
-    w.seg_count = a.take<int>((size_t)dm.n * (dm.nsegs + 1));
+    w.nblk = sq_div_up(dm.nsegs, SPB);
     w.seg_off = a.take<int>((size_t)dm.n * (dm.nsegs + 1));
     w.totals = a.take<int>(dm.n);
     w.run_start = a.take<int>((size_t)dm.n * dm.maxruns);
     w.run_end = a.take<int>((size_t)dm.n * dm.maxruns);
     w.parent = a.take<int>((size_t)dm.n * dm.maxruns);
     w.chunk_count = a.take<int>((size_t)dm.n * (dm.nchunks + 1));
-    w.chunk_off = a.take<int>((size_t)dm.n * (dm.nchunks + 1));
     w.nroots = a.take<int>(dm.n);
     w.rootlist = a.take<int>((size_t)dm.n * max_rows);
     w.sorted_root = a.take<int>((size_t)dm.n * max_rows);
     w.class_base = a.take<int>((size_t)dm.n * 256);
+    const size_t z0 = a.off;
+    w.status = a.take<unsigned long long>((size_t)dm.n * w.nblk);
     w.acc = a.take<unsigned long long>((size_t)dm.n * max_rows * 4);
+    w.ticket = a.take<int>(dm.n);
+    w.zero_bytes = a.off - z0;
     w.bytes = a.off;
     return w;
 }
@@ -540,21 +601,19 @@ extern "C" int sq_label_centroids(sq_handle_t h, const uint8_t *mask, int n, int
     SQ_REQUIRE(w.bytes <= ws_bytes, SQ_ENOMEM, "label: workspace %zu < %zu bytes", ws_bytes, w.bytes);
     cudaStream_t st = (cudaStream_t)stream_;
 
-    SQ_CUDA(cudaMemsetAsync(w.acc, 0, (size_t)n * max_rows * 4 * sizeof(unsigned long long), st));
+    SQ_CUDA(cudaMemsetAsync(w.status, 0, w.zero_bytes, st));
     if (labels) SQ_CUDA(cudaMemsetAsync(labels, 0, (size_t)n * dm.vox * sizeof(int32_t), st));
-    const dim3 seg_grid(sq_div_up(dm.nsegs, 8), n);
-    run_count<<<seg_grid, 256, 0, st>>>(mask, w.seg_count, dm);
-    scan_i32<<<n, 1024, 0, st>>>(w.seg_count, w.seg_off, w.totals, dm.nsegs, dm.nsegs + 1, 1);
-    run_emit<<<seg_grid, 256, 0, st>>>(mask, w.seg_off, w.run_start, w.run_end, w.parent, dm);
+    run_scan_emit<<<dim3(w.nblk, n), 256, 0, st>>>(mask, w.status, w.ticket, w.seg_off, w.totals, w.run_start, w.run_end,
+                                                   w.parent, dm, w.nblk);
     SQ_CHECK_LAUNCH();
     // O(runs) kernels: the run count lives on the device, so launch a fixed grid and stride
     const int rblocks = std::min(dm.nchunks * (CHUNK / 256), 4 * h->sm_count);
+    const int cblocks = std::min(dm.nchunks, std::max(1, 2 * h->sm_count / n));
     run_merge<<<dim3(rblocks, n), 256, 0, st>>>(mask, w.seg_off, w.totals, w.run_start, w.run_end,
                                                 w.parent, dm);
-    run_compress<<<dim3(dm.nchunks, n), CHUNK_THREADS, 0, st>>>(w.parent, w.totals, w.chunk_count, dm);
-    scan_i32<<<n, 1024, 0, st>>>(w.chunk_count, w.chunk_off, w.nroots, dm.nchunks, dm.nchunks + 1, 0);
-    root_emit<<<dim3(dm.nchunks, n), CHUNK_THREADS, 0, st>>>(w.parent, w.totals, w.chunk_count,
-                                                            w.chunk_off, w.rootlist, dm, max_rows);
+    run_compress<<<dim3(cblocks, n), CHUNK_THREADS, 0, st>>>(w.parent, w.totals, w.chunk_count, dm);
+    root_emit<<<dim3(cblocks, n), CHUNK_THREADS, 0, st>>>(w.parent, w.totals, w.chunk_count, w.nroots, w.rootlist, dm,
+                                                         max_rows);
     ccl_order<<<n, 256, 0, st>>>(mask, w.run_start, w.parent, w.rootlist, w.nroots, w.sorted_root,
                                  w.class_base, dm, max_rows);
     SQ_CHECK_LAUNCH();
