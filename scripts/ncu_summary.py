@@ -66,7 +66,7 @@ def full(src, dst, dst_json):
     for r in data:
         out.append((short(r[col('Kernel Name')]), val(r, 'gpu__time_duration.sum', 'us'),
                     val(r, 'dram__bytes_read.sum', 'MB'), val(r, 'dram__bytes_write.sum', 'MB'),
-                    val(r, 'dram__throughput.avg.pct_of_peak_sustained_elapsed'),
+                    val(r, 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed'),
                     val(r, 'sm__inst_executed_pipe_tensor_subpipe_hmma.avg.pct_of_peak_sustained_active'),
                     val(r, 'sm__pipe_tc_cycles_active.avg.pct_of_peak_sustained_active'),
                     val(r, 'smsp__issue_active.avg.pct_of_peak_sustained_active'),
@@ -75,11 +75,13 @@ def full(src, dst, dst_json):
         f.write('kernel,us,dram_read_MB,dram_write_MB,dram_pct,hmma_issue_pct,tc_pipe_pct,issue_pct,regs,grid\n')
         for o in out:
             f.write('"%s",%.1f,%.1f,%.1f,%.1f,%.2f,%.1f,%.1f,%.0f,%.0f\n' % o)
-    conv = [o for o in out if o[0].startswith('conv_tc_kernel') or o[0].startswith('conv_xc_kernel')]
+    conv = [o for o in out if o[0].startswith(('conv_tc_kernel', 'conv_xc_kernel', 'conv_qd_kernel', 'conv_qf_kernel',
+                                               'conv_qu_kernel', 'first_conv_kernel'))]
     if conv:
         js = {'launches': len(conv),
               'avg_dram_bytes_per_launch': sum((o[2] + o[3]) for o in conv) / len(conv) * 1e6,
               'total_us': sum(o[1] for o in conv),
+              'total_dram_bytes': sum((o[2] + o[3]) for o in conv) * 1e6,
               'time_weighted_tc_pipe_pct': sum(o[1] * o[6] for o in conv) / sum(o[1] for o in conv),
               'source': 'ncu --set full --clock-control none, one forward pass'}
         json.dump(js, open(dst_json, 'w'), indent=1)

@@ -1657,6 +1657,7 @@ conv_qf_kernel(const __grid_constant__ CUtensorMap mapIn, const bf16 *__restrict
 #define QF_T0() const long long t0_ = phase_dbg ? clock64() : 0
 #define QF_T1(i) if (phase_dbg) dacc[i] += clock64() - t0_
     long long dacc[6] = {0, 0, 0, 0, 0, 0};
+    const long long t_kernel0 = clock64();
 #else
 #define QF_W(i, stmt) do { stmt; } while (0)
 #define QF_T0() do { } while (0)
@@ -1920,6 +1921,7 @@ conv_qf_kernel(const __grid_constant__ CUtensorMap mapIn, const bf16 *__restrict
     // per role (producer, MMA, first builder warp, first epilogue warp): clocks spent in each wait
     if (phase_dbg && lane == 0 && (warp <= 2 || warp == 2 + QF::BLD_WARPS)) {
         const int role = warp <= 2 ? warp : 3;
+        dacc[5] = clock64() - t_kernel0;                 // the role's whole lifetime, in clock64 ticks
         for (int i = 0; i < 6; ++i) phase_dbg[(blockIdx.x * 4 + role) * 8 + i] = dacc[i];
     }
 #endif
@@ -1939,20 +1941,24 @@ conv_qf_kernel(const __grid_constant__ CUtensorMap mapIn, const bf16 *__restrict
 // bit-identical to the two-launch quad path (same MMAs, same bf16 rounding of the intermediate).  Structure of
 // conv_qf_kernel with two differences: "conv1" is the 2x2 stride-2 up-conv = a 1x1 conv (cin -> 4 x 16) over the
 // 10 x 34 half-resolution pixels of conv's halo patch, whose A operand is the TMA-fetched patch of the level-1
-// tensor itself (no builders); and the conv reads a second source, the skip tensor, through a 4-stage ring of
-// one-k-step TMA boxes that is consumed BEFORE the on-chip patch P (it is ready earlier).  One CTA per SM:
+// tensor itself (no builders); and the conv reads a second source, the skip tensor, through an 8-stage ring of
+// one-k-step TMA boxes (two tiles of prefetch).  One CTA per SM:
 //   warp 0       TMA: level-1 patch (A1) + 4 skip k-steps per tile
 //   warp 1       MMA: up-conv 3 M-tiles x ksu k-steps -> acc1; conv: 4 skip k-steps + 4 P k-steps, 64 MMAs -> acc2
 //   warps 2-17   epilogue 1: acc1 + bias -> bf16 -> P (zeros outside the frame); epilogue 2: acc2 -> ReLU -> quad tensor
+// Schedule (two balanced phases per tile): the tensor pipe runs  [P half of tile i-1] [up-conv + skip half of tile i]
+// while the epilogue warps run  [epilogue 1 of tile i, under the skip half of tile i] [epilogue 2 of tile i-1, under
+// the P half of tile i]; P is single-buffered (free once the P half of the previous tile has retired), the
+// conv accumulators are double-buffered.
 struct QU {
     static constexpr int TH = 32, PW = 10, PH = 34, PROWS = PW * PH;
     static constexpr int KSTEP_BYTES = 2 * PROWS * 16;                    // 16 channels of a patch
     static constexpr int A1_BYTES = (2 * KSTEP_BYTES + 1024 + 127) / 128 * 128;   // up to 32 input channels (+ M-tile over-read)
     static constexpr int P_BYTES = 4 * KSTEP_BYTES;
     static constexpr int WU_BYTES = 2 * 2 * 64 * 16, W_BYTES = 8 * 4 * 2 * 64 * 16;
-    static constexpr int NRING = 4;
+    static constexpr int NRING = 8;
     static constexpr int OFF_WU = 0, OFF_W = WU_BYTES, OFF_A1 = OFF_W + W_BYTES, OFF_P = OFF_A1 + A1_BYTES,
-                         OFF_RING = OFF_P + 2 * P_BYTES, SMEM = OFF_RING + NRING * KSTEP_BYTES;
+                         OFF_RING = OFF_P + P_BYTES, SMEM = OFF_RING + NRING * KSTEP_BYTES;
     static constexpr int EPI_WARPS = 16, THREADS = 32 * (2 + EPI_WARPS);
     static_assert(OFF_A1 % 128 == 0 && OFF_P % 128 == 0 && OFF_RING % 128 == 0 && KSTEP_BYTES % 128 == 0, "alignment");
     static_assert(SMEM + 1024 <= 232448, "shared memory");
@@ -1968,7 +1974,7 @@ conv_qu_kernel(const __grid_constant__ CUtensorMap mapCur, const __grid_constant
     // up-conv's epilogue, ep.sc2 / sh2: the conv's.
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
-    __shared__ uint64_t w_bar, a1_full, a1_empty, acc1_full, acc1_empty, p_full[2], p_empty[2],
+    __shared__ uint64_t w_bar, a1_full, a1_empty, acc1_full, acc1_empty, p_full, p_empty,
         ring_full[QU::NRING], ring_empty[QU::NRING], acc2_full[2], acc2_empty[2];
     __shared__ uint32_t tmem_base_sh;
 
@@ -1981,10 +1987,8 @@ conv_qu_kernel(const __grid_constant__ CUtensorMap mapCur, const __grid_constant
         tc::mbar_init(&w_bar, 1);
         tc::mbar_init(&a1_full, 1); tc::mbar_init(&a1_empty, 1);
         tc::mbar_init(&acc1_full, 1); tc::mbar_init(&acc1_empty, QU::EPI_WARPS);
-        for (int i = 0; i < 2; ++i) {
-            tc::mbar_init(&p_full[i], QU::EPI_WARPS); tc::mbar_init(&p_empty[i], 1);
-            tc::mbar_init(&acc2_full[i], 1); tc::mbar_init(&acc2_empty[i], QU::EPI_WARPS);
-        }
+        tc::mbar_init(&p_full, QU::EPI_WARPS); tc::mbar_init(&p_empty, 1);
+        for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc2_full[i], 1); tc::mbar_init(&acc2_empty[i], QU::EPI_WARPS); }
         for (int i = 0; i < QU::NRING; ++i) { tc::mbar_init(&ring_full[i], 1); tc::mbar_init(&ring_empty[i], 1); }
         tc::fence_barrier_init();
         tc::tma_prefetch_desc(&mapCur);
@@ -2035,7 +2039,33 @@ conv_qu_kernel(const __grid_constant__ CUtensorMap mapCur, const __grid_constant
         uint32_t rphase = 0;
         tc::mbar_wait(&w_bar, 0);
         for (int it = 0; it <= nt; ++it) {
+            if (it >= 1) {
+                // ---- P half of tile it-1: the up-sampled patch written by epilogue 1
+                const int i2 = it - 1, b = i2 & 1;
+                const uint32_t d0 = tmem_base + ACC2 + b * 128;
+                tc::mbar_wait(&p_full, i2 & 1);
+                tc::tc_fence_after();
+                if (tc::elect_one()) {
+                    const uint32_t p_lo = (((sbase + QU::OFF_P) >> 4) & 0x3FFFu) | lboP;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int iy = k >> 1, ix = k & 1;
+#pragma unroll
+                        for (int j = 0; j < 2; ++j)
+#pragma unroll
+                            for (int tp = 0; tp < 4; ++tp)
+                                tc::umma_bf16_parts(d0 + j * 64,
+                                                    p_lo + (uint32_t)(k * (QU::KSTEP_BYTES >> 4) + (j * 16 + (tp >> 1) + 1 - iy) * QU::PW + (tp & 1) + 1 - ix),
+                                                    hiP, w_lo + (uint32_t)((k * 4 + tp) * 128), hi128, idesc, 1u);
+                    }
+                    tc::umma_commit(&p_empty);
+                    tc::umma_commit(&acc2_full[b]);
+                }
+                __syncwarp();
+            }
             if (it < nt) {
+                // ---- up-conv of tile it, then the skip half of its conv (prefetched through the ring)
+                const int b = it & 1;
                 tc::mbar_wait(&a1_full, it & 1);
                 tc::mbar_wait(&acc1_empty, (it & 1) ^ 1);
                 tc::tc_fence_after();
@@ -2049,13 +2079,9 @@ conv_qu_kernel(const __grid_constant__ CUtensorMap mapCur, const __grid_constant
                     tc::umma_commit(&acc1_full);
                 }
                 __syncwarp();
-            }
-            if (it >= 1) {
-                const int i2 = it - 1, b = i2 & 1;
-                tc::mbar_wait(&acc2_empty[b], ((i2 >> 1) & 1) ^ 1);
+                tc::mbar_wait(&acc2_empty[b], ((it >> 1) & 1) ^ 1);
                 tc::tc_fence_after();
                 const uint32_t d0 = tmem_base + ACC2 + b * 128;
-                // the skip tensor's four k-steps first (prefetched through the ring) ...
                 for (int ks = 0; ks < 4; ++ks) {
                     tc::mbar_wait(&ring_full[rs], rphase);
                     tc::tc_fence_after();
@@ -2073,26 +2099,6 @@ conv_qu_kernel(const __grid_constant__ CUtensorMap mapCur, const __grid_constant
                     __syncwarp();
                     if (++rs == QU::NRING) { rs = 0; rphase ^= 1; }
                 }
-                // ... then the up-sampled patch written by epilogue 1
-                tc::mbar_wait(&p_full[b], (i2 >> 1) & 1);
-                tc::tc_fence_after();
-                if (tc::elect_one()) {
-                    const uint32_t p_lo = (((sbase + QU::OFF_P + b * QU::P_BYTES) >> 4) & 0x3FFFu) | lboP;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const int iy = k >> 1, ix = k & 1;
-#pragma unroll
-                        for (int j = 0; j < 2; ++j)
-#pragma unroll
-                            for (int tp = 0; tp < 4; ++tp)
-                                tc::umma_bf16_parts(d0 + j * 64,
-                                                    p_lo + (uint32_t)(k * (QU::KSTEP_BYTES >> 4) + (j * 16 + (tp >> 1) + 1 - iy) * QU::PW + (tp & 1) + 1 - ix),
-                                                    hiP, w_lo + (uint32_t)((k * 4 + tp) * 128), hi128, idesc, 1u);
-                    }
-                    tc::umma_commit(&p_empty[b]);
-                    tc::umma_commit(&acc2_full[b]);
-                }
-                __syncwarp();
             }
         }
     } else {
@@ -2116,12 +2122,11 @@ conv_qu_kernel(const __grid_constant__ CUtensorMap mapCur, const __grid_constant
         for (int it = 0; it <= nt; ++it) {
             if (it < nt) {
                 // ---- epilogue 1: the up-conv's accumulators (+ bias, no ReLU) -> the bf16 halo patch of the conv
-                const int b = it & 1;
                 const int x0 = tx * 8 - 1, y0 = ty * QU::TH - 1;
                 tc::mbar_wait(&acc1_full, it & 1);
-                tc::mbar_wait(&p_empty[b], ((it >> 1) & 1) ^ 1);
+                tc::mbar_wait(&p_empty, (it & 1) ^ 1);
                 tc::tc_fence_after();
-                uint8_t *P = smem + QU::OFF_P + b * QU::P_BYTES + (2 * g) * (QU::PROWS * 16) + r * 16;
+                uint8_t *P = smem + QU::OFF_P + (2 * g) * (QU::PROWS * 16) + r * 16;
                 const bool border = x0 < 0 || y0 < 0 || x0 + QU::PW > W || y0 + QU::PH > H;
                 uint32_t v[3][16];
                 tc::tmem_ld16(tmem_base + lane_addr + ACC1 + g * 16, v[0]);
@@ -2151,7 +2156,7 @@ conv_qu_kernel(const __grid_constant__ CUtensorMap mapCur, const __grid_constant
                 tc::fence_proxy_async();
                 tc::tc_fence_before();
                 __syncwarp();
-                if (lane == 0) { tc::mbar_arrive(&p_full[b]); tc::mbar_arrive(&acc1_empty); }
+                if (lane == 0) { tc::mbar_arrive(&p_full); tc::mbar_arrive(&acc1_empty); }
             }
             if (it >= 1) {
                 // ---- epilogue 2: the conv's accumulators -> ReLU -> quad tensor
@@ -3043,8 +3048,8 @@ int launch_qf(sq_unet_s *u, const SqLayer &L1, const SqLayer &L2, const float *i
         const double tpc = (double)tiles / grid;
         fprintf(stderr, "qf_phase %.3f ms, tiles/CTA=%.0f (%.0f clk/tile at 1.965 GHz) | per tile clk: producer wait raw_empty %.0f | mma wait a1_full %.0f "
                 "acc1_empty %.0f p_full %.0f acc2_empty %.0f | builders wait raw_full %.0f a1_empty %.0f | epilogue wait acc1_full %.0f "
-                "p_empty %.0f acc2_full %.0f; work: epilogue 1 %.0f, epilogue 2 %.0f\n", ms, tpc, ms * 1.965e6 / tpc, a[0] / tpc, a[8] / tpc, a[9] / tpc, a[10] / tpc, a[11] / tpc,
-                a[16] / tpc, a[17] / tpc, a[24] / tpc, a[25] / tpc, a[26] / tpc, a[27] / tpc, a[28] / tpc);
+                "p_empty %.0f acc2_full %.0f; work: epilogue 1 %.0f, epilogue 2 %.0f; MMA warp lifetime %.0f ticks = %.3f GHz-equivalent\n", ms, tpc, ms * 1.965e6 / tpc, a[0] / tpc, a[8] / tpc, a[9] / tpc, a[10] / tpc, a[11] / tpc,
+                a[16] / tpc, a[17] / tpc, a[24] / tpc, a[25] / tpc, a[26] / tpc, a[27] / tpc, a[28] / tpc, a[13], a[13] / (ms * 1e6));
     }
 #endif
     return SQ_OK;
