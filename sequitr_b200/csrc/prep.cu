@@ -4,6 +4,7 @@
 //   ImageBGSubtract  reference pipeline.py:360-405   least-squares quadratic background surface
 // All three are HBM-bound: one or two streaming passes over a float32 (N,H,W,C) stack.
 #include "sq_common.cuh"
+#include <cuda_bf16.h>
 #include <cmath>
 
 namespace {
@@ -422,9 +423,61 @@ int norm_launch(const T *in, float *out, int n, long long npix, int c, double *p
     SQ_CHECK_LAUNCH();
     norm_final<<<(n * c + 3) / 4, 128, 0, st>>>(part, npix, n * c, stats);
     SQ_CHECK_LAUNCH();
+    if (!out) return SQ_OK;                            // moments only: the consumer applies them itself
     norm_apply<T><<<dim3((unsigned)((npix * c + 1023) / 1024), n), 256, 0, st>>>(in, out, npix * c, c, stats);
     SQ_CHECK_LAUNCH();
     return SQ_OK;
+}
+
+// ImageNorm of single-channel raw frames with the result rounded to bf16 (RNE) -- what the UNet's first conv does
+// with its float32 input anyway (bf16 contract): 2 B/px out instead of 4, and the fused first pair loads it as is.
+template <typename T>
+__global__ void norm_apply_bf16(const T *__restrict__ in, __nv_bfloat16 *__restrict__ out, long long per_image,
+                                const float2 *__restrict__ stats)
+{
+    const int n = blockIdx.y;
+    const float2 st = stats[n];
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // four pixels per thread
+    if (i >= (per_image >> 2)) return;
+    float4 f = load4<T>(in + (size_t)n * per_image + 4 * i);
+    f.x = __fdiv_rn(__fsub_rn(f.x, st.x), st.y);
+    f.y = __fdiv_rn(__fsub_rn(f.y, st.x), st.y);
+    f.z = __fdiv_rn(__fsub_rn(f.z, st.x), st.y);
+    f.w = __fdiv_rn(__fsub_rn(f.w, st.x), st.y);
+    __nv_bfloat162 lo = __floats2bfloat162_rn(f.x, f.y), hi = __floats2bfloat162_rn(f.z, f.w);
+    uint2 o;
+    o.x = *reinterpret_cast<unsigned *>(&lo);
+    o.y = *reinterpret_cast<unsigned *>(&hi);
+    reinterpret_cast<uint2 *>(out + (size_t)n * per_image)[i] = o;
+}
+
+// internal (the host pipeline of the UNet): uint16 frames -> normalised bf16 frames; hgt * wid must be a multiple of 4
+int sq_image_norm_u16_to_bf16(sq_handle_t h, const uint16_t *in, void *out_bf16, int n, int hgt, int wid, void *ws,
+                              size_t ws_bytes, cudaStream_t st)
+{
+    SqArena a(ws, ws_bytes);
+    double *part = a.take<double>((size_t)n * PREP_BLOCKS * 6);
+    float2 *stats = (float2 *)a.take<double>((size_t)n * 8);
+    SQ_REQUIRE(a.ok(), SQ_ENOMEM, "image_norm: workspace %zu < %zu bytes", ws_bytes, a.off);
+    const long long npix = (long long)hgt * wid;
+    SQ_REQUIRE((npix & 3) == 0, SQ_EINVAL, "image_norm(bf16): frame size must be a multiple of 4 pixels");
+    SQ_TRY(norm_launch(in, (float *)nullptr, n, npix, 1, part, stats, st));
+    norm_apply_bf16<uint16_t><<<dim3((unsigned)((npix / 4 + 255) / 256), n), 256, 0, st>>>(in, (__nv_bfloat16 *)out_bf16, npix, stats);
+    SQ_CHECK_LAUNCH();
+    return SQ_OK;
+}
+
+// ImageNorm's moments of raw uint16 frames only (internal: the fused first pair of the UNet applies them in its
+// loader); *stats = n float2 (mean, std) inside the workspace, valid in stream order
+int sq_image_norm_stats_u16(sq_handle_t h, const uint16_t *in, int n, int hgt, int wid, void *ws, size_t ws_bytes,
+                            cudaStream_t st, const float2 **stats_out)
+{
+    SqArena a(ws, ws_bytes);
+    double *part = a.take<double>((size_t)n * PREP_BLOCKS * 6);
+    float2 *stats = (float2 *)a.take<double>((size_t)n * 8);
+    SQ_REQUIRE(a.ok(), SQ_ENOMEM, "image_norm: workspace %zu < %zu bytes", ws_bytes, a.off);
+    *stats_out = stats;
+    return norm_launch(in, (float *)nullptr, n, (long long)hgt * wid, 1, part, stats, st);
 }
 
 extern "C" int sq_image_norm_raw(sq_handle_t h, const void *in, int in_dtype, float *out, int n, int hgt,

@@ -555,7 +555,8 @@ static int segment_localise_impl(sq_unet_t u, const void *frames_host, int in_dt
     // over the whole batch of masks and only the small centroid tables travel back.
     const size_t px1 = (size_t)hgt * wid, px = (size_t)n * px1;
     const size_t esz = in_dtype == SQ_U8 ? 1 : (in_dtype == SQ_U16 ? 2 : 4);
-    const bool staged = in_dtype != SQ_F32 || normalise;      // raw chunk -> float32 chunk on the device
+    const bool fuse_norm = normalise && in_dtype == SQ_U16 && u->mode == SQ_MODE_BF16_TC && sq_tc_can_take_raw_u16(u, hgt, wid);
+    const bool staged = !fuse_norm && (in_dtype != SQ_F32 || normalise);      // raw chunk -> float32 chunk on the device
     // Chunk schedule 1, 1, 2, 4, 8, 8, ...: the first copy (the only one nothing can hide) is one frame;
     // steady-state chunks are as large as the bench batch (the net runs ~5 % faster on 8 frames than on 4).
     // Chunk size is bounded by memory: 2 input buffers + the net's workspace per chunk.
@@ -580,14 +581,14 @@ static int segment_localise_impl(sq_unet_t u, const void *frames_host, int in_dt
     const size_t chunk_elems = (size_t)ch * px1 * u->cin;
     SqArena probe(nullptr, 0);
     probe.take<char>(2 * chunk_elems * esz);
-    if (staged) probe.take<float>(chunk_elems);
+    if (staged || fuse_norm) probe.take<float>(chunk_elems);
     probe.take<uint8_t>(px);
     probe.take<float>((size_t)n * max_rows * 5);
     probe.take<int32_t>(n);
     SQ_TRY(sq_reserve_device(h, probe.off + sq_align_up(unet_ws) + sq_align_up(lab_ws) + sq_align_up(prep_ws) + 1024));
     SqArena a(h->dev_arena, h->dev_arena_bytes);
     char *frames = a.take<char>(2 * chunk_elems * esz);
-    float *stage = staged ? a.take<float>(chunk_elems) : nullptr;
+    float *stage = (staged || fuse_norm) ? a.take<float>(chunk_elems) : nullptr;
     uint8_t *mask = a.take<uint8_t>(px);
     float *table = a.take<float>((size_t)n * max_rows * 5);
     int32_t *counts = a.take<int32_t>(n);
@@ -606,6 +607,22 @@ static int segment_localise_impl(sq_unet_t u, const void *frames_host, int in_dt
         SQ_CUDA(cudaEventRecord(h->ev_h2d[b], cs));
         SQ_CUDA(cudaStreamWaitEvent(st, h->ev_h2d[b], 0));
         const float *net_in = (const float *)buf;
+        if (fuse_norm) {
+            // uint16 frames + ImageNorm: widened, normalised and rounded to bf16 ONCE (2 B/px, into the stage buffer); the
+            // fused first pair of the UNet loads that as is -- no float32 copy of the chunk.  SQ_QNORM=2: only the
+            // moments are computed here and the first pair's loader normalises the raw values itself (slower).
+            const char *qn = getenv("SQ_QNORM");
+            if (qn && atoi(qn) == 2) {
+                const float2 *stats = nullptr;
+                SQ_TRY(sq_image_norm_stats_u16(h, (const uint16_t *)buf, nc, hgt, wid, w3, prep_ws, st, &stats));
+                SQ_TRY(sq_tc_forward_raw_u16(u, (const uint16_t *)buf, stats, nc, hgt, wid, mask + (size_t)f0 * px1, w1, unet_ws, st));
+            } else {
+                SQ_TRY(sq_image_norm_u16_to_bf16(h, (const uint16_t *)buf, stage, nc, hgt, wid, w3, prep_ws, st));
+                SQ_TRY(sq_tc_forward_raw_u16(u, (const uint16_t *)stage, nullptr, nc, hgt, wid, mask + (size_t)f0 * px1, w1, unet_ws, st));
+            }
+            SQ_CUDA(cudaEventRecord(h->ev_done[b], st));
+            continue;
+        }
         if (staged) {
             // widen (exact for 8/16-bit integers) and optionally normalise; the raw buffer is free as
             // soon as the cast has run, the float32 stage is consumed in stream order

@@ -57,5 +57,16 @@ int sq_tc_workspace_bytes(sq_unet_s *u, int n, int d, int hgt, int wid, size_t *
 int sq_tc_forward(sq_unet_s *u, const float *in, int n, int d, int hgt, int wid, float *probs,
                   uint8_t *mask, float *logits, void *ws, size_t ws_bytes, cudaStream_t st);
 
+// 16-bit frames straight into the fused first pair (no float32 copy of the frames): stats == NULL: `frames16` holds
+// bf16 values (the normalised frames, sq_image_norm_u16_to_bf16); stats != NULL: raw uint16 camera values that the
+// loader normalises itself with the per-frame (mean, std) (SQ_QNORM=2, measured slower)
+bool sq_tc_can_take_raw_u16(sq_unet_s *u, int hgt, int wid);
+int sq_tc_forward_raw_u16(sq_unet_s *u, const uint16_t *frames16, const float2 *stats, int n, int hgt, int wid,
+                          uint8_t *mask, void *ws, size_t ws_bytes, cudaStream_t st);
+int sq_image_norm_stats_u16(sq_handle_t h, const uint16_t *in, int n, int hgt, int wid, void *ws, size_t ws_bytes,
+                            cudaStream_t st, const float2 **stats_out);
+int sq_image_norm_u16_to_bf16(sq_handle_t h, const uint16_t *in, void *out_bf16, int n, int hgt, int wid, void *ws,
+                              size_t ws_bytes, cudaStream_t st);
+
 // timer helpers (unet.cu)
 void sq_timer_mark(sq_unet_s *u, cudaStream_t st, const char *name, double flops);

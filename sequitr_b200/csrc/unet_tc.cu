@@ -1648,8 +1648,13 @@ struct QfEpi {
     float sc1[16], sh1[16], sc2[16], sh2[16];
 };
 
+// RAW16: the frames are raw uint16 camera values and ImageNorm (pipeline.py:338-356: (x - mean) / std per frame, in
+// float32 exactly as sq_image_norm does) is applied by the builders while they pack the im2col -- the float32 copy
+// of the frames never exists.  stats: (mean, std) per frame.
+template <bool RAW16>
 __global__ void __launch_bounds__(QF::THREADS, 1)
 conv_qf_kernel(const __grid_constant__ CUtensorMap mapIn, const bf16 *__restrict__ wts, const QfEpi ep,
+               const float2 *__restrict__ stats,
                bf16 *__restrict__ out, bf16 *__restrict__ out_pool, int nimg, int H, int W, long long *phase_dbg)
 {
 #ifdef SQ_XC_PHASE_DIAG
@@ -1706,10 +1711,11 @@ conv_qf_kernel(const __grid_constant__ CUtensorMap mapIn, const bf16 *__restrict
                 const int t = blockIdx.x + it * gridDim.x, b = it & 1;
                 const int tx = t % tiles_x, ty = (t / tiles_x) % tiles_y, n = t / (tiles_x * tiles_y);
                 QF_W(0, tc::mbar_wait(&raw_empty[b], ((it >> 1) & 1) ^ 1));
-                tc::mbar_arrive_expect_tx(&raw_full[b], QF::RAW_W * QF::RAW_H * 4);
+                tc::mbar_arrive_expect_tx(&raw_full[b], QF::RAW_W * QF::RAW_H * (RAW16 ? 2 : 4));
                 // frame pixels (16 tx - 3 ..., 64 ty - 3 ...): the 4 x 4 windows of quad pixels (8 tx - 1 ..., 32 ty - 1 ...);
-                // the box starts at column 16 tx - 4 so that every row of it is 16-byte aligned in global memory
-                tc::tma_load_3d(smem + QF::OFF_RAW + b * QF::RAW_BYTES, &mapIn, &raw_full[b], 16 * tx - 4, 64 * ty - 3, n);
+                // the box starts at column 16 tx - 4 (uint16: 16 tx - 8) so that every row of it is 16-byte aligned
+                // in global memory
+                tc::tma_load_3d(smem + QF::OFF_RAW + b * QF::RAW_BYTES, &mapIn, &raw_full[b], 16 * tx - (RAW16 ? 8 : 4), 64 * ty - 3, n);
             }
         }
     } else if (warp == 1) {
@@ -1779,26 +1785,86 @@ conv_qf_kernel(const __grid_constant__ CUtensorMap mapIn, const bf16 *__restrict
             const int b = it & 1;
             QF_W(0, tc::mbar_wait(&raw_full[b], (it >> 1) & 1));
             QF_W(1, tc::mbar_wait(&a1_empty[b], ((it >> 1) & 1) ^ 1));
-            const float *raw = reinterpret_cast<const float *>(smem + QF::OFF_RAW + b * QF::RAW_BYTES);
             uint8_t *a1 = smem + QF::OFF_A1 + b * QF::A1_BYTES;
+            if constexpr (!RAW16) {
+                const float *raw = reinterpret_cast<const float *>(smem + QF::OFF_RAW + b * QF::RAW_BYTES);
 #pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                const int p = bt + 128 * k;
-                if (p < QF::PROWS) {
-                    uint32_t o[8];
+                for (int k = 0; k < 3; ++k) {
+                    const int p = bt + 128 * k;
+                    if (p < QF::PROWS) {
+                        uint32_t o[8];
 #pragma unroll
-                    for (int wy = 0; wy < 4; ++wy) {
-                        // window columns 2 px + 1 .. 2 px + 4 of the staged row (the box starts one column early)
-                        const float2 c0 = *reinterpret_cast<const float2 *>(raw + roff[k] + wy * QF::RAW_W);
-                        const float2 c1 = *reinterpret_cast<const float2 *>(raw + roff[k] + wy * QF::RAW_W + 2);
-                        const float2 c2 = *reinterpret_cast<const float2 *>(raw + roff[k] + wy * QF::RAW_W + 4);
-                        o[2 * wy] = pack_bf16(c0.y, c1.x);
-                        o[2 * wy + 1] = pack_bf16(c1.y, c2.x);
+                        for (int wy = 0; wy < 4; ++wy) {
+                            // window columns 2 px + 1 .. 2 px + 4 of the staged row (the box starts one column early)
+                            const float2 c0 = *reinterpret_cast<const float2 *>(raw + roff[k] + wy * QF::RAW_W);
+                            const float2 c1 = *reinterpret_cast<const float2 *>(raw + roff[k] + wy * QF::RAW_W + 2);
+                            const float2 c2 = *reinterpret_cast<const float2 *>(raw + roff[k] + wy * QF::RAW_W + 4);
+                            o[2 * wy] = pack_bf16(c0.y, c1.x);
+                            o[2 * wy + 1] = pack_bf16(c1.y, c2.x);
+                        }
+                        *reinterpret_cast<uint4 *>(a1 + p * 16) = make_uint4(o[0], o[1], o[2], o[3]);
+                        *reinterpret_cast<uint4 *>(a1 + QF::A1_ROWS * 16 + p * 16) = make_uint4(o[4], o[5], o[6], o[7]);
                     }
-                    *reinterpret_cast<uint4 *>(a1 + p * 16) = make_uint4(o[0], o[1], o[2], o[3]);
-                    *reinterpret_cast<uint4 *>(a1 + QF::A1_ROWS * 16 + p * 16) = make_uint4(o[4], o[5], o[6], o[7]);
+                }
+            } else {
+                // raw uint16 values, window columns 2 px + 5 .. 2 px + 8 of the staged row (the box starts five columns
+                // early); normalised in float32; positions outside the frame are the conv's zero padding, not (0 - mean) / std
+                const uint32_t *raw = reinterpret_cast<const uint32_t *>(smem + QF::OFF_RAW + b * QF::RAW_BYTES);
+                const int t = blockIdx.x + it * gridDim.x;
+                const int tx = t % tiles_x, ty = (t / tiles_x) % tiles_y, n = t / (tiles_x * tiles_y);
+                if (stats == nullptr) {
+                    // the 16-bit values ARE bf16 (normalised frames rounded once by sq_image_norm_u16_to_bf16; TMA's
+                    // zero fill outside the frame is the conv's zero padding): the im2col is a byte shuffle
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        const int p = bt + 128 * k;
+                        if (p < QF::PROWS) {
+                            const int py = p / QF::PW, px = p - py * QF::PW;
+                            uint32_t o[8];
+#pragma unroll
+                            for (int wy = 0; wy < 4; ++wy) {
+                                const uint32_t *rw = raw + (2 * py + wy) * (QF::RAW_W / 2) + px + 2;
+                                const uint32_t w0 = rw[0], w1 = rw[1], w2 = rw[2];
+                                o[2 * wy] = __byte_perm(w0, w1, 0x5432);          // columns 2px+5, 2px+6
+                                o[2 * wy + 1] = __byte_perm(w1, w2, 0x5432);      // columns 2px+7, 2px+8
+                            }
+                            *reinterpret_cast<uint4 *>(a1 + p * 16) = make_uint4(o[0], o[1], o[2], o[3]);
+                            *reinterpret_cast<uint4 *>(a1 + QF::A1_ROWS * 16 + p * 16) = make_uint4(o[4], o[5], o[6], o[7]);
+                        }
+                    }
+                    goto built;
+                }
+                const float2 ms = __ldg(stats + n);
+                const int X0 = 16 * tx - 3, Y0 = 64 * ty - 3, H0 = 2 * H, W0 = 2 * W;
+                const bool border = X0 < 0 || Y0 < 0 || X0 + 2 * QF::PW + 2 > W0 || Y0 + 2 * QF::PH + 2 > H0;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const int p = bt + 128 * k;
+                    if (p < QF::PROWS) {
+                        const int py = p / QF::PW, px = p - py * QF::PW;
+                        uint32_t o[8];
+#pragma unroll
+                        for (int wy = 0; wy < 4; ++wy) {
+                            const uint32_t *rw = raw + (2 * py + wy) * (QF::RAW_W / 2) + px + 2;
+                            const uint32_t w0 = rw[0], w1 = rw[1], w2 = rw[2];
+                            float f[4] = {(float)(w0 >> 16), (float)(w1 & 0xffffu), (float)(w1 >> 16), (float)(w2 & 0xffffu)};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                f[e] = __fdiv_rn(__fsub_rn(f[e], ms.x), ms.y);
+                                if (border) {
+                                    const int Y = Y0 + 2 * py + wy, X = X0 + 2 * px + e;
+                                    if (Y < 0 || Y >= H0 || X < 0 || X >= W0) f[e] = 0.0f;
+                                }
+                            }
+                            o[2 * wy] = pack_bf16(f[0], f[1]);
+                            o[2 * wy + 1] = pack_bf16(f[2], f[3]);
+                        }
+                        *reinterpret_cast<uint4 *>(a1 + p * 16) = make_uint4(o[0], o[1], o[2], o[3]);
+                        *reinterpret_cast<uint4 *>(a1 + QF::A1_ROWS * 16 + p * 16) = make_uint4(o[4], o[5], o[6], o[7]);
+                    }
                 }
             }
+        built:
             tc::fence_proxy_async();
             __syncwarp();
             if (lane == 0) { tc::mbar_arrive(&a1_full[b]); tc::mbar_arrive(&raw_empty[b]); }
@@ -2989,28 +3055,31 @@ bool qfuse_enabled()
     return !e || atoi(e) != 0;
 }
 
-// down0/conv1 + down0/conv2 + pool in one launch (conv_qf_kernel); g.H, g.W: the quad image
-int launch_qf(sq_unet_s *u, const SqLayer &L1, const SqLayer &L2, const float *in, bf16 *out, bf16 *out_pool,
-              const TcGeo &g, cudaStream_t st)
+// down0/conv1 + down0/conv2 + pool in one launch (conv_qf_kernel); g.H, g.W: the quad image.  raw16 != NULL: the
+// frames are raw uint16 values normalised in the loader with the per-frame (mean, std) in `stats`.
+int launch_qf(sq_unet_s *u, const SqLayer &L1, const SqLayer &L2, const float *in, const uint16_t *raw16,
+              const float2 *stats, bf16 *out, bf16 *out_pool, const TcGeo &g, cudaStream_t st)
 {
     sq_encode_tiled_fn enc = sq_get_encode_tiled();
     SQ_REQUIRE(enc, SQ_ECUDA, "cuTensorMapEncodeTiled entry point not available");
     const int H0 = 2 * g.H, W0 = 2 * g.W;
+    const size_t esz = raw16 ? 2 : 4;
     CUtensorMap m;
     cuuint64_t dims[3] = {(cuuint64_t)W0, (cuuint64_t)H0, (cuuint64_t)g.nimg};
-    cuuint64_t strides[2] = {(cuuint64_t)W0 * 4, (cuuint64_t)H0 * W0 * 4};
+    cuuint64_t strides[2] = {(cuuint64_t)W0 * esz, (cuuint64_t)H0 * W0 * esz};
     cuuint32_t box[3] = {(cuuint32_t)QF::RAW_W, (cuuint32_t)QF::RAW_H, 1};
     cuuint32_t es[3] = {1, 1, 1};
-    CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)in, dims, strides, box, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    SQ_REQUIRE(r == CUDA_SUCCESS, SQ_ECUDA, "cuTensorMapEncodeTiled failed (%d) for the fp32 frames (%d,%d,%d)", (int)r,
+    CUresult r = enc(&m, raw16 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+                     raw16 ? (void *)raw16 : (void *)in, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    SQ_REQUIRE(r == CUDA_SUCCESS, SQ_ECUDA, "cuTensorMapEncodeTiled failed (%d) for the frames (%d,%d,%d)", (int)r,
                g.nimg, H0, W0);
     const size_t smem = (size_t)QF::SMEM + 1024;
-    static size_t attr_smem[64] = {0};
-    size_t &have = attr_smem[u->h->device & 63];
+    static size_t attr_smem[64][2] = {{0}};
+    size_t &have = attr_smem[u->h->device & 63][raw16 ? 1 : 0];
     if (smem > have) {
-        SQ_CUDA(cudaFuncSetAttribute(conv_qf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (raw16) SQ_CUDA(cudaFuncSetAttribute(conv_qf_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        else SQ_CUDA(cudaFuncSetAttribute(conv_qf_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         have = smem;
     }
     const int tiles = g.nimg * ((g.W + 7) / 8) * ((g.H + QF::TH - 1) / QF::TH);
@@ -3032,7 +3101,12 @@ int launch_qf(sq_unet_s *u, const SqLayer &L1, const SqLayer &L2, const float *i
         const std::vector<float> &s2 = u->host[L2.scope + "/_scale"].data, &t2 = u->host[L2.scope + "/_shift"].data;
         for (int i = 0; i < 16; ++i) { ep.sc1[i] = s1[i]; ep.sh1[i] = t1[i]; ep.sc2[i] = s2[i]; ep.sh2[i] = t2[i]; }
     }
-    conv_qf_kernel<<<grid, QF::THREADS, smem, st>>>(m, (const bf16 *)L2.w_qf, ep, out, out_pool, g.nimg, g.H, g.W, phase_dbg);
+    if (raw16)
+        conv_qf_kernel<true><<<grid, QF::THREADS, smem, st>>>(m, (const bf16 *)L2.w_qf, ep, stats, out, out_pool, g.nimg, g.H,
+                                                             g.W, phase_dbg);
+    else
+        conv_qf_kernel<false><<<grid, QF::THREADS, smem, st>>>(m, (const bf16 *)L2.w_qf, ep, nullptr, out, out_pool, g.nimg,
+                                                              g.H, g.W, phase_dbg);
     ++u->last_launches;
     SQ_CHECK_LAUNCH();
 #ifdef SQ_XC_PHASE_DIAG
@@ -3286,7 +3360,8 @@ int sq_tc_finalize(sq_unet_s *u)
 namespace {
 
 int tc_run(sq_unet_s *u, bool dry, const float *in, int n, int dep, int hgt, int wid, float *probs,
-           uint8_t *mask, float *logits, void *ws, size_t ws_bytes, cudaStream_t st, size_t *need)
+           uint8_t *mask, float *logits, void *ws, size_t ws_bytes, cudaStream_t st, size_t *need,
+           const uint16_t *raw16 = nullptr, const float2 *stats16 = nullptr)
 {
     SqArena a(dry ? nullptr : ws, dry ? 0 : ws_bytes);
     const int nl = u->nlev;
@@ -3340,7 +3415,9 @@ int tc_run(sq_unet_s *u, bool dry, const float *in, int n, int dep, int hgt, int
         const bool fuse_first = l == 0 && !vol && u->cin == 1 && c1->cout == 16 && c2->cout == 16 && nl > 1 &&
                                 first_fusion_enabled();
         // quad layout: both convs of level 0 in one launch (the first conv's output stays on chip)
-        const bool qfuse = l == 0 && quad && c2->w_qf && (wid % 4 == 0) && ((uintptr_t)in % 16 == 0) && qfuse_enabled();
+        const bool qfuse = l == 0 && quad && c2->w_qf && (wid % (raw16 ? 8 : 4) == 0) &&
+                           ((uintptr_t)(raw16 ? (const void *)raw16 : (const void *)in) % 16 == 0) && qfuse_enabled();
+        if (l == 0) SQ_REQUIRE(!raw16 || qfuse, SQ_ESTATE, "unet(bf16): raw uint16 frames need the fused first pair");
         if (l == 0 && vol) {
             const float *wf = (const float *)c1->w_tc;
             const int key = u->cin * 1000 + c1->cout;
@@ -3427,7 +3504,7 @@ int tc_run(sq_unet_s *u, bool dry, const float *in, int n, int dep, int hgt, int
         if (l < nl - 1) pool_fused[l + 1] = fuse_pool;
         bf16 *pool_dst = !fuse_pool ? nullptr : (vol ? xyp[l + 1] : pooled[l + 1]);
         if (qfuse) {
-            SQ_TRY(launch_qf(u, *c1, *c2, in, skip[0], pool_dst, geoq, st));
+            SQ_TRY(launch_qf(u, *c1, *c2, in, raw16, stats16, skip[0], pool_dst, geoq, st));
             const char *pname = u->aux_names.emplace(c1->scope, c1->scope + "+conv2").first->second.c_str();
             sq_timer_mark(u, st, pname, (c1->flops_per_px + c2->flops_per_px) * px);
             continue;
@@ -3544,6 +3621,28 @@ int tc_run(sq_unet_s *u, bool dry, const float *in, int n, int dep, int hgt, int
 int sq_tc_workspace_bytes(sq_unet_s *u, int n, int d, int hgt, int wid, size_t *bytes)
 {
     return tc_run(u, true, nullptr, n, d, hgt, wid, nullptr, nullptr, nullptr, nullptr, 0, nullptr, bytes);
+}
+
+bool sq_tc_can_take_raw_u16(sq_unet_s *u, int hgt, int wid)
+{
+    // the conditions under which tc_run routes level 0 through conv_qf_kernel (SQ_QNORM=0: keep the float32 stage)
+    const char *e = getenv("SQ_QNORM");
+    if (e && atoi(e) == 0) return false;
+    if (u->mode != SQ_MODE_BF16_TC || u->ndim != 2 || u->nlev < 2 || u->filters[0] != 16 || u->cin != 1 || u->nout < 2 ||
+        u->nout > 4 || (hgt % 2) || (wid % 8) || !quad_enabled() || !qfuse_enabled() || first_fusion_enabled() || pair_enabled())
+        return false;
+    for (const SqLayer &L : u->layers) {
+        if (L.scope == "UNet/down0/conv2" && !L.w_qf) return false;
+        if (L.level == 0 && L.kind != SqLayer::HEAD && L.scope != "UNet/down0/conv1" && !L.w_qd) return false;
+    }
+    return true;
+}
+
+int sq_tc_forward_raw_u16(sq_unet_s *u, const uint16_t *raw, const float2 *stats, int n, int hgt, int wid,
+                          uint8_t *mask, void *ws, size_t ws_bytes, cudaStream_t st)
+{
+    SQ_REQUIRE(((uintptr_t)mask % 2) == 0, SQ_EINVAL, "unet(bf16): mask pointer must be 2-byte aligned");
+    return tc_run(u, false, nullptr, n, 1, hgt, wid, nullptr, mask, nullptr, ws, ws_bytes, st, nullptr, raw, stats);
 }
 
 int sq_tc_forward(sq_unet_s *u, const float *in, int n, int d, int hgt, int wid, float *probs,

@@ -128,3 +128,26 @@ def test_raw_camera_frames_through_the_hot_path(sq, tmp_path):
     t8, m8 = net.segment_and_localise(raw8, return_mask=True, normalise=True)
     x8 = ops.image_norm(torch.from_numpy(raw8.astype(np.float32)[..., None]).cuda()).cpu().numpy()
     np.testing.assert_array_equal(m8, net.segment_and_localise(x8, return_mask=True)[1])
+
+
+@pytest.mark.parametrize('shape', [(70, 120), (256, 264)])
+def test_image_norm_feeds_the_fused_first_pair_in_16_bits(sq, monkeypatch, shape):
+    """uint16 frames + ImageNorm on the host-call route: by default the frames are widened, normalised
+    ((x - mean) / std in float32, the arithmetic of sq_image_norm) and rounded to bf16 ONCE (2 B/px) and
+    conv_qf_kernel's builders load that as is; SQ_QNORM=2: only the moments are computed up front and the builders
+    normalise the raw values themselves; SQ_QNORM=0: the float32 stage of round 1.  Same bits on all three."""
+    from sequitr_b200 import synth
+    from sequitr_b200.networks import UNet2D
+    filters = (16, 32)
+    net = UNet2D({'filters': filters, 'shape': shape, 'bridge': 'concat', 'compute': 'bf16'})
+    net.load_weights(synth.blob_detector_weights(filters, 1, 2, seed=1))
+    x = synth.frames(9, shape[0], shape[1], 1, seed=4, n_objects=6)[..., 0]
+    raw = np.clip(x * 400.0 + 3000.0, 0, 65535).astype(np.uint16)
+    t_bf16, m_bf16 = net.segment_and_localise(raw, return_mask=True, normalise=True)
+    for mode in ('0', '2'):
+        monkeypatch.setenv('SQ_QNORM', mode)
+        t_other, m_other = net.segment_and_localise(raw, return_mask=True, normalise=True)
+        np.testing.assert_array_equal(m_bf16, m_other)
+        for a, b in zip(t_bf16, t_other):
+            np.testing.assert_array_equal(a, b)
+    assert sum(len(t) for t in t_bf16) >= 9
