@@ -175,6 +175,19 @@ def test_w3_edge_cases_and_properties(sq):
                                rtol=RTOL64, atol=0)
 
 
+def test_w3_full_size_2048_against_the_cropped_oracle(sq):
+    """BASELINE configs[1] size: 2048^2 instance labels, ~600 instances, w0 = 10, sigma = 5, against the exact
+    per-instance oracle (cropped transforms; tests/test_oracle_weightmap.py pins it to the brute-force one)."""
+    from sequitr_b200 import ops
+    lab = synth.instance_labels(2048, 2048, 600, seed=3)
+    ref = wo.weightmap_w3(lab, 10., 5., margin=48)             # 10 exp(-48^2 / 50) ~ 1e-19: far below one ulp of 1.0
+    got = ops.weightmap_unet_host(lab, 10., 5., out_dtype='float64')
+    np.testing.assert_allclose(got, ref, rtol=RTOL64, atol=0)
+    assert (ref > 1.5).sum() > 1000                            # the gap term is exercised
+    got32 = ops.weightmap_unet_host(lab, 10., 5., out_dtype='float32')
+    np.testing.assert_allclose(got32, ref.astype(np.float32), rtol=1.2e-7, atol=0)      # the fp64 map rounded once
+
+
 def test_device_api(sq):
     import torch
     from sequitr_b200 import ops

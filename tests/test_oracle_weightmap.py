@@ -88,3 +88,17 @@ def test_image_labels_and_names():
     assert wo.weights_folder_name(10., 3.) == 'weights_w0-10.00_sigma-3.00'
     assert wo.weights_folder_name(10., 3., False) == 'weights'
     assert wo.weights_file_name('pos1_GFP_0001.tif') == 'pos1_GFP_weights.tif'
+
+
+def test_cropped_w3_oracle_equals_the_brute_force_one():
+    """The per-instance cropped oracle used at BASELINE's 2048^2 size against the brute-force oracle: identical
+    squared distances up to the margin and weight maps equal to the last bit of the exp term that can matter."""
+    from sequitr_b200 import synth
+    lab = synth.instance_labels(200, 260, 30, seed=4, rmin=4, rmax=10)
+    d1, d2 = wo.two_nearest_instances_d2(lab)
+    c1, c2 = wo.two_nearest_instances_d2_cropped(lab, 48)
+    near1, near2 = d1 <= 48 * 48, d2 <= 48 * 48
+    np.testing.assert_array_equal(c1[near1], d1[near1])
+    np.testing.assert_array_equal(c2[near2], d2[near2])
+    assert (c1[~near1] > 48 * 48).all() and (c2[~near2] > 48 * 48).all()
+    np.testing.assert_allclose(wo.weightmap_w3(lab, 10., 5., margin=48), wo.weightmap_w3(lab, 10., 5.), rtol=1e-15, atol=0)
