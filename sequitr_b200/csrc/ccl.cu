@@ -118,13 +118,13 @@ __device__ __forceinline__ unsigned warp_inclusive_scan(unsigned v, int lane)
 }
 
 // Single-pass front end: runs per segment, their raster-order slots (an exclusive prefix sum over the
-// frame's segments) and the run lists, in ONE kernel that reads the mask once.  A block owns SPB = 32
-// consecutive segments (warp w: segments 4w .. 4w+3); the prefix across blocks is a decoupled look-back
+// frame's segments) and the run lists, in ONE kernel that reads the mask once.  A block owns SPB = 128
+// consecutive segments (warp w: segments 16w .. 16w+15; 64 blocks per 2048^2 frame, so a look-back is two rounds); the prefix across blocks is a decoupled look-back
 // (Merrill & Garland): every block publishes its aggregate, then its inclusive prefix, in one 64-bit status
 // word (flag << 32 | value) and warp 0 walks back over its predecessors' words, 32 at a time.  Blocks take
 // their index from a per-frame ticket counter, so a block only ever waits for blocks that are already running.
 // grid (ceil(nsegs / SPB), n), block 256.  status / ticket are zeroed by the caller.
-constexpr int SPB = 32;
+constexpr int SPB = 128, SPW = SPB / 8, SPL = SPB / 32;     // segments per block / per warp / per lane of the block scan
 constexpr unsigned long long ST_AGG = 1ull << 32, ST_PREFIX = 2ull << 32;
 
 __global__ void __launch_bounds__(256)
@@ -138,10 +138,10 @@ run_scan_emit(const uint8_t *__restrict__ mask, unsigned long long *__restrict__
     __syncthreads();
     const int bid = s_bid;
     const uint8_t *fm = mask + (long long)f * dm.vox;
-    unsigned sb[4], eb[4], pre[4];
+    unsigned sb[SPW], eb[SPW], pre[SPW];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int s = bid * SPB + wid * 4 + k;
+    for (int k = 0; k < SPW; ++k) {
+        const int s = bid * SPB + wid * SPW + k;
         sb[k] = eb[k] = pre[k] = 0;
         unsigned tot = 0;
         if (s < dm.nsegs) {
@@ -151,14 +151,18 @@ run_scan_emit(const uint8_t *__restrict__ mask, unsigned long long *__restrict__
             pre[k] = incl - c;                                  // exclusive (starts | ends << 16) within the segment
             tot = __shfl_sync(0xffffffffu, incl, 31) & 0xffffu;
         }
-        if (lane == 0) s_tot[wid * 4 + k] = (int)tot;
+        if (lane == 0) s_tot[wid * SPW + k] = (int)tot;
     }
     __syncthreads();
     if (wid == 0) {
-        const int v = s_tot[lane];
-        const int incl = (int)warp_inclusive_scan((unsigned)v, lane);
+        int v[SPL], lsum = 0;
+#pragma unroll
+        for (int q = 0; q < SPL; ++q) { v[q] = s_tot[lane * SPL + q]; lsum += v[q]; }
+        const int incl = (int)warp_inclusive_scan((unsigned)lsum, lane);
         const int agg = __shfl_sync(0xffffffffu, incl, 31);
-        s_tot[lane] = incl - v;                                 // exclusive prefix of the segment within the block
+        int run = incl - lsum;
+#pragma unroll
+        for (int q = 0; q < SPL; ++q) { s_tot[lane * SPL + q] = run; run += v[q]; }     // exclusive prefix within the block
         volatile unsigned long long *st = status + (long long)f * nblk;
         int excl = 0;
         if (bid > 0) {
@@ -193,10 +197,10 @@ run_scan_emit(const uint8_t *__restrict__ mask, unsigned long long *__restrict__
     __syncthreads();
     const long long rb = (long long)f * dm.maxruns;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int s = bid * SPB + wid * 4 + k;
+    for (int k = 0; k < SPW; ++k) {
+        const int s = bid * SPB + wid * SPW + k;
         if (s >= dm.nsegs) break;
-        const int base = s_excl + s_tot[wid * 4 + k];
+        const int base = s_excl + s_tot[wid * SPW + k];
         if (lane == 0) seg_off[(long long)f * (dm.nsegs + 1) + s] = base;
         unsigned a = sb[k], e = eb[k];
         if (!(a | e)) continue;
