@@ -77,7 +77,9 @@ class Group(object):
             raise ValueError('Unable to create dataset (name already exists): %s' % name)
         if data is None:
             data = np.zeros(shape, dtype=dtype or 'float32')
-        arr = np.ascontiguousarray(np.asarray(data, dtype=dtype))
+        arr = np.asarray(data, dtype=dtype)
+        if arr.ndim:                                 # (ascontiguousarray would turn a scalar into shape (1,))
+            arr = np.ascontiguousarray(arr)
         _datatype_message(arr.dtype)             # fail now for unsupported types
         node._children[leaf] = Dataset(arr)
         return node._children[leaf]

@@ -98,6 +98,22 @@ def test_full_size_frame_2048(sq):
         np.testing.assert_array_equal(x[:, 4], y[:, 4])
 
 
+@pytest.mark.parametrize('shape,n', [((4096, 4096), 1), ((1500, 3000), 3), ((33, 5000), 4), ((700, 40), 9)])
+def test_look_back_scan_over_many_and_few_blocks(sq, shape, n):
+    """The single-pass front end places runs in raster order with a decoupled look-back scan over blocks of 128 row
+    segments: 256 blocks per frame at 4096^2 (eight look-back rounds), ragged last blocks, rows shorter than one
+    segment, several frames with their own tickets -- all bit-identical to SciPy."""
+    from sequitr_b200 import ops
+    m = np.stack([synth.class_mask(shape[0], shape[1], max(4, shape[0] * shape[1] // 7000), n_classes=2, seed=10 + s,
+                                   rmin=3, rmax=12) for s in range(n)])
+    _check(ops, m)
+    # worst case for the run lists: a checkerboard of single-pixel runs in the top-left corner of every frame
+    cb = np.zeros_like(m)
+    cb[:, :32:2, :64:2] = 1
+    cb[:, 1:32:2, 1:64:2] = 2
+    _check(ops, cb)
+
+
 def test_device_api_equals_host_api(sq):
     import torch
     from sequitr_b200 import ops

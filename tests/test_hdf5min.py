@@ -138,3 +138,46 @@ def test_handler_reads_back_what_it_wrote(tmp_path):
     r = utils.HDF5FileHandler(fn, read_only=True)
     assert r.hdf['frames']['frame_0']['coords'].shape == (3, 5)
     r.close()
+
+
+def test_random_trees_round_trip(tmp_path):
+    """Seeded random group trees (depth <= 4, 0-40 children per group, names of 1-40 characters incl. UTF-8, every
+    supported dtype, ranks 0-3, empty arrays): written, parsed back, compared."""
+    rng = np.random.default_rng(7)
+    dtypes = [np.float32, np.float64, np.int8, np.uint8, np.int16, np.uint16, np.int32, np.uint32, np.int64, np.uint64]
+    alphabet = list('abcXYZ_0123456789-. ') + ['é', 'µ']
+
+    def name():
+        return ''.join(rng.choice(alphabet, size=int(rng.integers(1, 41)))).strip() or 'n'
+
+    def fill(group, depth, want):
+        for _ in range(int(rng.integers(0, 41 if depth < 2 else 6))):
+            nm = name()
+            if nm in want or '/' in nm:
+                continue
+            if depth < 4 and rng.random() < 0.3:
+                want[nm] = {}
+                fill(group.create_group(nm), depth + 1, want[nm])
+            else:
+                shape = tuple(int(v) for v in rng.integers(0, 5, size=int(rng.integers(0, 4))))
+                arr = (rng.random(shape) * 200 - 100).astype(dtypes[int(rng.integers(len(dtypes)))])
+                group.create_dataset(nm, data=arr)
+                want[nm] = arr
+
+    def check(group, want):
+        assert group.keys() == sorted(want)
+        for nm, v in want.items():
+            if isinstance(v, dict):
+                check(group[nm], v)
+            else:
+                got = group[nm]
+                assert got.shape == v.shape and got.dtype == v.dtype
+                np.testing.assert_array_equal(np.asarray(got), v)
+
+    for trial in range(5):
+        fn = str(tmp_path / ('r%d.hdf5' % trial))
+        want = {}
+        with hdf5min.File(fn, 'w') as f:
+            fill(f, 0, want)
+        with hdf5min.File(fn, 'r') as r:
+            check(r, want)
