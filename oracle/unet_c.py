@@ -161,17 +161,23 @@ def _affine(weights, scope):
     return np.ones_like(bias), bias
 
 
-def unet_forward(x, weights, filters, bridge='concat', contract='fp32', return_all=False):
+def unet_forward(x, weights, filters, bridge='concat', contract='fp32', return_all=False, exact_tail=False):
     """x: (N,H,W,Cin) or (N,D,H,W,Cin) float32.  Returns dict with 'logits',
-    'probs', 'mask' (and 'net', the per-layer outputs, if return_all)."""
+    'probs', 'mask' (and 'net', the per-layer outputs, if return_all).
+    ``exact_tail`` (experiment, contract 'bf16' only): the last block (up0/conv1, up0/conv2) and the head run
+    in full fp32 on unrounded weights -- the limit of a tf32 / 3xbf16-split variant of those layers -- while
+    everything before keeps the bf16 contract (scripts/exact_tail_experiment.py)."""
     rb = round_bf16 if contract == 'bf16' else (lambda a: _f32(a))
-    W = {k: (rb(v) if k.endswith('/kernel') else _f32(v)) for k, v in weights.items()}
+    exact = (lambda a: _f32(a))
+    tail = ('UNet/up0/conv1/kernel', 'UNet/up0/conv2/kernel', 'UNet/to_image/kernel') if exact_tail else ()
+    W = {k: (rb(v) if k.endswith('/kernel') and k not in tail else _f32(v)) for k, v in weights.items()}
 
     def block(x0, x1, scope):
+        r = exact if (exact_tail and scope == 'UNet/up0') else rb
         s, t = _affine(W, scope + '/conv1')
-        y = rb(conv(x0, x1, W[scope + '/conv1/kernel'], s, t, True))
+        y = r(conv(x0, x1, W[scope + '/conv1/kernel'], s, t, True))
         s, t = _affine(W, scope + '/conv2')
-        return rb(conv(y, None, W[scope + '/conv2/kernel'], s, t, True))
+        return r(conv(y, None, W[scope + '/conv2/kernel'], s, t, True))
 
     x = rb(x)
     net = [block(x, None, 'UNet/down0')]

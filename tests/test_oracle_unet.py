@@ -51,3 +51,17 @@ def test_bf16_rounding():
     import torch
     want = torch.from_numpy(v).to(torch.bfloat16).float().numpy()
     np.testing.assert_array_equal(unet_c.round_bf16(v), want)
+
+
+def test_exact_tail_experiment_contract():
+    """oracle-only switch used by scripts/exact_tail_experiment.py: the bf16 contract with the last block and the
+    head in full fp32 sits between the bf16 and the fp32 contracts."""
+    from oracle import unet_c
+    from sequitr_b200 import synth
+    filters = (16, 32)
+    w = synth.unet_weights(filters, 1, 2, bridge='concat', seed=3)
+    x = synth.frames(1, 48, 64, 1, seed=2, n_objects=3)
+    f32 = unet_c.unet_forward(x, w, filters, 'concat', contract='fp32')['logits']
+    b16 = unet_c.unet_forward(x, w, filters, 'concat', contract='bf16')['logits']
+    mix = unet_c.unet_forward(x, w, filters, 'concat', contract='bf16', exact_tail=True)['logits']
+    assert 0 < np.abs(mix - f32).mean() < np.abs(b16 - f32).mean()
