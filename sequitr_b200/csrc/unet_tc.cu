@@ -2025,7 +2025,8 @@ struct QU {
     static constexpr int NRING = 8;
     static constexpr int OFF_WU = 0, OFF_W = WU_BYTES, OFF_A1 = OFF_W + W_BYTES, OFF_P = OFF_A1 + A1_BYTES,
                          OFF_RING = OFF_P + P_BYTES, SMEM = OFF_RING + NRING * KSTEP_BYTES;
-    static constexpr int EPI_WARPS = 16, THREADS = 32 * (2 + EPI_WARPS);
+    // two MMA-issuing warps (one per sub-tile): a single thread sustains one 128x64x16 MMA per ~70 clk here, the pipe 48
+    static constexpr int MMA_WARPS = 2, EPI_WARPS = 16, THREADS = 32 * (1 + MMA_WARPS + EPI_WARPS);
     static_assert(OFF_A1 % 128 == 0 && OFF_P % 128 == 0 && OFF_RING % 128 == 0 && KSTEP_BYTES % 128 == 0, "alignment");
     static_assert(SMEM + 1024 <= 232448, "shared memory");
 };
@@ -2033,8 +2034,15 @@ struct QU {
 __global__ void __launch_bounds__(QU::THREADS, 1)
 conv_qu_kernel(const __grid_constant__ CUtensorMap mapCur, const __grid_constant__ CUtensorMap mapSkip,
                const bf16 *__restrict__ wup, const bf16 *__restrict__ wts, const QfEpi ep, int ksu,
-               bf16 *__restrict__ out, int nimg, int H, int W)
+               bf16 *__restrict__ out, int nimg, int H, int W, long long *phase_dbg)
 {
+#ifdef SQ_XC_PHASE_DIAG
+#define QU_W(i, stmt) do { const long long t_ = phase_dbg ? clock64() : 0; stmt; if (phase_dbg) dacc[i] += clock64() - t_; } while (0)
+    long long dacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const long long t_kernel0 = clock64();
+#else
+#define QU_W(i, stmt) do { stmt; } while (0)
+#endif
     // H, W: the quad image.  wup: the up-conv as a 1x1 conv (ksu k-steps x 2 KB), wts: conv1's quad weights with
     // permuted output columns (8 k-steps: up-sampled source parities 0-3, skip parities 0-3).  ep.sc1 / sh1: the
     // up-conv's epilogue, ep.sc2 / sh2: the conv's.
@@ -2051,11 +2059,11 @@ conv_qu_kernel(const __grid_constant__ CUtensorMap mapCur, const __grid_constant
 
     if (threadIdx.x == 0) {
         tc::mbar_init(&w_bar, 1);
-        tc::mbar_init(&a1_full, 1); tc::mbar_init(&a1_empty, 1);
-        tc::mbar_init(&acc1_full, 1); tc::mbar_init(&acc1_empty, QU::EPI_WARPS);
-        tc::mbar_init(&p_full, QU::EPI_WARPS); tc::mbar_init(&p_empty, 1);
-        for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc2_full[i], 1); tc::mbar_init(&acc2_empty[i], QU::EPI_WARPS); }
-        for (int i = 0; i < QU::NRING; ++i) { tc::mbar_init(&ring_full[i], 1); tc::mbar_init(&ring_empty[i], 1); }
+        tc::mbar_init(&a1_full, 1); tc::mbar_init(&a1_empty, QU::MMA_WARPS);
+        tc::mbar_init(&acc1_full, QU::MMA_WARPS); tc::mbar_init(&acc1_empty, QU::EPI_WARPS);
+        tc::mbar_init(&p_full, QU::EPI_WARPS); tc::mbar_init(&p_empty, QU::MMA_WARPS);
+        for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc2_full[i], QU::MMA_WARPS); tc::mbar_init(&acc2_empty[i], QU::EPI_WARPS); }
+        for (int i = 0; i < QU::NRING; ++i) { tc::mbar_init(&ring_full[i], 1); tc::mbar_init(&ring_empty[i], QU::MMA_WARPS); }
         tc::fence_barrier_init();
         tc::tma_prefetch_desc(&mapCur);
         tc::tma_prefetch_desc(&mapSkip);
@@ -2080,19 +2088,20 @@ conv_qu_kernel(const __grid_constant__ CUtensorMap mapCur, const __grid_constant
                 const int t = blockIdx.x + it * gridDim.x;
                 const int tx = t % tiles_x, ty = (t / tiles_x) % tiles_y, n = t / (tiles_x * tiles_y);
                 const int x0 = tx * 8 - 1, y0 = ty * QU::TH - 1;
-                tc::mbar_wait(&a1_empty, (it & 1) ^ 1);
+                QU_W(0, tc::mbar_wait(&a1_empty, (it & 1) ^ 1));
                 tc::mbar_arrive_expect_tx(&a1_full, (uint32_t)(ksu * QU::KSTEP_BYTES));
                 tc::tma_load_5d(smem + QU::OFF_A1, &mapCur, &a1_full, x0 * 8, y0, 0, 0, n);
                 for (int ks = 0; ks < 4; ++ks) {
-                    tc::mbar_wait(&ring_empty[rs], rphase ^ 1);
+                    QU_W(1, tc::mbar_wait(&ring_empty[rs], rphase ^ 1));
                     tc::mbar_arrive_expect_tx(&ring_full[rs], QU::KSTEP_BYTES);
                     tc::tma_load_5d(smem + QU::OFF_RING + rs * QU::KSTEP_BYTES, &mapSkip, &ring_full[rs], x0 * 8, y0, ks * 2, 0, n);
                     if (++rs == QU::NRING) { rs = 0; rphase ^= 1; }
                 }
             }
         }
-    } else if (warp == 1) {
-        // ======================================================= MMA issuer
+    } else if (warp <= QU::MMA_WARPS) {
+        // ======================================================= MMA issuers: warp 1 owns sub-tile 0, warp 2 sub-tile 1
+        const int jw = warp - 1;
         const uint32_t idesc = tc::instr_desc_bf16(128, 64);
         const uint32_t sbase = tc::smem_u32(smem);
         const uint32_t hi128 = ((128u >> 4) & 0x3FFFu) | (1u << 14);
@@ -2109,20 +2118,18 @@ conv_qu_kernel(const __grid_constant__ CUtensorMap mapCur, const __grid_constant
                 // ---- P half of tile it-1: the up-sampled patch written by epilogue 1
                 const int i2 = it - 1, b = i2 & 1;
                 const uint32_t d0 = tmem_base + ACC2 + b * 128;
-                tc::mbar_wait(&p_full, i2 & 1);
+                QU_W(0, tc::mbar_wait(&p_full, i2 & 1));
                 tc::tc_fence_after();
                 if (tc::elect_one()) {
                     const uint32_t p_lo = (((sbase + QU::OFF_P) >> 4) & 0x3FFFu) | lboP;
+                    const uint32_t pj = p_lo + (uint32_t)(jw * 16 * QU::PW), dj = d0 + jw * 64;
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const int iy = k >> 1, ix = k & 1;
 #pragma unroll
-                        for (int j = 0; j < 2; ++j)
-#pragma unroll
-                            for (int tp = 0; tp < 4; ++tp)
-                                tc::umma_bf16_parts(d0 + j * 64,
-                                                    p_lo + (uint32_t)(k * (QU::KSTEP_BYTES >> 4) + (j * 16 + (tp >> 1) + 1 - iy) * QU::PW + (tp & 1) + 1 - ix),
-                                                    hiP, w_lo + (uint32_t)((k * 4 + tp) * 128), hi128, idesc, 1u);
+                        for (int tp = 0; tp < 4; ++tp)
+                            tc::umma_bf16_parts(dj, pj + (uint32_t)(k * (QU::KSTEP_BYTES >> 4) + ((tp >> 1) + 1 - iy) * QU::PW + (tp & 1) + 1 - ix),
+                                                hiP, w_lo + (uint32_t)((k * 4 + tp) * 128), hi128, idesc, 1u);
                     }
                     tc::umma_commit(&p_empty);
                     tc::umma_commit(&acc2_full[b]);
@@ -2132,34 +2139,31 @@ conv_qu_kernel(const __grid_constant__ CUtensorMap mapCur, const __grid_constant
             if (it < nt) {
                 // ---- up-conv of tile it, then the skip half of its conv (prefetched through the ring)
                 const int b = it & 1;
-                tc::mbar_wait(&a1_full, it & 1);
-                tc::mbar_wait(&acc1_empty, (it & 1) ^ 1);
+                QU_W(1, tc::mbar_wait(&a1_full, it & 1));
+                QU_W(2, tc::mbar_wait(&acc1_empty, (it & 1) ^ 1));
                 tc::tc_fence_after();
                 if (tc::elect_one()) {
-                    for (int k = 0; k < ksu; ++k)
-#pragma unroll
-                        for (int m = 0; m < 3; ++m)
+                    for (int m = jw; m < 3; m += QU::MMA_WARPS)              // M-tiles 0, 2 / 1
+                        for (int k = 0; k < ksu; ++k)
                             tc::umma_bf16_parts(tmem_base + ACC1 + m * 64, a1_lo + (uint32_t)(k * (QU::KSTEP_BYTES >> 4) + m * 128), hi128,
                                                 wu_lo + (uint32_t)(k * 128), hi128, idesc, k > 0 ? 1u : 0u);
                     tc::umma_commit(&a1_empty);
                     tc::umma_commit(&acc1_full);
                 }
                 __syncwarp();
-                tc::mbar_wait(&acc2_empty[b], ((it >> 1) & 1) ^ 1);
+                QU_W(3, tc::mbar_wait(&acc2_empty[b], ((it >> 1) & 1) ^ 1));
                 tc::tc_fence_after();
                 const uint32_t d0 = tmem_base + ACC2 + b * 128;
                 for (int ks = 0; ks < 4; ++ks) {
-                    tc::mbar_wait(&ring_full[rs], rphase);
+                    QU_W(4, tc::mbar_wait(&ring_full[rs], rphase));
                     tc::tc_fence_after();
                     if (tc::elect_one()) {
                         const uint32_t s_lo = (((sbase + QU::OFF_RING + rs * QU::KSTEP_BYTES) >> 4) & 0x3FFFu) | lboP;
                         const int iy = ks >> 1, ix = ks & 1;
 #pragma unroll
-                        for (int j = 0; j < 2; ++j)
-#pragma unroll
-                            for (int tp = 0; tp < 4; ++tp)
-                                tc::umma_bf16_parts(d0 + j * 64, s_lo + (uint32_t)((j * 16 + (tp >> 1) + 1 - iy) * QU::PW + (tp & 1) + 1 - ix), hiP,
-                                                    w_lo + (uint32_t)(((4 + ks) * 4 + tp) * 128), hi128, idesc, (ks > 0 || tp > 0) ? 1u : 0u);
+                        for (int tp = 0; tp < 4; ++tp)
+                            tc::umma_bf16_parts(d0 + jw * 64, s_lo + (uint32_t)((jw * 16 + (tp >> 1) + 1 - iy) * QU::PW + (tp & 1) + 1 - ix), hiP,
+                                                w_lo + (uint32_t)(((4 + ks) * 4 + tp) * 128), hi128, idesc, (ks > 0 || tp > 0) ? 1u : 0u);
                         tc::umma_commit(&ring_empty[rs]);
                     }
                     __syncwarp();
@@ -2169,7 +2173,7 @@ conv_qu_kernel(const __grid_constant__ CUtensorMap mapCur, const __grid_constant
         }
     } else {
         // ========================================================= epilogue
-        const int g = (warp - 2) >> 2, q4 = warp & 3;
+        const int g = (warp - 1 - QU::MMA_WARPS) >> 2, q4 = warp & 3;
         const int r = q4 * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(q4 * 32) << 16;
         int ppy[3], ppx[3];
@@ -2189,9 +2193,10 @@ conv_qu_kernel(const __grid_constant__ CUtensorMap mapCur, const __grid_constant
             if (it < nt) {
                 // ---- epilogue 1: the up-conv's accumulators (+ bias, no ReLU) -> the bf16 halo patch of the conv
                 const int x0 = tx * 8 - 1, y0 = ty * QU::TH - 1;
-                tc::mbar_wait(&acc1_full, it & 1);
-                tc::mbar_wait(&p_empty, (it & 1) ^ 1);
+                QU_W(0, tc::mbar_wait(&acc1_full, it & 1));
+                QU_W(1, tc::mbar_wait(&p_empty, (it & 1) ^ 1));
                 tc::tc_fence_after();
+                const long long te1_ = clock64();
                 uint8_t *P = smem + QU::OFF_P + (2 * g) * (QU::PROWS * 16) + r * 16;
                 const bool border = x0 < 0 || y0 < 0 || x0 + QU::PW > W || y0 + QU::PH > H;
                 uint32_t v[3][16];
@@ -2223,14 +2228,18 @@ conv_qu_kernel(const __grid_constant__ CUtensorMap mapCur, const __grid_constant
                 tc::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) { tc::mbar_arrive(&p_full); tc::mbar_arrive(&acc1_empty); }
+#ifdef SQ_XC_PHASE_DIAG
+                dacc[3] += clock64() - te1_;
+#endif
             }
             if (it >= 1) {
                 // ---- epilogue 2: the conv's accumulators -> ReLU -> quad tensor
                 const int i2 = it - 1, b = i2 & 1;
                 const int y = ty2 * QU::TH + j2 * 16 + (r >> 3), x = tx2 * 8 + (r & 7);
                 const bool valid = (y < H) && (x < W);
-                tc::mbar_wait(&acc2_full[b], (i2 >> 1) & 1);
+                QU_W(2, tc::mbar_wait(&acc2_full[b], (i2 >> 1) & 1));
                 tc::tc_fence_after();
+                const long long te2_ = clock64();
                 uint32_t v[32];
                 tc::tmem_ld32(tmem_base + lane_addr + ACC2 + b * 128 + j2 * 64 + c8 * 32, v);
                 tc::tmem_ld_wait();
@@ -2250,6 +2259,9 @@ conv_qu_kernel(const __grid_constant__ CUtensorMap mapCur, const __grid_constant
                     }
                     if (valid) *reinterpret_cast<uint4 *>(po + (size_t)(2 * q) * plane) = make_uint4(o[0], o[1], o[2], o[3]);
                 }
+#ifdef SQ_XC_PHASE_DIAG
+                dacc[4] += clock64() - te2_;
+#endif
             }
             tx2 = tx; ty2 = ty; n2 = n;
             tx += dtx;
@@ -2259,6 +2271,14 @@ conv_qu_kernel(const __grid_constant__ CUtensorMap mapCur, const __grid_constant
             n += dn;
         }
     }
+#ifdef SQ_XC_PHASE_DIAG
+    if (phase_dbg && lane == 0 && (warp <= 1 || warp == 1 + QU::MMA_WARPS)) {      // producer, first MMA warp, first epilogue warp
+        const int role = warp <= 1 ? warp : 2;
+        dacc[7] = clock64() - t_kernel0;
+        for (int i = 0; i < 8; ++i) phase_dbg[(blockIdx.x * 3 + role) * 8 + i] = dacc[i];
+    }
+#endif
+#undef QU_W
     tc::tc_fence_before();
     __syncthreads();
     if (warp == 1) {
@@ -3159,10 +3179,36 @@ int launch_qu(sq_unet_s *u, const SqLayer &Lu, const SqLayer &L1, const bf16 *cu
     }
     const int tiles = g.nimg * ((g.W + 7) / 8) * ((g.H + QU::TH - 1) / QU::TH);
     const int grid = std::min(tiles, u->h->sm_count / grid_div());
+    long long *phase_dbg = nullptr;
+#ifdef SQ_XC_PHASE_DIAG
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (getenv("SQ_XC_PHASE")) {
+        SQ_CUDA(cudaMalloc(&phase_dbg, (size_t)grid * 24 * sizeof(long long)));
+        SQ_CUDA(cudaMemset(phase_dbg, 0, (size_t)grid * 24 * sizeof(long long)));
+        cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, st);
+    }
+#endif
     conv_qu_kernel<<<grid, QU::THREADS, smem, st>>>(mc, ms, (const bf16 *)Lu.w_qd, (const bf16 *)L1.w_qu, ep, ksu, out, g.nimg,
-                                                   g.H, g.W);
+                                                   g.H, g.W, phase_dbg);
     ++u->last_launches;
     SQ_CHECK_LAUNCH();
+#ifdef SQ_XC_PHASE_DIAG
+    if (phase_dbg) {
+        cudaEventRecord(e1, st);
+        SQ_CUDA(cudaStreamSynchronize(st));
+        float ms_ = 0; cudaEventElapsedTime(&ms_, e0, e1);
+        std::vector<long long> h((size_t)grid * 24);
+        SQ_CUDA(cudaMemcpy(h.data(), phase_dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+        SQ_CUDA(cudaFree(phase_dbg));
+        double a[24] = {0};
+        for (int b2 = 0; b2 < grid; ++b2) for (int i = 0; i < 24; ++i) a[i] += (double)h[(size_t)b2 * 24 + i] / grid;
+        const double tpc = (double)tiles / grid;
+        fprintf(stderr, "qu_phase %.3f ms, tiles/CTA=%.0f, %.0f ticks/tile (MMA warp lifetime) | per tile: producer wait a1_empty %.0f ring_empty %.0f | "
+                "mma wait p_full %.0f a1_full %.0f acc1_empty %.0f acc2_empty %.0f ring_full %.0f | epilogue wait acc1_full %.0f p_empty %.0f "
+                "acc2_full %.0f; work: epilogue 1 %.0f, epilogue 2 %.0f\n", ms_, tpc, a[15] / tpc, a[0] / tpc, a[1] / tpc, a[8] / tpc, a[9] / tpc,
+                a[10] / tpc, a[11] / tpc, a[12] / tpc, a[16] / tpc, a[17] / tpc, a[18] / tpc, a[19] / tpc, a[20] / tpc);
+    }
+#endif
     return SQ_OK;
 }
 
