@@ -1638,7 +1638,9 @@ struct QF {
     static constexpr int W2_BYTES = 4 * 4 * 2 * 64 * 16, B1_BYTES = 2 * 64 * 16;
     static constexpr int OFF_B1 = 0, OFF_W2 = B1_BYTES, OFF_A1 = OFF_W2 + W2_BYTES, OFF_RAW = OFF_A1 + 2 * A1_BYTES,
                          OFF_P = OFF_RAW + 2 * RAW_BYTES, SMEM = OFF_P + 2 * P_BYTES;
-    static constexpr int EPI_WARPS = 16, BLD_WARPS = 4, THREADS = 32 * (2 + BLD_WARPS + EPI_WARPS);
+    // two MMA-issuing warps (one per conv2 sub-tile; a single thread issues one 128x64x16 MMA per ~70 clk, the pipe takes 48)
+    static constexpr int MMA_WARPS = 2, EPI_WARPS = 16, BLD_WARPS = 4, FIRST_BLD = 1 + MMA_WARPS,
+                         FIRST_EPI = FIRST_BLD + BLD_WARPS, THREADS = 32 * (FIRST_EPI + EPI_WARPS);
     static_assert(OFF_A1 % 128 == 0 && OFF_RAW % 128 == 0 && OFF_P % 128 == 0 && P_BYTES % 128 == 0, "alignment");
 };
 
@@ -1684,11 +1686,11 @@ conv_qf_kernel(const __grid_constant__ CUtensorMap mapIn, const bf16 *__restrict
         tc::mbar_init(&w_bar, 1);
         for (int i = 0; i < 2; ++i) {
             tc::mbar_init(&raw_full[i], 1); tc::mbar_init(&raw_empty[i], QF::BLD_WARPS);
-            tc::mbar_init(&a1_full[i], QF::BLD_WARPS); tc::mbar_init(&a1_empty[i], 1);
-            tc::mbar_init(&p_full[i], QF::EPI_WARPS); tc::mbar_init(&p_empty[i], 1);
-            tc::mbar_init(&acc2_full[i], 1); tc::mbar_init(&acc2_empty[i], QF::EPI_WARPS);
+            tc::mbar_init(&a1_full[i], QF::BLD_WARPS); tc::mbar_init(&a1_empty[i], QF::MMA_WARPS);
+            tc::mbar_init(&p_full[i], QF::EPI_WARPS); tc::mbar_init(&p_empty[i], QF::MMA_WARPS);
+            tc::mbar_init(&acc2_full[i], QF::MMA_WARPS); tc::mbar_init(&acc2_empty[i], QF::EPI_WARPS);
         }
-        tc::mbar_init(&acc1_full, 1); tc::mbar_init(&acc1_empty, QF::EPI_WARPS);
+        tc::mbar_init(&acc1_full, QF::MMA_WARPS); tc::mbar_init(&acc1_empty, QF::EPI_WARPS);
         tc::fence_barrier_init();
         tc::tma_prefetch_desc(&mapIn);
     }
@@ -1718,8 +1720,9 @@ conv_qf_kernel(const __grid_constant__ CUtensorMap mapIn, const bf16 *__restrict
                 tc::tma_load_3d(smem + QF::OFF_RAW + b * QF::RAW_BYTES, &mapIn, &raw_full[b], 16 * tx - (RAW16 ? 8 : 4), 64 * ty - 3, n);
             }
         }
-    } else if (warp == 1) {
-        // ======================================================= MMA issuer
+    } else if (warp <= QF::MMA_WARPS) {
+        // ======================================================= MMA issuers: warp 1 owns conv2 sub-tile 0, warp 2 sub-tile 1
+        const int jw = warp - 1;
         const uint32_t idesc = tc::instr_desc_bf16(128, 64);
         const uint32_t sbase = tc::smem_u32(smem);
         const uint32_t hi128 = ((128u >> 4) & 0x3FFFu) | (1u << 14);                 // SBO = 128 (A1, B1, W2)
@@ -1736,8 +1739,7 @@ conv_qf_kernel(const __grid_constant__ CUtensorMap mapIn, const bf16 *__restrict
                 if (tc::elect_one()) {
                     const uint32_t a1_lo = (((sbase + QF::OFF_A1 + b * QF::A1_BYTES) >> 4) & 0x3FFFu) |
                                            ((((uint32_t)QF::A1_ROWS * 16u) >> 4) << 16);
-#pragma unroll
-                    for (int m = 0; m < QF::MT1; ++m)
+                    for (int m = jw; m < QF::MT1; m += QF::MMA_WARPS)           // M-tiles 0, 2 / 1
                         tc::umma_bf16_parts(tmem_base + ACC1 + m * 64, a1_lo + m * (2048 >> 4), hi128, b1_lo, hi128, idesc, 0u);
                     tc::umma_commit(&a1_empty[b]);
                     tc::umma_commit(&acc1_full);
@@ -1757,14 +1759,12 @@ conv_qf_kernel(const __grid_constant__ CUtensorMap mapIn, const bf16 *__restrict
                     for (int k = 0; k < 4; ++k) {
                         const int iy = k >> 1, ix = k & 1;
 #pragma unroll
-                        for (int j = 0; j < 2; ++j)
-#pragma unroll
-                            for (int tp = 0; tp < 4; ++tp) {
-                                const uint32_t a_off = (uint32_t)(k * (2 * QF::PROWS) + (j * 16 + (tp >> 1) + 1 - iy) * QF::PW +
-                                                                  (tp & 1) + 1 - ix);
-                                tc::umma_bf16_parts(d0 + j * 64, p_lo + a_off, hiP, w2_lo + (uint32_t)((k * 4 + tp) * (2048 >> 4)),
-                                                    hi128, idesc, (k > 0 || tp > 0) ? 1u : 0u);
-                            }
+                        for (int tp = 0; tp < 4; ++tp) {
+                            const uint32_t a_off = (uint32_t)(k * (2 * QF::PROWS) + (jw * 16 + (tp >> 1) + 1 - iy) * QF::PW +
+                                                              (tp & 1) + 1 - ix);
+                            tc::umma_bf16_parts(d0 + jw * 64, p_lo + a_off, hiP, w2_lo + (uint32_t)((k * 4 + tp) * (2048 >> 4)),
+                                                hi128, idesc, (k > 0 || tp > 0) ? 1u : 0u);
+                        }
                     }
                     tc::umma_commit(&p_empty[b]);
                     tc::umma_commit(&acc2_full[b]);
@@ -1772,9 +1772,9 @@ conv_qf_kernel(const __grid_constant__ CUtensorMap mapIn, const bf16 *__restrict
                 __syncwarp();
             }
         }
-    } else if (warp < 2 + QF::BLD_WARPS) {
+    } else if (warp < QF::FIRST_EPI) {
         // ===================================================== im2col builders
-        const int bt = threadIdx.x - 64;                     // 0 .. 127
+        const int bt = threadIdx.x - 32 * QF::FIRST_BLD;     // 0 .. 127
         int roff[3];                                         // this thread's rows p = bt + 128 k: window origin in the halo
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
@@ -1871,7 +1871,7 @@ conv_qf_kernel(const __grid_constant__ CUtensorMap mapIn, const bf16 *__restrict
         }
     } else {
         // ========================================================= epilogue
-        const int g = (warp - 2 - QF::BLD_WARPS) >> 2, q4 = warp & 3;
+        const int g = (warp - QF::FIRST_EPI) >> 2, q4 = warp & 3;
         const int r = q4 * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(q4 * 32) << 16;
         int ppy[3], ppx[3];
@@ -1985,8 +1985,8 @@ conv_qf_kernel(const __grid_constant__ CUtensorMap mapIn, const bf16 *__restrict
     }
 #ifdef SQ_XC_PHASE_DIAG
     // per role (producer, MMA, first builder warp, first epilogue warp): clocks spent in each wait
-    if (phase_dbg && lane == 0 && (warp <= 2 || warp == 2 + QF::BLD_WARPS)) {
-        const int role = warp <= 2 ? warp : 3;
+    if (phase_dbg && lane == 0 && (warp <= 1 || warp == QF::FIRST_BLD || warp == QF::FIRST_EPI)) {
+        const int role = warp <= 1 ? warp : (warp == QF::FIRST_BLD ? 2 : 3);
         dacc[5] = clock64() - t_kernel0;                 // the role's whole lifetime, in clock64 ticks
         for (int i = 0; i < 6; ++i) phase_dbg[(blockIdx.x * 4 + role) * 8 + i] = dacc[i];
     }
