@@ -2026,7 +2026,10 @@ struct QU {
     static constexpr int OFF_WU = 0, OFF_W = WU_BYTES, OFF_A1 = OFF_W + W_BYTES, OFF_P = OFF_A1 + A1_BYTES,
                          OFF_RING = OFF_P + P_BYTES, SMEM = OFF_RING + NRING * KSTEP_BYTES;
     // two MMA-issuing warps (one per sub-tile): a single thread sustains one 128x64x16 MMA per ~70 clk here, the pipe 48
-    static constexpr int MMA_WARPS = 2, EPI_WARPS = 16, THREADS = 32 * (1 + MMA_WARPS + EPI_WARPS);
+    // warp 0: weights + level-1 patches; warps 1-2: MMA; warp 3: the skip ring's own TMA producer (decoupled from the
+    // single-buffered level-1 patch, so the ring really runs two tiles ahead); warps 4-19: epilogue
+    static constexpr int MMA_WARPS = 2, RING_WARP = 1 + MMA_WARPS, FIRST_EPI = RING_WARP + 1, EPI_WARPS = 16,
+                         THREADS = 32 * (FIRST_EPI + EPI_WARPS);
     static_assert(OFF_A1 % 128 == 0 && OFF_P % 128 == 0 && OFF_RING % 128 == 0 && KSTEP_BYTES % 128 == 0, "alignment");
     static_assert(SMEM + 1024 <= 232448, "shared memory");
 };
@@ -2082,8 +2085,6 @@ conv_qu_kernel(const __grid_constant__ CUtensorMap mapCur, const __grid_constant
             tc::bulk_load(smem + QU::OFF_WU, wup, (uint32_t)(ksu * 2048), &w_bar);
             for (int q = 0; q < 8; ++q)
                 tc::bulk_load(smem + QU::OFF_W + q * 8192, wts + q * 4096, 8192, &w_bar);
-            int rs = 0;
-            uint32_t rphase = 0;
             for (int it = 0; it < nt; ++it) {
                 const int t = blockIdx.x + it * gridDim.x;
                 const int tx = t % tiles_x, ty = (t / tiles_x) % tiles_y, n = t / (tiles_x * tiles_y);
@@ -2091,6 +2092,17 @@ conv_qu_kernel(const __grid_constant__ CUtensorMap mapCur, const __grid_constant
                 QU_W(0, tc::mbar_wait(&a1_empty, (it & 1) ^ 1));
                 tc::mbar_arrive_expect_tx(&a1_full, (uint32_t)(ksu * QU::KSTEP_BYTES));
                 tc::tma_load_5d(smem + QU::OFF_A1, &mapCur, &a1_full, x0 * 8, y0, 0, 0, n);
+            }
+        }
+    } else if (warp == QU::RING_WARP) {
+        // ===================================================== TMA producer of the skip ring
+        if (lane == 0) {
+            int rs = 0;
+            uint32_t rphase = 0;
+            for (int it = 0; it < nt; ++it) {
+                const int t = blockIdx.x + it * gridDim.x;
+                const int tx = t % tiles_x, ty = (t / tiles_x) % tiles_y, n = t / (tiles_x * tiles_y);
+                const int x0 = tx * 8 - 1, y0 = ty * QU::TH - 1;
                 for (int ks = 0; ks < 4; ++ks) {
                     QU_W(1, tc::mbar_wait(&ring_empty[rs], rphase ^ 1));
                     tc::mbar_arrive_expect_tx(&ring_full[rs], QU::KSTEP_BYTES);
@@ -2173,7 +2185,7 @@ conv_qu_kernel(const __grid_constant__ CUtensorMap mapCur, const __grid_constant
         }
     } else {
         // ========================================================= epilogue
-        const int g = (warp - 1 - QU::MMA_WARPS) >> 2, q4 = warp & 3;
+        const int g = (warp - QU::FIRST_EPI) >> 2, q4 = warp & 3;
         const int r = q4 * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(q4 * 32) << 16;
         int ppy[3], ppx[3];
@@ -2272,7 +2284,7 @@ conv_qu_kernel(const __grid_constant__ CUtensorMap mapCur, const __grid_constant
         }
     }
 #ifdef SQ_XC_PHASE_DIAG
-    if (phase_dbg && lane == 0 && (warp <= 1 || warp == 1 + QU::MMA_WARPS)) {      // producer, first MMA warp, first epilogue warp
+    if (phase_dbg && lane == 0 && (warp <= 1 || warp == QU::FIRST_EPI)) {           // producer, first MMA warp, first epilogue warp
         const int role = warp <= 1 ? warp : 2;
         dacc[7] = clock64() - t_kernel0;
         for (int i = 0; i < 8; ++i) phase_dbg[(blockIdx.x * 3 + role) * 8 + i] = dacc[i];
