@@ -24,10 +24,18 @@
 //   conv_xc_kernel  conv 3x3(x3) for Cout <= 32 with several k-steps per tile: the three horizontal
 //                   taps folded into N = 3*Cout (3 MMAs per k-step), combined by lane shuffles in the
 //                   epilogue; weights resident in shared memory
+//   conv_qd_kernel  level 0 of planar nets with 16 filters on the QUAD (space-to-depth) layout: a 2x2 pixel block is
+//                   one pixel of a half-resolution image with 64 channels, a 3x3 conv 16 -> 16 becomes four 128 x 64 x 16
+//                   MMAs per input parity (the other weight blocks are zero), the up-conv a 1x1 conv, pool / head in-thread
+//   conv_qf_kernel  down0/conv1 + down0/conv2 + pool in ONE launch (the first conv as an im2col GEMM, its output stays
+//                   in shared memory as conv2's halo patch)
+//   conv_qu_kernel  up0/upscale + up0/conv1 in ONE launch (the up-sampled patch stays in shared memory, the skip
+//                   tensor streams through a TMA ring)
 // Epilogue variants: plain store, store + fused 2x2 max-pool, fused 1x1 head + softmax + argmax.
-// Run-time switches (A/B measurements and tests; defaults are the measured optimum): SQ_XC=0/2 disables /
-// forces the x-combined kernel, SQ_CLUSTER=1 runs the Cout >= 128 convs as weight-multicasting CTA pairs,
-// SQ_FUSE_FIRST=1 computes down0/conv1 with builder warps inside down0/conv2's producer (NBLD > 0 below).
+// Run-time switches (A/B measurements and tests; defaults are the measured optimum): SQ_QUAD=0 keeps level 0 on the
+// full-resolution kernels, SQ_QFUSE=0 / SQ_QUP=0 split the fused level-0 pairs, SQ_XC=0/2 disables / forces the
+// x-combined kernel, SQ_CLUSTER=1 runs the Cout >= 128 convs as weight-multicasting CTA pairs, SQ_FUSE_FIRST=1 /
+// SQ_PAIR=1 are the (slower) on-chip hand-offs of rounds 1-2 on the full-resolution layout.
 // The first conv (Cin <= 4: K = 9..108 -- warp-level mma.sync on a staged halo tile), the depth
 // half of the 2x2x2 pool, the element-wise bridges and the stand-alone head are bandwidth-bound
 // CUDA-core kernels on the same layout.
