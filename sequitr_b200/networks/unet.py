@@ -413,6 +413,15 @@ class UNet(object):
         """uint8 class mask (N,[D,]H,W)."""
         return self.predict(features, want=('mask',))['mask']
 
+    def _result_buffers(self, n, max_rows):
+        key = (int(n), int(max_rows))
+        cache = self.__dict__.setdefault('_result_cache', {})
+        if key not in cache:
+            from ..utils import pinned_array
+            cache.clear()                                   # one size at a time: a stack is processed in equal calls
+            cache[key] = (pinned_array((n, max_rows, 5), np.float32), pinned_array((n,), np.int32))
+        return cache[key]
+
     def segment_and_localise(self, frames, frame0=0, max_rows=4096, return_mask=False, normalise=False):
         """The whole hot path on HOST frames (2-D): H2D -> UNet -> argmax -> label-and-
         localise -> D2H.  frames float32 (N,H,W,Cin), or RAW uint8 / uint16 camera frames as the
@@ -434,8 +443,9 @@ class UNet(object):
         n, h, w = frames.shape[:3]
         mask = np.empty((n, h, w), dtype=np.uint8) if return_mask else None
         while True:
-            table = np.empty((n, max_rows, 5), dtype=np.float32)
-            counts = np.empty((n,), dtype=np.int32)
+            # the result buffers are page-locked and kept with the net: the tables then come back by DMA instead of a
+            # staged copy into pageable memory, and a time-lapse job does not allocate per call
+            table, counts = self._result_buffers(n, max_rows)
             st = lib.sq_segment_localise_raw_host(plan, frames.ctypes.data, code, int(bool(normalise)), n, h, w,
                                                   frame0, table.ctypes.data, counts.ctypes.data, max_rows,
                                                   _lib.ptr(mask))
