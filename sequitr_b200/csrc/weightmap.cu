@@ -19,6 +19,7 @@
 // Both kernels are HBM/L2-bound integer work: 1 B (W1) or 4 B (W3) in and one
 // float out per pixel; the uint16 / 12-byte intermediates stay L2-resident.
 #include "sq_common.cuh"
+#include <cstdlib>
 #include <cmath>
 
 namespace {
@@ -679,6 +680,108 @@ inst_cols_dpx(const int *__restrict__ la, const int *__restrict__ lb, const unsi
     }
 }
 
+// W3 row pass on the row's RUN LIST (default when the row fits: wid <= 3072).  Same results as inst_rows_bits below,
+// which answers every pixel with its own bit-scan walk (~100 instructions and up to 8 dependent label loads per
+// pixel); here the row is turned into runs once (start, end, label, nearest run with ANOTHER label on either side),
+// and a pixel only ranks itself among the run starts and looks at <= 4 candidates: own run, or the two runs framing
+// its gap, plus their different-label neighbours -- exactly the candidates the walk would have found, in the same
+// order (own, left near / far, right near / far).
+// grid (hgt, n), block 256, dyn smem: 4 * (nw + 1) words + wid * 12 bytes.
+__global__ void __launch_bounds__(256)
+inst_rows_runs(const int *__restrict__ labels, int *__restrict__ la, int *__restrict__ lb,
+               unsigned char *__restrict__ da, unsigned char *__restrict__ db, int *__restrict__ big, int hgt, int wid,
+               int R)
+{
+    extern __shared__ unsigned bits[];
+    const long long ro = ((long long)blockIdx.y * hgt + blockIdx.x) * wid;
+    const int *lr = labels + ro;
+    const int nw = (wid + 31) >> 5;
+    unsigned *sbits = bits, *ebits = bits + (nw + 1);
+    int *spre = reinterpret_cast<int *>(bits + 2 * (nw + 1)), *epre = spre + (nw + 1);   // exclusive bit counts per word
+    int *rl = epre + (nw + 1);                                                     // run label
+    unsigned short *rs = reinterpret_cast<unsigned short *>(rl + wid), *re = rs + wid, *pd = re + wid, *nd = pd + wid;
+    constexpr unsigned short NONE = 0xffffu;
+    const int lane = threadIdx.x & 31;
+    for (int x = threadIdx.x; x < nw * 32; x += blockDim.x) {
+        int l = 0, lp = 0, ln = 0;
+        if (x < wid) {
+            l = lr[x];
+            lp = x > 0 ? lr[x - 1] : 0;
+            ln = x + 1 < wid ? lr[x + 1] : 0;
+        }
+        const bool fg = l > 0;
+        if (l > (int)IP_LMASK) big[blockIdx.y] = 1;          // label too wide for the packed keys (benign race)
+        const unsigned sb = __ballot_sync(0xffffffffu, fg && lp != l);
+        const unsigned eb = __ballot_sync(0xffffffffu, fg && ln != l);
+        if (lane == 0) { sbits[x >> 5] = sb; ebits[x >> 5] = eb; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {                                   // exclusive prefix of the per-word bit counts
+        int cs = 0, ce = 0;
+        for (int w0 = 0; w0 < nw; w0 += 32) {
+            const int w = w0 + lane;
+            const int ps = w < nw ? __popc(sbits[w]) : 0, pe = w < nw ? __popc(ebits[w]) : 0;
+            int is = ps, ie = pe;
+            for (int o = 1; o < 32; o <<= 1) {
+                const int ts = __shfl_up_sync(0xffffffffu, is, o), te = __shfl_up_sync(0xffffffffu, ie, o);
+                if (lane >= o) { is += ts; ie += te; }
+            }
+            if (w < nw) { spre[w] = cs + is - ps; epre[w] = ce + ie - pe; }
+            cs += __shfl_sync(0xffffffffu, is, 31);
+            ce += __shfl_sync(0xffffffffu, ie, 31);
+        }
+        if (lane == 0) { spre[nw] = cs; epre[nw] = ce; }
+    }
+    __syncthreads();
+    const int nruns = spre[nw];
+    for (int w = threadIdx.x; w < nw; w += blockDim.x) {      // the k-th start bit and the k-th end bit frame run k
+        unsigned a = sbits[w], e = ebits[w];
+        int ks = spre[w], ke = epre[w];
+        while (a) { const int b = __ffs(a) - 1; a &= a - 1; const int x = (w << 5) + b; rs[ks] = (unsigned short)x; rl[ks] = lr[x]; ++ks; }
+        while (e) { const int b = __ffs(e) - 1; e &= e - 1; re[ke++] = (unsigned short)((w << 5) + b); }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < nruns; k += blockDim.x) {   // nearest run with another label, within reach
+        const int l = rl[k];
+        int j = k - 1;
+        while (j >= 0 && rl[j] == l && (int)rs[k] - (int)re[j] <= R) --j;
+        pd[k] = (j >= 0 && rl[j] != l) ? (unsigned short)j : NONE;
+        j = k + 1;
+        while (j < nruns && rl[j] == l && (int)rs[j] - (int)re[k] <= R) ++j;
+        nd[k] = (j < nruns && rl[j] != l) ? (unsigned short)j : NONE;
+    }
+    __syncthreads();
+    for (int x = threadIdx.x; x < wid; x += blockDim.x) {
+        const int w = x >> 5;
+        const int k = spre[w] + __popc(sbits[w] & (0xffffffffu >> (31 - (x & 31)))) - 1;   // last run starting at or before x
+        Best2 b = {0, 0, INF32, INF32};
+        const bool inside = k >= 0 && x <= (int)re[k];
+        int lft, rgt;                                         // nearest candidate runs on either side
+        if (inside) {
+            best2_insert(b, rl[k], 0u);
+            lft = pd[k] == NONE ? -1 : (int)pd[k];
+            rgt = nd[k] == NONE ? -1 : (int)nd[k];
+        } else {
+            lft = k;
+            rgt = k + 1 < nruns ? k + 1 : -1;
+        }
+        if (lft >= 0 && x - (int)re[lft] <= R) {
+            best2_insert(b, rl[lft], (unsigned)(x - (int)re[lft]));
+            if (!inside && pd[lft] != NONE && x - (int)re[pd[lft]] <= R)
+                best2_insert(b, rl[pd[lft]], (unsigned)(x - (int)re[pd[lft]]));
+        }
+        if (rgt >= 0 && (int)rs[rgt] - x <= R) {
+            best2_insert(b, rl[rgt], (unsigned)((int)rs[rgt] - x));
+            if (!inside && nd[rgt] != NONE && (int)rs[nd[rgt]] - x <= R)
+                best2_insert(b, rl[nd[rgt]], (unsigned)((int)rs[nd[rgt]] - x));
+        }
+        la[ro + x] = b.la;
+        lb[ro + x] = b.lb;
+        da[ro + x] = b.la ? (unsigned char)min(b.da, 254u) : INF8;
+        db[ro + x] = b.lb ? (unsigned char)min(b.db, 254u) : INF8;
+    }
+}
+
 // W3 row pass.  grid (hgt, n), block 256, dyn smem: 2 * ceil(wid/32) words (run starts, run ends)
 __global__ void inst_rows_bits(const int *__restrict__ labels, int *__restrict__ la,
                                int *__restrict__ lb, unsigned char *__restrict__ da,
@@ -964,7 +1067,13 @@ extern "C" int sq_weightmap_unet(sq_handle_t h, const int32_t *labels, int n, in
     if (rmax <= WR_MAX) {
         unsigned char *da8 = reinterpret_cast<unsigned char *>(da), *db8 = reinterpret_cast<unsigned char *>(db);
         SQ_CUDA(cudaMemsetAsync(big, 0, n * sizeof(int), st));
-        inst_rows_bits<<<dim3(hgt, n), 256, (size_t)((wid + 31) / 32) * 8, st>>>(labels, la, lb, da8, db8, big, hgt, wid, rmax);
+        // row pass on the run list when its shared memory fits the default 48 KB (wid <= 3072), else the bit-scan walk
+        const size_t runs_smem = (size_t)((wid + 31) / 32 + 1) * 16 + (size_t)wid * 12;
+        static const bool walk_only = getenv("SQ_W3_ROWWALK") != nullptr;     // A/B switch
+        if (runs_smem <= 48 * 1024 && wid < 65535 && !walk_only)
+            inst_rows_runs<<<dim3(hgt, n), 256, runs_smem, st>>>(labels, la, lb, da8, db8, big, hgt, wid, rmax);
+        else
+            inst_rows_bits<<<dim3(hgt, n), 256, (size_t)((wid + 31) / 32) * 8, st>>>(labels, la, lb, da8, db8, big, hgt, wid, rmax);
         {
             // DPX column pass (labels < 2^18); frames flagged by the row pass fall through to the scan kernel
             const dim3 dgrid(sq_div_up(wid, IP_TW), sq_div_up(hgt, IP_TH), n);
