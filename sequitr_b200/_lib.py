@@ -146,6 +146,15 @@ def handle(device=None):
     return _handles[device]
 
 
+def new_handle(device):
+    """A library handle of its own (own streams, own device arena) on `device`: host calls through plans built on
+    different handles can run concurrently.  The caller destroys it (sq_destroy)."""
+    handle(device)                                  # same availability checks as the shared handle
+    h = c_void_p()
+    check(load().sq_create(int(device), ctypes.byref(h)))
+    return h
+
+
 def ptr(t):
     """Raw pointer of a torch tensor / numpy array / None."""
     if t is None:

@@ -61,6 +61,8 @@ class UNet(object):
 
     def __init__(self, params, mode=ModeKeys.PREDICT):
         self._mode = mode
+        self.params = dict(params)
+        self._handle = None                     # a library handle of this network's own (params['private_handle'])
         self.name = params.get('name', 'UNet2d_test')
         self.filters = tuple(params.get('filters', DEFAULT_FILTERS))
         self.dropout = params.get('dropout', DEFAULT_DROPOUT)
@@ -263,8 +265,24 @@ class UNet(object):
     def __del__(self):
         try:
             self._drop_plan()
+            h = getattr(self, '_handle', None)
+            if h is not None:
+                _lib.load().sq_destroy(h)
+                self._handle = None
         except Exception:
             pass
+
+    def twin(self):
+        """A second network with the same parameters and weights on the same GPU but with a library handle of its
+        own: its host calls (``segment_and_localise``) run concurrently with this one's, so the copy ramp and the
+        label / read-back tail of one call hide under the other's convolutions (``shard.segment_stack(overlap=True)``)."""
+        self._ensure_plan()
+        params = dict(self.params)
+        params['device'] = self._device
+        params['private_handle'] = True
+        other = type(self)(params)
+        other.load_weights(self._weights)
+        return other
 
     def _ensure_plan(self, device=None):
         """The CUDA plan lives on ONE device: the first one it is used on (default: the current
@@ -297,7 +315,10 @@ class UNet(object):
         self._device = int(device)
         device = self._device
         self._ws = ops.Workspace(device='cuda:%d' % device)
-        _lib.check(lib.sq_unet_create(_lib.handle(device), self.ndim, self.n_inputs, self.n_outputs, filt,
+        if self.params.get('private_handle') and getattr(self, '_handle', None) is None:
+            self._handle = _lib.new_handle(device)      # this network's own streams / arena (see twin())
+        hnd = getattr(self, '_handle', None) or _lib.handle(device)
+        _lib.check(lib.sq_unet_create(hnd, self.ndim, self.n_inputs, self.n_outputs, filt,
                                       len(self.filters), _lib.BRIDGE_CODES[self.bridge_type], mode,
                                       ctypes.byref(plan)))
         try:

@@ -33,16 +33,44 @@ def tables_digest(tables):
     return h.hexdigest()
 
 
-def segment_stack(net, frames, frame0=0, frames_per_call=250, max_rows=4096, normalise=True):
+def segment_stack(net, frames, frame0=0, frames_per_call=250, max_rows=4096, normalise=True, overlap=False):
     """Run this rank's contiguous frame range ``frames`` (host array (n,H,W[,C]); camera-native
     uint8 / uint16 or float32) through ``net.segment_and_localise`` call by call and return the list of
     per-frame tables, rows carrying GLOBAL frame indices (``frame0`` = global index of ``frames[0]``):
-    the loop a Sequitr job runs over a time-lapse (reference utils.py:531-578), one rank's share of it."""
-    out = []
+    the loop a Sequitr job runs over a time-lapse (reference utils.py:531-578), one rank's share of it.
+
+    ``overlap``: two host threads alternate the calls, the second through ``net.twin()`` (same weights, its own
+    library handle and streams): the one-frame copy ramp at the start of a call and the label-and-localise /
+    read-back tail at its end then hide under the other call's convolutions.  Same tables, same order."""
     n = len(frames)
-    for s in range(0, n, frames_per_call):
-        out.extend(net.segment_and_localise(frames[s:s + frames_per_call], frame0=frame0 + s,
-                                            max_rows=max_rows, normalise=normalise))
+    starts = list(range(0, n, frames_per_call))
+
+    def run(worker, s):
+        return worker.segment_and_localise(frames[s:s + frames_per_call], frame0=frame0 + s, max_rows=max_rows,
+                                           normalise=normalise)
+
+    if not overlap or len(starts) < 2:
+        out = []
+        for s in starts:
+            out.extend(run(net, s))
+        return out
+    from concurrent.futures import ThreadPoolExecutor
+    twin = getattr(net, '_overlap_twin', None)
+    if twin is None:
+        twin = net._overlap_twin = net.twin()
+    results = [None] * len(starts)
+
+    def lane(worker, idx):
+        for i in idx:
+            results[i] = run(worker, starts[i])
+
+    with ThreadPoolExecutor(2) as pool:
+        futs = [pool.submit(lane, net, range(0, len(starts), 2)), pool.submit(lane, twin, range(1, len(starts), 2))]
+        for f in futs:
+            f.result()
+    out = []
+    for r in results:
+        out.extend(r)
     return out
 
 

@@ -151,3 +151,20 @@ def test_image_norm_feeds_the_fused_first_pair_in_16_bits(sq, monkeypatch, shape
         for a, b in zip(t_bf16, t_other):
             np.testing.assert_array_equal(a, b)
     assert sum(len(t) for t in t_bf16) >= 9
+
+
+def test_overlapped_stack_calls_give_the_same_tables(sq):
+    """shard.segment_stack(overlap=True): two host threads, the second through net.twin() (same weights, its own
+    library handle, streams and device arena), alternate the calls -- tables identical to the sequential walk."""
+    from sequitr_b200 import shard, synth
+    from sequitr_b200.networks import UNet2D
+    filters = (16, 32, 64)
+    net = UNet2D({'filters': filters, 'shape': (128, 160), 'bridge': 'concat', 'compute': 'bf16'})
+    net.load_weights(synth.blob_detector_weights(filters, 1, 2, seed=1))
+    x = synth.frames(37, 128, 160, 1, seed=6, n_objects=5)[..., 0]
+    raw = np.clip(x * 400.0 + 3000.0, 0, 65535).astype(np.uint16)
+    seq = shard.segment_stack(net, raw, frame0=100, frames_per_call=8, max_rows=256)
+    for _ in range(2):
+        over = shard.segment_stack(net, raw, frame0=100, frames_per_call=8, max_rows=256, overlap=True)
+        assert len(over) == 37 and shard.tables_digest(over) == shard.tables_digest(seq)
+    assert sum(len(t) for t in seq) >= 37 and seq[5][0, 0] == 105.0

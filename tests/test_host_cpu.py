@@ -389,3 +389,9 @@ def test_segment_stack_and_digest_with_a_stub_network():
     assert shard.tables_digest(merged) == shard.tables_digest(whole)
     merged[5] = merged[5] + 1
     assert shard.tables_digest(merged) != shard.tables_digest(whole)
+    # overlap=True: two host threads alternate the calls (the odd ones through net.twin()); same tables, same order
+    s2, s3 = Stub(), Stub()
+    s2.twin = lambda: s3
+    over = shard.segment_stack(s2, stack, frame0=0, frames_per_call=4, overlap=True)
+    assert shard.tables_digest(over) == shard.tables_digest(whole)
+    assert [c[1] for c in s2.calls] == [0, 8, 16] and [c[1] for c in s3.calls] == [4, 12, 20]
