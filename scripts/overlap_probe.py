@@ -13,7 +13,7 @@ from sequitr_b200.networks import UNet2D              # noqa: E402
 n = int(os.environ.get('N', 512))
 per_call = int(os.environ.get('CALL', 64))
 filters = (16, 32, 64, 128, 256)
-stack = synth.camera_stack(0, n, 2048, 2048, seed=1234, workers=8)
+stack = synth.camera_stack(0, n, 2048, 2048, seed=1234, workers=8)   # forked renderers: BEFORE CUDA is initialised
 t = torch.from_numpy(stack)
 torch.cuda.cudart().cudaHostRegister(t.data_ptr(), t.numel() * 2, 0)
 net = UNet2D({'filters': filters, 'shape': (2048, 2048), 'bridge': 'concat', 'compute': 'bf16'})

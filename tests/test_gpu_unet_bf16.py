@@ -184,6 +184,30 @@ def test_full_size_2048_against_fp32_exact_mode(sq):
     _fp32_parity('2048^2 seed 77', a['mask'], tables, b['mask'], b['logits'])
 
 
+def test_full_size_2048_is_batch_and_route_independent(sq):
+    """BASELINE configs[2] frame size, size-independent properties of the benchmarked path: a frame's mask does not
+    depend on which other frames share its launch (tiles of neighbouring frames interleave in the persistent kernels),
+    nor on the route it takes (device tensors through predict, uint16 host frames through the host call with
+    ImageNorm on the device, the float32 stage, or two host threads on two library handles)."""
+    import torch
+    from sequitr_b200 import ops, shard
+    filters = (16, 32, 64, 128, 256)
+    w = synth.blob_detector_weights(filters, 1, 2, seed=1)
+    net = _net(filters, (2048, 2048), 'concat', 1, 2, w)
+    raw = synth.camera_stack(40, 45, 2048, 2048, seed=1234, workers=1)                  # uint16 frames 40..44
+    xn = ops.image_norm(torch.from_numpy(raw.astype(np.float32)[..., None]).cuda())
+    m5 = net.predict(xn, want=('mask',))['mask'].cpu().numpy()
+    m1 = net.predict(xn[2:3], want=('mask',))['mask'].cpu().numpy()
+    np.testing.assert_array_equal(m5[2:3], m1)
+    m2 = net.predict(xn[[4, 0]], want=('mask',))['mask'].cpu().numpy()
+    np.testing.assert_array_equal(m2, m5[[4, 0]])
+    tables, mh = net.segment_and_localise(raw, frame0=40, return_mask=True, normalise=True)
+    np.testing.assert_array_equal(mh, m5)
+    assert all(len(t) > 100 and (t[:, 0] == 40 + i).all() for i, t in enumerate(tables))
+    over = shard.segment_stack(net, raw, frame0=40, frames_per_call=2, max_rows=4096, overlap=True)
+    assert shard.tables_digest(over) == shard.tables_digest(tables)
+
+
 def test_unsupported_configs_fail_loudly(sq):
     from sequitr_b200.networks import UNet2D, UNet3D
     net = UNet2D({'filters': (8, 16), 'shape': (16, 16), 'bridge': 'concat', 'compute': 'bf16'})
