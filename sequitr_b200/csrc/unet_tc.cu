@@ -1332,11 +1332,19 @@ struct QCfg {
 
 constexpr int QD_MAX_STAGES = 8;
 
+// The layer's folded epilogue (16 channels, the same for the four parities) and the fused head's weights, passed BY
+// VALUE: the epilogue warps read them as constant-bank operands of their FFMAs.  ncu on the head variant with these
+// tables in shared memory: 20 % short-scoreboard + 10 % MIO-throttle stalls (16 LDS.128 per 16-column work item).
+struct QdEpi {
+    float sc[16], sh[16];
+    float hw[4][16], hb[4];        // head: [class][channel], bias[class]
+};
+
 template <int S, int NTAP, int KPS, int EPI, int HK>
 __global__ void __launch_bounds__(TC_THREADS, 2)
 conv_qd_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
-               int ks0, int ks1, const bf16 *__restrict__ wts, const float *__restrict__ scale,
-               const float *__restrict__ shift, bf16 *__restrict__ out, bf16 *__restrict__ out_pool,
+               int ks0, int ks1, const bf16 *__restrict__ wts, const QdEpi ep, bf16 *__restrict__ out,
+               bf16 *__restrict__ out_pool,
                HeadArgs head, int nimg, int H, int W, int relu, int nstages, int wres, long long *phase_dbg)
 {
 #ifdef SQ_XC_PHASE_DIAG
@@ -1356,8 +1364,6 @@ conv_qd_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     uint8_t *smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
     __shared__ uint64_t full_bar[QD_MAX_STAGES], empty_bar[QD_MAX_STAGES], tfull_bar[2], tempty_bar[2], w_bar;
     __shared__ uint32_t tmem_base_sh;
-    __shared__ __align__(16) float s_scale[COUT], s_shift[COUT];
-    __shared__ __align__(16) float s_head[EPI == EPI_HEAD ? 16 * HK + HK : 4];      // [k][c] then bias[k]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_x = (W + 7) >> 3, tiles_y = (H + C::TH - 1) / C::TH;
@@ -1374,11 +1380,6 @@ conv_qd_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         tc::tma_prefetch_desc(&mapA1);
     }
     if (warp == 1) { tc::tmem_alloc(&tmem_base_sh, TMEM_COLS); tc::tmem_relinquish(); }
-    for (int i = threadIdx.x; i < COUT; i += TC_THREADS) { s_scale[i] = scale[i]; s_shift[i] = shift[i]; }
-    if constexpr (EPI == EPI_HEAD) {
-        for (int i = threadIdx.x; i < 16 * HK; i += TC_THREADS) s_head[(i % HK) * 16 + i / HK] = head.w[i];
-        for (int i = threadIdx.x; i < HK; i += TC_THREADS) s_head[16 * HK + i] = head.w[16 * HK + i];
-    }
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
@@ -1481,18 +1482,13 @@ conv_qd_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         int tx = (int)blockIdx.x % tiles_x, ty = ((int)blockIdx.x / tiles_x) % tiles_y, n = (int)blockIdx.x / tpi;
         const int dtx = gstep % tiles_x, dty = (gstep / tiles_x) % tiles_y, dn = gstep / tpi;
         // convert one 16-column group: scale / shift (+ ReLU) -> 8 packed bf16 pairs
-        auto convert = [&](const uint32_t *v, int c16, uint32_t *o) {
+        auto convert = [&](const uint32_t *v, uint32_t *o) {
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-                const float4 sc = *reinterpret_cast<const float4 *>(s_scale + c16 * 16 + 4 * g);
-                const float4 sh = *reinterpret_cast<const float4 *>(s_shift + c16 * 16 + 4 * g);
-                __nv_bfloat162 p0 = __floats2bfloat162_rn(fmaf(__uint_as_float(v[4 * g]), sc.x, sh.x),
-                                                          fmaf(__uint_as_float(v[4 * g + 1]), sc.y, sh.y));
-                __nv_bfloat162 p1 = __floats2bfloat162_rn(fmaf(__uint_as_float(v[4 * g + 2]), sc.z, sh.z),
-                                                          fmaf(__uint_as_float(v[4 * g + 3]), sc.w, sh.w));
-                if (relu) { p0 = __hmax2(p0, zero2); p1 = __hmax2(p1, zero2); }
-                o[2 * g] = *reinterpret_cast<uint32_t *>(&p0);
-                o[2 * g + 1] = *reinterpret_cast<uint32_t *>(&p1);
+            for (int e = 0; e < 8; ++e) {
+                __nv_bfloat162 p = __floats2bfloat162_rn(fmaf(__uint_as_float(v[2 * e]), ep.sc[2 * e], ep.sh[2 * e]),
+                                                         fmaf(__uint_as_float(v[2 * e + 1]), ep.sc[2 * e + 1], ep.sh[2 * e + 1]));
+                if (relu) p = __hmax2(p, zero2);
+                o[e] = *reinterpret_cast<uint32_t *>(&p);
             }
         };
         int it = 0;
@@ -1519,8 +1515,8 @@ conv_qd_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 tc::tmem_ld16(tbase + j * COUT + cb * 16, vb);
                 tc::tmem_ld_wait();
                 uint32_t oa[8], ob[8];
-                convert(va, ca, oa);
-                convert(vb, cb, ob);
+                convert(va, oa);
+                convert(vb, ob);
                 if constexpr (EPI == EPI_HEAD) {
                     // the head consumes the activation as it would have been stored (bf16); 16-column group c16 is
                     // level-0 pixel (2y + oy, 2x + ox), (oy, ox) = (c16 >> 1, c16 & 1): ca / cb are ox = 0 / 1 of row `half`
@@ -1541,21 +1537,14 @@ conv_qd_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                         }
 #pragma unroll
                         for (int k = 0; k < HK; ++k) {
-                            const float4 *wk = reinterpret_cast<const float4 *>(s_head + k * 16);
 #pragma unroll
-                            for (int g = 0; g < 4; ++g) {
-                                const float4 w4 = wk[g];
-                                hl[k] = fmaf(f[4 * g], w4.x, hl[k]);
-                                hl[k] = fmaf(f[4 * g + 1], w4.y, hl[k]);
-                                hl[k] = fmaf(f[4 * g + 2], w4.z, hl[k]);
-                                hl[k] = fmaf(f[4 * g + 3], w4.w, hl[k]);
-                            }
+                            for (int c = 0; c < 16; ++c) hl[k] = fmaf(f[c], ep.hw[k][c], hl[k]);
                         }
                         int bk = 0;
                         float m = -INFINITY;
 #pragma unroll
                         for (int k = 0; k < HK; ++k) {
-                            hl[k] += s_head[16 * HK + k];
+                            hl[k] += ep.hb[k];
                             if (hl[k] > m) { m = hl[k]; bk = k; }
                         }
                         best[u] = bk;
@@ -3068,8 +3057,20 @@ int launch_qd(sq_unet_s *u, const SqLayer &L, const bf16 *in0, int cb0, const bf
         SQ_CUDA(cudaMemset(phase_dbg, 0, (size_t)grid * 8 * sizeof(long long)));
     }
 #endif
-    kern<<<grid, TC_THREADS, smem, st>>>(m0, m1, ks0, ks1, (const bf16 *)L.w_qd, L.scale_q, L.shift_q, out, out_pool,
-                                         head, nimg, H, W, relu, nstages, wres, phase_dbg);
+    QdEpi ep = {};
+    {
+        const std::vector<float> &s0 = u->host[L.scope + "/_scale"].data, &t0 = u->host[L.scope + "/_shift"].data;
+        for (int i = 0; i < 16; ++i) { ep.sc[i] = s0[i]; ep.sh[i] = t0[i]; }
+        if (EPI == EPI_HEAD) {
+            // bf16-rounded head weights [channel][class] and the fp32 bias, as the stand-alone head and the other fused heads use them
+            const std::vector<float> &hk = u->host["UNet/to_image/kernel"].data, &hb = u->host["UNet/to_image/bias"].data;
+            for (int c = 0; c < 16; ++c)
+                for (int k2 = 0; k2 < HK; ++k2) ep.hw[k2][c] = host_bf16_round(hk[(size_t)c * HK + k2]);
+            for (int k2 = 0; k2 < HK; ++k2) ep.hb[k2] = hb[k2];
+        }
+    }
+    kern<<<grid, TC_THREADS, smem, st>>>(m0, m1, ks0, ks1, (const bf16 *)L.w_qd, ep, out, out_pool, head, nimg, H, W, relu,
+                                         nstages, wres, phase_dbg);
     ++u->last_launches;
     SQ_CHECK_LAUNCH();
     if (phase_dbg) {
