@@ -122,14 +122,23 @@ struct HeadArgs {
 // never goes to HBM: warps FIRST_BLD.. compute it for each 66 x 10 halo patch (mma.sync.m16n8k16 on the
 // L1-cached fp32 frame, exactly the fragments and epilogue of first_conv_kernel, zeros outside the image =
 // this layer's SAME padding) and write it into the stage in the layout TMA would have produced.
+// The folded epilogue of a 3x3 conv with 32..128 output channels, passed BY VALUE next to the device arrays: the plain
+// store epilogue then reads scale / shift as constant-bank operands of its FFMAs instead of 8 LDS.128 per work item
+// (ncu: 26 % short-scoreboard stalls in these kernels).  Work items are split between the two epilogue groups by
+// sub-tile, so the channel chunk -- and with it every table index -- is a compile-time constant.
+struct TcEpi {
+    float sc[128], sh[128];
+};
+
 template <int COUT, int S, bool UP, int NBUF, int MINB, int EPI, int HK, int NMMA, bool CL, int NBLD = 0>
 __global__ void __launch_bounds__(TC_THREADS + 32 * (NMMA - 1) + 32 * NBLD, MINB)
 conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                int ks0, int ks1, const bf16 *__restrict__ wts, const float *__restrict__ scale,
                const float *__restrict__ shift, bf16 *__restrict__ out, bf16 *__restrict__ out_pool,
                HeadArgs head, int nimg, int H, int W, int relu, int nstages, int D, int KZ,
-               int out_mul, int out_off, FirstArgs first)
+               int out_mul, int out_off, FirstArgs first, const __grid_constant__ TcEpi epc)
 {
+    constexpr bool CONST_EPI = !UP && EPI == EPI_STORE && COUT >= 32 && COUT <= 128 && (S % EPI_GROUPS) == 0;
     static_assert(NBLD == 0 || (!UP && !CL), "fused first conv: plain 3x3 conv launches only");
     constexpr int FIRST_BLD = 1 + NMMA + 4 * EPI_GROUPS;       // first builder warp
     // Volumes: activations are [n][z][c/8][y][x][8]; a (z-slice, image) pair is one "image" np =
@@ -426,6 +435,43 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                             bf16 *p = out_pool + ((((size_t)n * CBo + c16 * 2) * Hp + (y >> 1)) * Wp + (x >> 1)) * 8;
                             *reinterpret_cast<uint4 *>(p) = make_uint4(o0[0], o0[1], o0[2], o0[3]);
                             *reinterpret_cast<uint4 *>(p + (size_t)Hp * Wp * 8) = make_uint4(o0[4], o0[5], o0[6], o0[7]);
+                        }
+                    }
+                }
+            } else if constexpr (CONST_EPI) {
+                // group `half` owns the sub-tiles j = half, half + 2, ...; per sub-tile the 16-channel chunks go two per
+                // TMEM round trip; scale / shift are constant-bank operands (epc), ReLU on the packed bf16 pair
+                constexpr int NC16 = COUT / 16;
+                const int x = tx * 8 + pw;
+                const size_t plane = (size_t)H * W * 8;
+#pragma unroll 1
+                for (int j = half; j < S; j += EPI_GROUPS) {
+                    const int y = ty * C::TH + (C::ILV ? 32 * (j / 2) + 2 * ph + (j & 1) : j * 16 + ph);
+                    const bool valid = live && (y < H) && (x < W);
+                    bf16 *prow = out + (((size_t)n * CBo * H + y) * W + x) * 8;
+                    const uint32_t tj = tmem_base + lane_addr + buf * C::ACC_COLS + j * COUT;
+#pragma unroll
+                    for (int cp = 0; cp < NC16; cp += 2) {
+                        uint32_t v[2][16];
+                        tc::tmem_ld16(tj + cp * 16, v[0]);
+                        tc::tmem_ld16(tj + cp * 16 + 16, v[1]);
+                        tc::tmem_ld_wait();
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            uint32_t o[8];
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) {
+                                const int c = (cp + u) * 16 + 2 * e;            // compile-time after unrolling
+                                __nv_bfloat162 p2 = __floats2bfloat162_rn(fmaf(__uint_as_float(v[u][2 * e]), epc.sc[c], epc.sh[c]),
+                                                                          fmaf(__uint_as_float(v[u][2 * e + 1]), epc.sc[c + 1], epc.sh[c + 1]));
+                                if (relu) p2 = __hmax2(p2, zero2);
+                                o[e] = *reinterpret_cast<uint32_t *>(&p2);
+                            }
+                            if (valid) {
+                                bf16 *p = prow + (size_t)(2 * (cp + u)) * plane;
+                                *reinterpret_cast<uint4 *>(p) = make_uint4(o[0], o[1], o[2], o[3]);
+                                *reinterpret_cast<uint4 *>(p + plane) = make_uint4(o[4], o[5], o[6], o[7]);
+                            }
                         }
                     }
                 }
@@ -2682,6 +2728,11 @@ int launch_tc(sq_unet_s *u, const SqLayer &L, const bf16 *in0, int cb0, const bf
     }
     const int threads = TC_THREADS + 32 * (NMMA - 1);
     const int tiles = nimg * g.D * ((W + 7) / 8) * ((H + C::TH - 1) / C::TH);
+    TcEpi epc;                                   // read by the plain-store epilogue of the 32..128-channel convs only
+    {
+        const std::vector<float> &s0 = u->host[L.scope + "/_scale"].data, &t0 = u->host[L.scope + "/_shift"].data;
+        for (int i = 0; i < 128; ++i) { epc.sc[i] = i < (int)s0.size() ? s0[i] : 1.0f; epc.sh[i] = i < (int)t0.size() ? t0[i] : 0.0f; }
+    }
     if (CL) {
         // persistent clusters: as many CTA pairs as can be co-resident (GPCs with an odd SM count leave one out)
         cudaLaunchConfig_t cfg = {};
@@ -2704,12 +2755,12 @@ int launch_tc(sq_unet_s *u, const SqLayer &L, const bf16 *in0, int cb0, const bf
         cfg.gridDim = dim3((unsigned)grid);
         SQ_CUDA(cudaLaunchKernelEx(&cfg, kern, m0, m1, cb0 / 2, in1 ? cb1 / 2 : 0, (const bf16 *)L.w_tc + g.w_off,
                                    (const float *)L.scale, (const float *)L.shift, out, out_pool, head, nimg, H, W,
-                                   relu, nstages, g.D, g.KZ, g.out_mul, g.out_off, FirstArgs{}));
+                                   relu, nstages, g.D, g.KZ, g.out_mul, g.out_off, FirstArgs{}, epc));
     } else {
         const int grid = std::min(tiles, MINB * u->h->sm_count / grid_div());
         kern<<<grid, threads, smem, st>>>(m0, m1, cb0 / 2, in1 ? cb1 / 2 : 0, (const bf16 *)L.w_tc + g.w_off, L.scale,
                                          L.shift, out, out_pool, head, nimg, H, W, relu, nstages, g.D, g.KZ,
-                                         g.out_mul, g.out_off, FirstArgs{});
+                                         g.out_mul, g.out_off, FirstArgs{}, epc);
     }
     ++u->last_launches;
     SQ_CHECK_LAUNCH();
@@ -2743,7 +2794,7 @@ int launch_tc_first_n(sq_unet_s *u, const SqLayer &L1, const SqLayer &L2, const 
     HeadArgs none = {};
     const FirstArgs fa = {in, (const float *)L1.w_tc, (const float *)L1.scale, (const float *)L1.shift};
     kern<<<grid, threads, smem, st>>>(m0, m0, 1, 0, (const bf16 *)L2.w_tc + g.w_off, L2.scale, L2.shift, out, out_pool,
-                                     none, nimg, H, W, 1, nstages, 1, 1, g.out_mul, g.out_off, fa);
+                                     none, nimg, H, W, 1, nstages, 1, 1, g.out_mul, g.out_off, fa, TcEpi{});
     ++u->last_launches;
     SQ_CHECK_LAUNCH();
     return SQ_OK;
