@@ -240,13 +240,38 @@ def main():
     sequitr_b200.require_gpu(local)
     dev = torch.device('cuda', local)
 
-    # page-lock the stack in place (cudaHostRegister) so the host call's copies are DMA at PCIe speed
-    stack_t = torch.from_numpy(stack)
-    pinned_how = 'cudaHostRegister'
-    if int(torch.cuda.cudart().cudaHostRegister(stack_t.data_ptr(), stack_t.numel() * 2, 0)) != 0:
-        stack_t = stack_t.pin_memory()
-        stack = stack_t.numpy()
-        pinned_how = 'copied into a pinned tensor'
+    # page-lock the stack in place (cudaHostRegister) so the host call's copies are DMA at PCIe speed.  The OS can
+    # refuse a multi-GB registration right after another process released one (the driver runs the arms back to
+    # back): the registration is retried, and if it stays refused the stack is read at the staged-copy rate and the
+    # frames of the e2e legs are copied into a pinned buffer -- the run never dies on it.  (One registration for the
+    # whole stack: a copy may not span two separately registered ranges.)
+    from sequitr_b200 import utils as sq_utils
+    pinned_frac = 0.0 if os.environ.get('SQ_BENCH_NOPIN') else sq_utils.pin_in_place(stack, retries=3, wait_s=0.3)    # (the variable forces the fallback: tests)
+    pinned_how = 'cudaHostRegister' if pinned_frac == 1.0 else 'cudaHostRegister refused (stack stays pageable)'
+    pinned_head = None
+    if pinned_frac < 1.0:
+        try:                                             # 1st fallback: a page-locked allocation of the whole stack
+            if os.environ.get('SQ_BENCH_NOPIN') == '2':
+                raise MemoryError('forced')
+            full = sq_utils.pinned_array(stack.shape, np.uint16)
+            full[...] = stack
+            stack = full
+            pinned_frac = 1.0
+            pinned_how += '; stack copied into a cudaHostAlloc buffer instead'
+        except Exception:
+            try:                                         # 2nd: only the frames of the e2e legs
+                head = sq_utils.pinned_array((min(len(stack), 6 * CALL),) + stack.shape[1:], np.uint16)
+                head[...] = stack[:len(head)]
+                pinned_head = head
+                pinned_how += '; first %d frames copied into a pinned buffer for the e2e legs' % len(head)
+            except Exception:
+                pinned_head = None
+
+    def frames_for_calls(s, n):
+        """Host frames [s, s+n) of this rank's stack: from the pinned head copy when only that is page-locked."""
+        if pinned_head is not None and s + n <= len(pinned_head):
+            return pinned_head[s:s + n]
+        return stack[s:s + n]
 
     net = UNet2D({'filters': FILTERS, 'shape': (H, W), 'bridge': 'concat', 'num_inputs': 1,
                   'num_outputs': 2, 'compute': 'bf16', 'device': local})
@@ -415,21 +440,25 @@ def main():
     #      at a time); inside, frames stream in chunks of 1, 1, 2, 4, 8, 8, ... (H2D of a chunk under the
     #      UNet of the previous one); widening + ImageNorm run on the device.  Every call reads DIFFERENT frames.
     nloc = hi - lo
-    net.segment_and_localise(stack[:CALL], frame0=lo, max_rows=max_rows, normalise=True)
-    net.segment_and_localise(stack[:CALL], frame0=lo, max_rows=max_rows, normalise=True)
+    net.segment_and_localise(frames_for_calls(0, CALL), frame0=lo, max_rows=max_rows, normalise=True)
+    net.segment_and_localise(frames_for_calls(0, CALL), frame0=lo, max_rows=max_rows, normalise=True)
     ncalls = max(2, min(4, nloc // CALL - 1))
     barrier()
     t0 = time.perf_counter()
     for c in range(ncalls):
         s = ((c + 1) * CALL) % max(nloc - CALL + 1, 1)
-        net.segment_and_localise(stack[s:s + CALL], frame0=lo + s, max_rows=max_rows, normalise=True)
+        net.segment_and_localise(frames_for_calls(s, CALL), frame0=lo + s, max_rows=max_rows, normalise=True)
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = world * ncalls * CALL / e2e_s
     d2h = B * max_rows * 5 * 4 + B * 4
 
     # ---- secondary: the same call fed float32 host frames (4 B/px over PCIe, no device-side ImageNorm)
-    f32 = torch.empty((CALL, H, W, 1), dtype=torch.float32).pin_memory()
+    try:
+        f32 = torch.empty((CALL, H, W, 1), dtype=torch.float32).pin_memory()
+    except Exception:                                    # the OS refused the page-locked allocation: pageable
+        torch.cuda.synchronize()
+        f32 = torch.empty((CALL, H, W, 1), dtype=torch.float32)
     f32.numpy()[..., 0] = (stack[:CALL].astype(np.float32) - 3000.0) / 400.0
     f32_np = f32.numpy()
     net.segment_and_localise(f32_np, frame0=lo, max_rows=max_rows)

@@ -67,6 +67,13 @@ int sq_destroy(sq_handle_t h);
 /* sm_count, compute capability major/minor, total device memory */
 int sq_device_info(sq_handle_t h, int *sm_count, int *cc_major, int *cc_minor, size_t *total_mem);
 
+/* Page-lock / release a host buffer the caller owns (cudaHostRegister), e.g. a frame stack read by a dataio reader
+ * (dataio/octopus.py:231-245), so that the *_host entry points copy it by DMA.  A refusal by the OS (transient right
+ * after another process released a large registration, or RLIMIT_MEMLOCK) returns SQ_ECUDA with the CUDA error state
+ * CLEARED: the caller simply goes on with pageable memory. */
+int sq_host_register(void *ptr, size_t bytes);
+int sq_host_unregister(void *ptr);
+
 /* ------------------------------------------------ label-and-localise (L1)
  * Replaces the per-frame / per-class loop of utils.CentroidWriter.write
  * (utils.py:531-566: scipy.ndimage.label :547 + center_of_mass :550).

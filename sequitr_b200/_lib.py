@@ -29,6 +29,8 @@ _SIGNATURES = {
     'sq_create': (c_int, [c_int, _P(c_void_p)]),
     'sq_destroy': (c_int, [c_void_p]),
     'sq_device_info': (c_int, [c_void_p, _P(c_int), _P(c_int), _P(c_int), _P(c_size_t)]),
+    'sq_host_register': (c_int, [c_void_p, c_size_t]),
+    'sq_host_unregister': (c_int, [c_void_p]),
     'sq_label_workspace_bytes': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, _P(c_size_t)]),
     'sq_label_centroids': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p,
                                    c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),

@@ -79,6 +79,30 @@ extern "C" int sq_device_info(sq_handle_t h, int *sm_count, int *cc_major, int *
     return SQ_OK;
 }
 
+extern "C" int sq_host_register(void *ptr, size_t bytes)
+{
+    SQ_REQUIRE(ptr && bytes, SQ_EINVAL, "sq_host_register: null buffer");
+    const cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterDefault);
+    if (e != cudaSuccess) {
+        cudaGetLastError();                       // do not leave a sticky error for the caller's next CUDA call
+        sq_set_error("sq_host_register: %zu bytes -> %s", bytes, cudaGetErrorString(e));
+        return SQ_ECUDA;
+    }
+    return SQ_OK;
+}
+
+extern "C" int sq_host_unregister(void *ptr)
+{
+    SQ_REQUIRE(ptr, SQ_EINVAL, "sq_host_unregister: null buffer");
+    const cudaError_t e = cudaHostUnregister(ptr);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        sq_set_error("sq_host_unregister: %s", cudaGetErrorString(e));
+        return SQ_ECUDA;
+    }
+    return SQ_OK;
+}
+
 int sq_reserve_pinned(sq_handle_s *h, size_t bytes)
 {
     if (bytes <= h->pinned_bytes) return SQ_OK;

@@ -128,5 +128,25 @@ def pinned_array(shape, dtype=np.float32):
     import torch
     tdt = {np.dtype(np.float32): torch.float32, np.dtype(np.uint16): torch.uint16,
            np.dtype(np.uint8): torch.uint8, np.dtype(np.int32): torch.int32}[np.dtype(dtype)]
-    t = torch.empty(tuple(int(v) for v in shape), dtype=tdt).pin_memory()
+    t = torch.empty(tuple(int(v) for v in shape), dtype=tdt, pin_memory=True)    # cudaHostAlloc, no pageable twin
     return t.numpy()                        # the array's .base keeps the pinned tensor alive
+
+
+def pin_in_place(array, retries=3, wait_s=0.5):
+    """Page-lock a host ndarray the caller already owns (e.g. a 16.8 GB frame stack) so that
+    ``UNet.segment_and_localise`` copies from it by DMA.  The whole array is ONE registration: a host->device copy may
+    not span two separately registered ranges (cudaMemcpyAsync answers "invalid argument"), so piecewise registration
+    is not an option.  The OS sometimes refuses a multi-GB registration right after another process released one;
+    the call is retried ``retries`` times and the CUDA error state is cleared each time (sq_host_register).  Returns
+    1.0 when the array is now page-locked, 0.0 when the OS refused: the array simply stays pageable and the host
+    calls run at the staged-copy rate."""
+    import time
+    from . import _lib
+    lib = _lib.load()
+    if array.nbytes == 0:
+        return 1.0
+    for attempt in range(retries):
+        if lib.sq_host_register(array.ctypes.data, array.nbytes) == _lib.SQ_OK:
+            return 1.0
+        time.sleep(wait_s)
+    return 0.0
