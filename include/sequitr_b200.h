@@ -41,6 +41,7 @@ extern "C" {
 
 typedef struct sq_handle_s *sq_handle_t;
 typedef struct sq_unet_s   *sq_unet_t;
+typedef struct sq_trainer_s *sq_trainer_t;
 
 /* bridge types, networks/unet.py:42 BRIDGE_TYPES */
 #define SQ_BRIDGE_NONE   0
@@ -229,6 +230,28 @@ int sq_tr_augment(sq_handle_t h, const float *image_dev, const uint8_t *label_de
                   int n, int hgt, int wid, int c, const float *transforms_host, const int *crop_host,
                   int ch, int cw, int num_outputs, float *image_out_dev, uint8_t *label_out_dev,
                   float *weights_out_dev, void *stream);
+
+/* Training step of the UNet (BASELINE config 5): what a tf.estimator model_fn does with the graph that
+ * networks/unet.py `build` :224-262 makes in TRAIN mode (`training` :170-172, dropout after every conv block
+ * :274-276) and the (image, {'label', 'weights'}) pairs tr_augment :348-401 yields.  The reference ships no loss
+ * and no optimiser for the UNet (its only optimiser is the GAN's tf.train.AdamOptimizer, gan.py:740-751), so the
+ * step is: forward with every activation kept -> sq_weighted_ce -> backward through every layer -> in-place update
+ * of the plan's kernels and biases with TensorFlow's Adam rule (optimizer 1) or plain SGD (optimizer 0).
+ *   - the plan must be SQ_MODE_FP32_EXACT with conv + bias layers (no folded affine); it serves inference with the
+ *     updated weights right after a step (read them with sq_trainer_read to load a bf16 plan)
+ *   - dropout: rate in [0,1); mask = counter-based hash of (seed, step, block, element) -- see train.cu
+ *   - image_dev float32 (n,[d,]hgt,wid,cin); labels_dev uint8 class ids (n,[d,]hgt,wid); weights_dev float32 same
+ *     shape; *loss_dev float64 on the device; apply_update 0 computes loss and gradients only
+ *   - sq_trainer_read: name "<scope>/kernel" or "<scope>/bias" (TF layouts, as sq_unet_load_weights takes them),
+ *     what 0 = current value, 1 = gradient of the last step */
+int sq_trainer_create(sq_unet_t u, int optimizer, float learning_rate, float beta1, float beta2, float epsilon,
+                      float dropout, unsigned long long seed, sq_trainer_t *out);
+int sq_trainer_destroy(sq_trainer_t t);
+int sq_trainer_workspace_bytes(sq_trainer_t t, int n, int d, int hgt, int wid, size_t *bytes);
+int sq_trainer_step(sq_trainer_t t, const float *image_dev, const uint8_t *labels_dev, const float *weights_dev,
+                    int n, int d, int hgt, int wid, int apply_update, double *loss_dev, void *workspace_dev,
+                    size_t workspace_bytes, void *stream);
+int sq_trainer_read(sq_trainer_t t, const char *name, int what, float *out_host, size_t count);
 
 /* The whole data-parallel hot path on HOST frames: H2D -> UNet -> argmax ->
  * label-and-localise -> D2H of the centroid tables (the call a Sequitr job

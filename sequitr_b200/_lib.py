@@ -60,6 +60,13 @@ _SIGNATURES = {
     'sq_weighted_ce_workspace_bytes': (c_int, [c_void_p, _P(c_size_t)]),
     'sq_weighted_ce': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_longlong, c_int, c_void_p,
                        c_void_p, c_void_p, c_size_t, c_void_p]),
+    'sq_trainer_create': (c_int, [c_void_p, c_int, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float,
+                                  ctypes.c_float, ctypes.c_ulonglong, _P(c_void_p)]),
+    'sq_trainer_destroy': (c_int, [c_void_p]),
+    'sq_trainer_workspace_bytes': (c_int, [c_void_p, c_int, c_int, c_int, c_int, _P(c_size_t)]),
+    'sq_trainer_step': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p,
+                                c_void_p, c_size_t, c_void_p]),
+    'sq_trainer_read': (c_int, [c_void_p, c_char_p, c_int, c_void_p, c_size_t]),
     'sq_tr_augment': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
                               c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     'sq_prep_workspace_bytes': (c_int, [c_void_p, c_int, c_int, _P(c_size_t)]),

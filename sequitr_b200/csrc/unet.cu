@@ -159,6 +159,27 @@ __global__ void softmax_argmax_kernel(const float *__restrict__ logits, long lon
     }
 }
 
+// tf.layers.dropout (reference networks/unet.py:274-276) with a counter-based generator, so that the oracle can
+// restate the mask: u = top 24 bits of splitmix64(splitmix64(seed ^ (block << 48)) + index) / 2^24, the element is
+// kept when u >= rate and divided by (1 - rate).
+__device__ __forceinline__ unsigned long long sq_mix64(unsigned long long z)
+{
+    z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ull;
+    z ^= z >> 27; z *= 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return z;
+}
+
+__global__ void dropout_fp32_kernel(float *__restrict__ x, long long n, float rate, unsigned long long seed,
+                                    int block_id)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long base = sq_mix64(seed ^ ((unsigned long long)block_id << 48));
+    const float u = (float)(sq_mix64(base + (unsigned long long)i) >> 40) * (1.0f / 16777216.0f);
+    x[i] = (u >= rate) ? __fdiv_rn(x[i], 1.0f - rate) : 0.0f;
+}
+
 }  // namespace
 
 // ================================================================== plumbing
@@ -225,7 +246,7 @@ int launch_conv(sq_unet_s *u, const SqLayer &L, const float *in0, const float *i
 // Shared by the workspace query (dry = true: no launches, null arena) and the real run.
 int fp32_run(sq_unet_s *u, bool dry, const float *in, int n, int d, int hgt, int wid, float *probs,
              uint8_t *mask, float *logits, void *ws, size_t ws_bytes, cudaStream_t st,
-             size_t *need)
+             size_t *need, SqTape *tape = nullptr)
 {
     const Geo g{n, d, hgt, wid};
     SqArena a(dry ? nullptr : ws, dry ? 0 : ws_bytes);
@@ -251,6 +272,18 @@ int fp32_run(sq_unet_s *u, bool dry, const float *in, int n, int d, int hgt, int
     if (need) *need = a.off;
     if (dry) return SQ_OK;
     SQ_REQUIRE(a.ok(), SQ_ENOMEM, "unet: workspace %zu < %zu bytes", ws_bytes, a.off);
+    if (tape) {
+        tape->down = down; tape->tmp = tmp; tape->pooled = pooled; tape->up = up; tape->merged = merged;
+        tape->upt = upt; tape->upo = upo; tape->logits = logit_buf;
+    }
+    auto dropout = [&](float *x, long long count, int block_id) -> int {
+        if (!tape || !(tape->drop_rate > 0.0f)) return SQ_OK;
+        dropout_fp32_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(x, count, tape->drop_rate, tape->seed,
+                                                                            block_id);
+        ++u->last_launches;
+        SQ_CHECK_LAUNCH();
+        return SQ_OK;
+    };
 
     u->last_launches = 0;
     sq_timer_mark(u, st, nullptr, 0);
@@ -278,6 +311,7 @@ int fp32_run(sq_unet_s *u, bool dry, const float *in, int n, int d, int hgt, int
         sq_timer_mark(u, st, c1->scope.c_str(), c1->flops_per_px * px);
         SQ_TRY(launch_conv(u, *c2, tmp[l], nullptr, px, D, H, W, 1, down[l], st));
         sq_timer_mark(u, st, c2->scope.c_str(), c2->flops_per_px * px);
+        SQ_TRY(dropout(down[l], px * u->filters[l], l));
     }
     const float *cur = down[nl - 1];
     for (int l = nl - 2; l >= 0; --l) {
@@ -312,6 +346,7 @@ int fp32_run(sq_unet_s *u, bool dry, const float *in, int n, int d, int hgt, int
         sq_timer_mark(u, st, c1->scope.c_str(), c1->flops_per_px * px);
         SQ_TRY(launch_conv(u, *c2, upt[l], nullptr, px, D, H, W, 1, upo[l], st));
         sq_timer_mark(u, st, c2->scope.c_str(), c2->flops_per_px * px);
+        SQ_TRY(dropout(upo[l], px * u->filters[l], nl + l));
         cur = upo[l];
     }
     const SqLayer *head = find_layer(u, "UNet/to_image");
@@ -336,6 +371,19 @@ int upload(sq_unet_s *u, const float *src, size_t count, float **dst)
 }
 
 }  // namespace
+
+int sq_fp32_workspace(sq_unet_s *u, int n, int d, int hgt, int wid, size_t *need)
+{
+    SQ_TRY(check_geometry(u, n, d, hgt, wid));
+    return fp32_run(u, true, nullptr, n, d, hgt, wid, nullptr, nullptr, nullptr, nullptr, 0, nullptr, need);
+}
+
+int sq_fp32_forward_tape(sq_unet_s *u, const float *in, int n, int d, int hgt, int wid, void *ws, size_t ws_bytes,
+                         cudaStream_t st, SqTape *tape)
+{
+    SQ_TRY(check_geometry(u, n, d, hgt, wid));
+    return fp32_run(u, false, in, n, d, hgt, wid, nullptr, nullptr, nullptr, ws, ws_bytes, st, nullptr, tape);
+}
 
 // ================================================================== C ABI
 extern "C" int sq_unet_create(sq_handle_t h, int ndim, int num_inputs, int num_outputs,

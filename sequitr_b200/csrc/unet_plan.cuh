@@ -68,5 +68,16 @@ int sq_image_norm_stats_u16(sq_handle_t h, const uint16_t *in, int n, int hgt, i
 int sq_image_norm_u16_to_bf16(sq_handle_t h, const uint16_t *in, void *out_bf16, int n, int hgt, int wid, void *ws,
                               size_t ws_bytes, cudaStream_t st);
 
+// ---- training step of the fp32 path (train.cu): the forward keeps every activation and says where
+struct SqTape {
+    std::vector<float *> down, tmp, pooled, up, merged, upt, upo;   // per level, as in fp32_run
+    float *logits = nullptr;
+    float drop_rate = 0.0f;       // tf.layers.dropout after conv2 of every block (networks/unet.py:274-276)
+    unsigned long long seed = 0;
+};
+int sq_fp32_workspace(sq_unet_s *u, int n, int d, int hgt, int wid, size_t *need);
+int sq_fp32_forward_tape(sq_unet_s *u, const float *in, int n, int d, int hgt, int wid, void *ws, size_t ws_bytes,
+                         cudaStream_t st, SqTape *tape);
+
 // timer helpers (unet.cu)
 void sq_timer_mark(sq_unet_s *u, cudaStream_t st, const char *name, double flops);

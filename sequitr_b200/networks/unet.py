@@ -205,9 +205,8 @@ class UNet(object):
             conv1 = self.conv_layer(x, filters)
         with self.variable_scope('conv2'):
             conv2 = self.conv_layer(conv1, filters)
-        # Dropout (tf.layers.dropout, networks/unet.py:274-276) is the identity unless training
-        if self.training:
-            raise NotImplementedError('the CUDA plan implements inference only (dropout off)')
+        # Dropout (tf.layers.dropout, networks/unet.py:274-276) is the identity unless training; in TRAIN mode the
+        # device applies it after conv2 of every block inside the training step (see ``Trainer``)
         return conv2
 
     def down_layer(self, x, filters, name=None):
@@ -271,6 +270,10 @@ class UNet(object):
                 self._handle = None
         except Exception:
             pass
+
+    def trainer(self, **kwargs):
+        """A ``Trainer`` bound to this network (``compute='fp32'``): ``loss = net.trainer().step(img, target)``."""
+        return Trainer(self, **kwargs)
 
     def twin(self):
         """A second network with the same parameters and weights on the same GPU but with a library handle of its
@@ -529,6 +532,120 @@ class UNet3D(_ConcreteUNet):
         if self.ndim != 3:
             raise ValueError('UNet3D needs a 3-D shape (width, height, slices)')
 
+
+
+class Trainer(object):
+    """The training step of a UNet on the device (BASELINE config 5): forward with dropout (rate
+    ``net.dropout``, reference networks/unet.py:274-276), weighted softmax cross-entropy over the per-pixel
+    ``weights`` map, backward through every layer, Adam (TensorFlow's update rule) or SGD update of the plan's kernels
+    and biases in place -- ``net.predict`` right after ``step`` uses the updated weights.  The reference ships neither
+    loss nor optimiser for the UNet (see ``sq_trainer_step`` in include/sequitr_b200.h); the inputs are what its
+    ``tr_augment`` yields: ``image`` (N,[D,]H,W,C) float32 and ``{'label': one-hot uint8 (N,[D,]H,W,K) or class ids
+    (N,[D,]H,W), 'weights': float32 (N,[D,]H,W[,1])}``.
+
+    The network must be built with ``compute='fp32'``; ``weights()`` returns the trained variables in the
+    ``load_weights`` layout (e.g. to load a ``compute='bf16'`` network for tensor-core inference)."""
+
+    def __init__(self, net, learning_rate=1e-3, optimizer='adam', beta1=0.9, beta2=0.999, epsilon=1e-8,
+                 dropout=None, seed=0):
+        if net.compute != 'fp32':
+            raise ValueError("the training step runs on a compute='fp32' network")
+        if optimizer not in ('sgd', 'adam'):
+            raise ValueError("optimizer must be 'sgd' or 'adam'")
+        self.net = net
+        self._plan = net._ensure_plan()
+        self._trainer = ctypes.c_void_p()
+        rate = net.dropout if dropout is None else dropout
+        _lib.check(_lib.load().sq_trainer_create(self._plan, 1 if optimizer == 'adam' else 0, learning_rate, beta1,
+                                                 beta2, epsilon, float(rate), int(seed),
+                                                 ctypes.byref(self._trainer)))
+        self._ws = ops.Workspace(device='cuda:%d' % net._device)
+
+    def close(self):
+        t = getattr(self, '_trainer', None)
+        if t is not None and t.value:
+            _lib.load().sq_trainer_destroy(t)
+        self._trainer = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check_alive(self):
+        if self._trainer is None or self.net._plan is None or self.net._plan.value != self._plan.value:
+            raise RuntimeError('the network was rebuilt (load_weights) after this trainer was made')
+
+    def step(self, image, target, weights=None, apply_update=True):
+        """One training step on a batch; returns the loss (float).  ``target``: the dict ``tr_augment`` returns,
+        or the labels with ``weights`` given separately."""
+        import torch
+        self._check_alive()
+        net = self.net
+        dev = 'cuda:%d' % net._device
+        if isinstance(target, dict):
+            target, weights = target['label'], target['weights']
+
+        def to_dev(v, dtype):
+            t = v if torch.is_tensor(v) else torch.from_numpy(np.ascontiguousarray(v))
+            return t.to(device=dev, dtype=dtype).contiguous()
+
+        x = to_dev(image, torch.float32)
+        if x.dim() != net.ndim + 2 or x.shape[-1] != net.n_inputs:
+            raise ValueError('image has shape %s, expected (N,%s%d)' %
+                             (tuple(x.shape), 'D,H,W,' if net.ndim == 3 else 'H,W,', net.n_inputs))
+        sp = tuple(x.shape[:-1])
+        lab = to_dev(target, torch.uint8)
+        wgt = to_dev(weights, torch.float32)
+        if tuple(wgt.shape) not in (sp, sp + (1,)):
+            raise ValueError('weights have shape %s, expected %s' % (tuple(wgt.shape), sp))
+        wgt = wgt.reshape(sp)
+        if tuple(lab.shape) == sp + (net.n_outputs,):
+            # one-hot (tr_augment :396-398): a pixel whose class lies beyond the K outputs has an all-zero row and
+            # contributes nothing to a softmax cross-entropy -- its weight is cleared
+            none = lab.sum(-1) == 0
+            lab = lab.argmax(-1).to(torch.uint8).contiguous()
+            if bool(none.any()):
+                wgt = torch.where(none, torch.zeros_like(wgt), wgt)
+        elif tuple(lab.shape) == sp + (1,):
+            lab = lab.reshape(sp)
+        elif tuple(lab.shape) != sp:
+            raise ValueError('labels have shape %s, expected %s (class ids) or %s (one-hot)' %
+                             (tuple(lab.shape), sp, sp + (net.n_outputs,)))
+        if int(lab.max()) >= net.n_outputs:
+            raise ValueError('class id %d >= num_outputs %d' % (int(lab.max()), net.n_outputs))
+        n = sp[0]
+        d, h, w = ((1,) + sp[1:3]) if net.ndim == 2 else sp[1:4]
+        lib = _lib.load()
+        need = ctypes.c_size_t()
+        _lib.check(lib.sq_trainer_workspace_bytes(self._trainer, n, d, h, w, ctypes.byref(need)))
+        ws = self._ws.get(need.value)
+        loss = torch.zeros(1, dtype=torch.float64, device=dev)
+        _lib.check(lib.sq_trainer_step(self._trainer, x.data_ptr(), lab.data_ptr(), wgt.data_ptr(), n, d, h, w,
+                                       1 if apply_update else 0, loss.data_ptr(), ws.data_ptr(), ws.numel(),
+                                       _lib.stream_ptr(x.device)))
+        return float(loss.item())
+
+    def _read(self, what):
+        self._check_alive()
+        lib = _lib.load()
+        out = {}
+        for name, arr in self.net._weights.items():
+            if not (name.endswith('/kernel') or name.endswith('/bias')):
+                continue
+            buf = np.empty(arr.shape, dtype=np.float32)
+            _lib.check(lib.sq_trainer_read(self._trainer, name.encode(), what, buf.ctypes.data, buf.size))
+            out[name] = buf
+        return out
+
+    def weights(self):
+        """The current kernels and biases, in the layout ``UNet.load_weights`` takes."""
+        return self._read(0)
+
+    def gradients(self):
+        """The gradients of the last step, same names and layouts."""
+        return self._read(1)
 
 
 def tr_augment(features, params, rng=None):
