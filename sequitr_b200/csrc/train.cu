@@ -15,6 +15,7 @@
 // (dgrad = the forward tcgen05 conv on flipped weights, wgrad = an MN-major UMMA with split pixels) is not built.
 #include "sq_common.cuh"
 #include "unet_plan.cuh"
+#include "conv_fp32_tile.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -28,12 +29,12 @@ struct sq_trainer_s {
     struct Slot { float *gw = nullptr, *gb = nullptr, *mw = nullptr, *vw = nullptr, *mb = nullptr, *vb = nullptr;
                   size_t wcount = 0; };
     std::vector<Slot> slots;      // one per layer of u->layers
+    float *wflip = nullptr;       // scratch for a layer's tap-reversed kernel (data gradients)
     std::vector<void *> allocs;
 };
 
 namespace {
 
-constexpr int WG_TILE = 64, WG_K = 16;
 
 // -------------------------------------------------------------------------------------------------- kernels
 // d(pre-activation) from d(block output): ReLU mask, and the 1/(1-rate) of a dropout that followed it (the stored
@@ -90,66 +91,80 @@ __global__ void dgrad_kernel(const float *__restrict__ dz, int CO, long long npi
 //                             B = dz.                 -> (taps, Cin, Cout)   = HWIO
 //   MODE 1 (2x2 stride-2 transposed conv):  A = d(output) at the fine pixel (2y+ky, 2x+kx) of coarse pixel p;
 //                             B = the layer input.    -> (taps, Cout, Cin)   = TF (kh, kw, out, in)
-// 256 threads, 64 x 64 tile of (a, b), 4 x 4 per thread, 16 pixels per shared-memory stage.
-template <int MODE>
+// 256 threads work on a TA x TB tile of (a, b) with 4 x 4 values per thread; a tile smaller than 64 x 64 leaves
+// threads over, which split the 64 pixels of a shared-memory stage between KG groups (summed in group order at the
+// end), so that narrow layers (16 or 32 channels, where most of the pixels are) do not pay for a 64 x 64 tile.
+template <int MODE, int TA, int TB>
 __global__ void __launch_bounds__(256) wgrad_kernel(const float *__restrict__ A0, int CA0,
                                                     const float *__restrict__ A1, int CA1,
                                                     const float *__restrict__ B, int CB, long long npix, int D,
                                                     int H, int W, int KD, int KH, int KW, long long chunk,
                                                     float *__restrict__ part)
 {
-    __shared__ float As[WG_K][WG_TILE + 4], Bs[WG_K][WG_TILE + 4];
+    constexpr int KS = 64;                         // pixels per stage
+    constexpr int TPG = (TA / 4) * (TB / 4);       // threads per group
+    constexpr int KG = 256 / TPG;                  // groups splitting the stage's pixels
+    __shared__ __align__(16) float As[KS][TA + 4];
+    __shared__ __align__(16) float Bs[KS][TB + 4];
+    __shared__ long long pa_s[KS];
+    __shared__ __align__(16) float red[(KG > 1) ? KG * TA * TB : 1];
     const int CA = CA0 + CA1;
-    const int btiles = (CB + WG_TILE - 1) / WG_TILE;
-    const int a0 = (blockIdx.x / btiles) * WG_TILE, b0 = (blockIdx.x % btiles) * WG_TILE;
+    const int btiles = (CB + TB - 1) / TB;
+    const int a0 = (blockIdx.x / btiles) * TA, b0 = (blockIdx.x % btiles) * TB;
     const int tap = blockIdx.y, ntap = gridDim.y;
     const int kx = tap % KW, ky = (tap / KW) % KH, kz = tap / (KW * KH);
     const long long p_lo = (long long)blockIdx.z * chunk, p_hi = min(npix, p_lo + chunk);
-    const int t = threadIdx.x, tk = t >> 4, tc = (t & 15) * 4;
-    const int ty = t >> 4, tx = t & 15;
+    const int t = threadIdx.x;
+    const int grp = t / TPG, idx = t % TPG;
+    const int ty = idx / (TB / 4), tx = idx % (TB / 4);
     float acc[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
 
-    for (long long p0 = p_lo; p0 < p_hi; p0 += WG_K) {
-        const long long p = p0 + tk;
-        float av[4] = {0.f, 0.f, 0.f, 0.f}, bv[4] = {0.f, 0.f, 0.f, 0.f};
-        if (p < p_hi) {
-            const int x = (int)(p % W);
-            const int y = (int)((p / W) % H);
-            const int z = (int)((p / ((long long)W * H)) % D);
-            const long long n = p / ((long long)W * H * D);
+    const long long frame = (long long)W * H * D;
+    for (long long p0 = p_lo; p0 < p_hi; p0 += KS) {
+        __syncthreads();                           // the previous stage has been consumed
+        if (t < KS) {
+            const long long p = p0 + t;
             long long pa = -1;
-            if (MODE == 0) {
-                const int xx = x + kx - KW / 2, yy = y + ky - KH / 2, zz = z + kz - KD / 2;
-                if (xx >= 0 && xx < W && yy >= 0 && yy < H && zz >= 0 && zz < D)
-                    pa = ((n * D + zz) * H + yy) * W + xx;
-            } else {
-                pa = ((n * (D * KD) + (long long)z * KD + kz) * (2 * H) + 2 * y + ky) * (2 * W) + 2 * x + kx;
-            }
-            if (pa >= 0) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int a = a0 + tc + j;
-                    if (a < CA0) av[j] = A0[pa * CA0 + a];
-                    else if (a < CA) av[j] = A1[pa * CA1 + (a - CA0)];
+            if (p < p_hi) {
+                const long long n = p / frame;
+                const int r = (int)(p - n * frame);
+                const int x = r % W, y = (r / W) % H, z = r / (W * H);
+                if (MODE == 0) {
+                    const int xx = x + kx - KW / 2, yy = y + ky - KH / 2, zz = z + kz - KD / 2;
+                    if (xx >= 0 && xx < W && yy >= 0 && yy < H && zz >= 0 && zz < D)
+                        pa = ((n * D + zz) * H + yy) * W + xx;
+                } else {
+                    pa = ((n * (D * KD) + (long long)z * KD + kz) * (2 * H) + 2 * y + ky) * (2 * W) + 2 * x + kx;
                 }
             }
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (b0 + tc + j < CB) bv[j] = B[p * CB + b0 + tc + j];
+            pa_s[t] = pa;
         }
         __syncthreads();
-#pragma unroll
-        for (int j = 0; j < 4; ++j) { As[tk][tc + j] = av[j]; Bs[tk][tc + j] = bv[j]; }
+        for (int e = t; e < KS * TA; e += 256) {
+            const int k = e / TA, a = a0 + e % TA;
+            const long long pa = pa_s[k];
+            float v = 0.0f;
+            if (pa >= 0) {
+                if (a < CA0) v = A0[pa * CA0 + a];
+                else if (a < CA) v = A1[pa * CA1 + (a - CA0)];
+            }
+            As[k][e % TA] = v;
+        }
+        for (int e = t; e < KS * TB; e += 256) {
+            const int k = e / TB, b = b0 + e % TB;
+            const long long p = p0 + k;
+            Bs[k][e % TB] = (p < p_hi && b < CB) ? B[p * CB + b] : 0.0f;
+        }
         __syncthreads();
-#pragma unroll
-        for (int k = 0; k < WG_K; ++k) {
-            float a[4], b[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) { a[i] = As[k][ty * 4 + i]; b[i] = Bs[k][tx * 4 + i]; }
+#pragma unroll 4
+        for (int k = grp; k < KS; k += KG) {
+            const float4 a4 = *reinterpret_cast<const float4 *>(&As[k][ty * 4]);
+            const float4 b4 = *reinterpret_cast<const float4 *>(&Bs[k][tx * 4]);
+            const float a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -157,13 +172,39 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const float *__restrict__ A0
         }
     }
     float *o = part + ((size_t)blockIdx.z * ntap + tap) * CA * CB;
+    if (KG == 1) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int a = a0 + ty * 4 + i, b = b0 + tx * 4 + j;
-            if (a < CA && b < CB) o[(size_t)a * CB + b] = acc[i][j];
+            for (int j = 0; j < 4; ++j) {
+                const int a = a0 + ty * 4 + i, b = b0 + tx * 4 + j;
+                if (a < CA && b < CB) o[(size_t)a * CB + b] = acc[i][j];
+            }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) red[(grp * TA + ty * 4 + i) * TB + tx * 4 + j] = acc[i][j];
+        __syncthreads();
+        for (int e = t; e < TA * TB; e += 256) {
+            float sum = 0.0f;
+            for (int g2 = 0; g2 < KG; ++g2) sum += red[g2 * TA * TB + e];
+            const int a = a0 + e / TB, b = b0 + e % TB;
+            if (a < CA && b < CB) o[(size_t)a * CB + b] = sum;
         }
+    }
+}
+
+// kernels with the taps reversed and the channel roles swapped: wT[taps-1-tap][co][ci] = w[tap][ci][co], so that the
+// data gradient of a SAME convolution is the forward convolution of dz with wT
+__global__ void flip_weights_kernel(const float *__restrict__ w, int taps, int C, int CO, float *__restrict__ wt)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)taps * C * CO) return;
+    const int co = (int)(i % CO);
+    const int ci = (int)((i / CO) % C);
+    const int tap = (int)(i / ((size_t)CO * C));
+    wt[((size_t)(taps - 1 - tap) * CO + co) * C + ci] = w[i];
 }
 
 // part[z][c] = sum over the pixels of chunk z of g[p][c]; 32 channels x 8 pixel lanes per block
@@ -336,19 +377,34 @@ int param_grads(sq_trainer_s *tr, int li, const float *x0, const float *x1, cons
     const int KH = up ? 2 : L.ksize, KW = KH;
     const int taps = KD * KH * KW;
     const int CA = up ? L.cout : L.cin0 + L.cin1, CB = up ? L.cin0 : L.cout;
-    const int tiles = ((CA + WG_TILE - 1) / WG_TILE) * ((CB + WG_TILE - 1) / WG_TILE);
+    const int TA = CA > 32 ? 64 : (CA > 16 ? 32 : 16), TB = CB > 32 ? 64 : (CB > 16 ? 32 : 16);
+    const int tiles = ((CA + TA - 1) / TA) * ((CB + TB - 1) / TB);
     int nsplit = pick_splits(u, npix_x, (long long)tiles * taps);
     while (nsplit > 1 && (size_t)nsplit * s.wcount > sc.part_count) --nsplit;
     SQ_REQUIRE((size_t)nsplit * s.wcount <= sc.part_count, SQ_ENOMEM, "trainer: scratch too small for '%s'",
                L.scope.c_str());
-    const long long chunk = ((npix_x + nsplit - 1) / nsplit + WG_K - 1) / WG_K * WG_K;
+    const long long chunk = ((npix_x + nsplit - 1) / nsplit + 63) / 64 * 64;
     dim3 grid((unsigned)tiles, (unsigned)taps, (unsigned)nsplit);
+#define SQ_WGRAD(MODE_, TA_, TB_, ...) wgrad_kernel<MODE_, TA_, TB_><<<grid, 256, 0, st>>>(__VA_ARGS__)
+#define SQ_WGRAD_TB(MODE_, TA_, ...)                                            \
+    do {                                                                        \
+        if (TB == 64) SQ_WGRAD(MODE_, TA_, 64, __VA_ARGS__);                    \
+        else if (TB == 32) SQ_WGRAD(MODE_, TA_, 32, __VA_ARGS__);               \
+        else SQ_WGRAD(MODE_, TA_, 16, __VA_ARGS__);                             \
+    } while (0)
+#define SQ_WGRAD_ANY(MODE_, ...)                                                \
+    do {                                                                        \
+        if (TA == 64) SQ_WGRAD_TB(MODE_, 64, __VA_ARGS__);                      \
+        else if (TA == 32) SQ_WGRAD_TB(MODE_, 32, __VA_ARGS__);                 \
+        else SQ_WGRAD_TB(MODE_, 16, __VA_ARGS__);                               \
+    } while (0)
     if (up)
-        wgrad_kernel<1><<<grid, 256, 0, st>>>(dz, L.cout, nullptr, 0, x0, L.cin0, npix_x, D, H, W, KD, KH, KW, chunk,
-                                              sc.part);
+        SQ_WGRAD_ANY(1, dz, L.cout, nullptr, 0, x0, L.cin0, npix_x, D, H, W, KD, KH, KW, chunk, sc.part);
     else
-        wgrad_kernel<0><<<grid, 256, 0, st>>>(x0, L.cin0, x1, L.cin1, dz, L.cout, npix_x, D, H, W, KD, KH, KW, chunk,
-                                              sc.part);
+        SQ_WGRAD_ANY(0, x0, L.cin0, x1, L.cin1, dz, L.cout, npix_x, D, H, W, KD, KH, KW, chunk, sc.part);
+#undef SQ_WGRAD_ANY
+#undef SQ_WGRAD_TB
+#undef SQ_WGRAD
     SQ_CHECK_LAUNCH();
     reduce_splits_kernel<<<(unsigned)((s.wcount + 255) / 256), 256, 0, st>>>(sc.part, s.wcount, nsplit, s.gw);
     SQ_CHECK_LAUNCH();
@@ -373,6 +429,16 @@ int conv_dgrad(sq_trainer_s *tr, int li, const float *dz, long long npix, int D,
     const int KD = (u->ndim == 3) ? L.ksize : 1;
     const int C = L.cin0 + L.cin1;
     const unsigned gx = (unsigned)((npix + 127) / 128);
+    if (sqtile::can_tile(L.cout, C) && !getenv("SQ_FP32_NOTILE")) {
+        // dx = SAME convolution of dz with the tap-reversed, channel-swapped kernel (conv_fp32_tile.cuh)
+        const int taps = KD * L.ksize * L.ksize;
+        const size_t cnt = (size_t)taps * C * L.cout;
+        flip_weights_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(L.w, taps, C, L.cout, tr->wflip);
+        SQ_CHECK_LAUNCH();
+        SQ_CUDA(sqtile::launch(dz, L.cout, nullptr, 0, npix, D, H, W, tr->wflip, KD, L.ksize, L.ksize, C, nullptr,
+                               nullptr, 0, dx, st));
+        return SQ_OK;
+    }
     if (C >= 8)
         dgrad_kernel<8><<<dim3(gx, (C + 7) / 8), 128, 0, st>>>(dz, L.cout, npix, D, H, W, L.w, KD, L.ksize, L.ksize, C, dx);
     else
@@ -480,6 +546,13 @@ extern "C" int sq_trainer_create(sq_unet_t u, int optimizer, float learning_rate
             delete tr;
             return rc;
         }
+    }
+    size_t wmax = 1;
+    for (const auto &s : tr->slots) wmax = std::max(wmax, s.wcount);
+    if (zalloc(wmax, &tr->wflip) != SQ_OK) {
+        for (void *p : tr->allocs) cudaFree(p);
+        delete tr;
+        return SQ_ECUDA;
     }
     *out = tr;
     return SQ_OK;

@@ -10,6 +10,7 @@
 // which makes logits and masks bit-identical to oracle/unet_ref.c.  It is the
 // verification mode; the throughput mode is SQ_MODE_BF16_TC (unet_tc.cu).
 #include "unet_plan.cuh"
+#include "conv_fp32_tile.cuh"
 #include <algorithm>
 #include <cmath>
 
@@ -126,6 +127,46 @@ __global__ void upconv_fp32_kernel(const float *__restrict__ in, long long nout,
     out[i] = acc + bias[co];
 }
 
+// The same transposed conv with one thread per INPUT pixel: all TAPS fine pixels x COT channels in registers, the
+// weight address is uniform across a warp (the per-output kernel above reads weights CI floats apart between
+// neighbouring threads).  Every output is still the chain fmaf(in[ci], w[tap][co][ci], acc) over ci, plus the bias.
+template <int TAPS, int COT>
+__global__ void upconv_fp32_px_kernel(const float *__restrict__ in, long long npix, int D, int H, int W, int CI,
+                                      const float *__restrict__ w, const float *__restrict__ bias, int CO,
+                                      float *__restrict__ out)
+{
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npix) return;
+    const int co0 = blockIdx.y * COT;
+    float acc[TAPS][COT];
+#pragma unroll
+    for (int tp = 0; tp < TAPS; ++tp)
+#pragma unroll
+        for (int j = 0; j < COT; ++j) acc[tp][j] = 0.0f;
+    const float *q = in + p * CI;
+    for (int ci = 0; ci < CI; ++ci) {
+        const float v = q[ci];
+#pragma unroll
+        for (int tp = 0; tp < TAPS; ++tp)
+#pragma unroll
+            for (int j = 0; j < COT; ++j)
+                if (co0 + j < CO) acc[tp][j] = fmaf(v, __ldg(w + ((size_t)tp * CO + co0 + j) * CI + ci), acc[tp][j]);
+    }
+    const int x = (int)(p % W);
+    const int y = (int)((p / W) % H);
+    const int z = (int)((p / ((long long)W * H)) % D);
+    const long long n = p / ((long long)W * H * D);
+    constexpr int UD = TAPS / 4;
+#pragma unroll
+    for (int tp = 0; tp < TAPS; ++tp) {
+        const int kx = tp & 1, ky = (tp >> 1) & 1, kz = tp >> 2;
+        float *o = out + ((((long long)n * D * UD + z * UD + kz) * (2 * H) + 2 * y + ky) * (2 * W) + 2 * x + kx) * CO;
+#pragma unroll
+        for (int j = 0; j < COT; ++j)
+            if (co0 + j < CO) o[co0 + j] = acc[tp][j] + bias[co0 + j];
+    }
+}
+
 __global__ void eltwise_fp32_kernel(const float *__restrict__ a, const float *__restrict__ b,
                                     long long n, int op, float *__restrict__ out)
 {
@@ -229,7 +270,11 @@ int launch_conv(sq_unet_s *u, const SqLayer &L, const float *in0, const float *i
     const int KD = (u->ndim == 3) ? L.ksize : 1;
     const int threads = 128;
     const unsigned gx = (unsigned)((npix + threads - 1) / threads);
-    if (L.cout % 16 == 0) {
+    if (sqtile::can_tile(L.cin0 + L.cin1, L.cout) && !getenv("SQ_FP32_NOTILE")) {
+        // same fmaf chain per output, staged through shared memory (conv_fp32_tile.cuh)
+        SQ_CUDA(sqtile::launch(in0, L.cin0, in1, L.cin1, npix, D, H, W, L.w, KD, L.ksize, L.ksize, L.cout, L.scale,
+                               L.shift, relu, out, st));
+    } else if (L.cout % 16 == 0) {
         conv_fp32_kernel<16><<<dim3(gx, L.cout / 16), threads, 0, st>>>(
             in0, L.cin0, in1, L.cin1, npix, D, H, W, L.w, KD, L.ksize, L.ksize, L.cout, L.scale,
             L.shift, relu, out);
@@ -325,9 +370,17 @@ int fp32_run(sq_unet_s *u, bool dry, const float *in, int n, int d, int hgt, int
         snprintf(scope, sizeof scope, "UNet/up%d/conv2", l);
         const SqLayer *c2 = find_layer(u, scope);
         const long long nout = px * us->cout;
-        upconv_fp32_kernel<<<(unsigned)((nout + threads - 1) / threads), threads, 0, st>>>(
-            cur, nout, (u->ndim == 3) ? (d >> (l + 1)) : 1, hgt >> (l + 1), wid >> (l + 1), us->cin0,
-            (u->ndim == 3) ? 2 : 1, us->w, us->shift, us->cout, up[l]);
+        {
+            const long long pin = level_pixels(u, g, l + 1);
+            const int Dc = (u->ndim == 3) ? (d >> (l + 1)) : 1, Hc = hgt >> (l + 1), Wc = wid >> (l + 1);
+            const unsigned gxp = (unsigned)((pin + 127) / 128);
+            if (u->ndim == 3)
+                upconv_fp32_px_kernel<8, 4><<<dim3(gxp, (us->cout + 3) / 4), 128, 0, st>>>(
+                    cur, pin, Dc, Hc, Wc, us->cin0, us->w, us->shift, us->cout, up[l]);
+            else
+                upconv_fp32_px_kernel<4, 8><<<dim3(gxp, (us->cout + 7) / 8), 128, 0, st>>>(
+                    cur, pin, Dc, Hc, Wc, us->cin0, us->w, us->shift, us->cout, up[l]);
+        }
         ++u->last_launches;
         SQ_CHECK_LAUNCH();
         sq_timer_mark(u, st, us->scope.c_str(), us->flops_per_px * px);
