@@ -435,6 +435,33 @@ def main():
         del net32, a, b, m32
         torch.cuda.empty_cache()
 
+    # ---- the training step of BASELINE configs[4] at tr_augment's default crop (4 crops of 512x512), aux key
+    train_res = None
+    if rank == 0 and world == 1 and not args.no_parity:
+        from sequitr_b200.networks.unet import ModeKeys
+        tnet = UNet2D({'filters': FILTERS, 'shape': (512, 512), 'bridge': 'concat', 'num_inputs': 1,
+                       'num_outputs': 2, 'compute': 'fp32', 'dropout': 0.4, 'device': local}, mode=ModeKeys.TRAIN)
+        tnet.load_weights(synth.unet_weights(FILTERS, 1, 2, ndim=2, bridge='concat', seed=1))
+        trainer = tnet.trainer(learning_rate=1e-3, seed=1)
+        timg = dev_pool[:1, :1024, :1024].reshape(1, 2, 512, 2, 512, 1).permute(0, 1, 3, 2, 4, 5).reshape(4, 512, 512, 1)
+        timg = timg.contiguous()
+        tlab = (timg[..., 0] > timg.mean()).to(torch.uint8).contiguous()
+        twgt = ops.weightmap_edt(tlab, 10., 5.).float()
+        losses = [trainer.step(timg, tlab, twgt) for _ in range(2)]          # warm-up
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        TS = 5
+        for _ in range(TS):
+            losses.append(trainer.step(timg, tlab, twgt))                    # the loss read-back synchronises
+        train_ms = (time.perf_counter() - t0) / TS * 1e3
+        train_res = {"ms_per_step": train_ms, "crops_per_s": 4 / train_ms * 1e3,
+                     "batch": "4 crops of 512x512x1 (tr_augment's default shape), dropout 0.4, Adam",
+                     "arithmetic": "fp32 CUDA cores (tiled conv / dgrad, split-pixel wgrad); not on tensor cores",
+                     "loss_first": losses[0], "loss_last": losses[-1]}
+        trainer.close()
+        del tnet, trainer
+        torch.cuda.empty_cache()
+
     # ---- e2e: the reference-facing host call on camera-native uint16 frames, host tables out.
     #      One call = CALL frames = CALL/B steps (a Sequitr job hands a stack to the network, not 8 frames
     #      at a time); inside, frames stream in chunks of 1, 1, 2, 4, 8, 8, ... (H2D of a chunk under the
@@ -542,6 +569,7 @@ def main():
             "roofline_hbm": roofline_hbm,
             "layers_ms_per_step": {k: round(v, 4) for k, v in layer_ms.items()},
             "parity": par,
+            "train_step": train_res,
             "cpu_baseline": cpu,
             "wall_s": time.perf_counter() - t_wall0,
         }
