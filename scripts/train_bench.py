@@ -25,6 +25,9 @@ def main():
         ('UNet2D 16-256 concat, batch 1 of 1024x1024x1', UNet2D, (16, 32, 64, 128, 256), (1, 1024, 1024), 2),
         ('UNet3D 16-64 concat, batch 1 of 32x256x256x1', UNet3D, (16, 32, 64), (1, 32, 256, 256), 3),
     ]
+    if os.environ.get('BIG'):
+        # BASELINE configs[4] at full size: one 64x1024x1024 z-stack (fp32 activations + gradients: ~75 GB)
+        cases.append(('UNet3D 16-64 concat, batch 1 of 64x1024x1024x1', UNet3D, (16, 32, 64), (1, 64, 1024, 1024), 3))
     only = os.environ.get('CASE')
     for i, (name, cls, filters, sp, ndim) in enumerate(cases):
         if only is not None and int(only) != i:

@@ -55,71 +55,73 @@ __global__ void __launch_bounds__(256) conv_fp32_tile_kernel(const float *__rest
         for (int j = 0; j < CT; ++j) acc[i][j] = 0.0f;
 
     const int nchunk = (C + KC - 1) / KC;
-    for (int kz = 0; kz < KD; ++kz)
-        for (int ky = 0; ky < KH; ++ky)
-            for (int kx = 0; kx < KW; ++kx) {
-                const int zz = z + kz - KD / 2, yy = y + ky - KH / 2, xx = x + kx - KW / 2;
-                const bool inb = p_ok && zz >= 0 && zz < D && yy >= 0 && yy < H && xx >= 0 && xx < W;
-                const long long pix = nb + ((long long)zz * H + yy) * W + xx;
-                const float *wk = w + (size_t)((kz * KH + ky) * KW + kx) * C * CO;
-                for (int ch = 0; ch < nchunk; ++ch) {
-                    const int c0 = ch * KC;
-                    float av[8];
+    const int ntap = KD * KH * KW, niter = ntap * nchunk;
+    constexpr int WPT = (KC * COT + 255) / 256;        // weight values a thread stages per chunk
+    float av[8], wv[WPT];
+    // global loads of iteration `it` (tap-major, then channel chunk: the oracle's order of K) into registers
+    auto fetch = [&](int it) {
+        const int tap = it / nchunk, c0 = (it - tap * nchunk) * KC;
+        const int kx = tap % KW, ky = (tap / KW) % KH, kz = tap / (KW * KH);
+        const int zz = z + kz - KD / 2, yy = y + ky - KH / 2, xx = x + kx - KW / 2;
+        const bool inb = p_ok && zz >= 0 && zz < D && yy >= 0 && yy < H && xx >= 0 && xx < W;
+        const long long pix = nb + ((long long)zz * H + yy) * W + xx;
+        const float *wk = w + (size_t)tap * C * CO;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int c = c0 + lc + j;
-                        float v = 0.0f;
-                        if (inb && c < C) v = (c < C0) ? in0[pix * C0 + c] : in1[pix * C1 + (c - C0)];
-                        av[j] = v;
-                    }
-                    // weights of this chunk: KC x COT values, 256 threads
-                    float wv[(KC * COT + 255) / 256];
+        for (int j = 0; j < 8; ++j) {
+            const int c = c0 + lc + j;
+            float v = 0.0f;
+            if (inb && c < C) v = (c < C0) ? in0[pix * C0 + c] : in1[pix * C1 + (c - C0)];
+            av[j] = v;
+        }
 #pragma unroll
-                    for (int j = 0; j < (KC * COT + 255) / 256; ++j) {
-                        const int e = t + j * 256;
-                        const int k = e / COT, co = e % COT;
-                        float v = 0.0f;
-                        if (e < KC * COT && c0 + k < C && co_base + co < CO)
-                            v = __ldg(wk + (size_t)(c0 + k) * CO + co_base + co);
-                        wv[j] = v;
-                    }
-                    __syncthreads();
+        for (int j = 0; j < WPT; ++j) {
+            const int e = t + j * 256;
+            const int k = e / COT, co = e % COT;
+            float v = 0.0f;
+            if (e < KC * COT && c0 + k < C && co_base + co < CO) v = __ldg(wk + (size_t)(c0 + k) * CO + co_base + co);
+            wv[j] = v;
+        }
+    };
+    fetch(0);
+    for (int it = 0; it < niter; ++it) {
+        const int c0 = (it % nchunk) * KC;
+        __syncthreads();                               // the previous chunk has been consumed
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) As[lc + j][lp] = av[j];
+        for (int j = 0; j < 8; ++j) As[lc + j][lp] = av[j];
 #pragma unroll
-                    for (int j = 0; j < (KC * COT + 255) / 256; ++j) {
-                        const int e = t + j * 256;
-                        if (e < KC * COT) Ws[e / COT][e % COT] = wv[j];
-                    }
-                    __syncthreads();
-                    const int kn = min(KC, C - c0);
-                    auto step = [&](int k) {
-                        const float4 a4 = *reinterpret_cast<const float4 *>(&As[k][pg]);
-                        const float a[4] = {a4.x, a4.y, a4.z, a4.w};
-                        float b[CT];
-                        if (CT == 2) {
-                            const float2 b2 = *reinterpret_cast<const float2 *>(&Ws[k][cg]);
-                            b[0] = b2.x; b[1] = b2.y;
-                        } else {
+        for (int j = 0; j < WPT; ++j) {
+            const int e = t + j * 256;
+            if (e < KC * COT) Ws[e / COT][e % COT] = wv[j];
+        }
+        __syncthreads();
+        if (it + 1 < niter) fetch(it + 1);             // in flight while this chunk is multiplied
+        const int kn = min(KC, C - c0);
+        auto step = [&](int k) {
+            const float4 a4 = *reinterpret_cast<const float4 *>(&As[k][pg]);
+            const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+            float b[CT];
+            if (CT == 2) {
+                const float2 b2 = *reinterpret_cast<const float2 *>(&Ws[k][cg]);
+                b[0] = b2.x; b[1] = b2.y;
+            } else {
 #pragma unroll
-                            for (int j = 0; j < CT; j += 4) {
-                                const float4 b4 = *reinterpret_cast<const float4 *>(&Ws[k][cg + j]);
-                                b[j] = b4.x; b[j + 1] = b4.y; b[j + 2] = b4.z; b[j + 3] = b4.w;
-                            }
-                        }
-#pragma unroll
-                        for (int i = 0; i < 4; ++i)
-#pragma unroll
-                            for (int j = 0; j < CT; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
-                    };
-                    if (kn == KC) {
-#pragma unroll
-                        for (int k = 0; k < KC; ++k) step(k);
-                    } else {
-                        for (int k = 0; k < kn; ++k) step(k);
-                    }
+                for (int j = 0; j < CT; j += 4) {
+                    const float4 b4 = *reinterpret_cast<const float4 *>(&Ws[k][cg + j]);
+                    b[j] = b4.x; b[j + 1] = b4.y; b[j + 2] = b4.z; b[j + 3] = b4.w;
                 }
             }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < CT; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        };
+        if (kn == KC) {
+#pragma unroll
+            for (int k = 0; k < KC; ++k) step(k);
+        } else {
+            for (int k = 0; k < kn; ++k) step(k);
+        }
+    }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const long long p = pbase + pg + i;

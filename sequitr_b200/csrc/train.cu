@@ -124,8 +124,10 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const float *__restrict__ A0
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
 
     const long long frame = (long long)W * H * D;
-    for (long long p0 = p_lo; p0 < p_hi; p0 += KS) {
-        __syncthreads();                           // the previous stage has been consumed
+    constexpr int NA = KS * TA / 256, NB = KS * TB / 256;      // values a thread stages per stage
+    float ra[NA], rb[NB];
+    // the A-pixel of stage pixel k (or -1 outside the frame), computed by thread k and shared
+    auto pixel_map = [&](long long p0) {
         if (t < KS) {
             const long long p = p0 + t;
             long long pa = -1;
@@ -143,8 +145,11 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const float *__restrict__ A0
             }
             pa_s[t] = pa;
         }
-        __syncthreads();
-        for (int e = t; e < KS * TA; e += 256) {
+    };
+    auto fetch = [&](long long p0) {
+#pragma unroll
+        for (int q = 0; q < NA; ++q) {
+            const int e = t + q * 256;
             const int k = e / TA, a = a0 + e % TA;
             const long long pa = pa_s[k];
             float v = 0.0f;
@@ -152,14 +157,31 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const float *__restrict__ A0
                 if (a < CA0) v = A0[pa * CA0 + a];
                 else if (a < CA) v = A1[pa * CA1 + (a - CA0)];
             }
-            As[k][e % TA] = v;
+            ra[q] = v;
         }
-        for (int e = t; e < KS * TB; e += 256) {
+#pragma unroll
+        for (int q = 0; q < NB; ++q) {
+            const int e = t + q * 256;
             const int k = e / TB, b = b0 + e % TB;
             const long long p = p0 + k;
-            Bs[k][e % TB] = (p < p_hi && b < CB) ? B[p * CB + b] : 0.0f;
+            rb[q] = (p < p_hi && b < CB) ? B[p * CB + b] : 0.0f;
         }
+    };
+    if (p_lo < p_hi) {
+        pixel_map(p_lo);
         __syncthreads();
+        fetch(p_lo);
+    }
+    for (long long p0 = p_lo; p0 < p_hi; p0 += KS) {
+        __syncthreads();                           // the previous stage has been consumed (and pa_s read)
+#pragma unroll
+        for (int q = 0; q < NA; ++q) { const int e = t + q * 256; As[e / TA][e % TA] = ra[q]; }
+#pragma unroll
+        for (int q = 0; q < NB; ++q) { const int e = t + q * 256; Bs[e / TB][e % TB] = rb[q]; }
+        const bool more = p0 + KS < p_hi;
+        if (more) pixel_map(p0 + KS);
+        __syncthreads();
+        if (more) fetch(p0 + KS);                  // in flight while this stage is multiplied
 #pragma unroll 4
         for (int k = grp; k < KS; k += KG) {
             const float4 a4 = *reinterpret_cast<const float4 *>(&As[k][ty * 4]);
