@@ -242,6 +242,9 @@ int sq_tr_augment(sq_handle_t h, const float *image_dev, const uint8_t *label_de
  *   - dropout: rate in [0,1); mask = counter-based hash of (seed, step, block, element) -- see train.cu
  *   - image_dev float32 (n,[d,]hgt,wid,cin); labels_dev uint8 class ids (n,[d,]hgt,wid); weights_dev float32 same
  *     shape; *loss_dev float64 on the device; apply_update 0 computes loss and gradients only
+ *   - data-parallel training (one process per GPU): every rank runs the step with apply_update 0 on
+ *     its share of the batch, the ranks all-reduce (average) the gradient arena -- ONE contiguous float32 buffer,
+ *     sq_trainer_grad_arena -- with one NCCL collective, then every rank calls sq_trainer_apply
  *   - sq_trainer_read: name "<scope>/kernel" or "<scope>/bias" (TF layouts, as sq_unet_load_weights takes them),
  *     what 0 = current value, 1 = gradient of the last step */
 int sq_trainer_create(sq_unet_t u, int optimizer, float learning_rate, float beta1, float beta2, float epsilon,
@@ -251,6 +254,8 @@ int sq_trainer_workspace_bytes(sq_trainer_t t, int n, int d, int hgt, int wid, s
 int sq_trainer_step(sq_trainer_t t, const float *image_dev, const uint8_t *labels_dev, const float *weights_dev,
                     int n, int d, int hgt, int wid, int apply_update, double *loss_dev, void *workspace_dev,
                     size_t workspace_bytes, void *stream);
+int sq_trainer_apply(sq_trainer_t t, void *stream);
+int sq_trainer_grad_arena(sq_trainer_t t, float **arena_dev, size_t *count);
 int sq_trainer_read(sq_trainer_t t, const char *name, int what, float *out_host, size_t count);
 
 /* The whole data-parallel hot path on HOST frames: H2D -> UNet -> argmax ->

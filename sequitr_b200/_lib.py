@@ -66,6 +66,8 @@ _SIGNATURES = {
     'sq_trainer_workspace_bytes': (c_int, [c_void_p, c_int, c_int, c_int, c_int, _P(c_size_t)]),
     'sq_trainer_step': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p,
                                 c_void_p, c_size_t, c_void_p]),
+    'sq_trainer_apply': (c_int, [c_void_p, c_void_p]),
+    'sq_trainer_grad_arena': (c_int, [c_void_p, _P(c_void_p), _P(c_size_t)]),
     'sq_trainer_read': (c_int, [c_void_p, c_char_p, c_int, c_void_p, c_size_t]),
     'sq_tr_augment': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
                               c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),

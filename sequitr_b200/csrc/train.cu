@@ -30,6 +30,8 @@ struct sq_trainer_s {
                   size_t wcount = 0; };
     std::vector<Slot> slots;      // one per layer of u->layers
     float *wflip = nullptr;       // scratch for a layer's tap-reversed kernel (data gradients)
+    float *garena = nullptr;      // all gradients, contiguous (one all-reduce for data-parallel training)
+    size_t gcount = 0;
     std::vector<void *> allocs;
 };
 
@@ -551,13 +553,26 @@ extern "C" int sq_trainer_create(sq_unet_t u, int optimizer, float learning_rate
         SQ_CUDA(cudaMemset(*p, 0, std::max<size_t>(count, 1) * sizeof(float)));
         return SQ_OK;
     };
+    // every gradient lives in ONE arena (kernel, bias, kernel, bias, ... in layer order; 64-float aligned pieces), so
+    // that a data-parallel caller all-reduces the step's gradients with a single collective
+    size_t gtotal = 0;
+    for (size_t i = 0; i < u->layers.size(); ++i) {
+        tr->slots[i].wcount = layer_wcount(u, u->layers[i]);
+        gtotal += (tr->slots[i].wcount + 63) / 64 * 64 + ((size_t)u->layers[i].cout + 63) / 64 * 64;
+    }
+    if (zalloc(gtotal, &tr->garena) != SQ_OK) {
+        delete tr;
+        return SQ_ECUDA;
+    }
+    tr->gcount = gtotal;
+    size_t goff = 0;
     for (size_t i = 0; i < u->layers.size(); ++i) {
         const SqLayer &L = u->layers[i];
         sq_trainer_s::Slot &s = tr->slots[i];
-        s.wcount = layer_wcount(u, L);
-        int rc = zalloc(s.wcount, &s.gw);
-        if (rc == SQ_OK) rc = zalloc(L.cout, &s.gb);
-        if (rc == SQ_OK && optimizer == 1) {
+        s.gw = tr->garena + goff; goff += (s.wcount + 63) / 64 * 64;
+        s.gb = tr->garena + goff; goff += ((size_t)L.cout + 63) / 64 * 64;
+        int rc = SQ_OK;
+        if (optimizer == 1) {
             rc = zalloc(s.wcount, &s.mw);
             if (rc == SQ_OK) rc = zalloc(s.wcount, &s.vw);
             if (rc == SQ_OK) rc = zalloc(L.cout, &s.mb);
@@ -711,23 +726,41 @@ extern "C" int sq_trainer_step(sq_trainer_t tr, const float *image_dev, const ui
     }
 
     // ---- optimiser
-    if (apply_update) {
-        ++tr->step;
-        const double t = (double)tr->step;
-        const float lr_t = (float)((double)tr->lr * std::sqrt(1.0 - std::pow((double)tr->beta2, t)) /
-                                   (1.0 - std::pow((double)tr->beta1, t)));
-        for (size_t i = 0; i < u->layers.size(); ++i) {
-            SqLayer &L = u->layers[i];
-            sq_trainer_s::Slot &s = tr->slots[i];
-            update_kernel<<<(unsigned)((s.wcount + 255) / 256), 256, 0, st>>>(L.w, s.gw, s.mw, s.vw, s.wcount,
-                                                                              tr->optimizer, tr->lr, lr_t, tr->beta1,
-                                                                              tr->beta2, tr->eps);
-            update_kernel<<<(unsigned)((L.cout + 255) / 256), 256, 0, st>>>(L.shift, s.gb, s.mb, s.vb, (size_t)L.cout,
-                                                                            tr->optimizer, tr->lr, lr_t, tr->beta1,
-                                                                            tr->beta2, tr->eps);
-        }
-        SQ_CHECK_LAUNCH();
+    if (apply_update) SQ_TRY(sq_trainer_apply(tr, stream_));
+    return SQ_OK;
+}
+
+// the optimiser update from the gradients that are in the arena now (a data-parallel caller runs the step with
+// apply_update = 0, all-reduces the arena, then calls this)
+extern "C" int sq_trainer_apply(sq_trainer_t tr, void *stream_)
+{
+    SQ_REQUIRE(tr, SQ_EINVAL, "trainer_apply: null pointer");
+    sq_unet_s *u = tr->u;
+    cudaStream_t st = (cudaStream_t)stream_;
+    SQ_CUDA(cudaSetDevice(u->h->device));
+    ++tr->step;
+    const double t = (double)tr->step;
+    const float lr_t = (float)((double)tr->lr * std::sqrt(1.0 - std::pow((double)tr->beta2, t)) /
+                               (1.0 - std::pow((double)tr->beta1, t)));
+    for (size_t i = 0; i < u->layers.size(); ++i) {
+        SqLayer &L = u->layers[i];
+        sq_trainer_s::Slot &s = tr->slots[i];
+        update_kernel<<<(unsigned)((s.wcount + 255) / 256), 256, 0, st>>>(L.w, s.gw, s.mw, s.vw, s.wcount,
+                                                                          tr->optimizer, tr->lr, lr_t, tr->beta1,
+                                                                          tr->beta2, tr->eps);
+        update_kernel<<<(unsigned)((L.cout + 255) / 256), 256, 0, st>>>(L.shift, s.gb, s.mb, s.vb, (size_t)L.cout,
+                                                                        tr->optimizer, tr->lr, lr_t, tr->beta1,
+                                                                        tr->beta2, tr->eps);
     }
+    SQ_CHECK_LAUNCH();
+    return SQ_OK;
+}
+
+extern "C" int sq_trainer_grad_arena(sq_trainer_t tr, float **arena_dev, size_t *count)
+{
+    SQ_REQUIRE(tr && arena_dev && count, SQ_EINVAL, "trainer_grad_arena: null pointer");
+    *arena_dev = tr->garena;
+    *count = tr->gcount;
     return SQ_OK;
 }
 

@@ -547,7 +547,7 @@ class Trainer(object):
     ``load_weights`` layout (e.g. to load a ``compute='bf16'`` network for tensor-core inference)."""
 
     def __init__(self, net, learning_rate=1e-3, optimizer='adam', beta1=0.9, beta2=0.999, epsilon=1e-8,
-                 dropout=None, seed=0):
+                 dropout=None, seed=0, data_parallel=None):
         if net.compute != 'fp32':
             raise ValueError("the training step runs on a compute='fp32' network")
         if optimizer not in ('sgd', 'adam'):
@@ -560,9 +560,34 @@ class Trainer(object):
                                                  beta2, epsilon, float(rate), int(seed),
                                                  ctypes.byref(self._trainer)))
         self._ws = ops.Workspace(device='cuda:%d' % net._device)
+        # data parallel (one process per GPU, torch.distributed initialised by the caller): every rank steps on its
+        # share of the batch, the gradient arena is averaged with ONE all-reduce, every rank applies the same update.
+        # None = on whenever a process group with more than one rank exists.
+        self.data_parallel = data_parallel
+        self._grad = None
+
+    def _grad_tensor(self):
+        """The trainer's gradient arena as a zero-copy float32 cuda tensor."""
+        import torch
+        if self._grad is None:
+            ptr, count = ctypes.c_void_p(), ctypes.c_size_t()
+            _lib.check(_lib.load().sq_trainer_grad_arena(self._trainer, ctypes.byref(ptr), ctypes.byref(count)))
+
+            class _Arena(object):
+                __cuda_array_interface__ = {'shape': (count.value,), 'typestr': '<f4', 'data': (ptr.value, False),
+                                            'version': 2}
+            self._grad = torch.as_tensor(_Arena(), device='cuda:%d' % self.net._device)
+        return self._grad
+
+    def _ranks(self):
+        import torch.distributed as dist
+        if self.data_parallel is False or not (dist.is_available() and dist.is_initialized()):
+            return 1
+        return dist.get_world_size()
 
     def close(self):
         t = getattr(self, '_trainer', None)
+        self._grad = None                       # the view dies with the arena
         if t is not None and t.value:
             _lib.load().sq_trainer_destroy(t)
         self._trainer = None
@@ -622,9 +647,16 @@ class Trainer(object):
         _lib.check(lib.sq_trainer_workspace_bytes(self._trainer, n, d, h, w, ctypes.byref(need)))
         ws = self._ws.get(need.value)
         loss = torch.zeros(1, dtype=torch.float64, device=dev)
+        ranks = self._ranks()
         _lib.check(lib.sq_trainer_step(self._trainer, x.data_ptr(), lab.data_ptr(), wgt.data_ptr(), n, d, h, w,
-                                       1 if apply_update else 0, loss.data_ptr(), ws.data_ptr(), ws.numel(),
-                                       _lib.stream_ptr(x.device)))
+                                       1 if (apply_update and ranks == 1) else 0, loss.data_ptr(), ws.data_ptr(),
+                                       ws.numel(), _lib.stream_ptr(x.device)))
+        if ranks > 1:
+            from .. import shard
+            with torch.cuda.device(x.device):
+                shard.average_gradients_(self._grad_tensor(), loss)
+            if apply_update:
+                _lib.check(lib.sq_trainer_apply(self._trainer, _lib.stream_ptr(x.device)))
         return float(loss.item())
 
     def _read(self, what):

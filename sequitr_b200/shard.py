@@ -74,6 +74,27 @@ def segment_stack(net, frames, frame0=0, frames_per_call=250, max_rows=4096, nor
     return out
 
 
+def average_gradients_(grad, loss=None, group=None):
+    """The one exchange step of data-parallel training: every rank computed the gradient of the mean
+    loss over ITS share of the batch into ``grad`` (the trainer's contiguous gradient arena, a float32 tensor); one
+    all-reduce sums them over the ranks and the result is divided by the world size in place -- the gradient of the
+    mean loss over the whole batch when the shares are equally large.  ``loss`` (a float64 tensor of one element) is
+    averaged the same way.  NCCL over NVLink / NVSwitch for cuda tensors, gloo for the CPU tests.  Returns the world
+    size (1 without an initialised process group: nothing to do)."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return 1
+    world = dist.get_world_size(group)
+    if world == 1:
+        return 1
+    dist.all_reduce(grad, op=dist.ReduceOp.SUM, group=group)
+    grad.div_(world)
+    if loss is not None:
+        dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=group)
+        loss.div_(world)
+    return world
+
+
 def bind_to_gpu_numa(device_index):
     """Pin the calling worker process to the CPUs NVML reports as closest to GPU ``device_index`` (one
     worker per GPU, the reference's model: core.py:41-42), so that the pinned frame buffers it allocates

@@ -143,3 +143,46 @@ def test_trainer_argument_errors(sq):
     net.load_weights(w)
     with pytest.raises(RuntimeError):
         tr.step(image, labels, wmap)                     # the plan the trainer was bound to is gone
+
+
+def _dp_worker(rank, world, port, out_dir):
+    import os
+    import sys
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+    filters, shape, cin, k = (8, 16, 32), (32, 32), 1, 2
+    w = synth.unet_weights(filters, cin, k, ndim=2, bridge='concat', seed=4)
+    image, labels, wmap = _batch(2, 4, shape, cin, k, seed=21)
+    net = _net(2, filters, cin, k, 'concat', shape, w, 0.0)
+    tr = net.trainer(learning_rate=0.05, optimizer='sgd')
+    share = slice(rank * 2, rank * 2 + 2)                      # this rank's half of the batch
+    losses = [tr.step(image[share], labels[share], wmap[share]) for _ in range(2)]
+    got = tr.weights()
+    if rank == 0:
+        # the same two steps on the whole batch in one process
+        ref_net = _net(2, filters, cin, k, 'concat', shape, w, 0.0)
+        ref = ref_net.trainer(learning_rate=0.05, optimizer='sgd', data_parallel=False)
+        ref_losses = [ref.step(image, labels, wmap) for _ in range(2)]
+        want = ref.weights()
+        err = max(float(np.abs(got[n] - want[n]).max()) for n in want)
+        np.save(os.path.join(out_dir, 'dp.npy'), np.array([err] + losses + ref_losses))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_data_parallel_step_equals_the_whole_batch_step(sq, tmp_path):
+    """Two ranks, half a batch each, ONE all-reduce of the gradient arena per step (NCCL): the weights after two SGD
+    steps equal those of a single process stepping on the whole batch (up to the fp32 order of the sums)."""
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs two GPUs (gpurun --gpus 2)')
+    mp.spawn(_dp_worker, args=(2, 29671, str(tmp_path)), nprocs=2, join=True)
+    res = np.load(str(tmp_path / 'dp.npy'))
+    assert res[0] <= 2e-6, res
+    np.testing.assert_allclose(res[1:3], res[3:5], rtol=1e-6)

@@ -50,3 +50,30 @@ def test_frame_ranges_partition():
             assert all(r[i][1] == r[i + 1][0] for i in range(g - 1))
             sizes = [b - a for a, b in r]
             assert max(sizes) - min(sizes) <= 1
+
+
+def _grad_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    from sequitr_b200 import shard
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    # without a process group the exchange step is a no-op
+    g0 = torch.arange(4, dtype=torch.float32)
+    assert shard.average_gradients_(g0) == 1 and g0.tolist() == [0., 1., 2., 3.]
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    # stand-in for the per-rank gradient arena and loss of a data-parallel training step
+    grad = torch.arange(6, dtype=torch.float32) * (rank + 1)
+    loss = torch.tensor([1.0 + rank], dtype=torch.float64)
+    assert shard.average_gradients_(grad, loss) == world
+    if rank == 0:
+        np.save(os.path.join(out_dir, 'grad.npy'), np.concatenate([grad.numpy().astype(np.float64), loss.numpy()]))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gradient_average(tmp_path):
+    mp.spawn(_grad_worker, args=(2, 29617, str(tmp_path)), nprocs=2, join=True)
+    res = np.load(str(tmp_path / 'grad.npy'))
+    np.testing.assert_allclose(res[:6], np.arange(6) * 1.5)       # mean of 1x and 2x
+    assert res[6] == 1.5
