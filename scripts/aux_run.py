@@ -18,7 +18,7 @@ lab8_d = (lab_d % 5).to(torch.uint8).contiguous()
 rs = np.random.RandomState(0)
 tr = np.stack([ops.rotation_transform(2 * np.pi * rs.uniform(), H, W) for _ in range(N)])
 cr = rs.randint(0, 1024, (N, 2)).astype(np.int32)
-for rep in range(2):
+for rep in range(int(os.environ.get('REPS', '2'))):
     wgt_d = ops.weightmap_edt(mask_d, 10., 5., 'float32')
     ops.weightmap_unet(lab_d, 10., 5., None, 'float32')
     ops.image_norm(frames_d)
