@@ -395,6 +395,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 for (int jp = 0; jp < S / 2; ++jp) {
                     const int y = ty * C::TH + 32 * jp + 2 * ph, x = tx * 8 + pw;
                     const bool valid = live && (y < H) && (x < W);
+                    // ONE 64-bit address chain per sub-tile pair; the 16-channel chunks are a constant byte stride apart
+                    // (the per-item `out + (((n*CBo + 2*c16)*H + y)*W + x)*8` cost ~70 integer instructions per item)
+                    const int Hp = H >> 1, Wp = W >> 1;
+                    const size_t plane_b = (size_t)H * W * 8 * sizeof(bf16), pplane_b = (size_t)Hp * Wp * 8 * sizeof(bf16);
+                    char *const pb = reinterpret_cast<char *>(out + (((size_t)n * CBo * H + y) * W + x) * 8);
+                    char *const qb = reinterpret_cast<char *>(out_pool + (((size_t)n * CBo * Hp + (y >> 1)) * Wp + (x >> 1)) * 8);
 #pragma unroll 1
                     for (int c16 = 0; c16 < COUT / 16; ++c16) {
                         if (((jp * (COUT / 16) + c16) % EPI_GROUPS) != half) continue;
@@ -408,22 +414,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                         for (int g = 0; g < 4; ++g) {
                             const float4 sc = *reinterpret_cast<const float4 *>(s_scale + c16 * 16 + 4 * g);
                             const float4 sh = *reinterpret_cast<const float4 *>(s_shift + c16 * 16 + 4 * g);
-                            o0[2 * g] = pack_bf16(fmaxf(fmaf(__uint_as_float(v0[4 * g]), sc.x, sh.x), 0.0f),
-                                                  fmaxf(fmaf(__uint_as_float(v0[4 * g + 1]), sc.y, sh.y), 0.0f));
-                            o0[2 * g + 1] = pack_bf16(fmaxf(fmaf(__uint_as_float(v0[4 * g + 2]), sc.z, sh.z), 0.0f),
-                                                      fmaxf(fmaf(__uint_as_float(v0[4 * g + 3]), sc.w, sh.w), 0.0f));
-                            o1[2 * g] = pack_bf16(fmaxf(fmaf(__uint_as_float(v1[4 * g]), sc.x, sh.x), 0.0f),
-                                                  fmaxf(fmaf(__uint_as_float(v1[4 * g + 1]), sc.y, sh.y), 0.0f));
-                            o1[2 * g + 1] = pack_bf16(fmaxf(fmaf(__uint_as_float(v1[4 * g + 2]), sc.z, sh.z), 0.0f),
-                                                      fmaxf(fmaf(__uint_as_float(v1[4 * g + 3]), sc.w, sh.w), 0.0f));
+                            // ReLU on the packed bf16 pair (max commutes with the monotone rounding): one HMNMX2 per pair
+                            // instead of two FMNMX
+                            o0[2 * g] = bf162_max(pack_bf16(fmaf(__uint_as_float(v0[4 * g]), sc.x, sh.x),
+                                                            fmaf(__uint_as_float(v0[4 * g + 1]), sc.y, sh.y)), 0u);
+                            o0[2 * g + 1] = bf162_max(pack_bf16(fmaf(__uint_as_float(v0[4 * g + 2]), sc.z, sh.z),
+                                                                fmaf(__uint_as_float(v0[4 * g + 3]), sc.w, sh.w)), 0u);
+                            o1[2 * g] = bf162_max(pack_bf16(fmaf(__uint_as_float(v1[4 * g]), sc.x, sh.x),
+                                                            fmaf(__uint_as_float(v1[4 * g + 1]), sc.y, sh.y)), 0u);
+                            o1[2 * g + 1] = bf162_max(pack_bf16(fmaf(__uint_as_float(v1[4 * g + 2]), sc.z, sh.z),
+                                                                fmaf(__uint_as_float(v1[4 * g + 3]), sc.w, sh.w)), 0u);
                         }
                         if (valid) {
-                            bf16 *p = out + ((((size_t)n * CBo + c16 * 2) * H + y) * W + x) * 8;
+                            char *p = pb + (size_t)c16 * (2 * plane_b);
                             *reinterpret_cast<uint4 *>(p) = make_uint4(o0[0], o0[1], o0[2], o0[3]);
-                            *reinterpret_cast<uint4 *>(p + (size_t)H * W * 8) = make_uint4(o0[4], o0[5], o0[6], o0[7]);
-                            p += (size_t)W * 8;                       // row y + 1 (H is even)
+                            *reinterpret_cast<uint4 *>(p + plane_b) = make_uint4(o0[4], o0[5], o0[6], o0[7]);
+                            p += (size_t)W * 8 * sizeof(bf16);                 // row y + 1 (H is even)
                             *reinterpret_cast<uint4 *>(p) = make_uint4(o1[0], o1[1], o1[2], o1[3]);
-                            *reinterpret_cast<uint4 *>(p + (size_t)H * W * 8) = make_uint4(o1[4], o1[5], o1[6], o1[7]);
+                            *reinterpret_cast<uint4 *>(p + plane_b) = make_uint4(o1[4], o1[5], o1[6], o1[7]);
                         }
 #pragma unroll
                         for (int e = 0; e < 8; ++e) {
@@ -431,10 +439,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                             o0[e] = bf162_max(m, __shfl_xor_sync(0xffffffffu, m, 1));
                         }
                         if (valid && (lane & 1) == 0) {
-                            const int Hp = H >> 1, Wp = W >> 1;
-                            bf16 *p = out_pool + ((((size_t)n * CBo + c16 * 2) * Hp + (y >> 1)) * Wp + (x >> 1)) * 8;
-                            *reinterpret_cast<uint4 *>(p) = make_uint4(o0[0], o0[1], o0[2], o0[3]);
-                            *reinterpret_cast<uint4 *>(p + (size_t)Hp * Wp * 8) = make_uint4(o0[4], o0[5], o0[6], o0[7]);
+                            char *q = qb + (size_t)c16 * (2 * pplane_b);
+                            *reinterpret_cast<uint4 *>(q) = make_uint4(o0[0], o0[1], o0[2], o0[3]);
+                            *reinterpret_cast<uint4 *>(q + pplane_b) = make_uint4(o0[4], o0[5], o0[6], o0[7]);
                         }
                     }
                 }
@@ -1997,25 +2004,31 @@ conv_qf_kernel(const __grid_constant__ CUtensorMap mapIn, const bf16 *__restrict
                 tc::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) tc::mbar_arrive(&acc2_empty[b]);          // the accumulators are in registers
-                uint32_t mx[4];
-                bf16 *po = out + ((((size_t)n2 * 8 + c8) * H + y) * W + x) * 8;
+                if (valid) {
+                    // ONE address per work item; the four parity planes are 2 * plane apart (a 64-bit add each -- written
+                    // as `po + 2 * q * plane` inside per-store `if (valid)` blocks the compiler rebuilt the whole 64-bit
+                    // product chain, ~30 integer instructions, in front of every 16-byte store)
+                    char *pq = reinterpret_cast<char *>(out + ((((size_t)n2 * 8 + c8) * H + y) * W + x) * 8);
+                    const size_t step2 = 2 * plane * sizeof(bf16);
+                    uint32_t mx[4];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    uint32_t o[4];
+                    for (int q = 0; q < 4; ++q) {
+                        uint32_t o[4];
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        __nv_bfloat162 h = __hmax2(__floats2bfloat162_rn(fmaf(__uint_as_float(v[q * 8 + 2 * e]), sc2[2 * e], sh2[2 * e]),
-                                                                         fmaf(__uint_as_float(v[q * 8 + 2 * e + 1]), sc2[2 * e + 1], sh2[2 * e + 1])),
-                                                   zero2);
-                        o[e] = *reinterpret_cast<uint32_t *>(&h);
+                        for (int e = 0; e < 4; ++e) {
+                            __nv_bfloat162 h = __hmax2(__floats2bfloat162_rn(fmaf(__uint_as_float(v[q * 8 + 2 * e]), sc2[2 * e], sh2[2 * e]),
+                                                                             fmaf(__uint_as_float(v[q * 8 + 2 * e + 1]), sc2[2 * e + 1], sh2[2 * e + 1])),
+                                                       zero2);
+                            o[e] = *reinterpret_cast<uint32_t *>(&h);
+                        }
+                        *reinterpret_cast<uint4 *>(pq) = make_uint4(o[0], o[1], o[2], o[3]);
+                        pq += step2;
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) mx[e] = (q == 0) ? o[e] : bf162_max(mx[e], o[e]);
                     }
-                    if (valid) *reinterpret_cast<uint4 *>(po + (size_t)(2 * q) * plane) = make_uint4(o[0], o[1], o[2], o[3]);
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) mx[e] = (q == 0) ? o[e] : bf162_max(mx[e], o[e]);
-                }
-                if (valid)
                     *reinterpret_cast<uint4 *>(out_pool + ((((size_t)n2 * 2 + c8) * H + y) * W + x) * 8) =
                         make_uint4(mx[0], mx[1], mx[2], mx[3]);
+                }
                 QF_T1(4);
             }
             tx2 = tx; ty2 = ty; n2 = n;
@@ -2301,18 +2314,23 @@ conv_qu_kernel(const __grid_constant__ CUtensorMap mapCur, const __grid_constant
                 tc::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) tc::mbar_arrive(&acc2_empty[b]);
-                bf16 *po = out + ((((size_t)n2 * 8 + c8) * H + y) * W + x) * 8;
+                if (valid) {
+                    // one address per work item, the parity planes a 64-bit add apart (see conv_qf_kernel's epilogue 2)
+                    char *pq = reinterpret_cast<char *>(out + ((((size_t)n2 * 8 + c8) * H + y) * W + x) * 8);
+                    const size_t step2 = 2 * plane * sizeof(bf16);
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    uint32_t o[4];
+                    for (int q = 0; q < 4; ++q) {
+                        uint32_t o[4];
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        __nv_bfloat162 h = __hmax2(__floats2bfloat162_rn(fmaf(__uint_as_float(v[q * 8 + 2 * e]), sc2[2 * e], sh2[2 * e]),
-                                                                         fmaf(__uint_as_float(v[q * 8 + 2 * e + 1]), sc2[2 * e + 1], sh2[2 * e + 1])),
-                                                   zero2);
-                        o[e] = *reinterpret_cast<uint32_t *>(&h);
+                        for (int e = 0; e < 4; ++e) {
+                            __nv_bfloat162 h = __hmax2(__floats2bfloat162_rn(fmaf(__uint_as_float(v[q * 8 + 2 * e]), sc2[2 * e], sh2[2 * e]),
+                                                                             fmaf(__uint_as_float(v[q * 8 + 2 * e + 1]), sc2[2 * e + 1], sh2[2 * e + 1])),
+                                                       zero2);
+                            o[e] = *reinterpret_cast<uint32_t *>(&h);
+                        }
+                        *reinterpret_cast<uint4 *>(pq) = make_uint4(o[0], o[1], o[2], o[3]);
+                        pq += step2;
                     }
-                    if (valid) *reinterpret_cast<uint4 *>(po + (size_t)(2 * q) * plane) = make_uint4(o[0], o[1], o[2], o[3]);
                 }
 #ifdef SQ_XC_PHASE_DIAG
                 dacc[4] += clock64() - te2_;
