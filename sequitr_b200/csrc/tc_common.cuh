@@ -80,8 +80,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, int li
 #else
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
-    for (uint32_t i = 0; i < (1u << 26); ++i)
+    for (uint32_t i = 0; i < (1u << 26); ++i) {
         if (mbar_try_wait(bar, parity)) return;
+#ifdef SQ_WAIT_NS
+        __nanosleep(SQ_WAIT_NS);          // experiment: back off instead of re-polling at once (power-capped runs)
+#endif
+    }
     printf("sequitr_b200: mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x,
            (int)threadIdx.x);
     __trap();
