@@ -237,8 +237,9 @@ int sq_tr_augment(sq_handle_t h, const float *image_dev, const uint8_t *label_de
  * and no optimiser for the UNet (its only optimiser is the GAN's tf.train.AdamOptimizer, gan.py:740-751), so the
  * step is: forward with every activation kept -> sq_weighted_ce -> backward through every layer -> in-place update
  * of the plan's kernels and biases with TensorFlow's Adam rule (optimizer 1) or plain SGD (optimizer 0).
- *   - the plan must be SQ_MODE_FP32_EXACT with conv + bias layers (no folded affine); it serves inference with the
- *     updated weights right after a step (read them with sq_trainer_read to load a bf16 plan)
+ *   - the plan must be SQ_MODE_FP32_EXACT; it serves inference with the updated weights right after a step (read them
+ *     with sq_trainer_read to load a bf16 plan).  Kernels and biases are trained; a layer's optional per-channel
+ *     affine (scale, shift = folded BN statistics) stays frozen: y = relu((conv + bias) * scale + shift)
  *   - dropout: rate in [0,1); mask = counter-based hash of (seed, step, block, element) -- see train.cu
  *   - image_dev float32 (n,[d,]hgt,wid,cin); labels_dev uint8 class ids (n,[d,]hgt,wid); weights_dev float32 same
  *     shape; *loss_dev float64 on the device; apply_update 0 computes loss and gradients only

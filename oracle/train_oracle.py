@@ -101,7 +101,12 @@ def forward_loss(params, image, labels, wmap, filters, bridge='concat', ndim=2, 
     keep_scale = float(np.float32(1.0) - np.float32(rate))
 
     def layer(x, scope):
-        return torch.relu(conv(x, params[scope + '/kernel'], params[scope + '/bias'], padding=1))
+        y = conv(x, params[scope + '/kernel'], params[scope + '/bias'], padding=1)
+        if scope + '/scale' in params:
+            # frozen per-channel affine (folded BN): (conv + bias) * scale + shift, constants of the step
+            bshape = (1, -1) + (1,) * ndim
+            y = y * params[scope + '/scale'].detach().reshape(bshape) + params[scope + '/shift'].detach().reshape(bshape)
+        return torch.relu(y)
 
     def block(x, scope, block_id):
         y = layer(layer(x, scope + '/conv1'), scope + '/conv2')
@@ -147,7 +152,8 @@ def gradients(weights, image, labels, wmap, filters, bridge='concat', ndim=2, ra
     params = _to_torch_params(weights, ndim)
     loss, logits = forward_loss(params, image, labels, wmap, filters, bridge, ndim, rate, step_seed(seed, step))
     loss.backward()
-    grads = {name: _from_torch_grad(name, p.grad, ndim) for name, p in params.items()}
+    grads = {name: _from_torch_grad(name, p.grad, ndim) for name, p in params.items()
+             if name.endswith('/kernel') or name.endswith('/bias')}        # scale / shift are frozen
     return float(loss.item()), grads, logits.detach().numpy()
 
 
@@ -155,7 +161,7 @@ class Adam(object):
     """TensorFlow's Adam update rule in float64 (optimizer='sgd': p -= lr * g)."""
 
     def __init__(self, weights, learning_rate=1e-3, beta1=0.9, beta2=0.999, epsilon=1e-8, optimizer='adam'):
-        self.w = {k: np.asarray(v, dtype=np.float64).copy() for k, v in weights.items()}
+        self.w = {k: np.asarray(v, dtype=np.float64).copy() for k, v in weights.items()}      # incl. frozen scale / shift
         self.m = {k: np.zeros_like(v) for k, v in self.w.items()}
         self.v = {k: np.zeros_like(v) for k, v in self.w.items()}
         self.lr, self.b1, self.b2, self.eps, self.optimizer = learning_rate, beta1, beta2, epsilon, optimizer

@@ -27,6 +27,10 @@ struct sq_trainer_s {
     unsigned long long seed = 0;
     long long step = 0;
     struct Slot { float *gw = nullptr, *gb = nullptr, *mw = nullptr, *vw = nullptr, *mb = nullptr, *vb = nullptr;
+                  // a layer with a frozen per-channel affine keeps its trainable bias b and the frozen shift t here;
+                  // the plan's epilogue shift is re-folded from them after every update
+                  float *bias = nullptr, *tsh = nullptr;
+                  bool affine = false;
                   size_t wcount = 0; };
     std::vector<Slot> slots;      // one per layer of u->layers
     float *wflip = nullptr;       // scratch for a layer's tap-reversed kernel (data gradients)
@@ -41,11 +45,24 @@ namespace {
 // -------------------------------------------------------------------------------------------------- kernels
 // d(pre-activation) from d(block output): ReLU mask, and the 1/(1-rate) of a dropout that followed it (the stored
 // output is the dropped one: it is > 0 exactly where the unit was active AND kept)
-__global__ void relu_bwd_kernel(float *__restrict__ g, const float *__restrict__ y, long long n, float keep)
+// With a frozen per-channel affine (folded BN: y = relu((conv + b) * s + t)) the gradient of the pre-affine sum is
+// that times s[c]: it feeds the weight gradient, the data gradient AND the bias gradient (dL/db = sum dz * s).
+__global__ void relu_bwd_kernel(float *__restrict__ g, const float *__restrict__ y, long long n, float keep,
+                                const float *__restrict__ scale, int C)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    g[i] = (y[i] > 0.0f) ? __fdiv_rn(g[i], keep) : 0.0f;
+    float v = (y[i] > 0.0f) ? __fdiv_rn(g[i], keep) : 0.0f;
+    if (scale) v *= scale[(int)(i % C)];
+    g[i] = v;
+}
+
+// the folded epilogue shift of a layer with a frozen affine, as sq_unet_finalize computes it: b * s + t, no fma
+__global__ void refold_kernel(const float *__restrict__ b, const float *__restrict__ s, const float *__restrict__ t,
+                              int C, float *__restrict__ shift)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < C) shift[c] = __fadd_rn(__fmul_rn(b[c], s[c]), t[c]);
 }
 
 // dx[p][ci] = sum_tap sum_co dz[p - off(tap)][co] * w[tap][ci][co]     (w HWIO / DHWIO, SAME padding)
@@ -471,9 +488,12 @@ int conv_dgrad(sq_trainer_s *tr, int li, const float *dz, long long npix, int D,
     return SQ_OK;
 }
 
-int relu_bwd(float *g, const float *y, long long n, float keep, cudaStream_t st)
+// li: the conv layer whose output y is (its frozen affine scale, if any, is applied to the gradient)
+int relu_bwd(sq_trainer_s *tr, int li, float *g, const float *y, long long n, float keep, cudaStream_t st)
 {
-    relu_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(g, y, n, keep);
+    const bool aff = tr->slots[li].affine;
+    relu_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(g, y, n, keep, aff ? tr->u->layers[li].scale : nullptr,
+                                                               tr->u->layers[li].cout);
     SQ_CHECK_LAUNCH();
     return SQ_OK;
 }
@@ -538,10 +558,6 @@ extern "C" int sq_trainer_create(sq_unet_t u, int optimizer, float learning_rate
                "into a bf16 plan for tensor-core inference");
     SQ_REQUIRE(optimizer == 0 || optimizer == 1, SQ_EINVAL, "trainer_create: optimizer 0 (SGD) or 1 (Adam)");
     SQ_REQUIRE(dropout >= 0.0f && dropout < 1.0f, SQ_EINVAL, "trainer_create: dropout rate in [0, 1)");
-    for (const SqLayer &L : u->layers)
-        SQ_REQUIRE(u->host.find(L.scope + "/scale") == u->host.end(), SQ_EUNSUPPORTED,
-                   "trainer_create: '%s' carries a folded per-channel affine; training supports conv + bias layers",
-                   L.scope.c_str());
     SQ_CUDA(cudaSetDevice(u->h->device));
     sq_trainer_s *tr = new sq_trainer_s();
     tr->u = u; tr->optimizer = optimizer; tr->lr = learning_rate; tr->beta1 = beta1; tr->beta2 = beta2;
@@ -572,7 +588,21 @@ extern "C" int sq_trainer_create(sq_unet_t u, int optimizer, float learning_rate
         s.gw = tr->garena + goff; goff += (s.wcount + 63) / 64 * 64;
         s.gb = tr->garena + goff; goff += ((size_t)L.cout + 63) / 64 * 64;
         int rc = SQ_OK;
-        if (optimizer == 1) {
+        auto sc_it = u->host.find(L.scope + "/scale");
+        if (sc_it != u->host.end()) {
+            s.affine = true;
+            rc = zalloc(L.cout, &s.bias);
+            if (rc == SQ_OK) rc = zalloc(L.cout, &s.tsh);
+            if (rc == SQ_OK) {
+                const auto &b = u->host.at(L.scope + "/bias").data, &t = u->host.at(L.scope + "/shift").data;
+                if (cudaMemcpy(s.bias, b.data(), L.cout * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess ||
+                    cudaMemcpy(s.tsh, t.data(), L.cout * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
+                    sq_set_error("trainer_create: upload of '%s' failed", L.scope.c_str());
+                    rc = SQ_ECUDA;
+                }
+            }
+        }
+        if (rc == SQ_OK && optimizer == 1) {
             rc = zalloc(s.wcount, &s.mw);
             if (rc == SQ_OK) rc = zalloc(s.wcount, &s.vw);
             if (rc == SQ_OK) rc = zalloc(L.cout, &s.mb);
@@ -664,11 +694,11 @@ extern "C" int sq_trainer_step(sq_trainer_t tr, const float *image_dev, const ui
         dims(l, &D, &H, &W);
         const int i2 = idx("UNet/up%d/conv2", l), i1 = idx("UNet/up%d/conv1", l), iu = idx("UNet/up%d/upscale", l);
         // conv2 (+ dropout)
-        SQ_TRY(relu_bwd(sp.g_upo[l], tape.upo[l], px * f, keep, st));
+        SQ_TRY(relu_bwd(tr, i2, sp.g_upo[l], tape.upo[l], px * f, keep, st));
         SQ_TRY(param_grads(tr, i2, tape.upt[l], nullptr, sp.g_upo[l], px, D, H, W, sp.sc, st));
         SQ_TRY(conv_dgrad(tr, i2, sp.g_upo[l], px, D, H, W, sp.g_upt[l], st));
         // conv1 over the bridged input
-        SQ_TRY(relu_bwd(sp.g_upt[l], tape.upt[l], px * f, 1.0f, st));
+        SQ_TRY(relu_bwd(tr, i1, sp.g_upt[l], tape.upt[l], px * f, 1.0f, st));
         const unsigned eg = (unsigned)((px * f + 255) / 256);
         if (u->bridge == SQ_BRIDGE_CONCAT) {
             SQ_TRY(param_grads(tr, i1, tape.up[l], tape.down[l], sp.g_upt[l], px, D, H, W, sp.sc, st));
@@ -707,10 +737,10 @@ extern "C" int sq_trainer_step(sq_trainer_t tr, const float *image_dev, const ui
         const int f = u->filters[l];
         dims(l, &D, &H, &W);
         const int i2 = idx("UNet/down%d/conv2", l), i1 = idx("UNet/down%d/conv1", l);
-        SQ_TRY(relu_bwd(sp.g_down[l], tape.down[l], px * f, keep, st));
+        SQ_TRY(relu_bwd(tr, i2, sp.g_down[l], tape.down[l], px * f, keep, st));
         SQ_TRY(param_grads(tr, i2, tape.tmp[l], nullptr, sp.g_down[l], px, D, H, W, sp.sc, st));
         SQ_TRY(conv_dgrad(tr, i2, sp.g_down[l], px, D, H, W, sp.g_tmp[l], st));
-        SQ_TRY(relu_bwd(sp.g_tmp[l], tape.tmp[l], px * f, 1.0f, st));
+        SQ_TRY(relu_bwd(tr, i1, sp.g_tmp[l], tape.tmp[l], px * f, 1.0f, st));
         const float *xin = (l == 0) ? image_dev : tape.pooled[l];
         SQ_TRY(param_grads(tr, i1, xin, nullptr, sp.g_tmp[l], px, D, H, W, sp.sc, st));
         if (l > 0) {
@@ -748,9 +778,11 @@ extern "C" int sq_trainer_apply(sq_trainer_t tr, void *stream_)
         update_kernel<<<(unsigned)((s.wcount + 255) / 256), 256, 0, st>>>(L.w, s.gw, s.mw, s.vw, s.wcount,
                                                                           tr->optimizer, tr->lr, lr_t, tr->beta1,
                                                                           tr->beta2, tr->eps);
-        update_kernel<<<(unsigned)((L.cout + 255) / 256), 256, 0, st>>>(L.shift, s.gb, s.mb, s.vb, (size_t)L.cout,
-                                                                        tr->optimizer, tr->lr, lr_t, tr->beta1,
-                                                                        tr->beta2, tr->eps);
+        update_kernel<<<(unsigned)((L.cout + 255) / 256), 256, 0, st>>>(s.affine ? s.bias : L.shift, s.gb, s.mb, s.vb,
+                                                                        (size_t)L.cout, tr->optimizer, tr->lr, lr_t,
+                                                                        tr->beta1, tr->beta2, tr->eps);
+        if (s.affine)
+            refold_kernel<<<(unsigned)((L.cout + 255) / 256), 256, 0, st>>>(s.bias, L.scale, s.tsh, L.cout, L.shift);
     }
     SQ_CHECK_LAUNCH();
     return SQ_OK;
@@ -780,7 +812,7 @@ extern "C" int sq_trainer_read(sq_trainer_t tr, const char *name, int what, floa
     const bool k = var == "kernel";
     const size_t have = k ? s.wcount : (size_t)L.cout;
     SQ_REQUIRE(count == have, SQ_EINVAL, "trainer_read: '%s' holds %zu values, not %zu", name, have, count);
-    const float *src = what ? (k ? s.gw : s.gb) : (k ? L.w : L.shift);
+    const float *src = what ? (k ? s.gw : s.gb) : (k ? L.w : (s.affine ? s.bias : L.shift));
     SQ_CUDA(cudaSetDevice(u->h->device));
     SQ_CUDA(cudaDeviceSynchronize());
     SQ_CUDA(cudaMemcpy(out_host, src, count * sizeof(float), cudaMemcpyDeviceToHost));

@@ -543,8 +543,9 @@ class Trainer(object):
     ``tr_augment`` yields: ``image`` (N,[D,]H,W,C) float32 and ``{'label': one-hot uint8 (N,[D,]H,W,K) or class ids
     (N,[D,]H,W), 'weights': float32 (N,[D,]H,W[,1])}``.
 
-    The network must be built with ``compute='fp32'``; ``weights()`` returns the trained variables in the
-    ``load_weights`` layout (e.g. to load a ``compute='bf16'`` network for tensor-core inference)."""
+    Kernels and biases are trained; a layer's optional per-channel affine (``scale`` / ``shift``, folded BN
+    statistics) stays frozen.  The network must be built with ``compute='fp32'``; ``weights()`` returns the variables
+    in the ``load_weights`` layout (e.g. to load a ``compute='bf16'`` network for tensor-core inference)."""
 
     def __init__(self, net, learning_rate=1e-3, optimizer='adam', beta1=0.9, beta2=0.999, epsilon=1e-8,
                  dropout=None, seed=0, data_parallel=None):
@@ -665,6 +666,8 @@ class Trainer(object):
         out = {}
         for name, arr in self.net._weights.items():
             if not (name.endswith('/kernel') or name.endswith('/bias')):
+                if what == 0:
+                    out[name] = arr.copy()          # frozen per-channel affine (scale / shift): not trained
                 continue
             buf = np.empty(arr.shape, dtype=np.float32)
             _lib.check(lib.sq_trainer_read(self._trainer, name.encode(), what, buf.ctypes.data, buf.size))

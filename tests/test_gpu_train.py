@@ -33,7 +33,7 @@ def _net(ndim, filters, cin, k, bridge, shape, weights, dropout):
 
 
 def _assert_grads(got, ref, tol=2e-4):
-    assert set(got) == set(ref)
+    assert set(got) == set(ref) and all(n.endswith(('/kernel', '/bias')) for n in got)
     for name in sorted(ref):
         scale = np.abs(ref[name]).max()
         err = np.abs(got[name].astype(np.float64) - ref[name]).max()
@@ -67,6 +67,42 @@ def test_loss_and_gradients_against_the_autograd_oracle(sq, ndim, bridge, filter
     for name, arr in tr.weights().items():
         assert (arr == w[name]).all(), name
     assert tr.step(image, labels, wmap, apply_update=False) == loss
+    tr.close()
+
+
+@pytest.mark.parametrize('ndim,shape', [(2, (16, 24)), (3, (8, 8, 8))])
+def test_layers_with_a_frozen_affine(sq, ndim, shape):
+    """conv_layer = conv + bias + optional per-channel affine (folded BN) + ReLU: kernels and
+    biases train, scale / shift stay frozen; the plan's folded epilogue shift follows the bias after every update."""
+    filters, cin, k, rate = (4, 8), 2, 3, 0.25
+    w = synth.unet_weights(filters, cin, k, ndim=ndim, bridge='concat', seed=6, affine=True)
+    assert any(n.endswith('/scale') for n in w)
+    image, labels, wmap = _batch(ndim, 2, shape, cin, k, seed=9)
+    net = _net(ndim, filters, cin, k, 'concat', shape, w, rate)
+    tr = net.trainer(learning_rate=0.05, optimizer='sgd', seed=3)
+    loss = tr.step(image, labels, wmap, apply_update=False)
+    ref_loss, ref_grads, _ = train_oracle.gradients(w, image, labels, wmap, filters, 'concat', ndim, rate=rate, seed=3,
+                                                    step=0)
+    assert abs(loss - ref_loss) <= 1e-5 * abs(ref_loss)
+    _assert_grads(tr.gradients(), ref_grads)
+    opt = train_oracle.Adam(w, learning_rate=0.05, optimizer='sgd')
+    for step in range(2):
+        loss = tr.step(image, labels, wmap)
+        ref_loss, grads, _ = train_oracle.gradients(opt.w, image, labels, wmap, filters, 'concat', ndim, rate=rate,
+                                                    seed=3, step=step)
+        assert abs(loss - ref_loss) <= 2e-5 * abs(ref_loss), step
+        opt.apply(grads)
+    got = tr.weights()
+    assert set(got) == set(w)
+    for name in sorted(got):
+        if name.endswith(('/scale', '/shift')):
+            assert (got[name] == w[name]).all(), name                      # frozen
+        else:
+            np.testing.assert_allclose(got[name], opt.w[name], rtol=0, atol=2e-6, err_msg=name)
+    # inference on the same plan uses the re-folded shift
+    logits = net.predict(image, want=('logits',))['logits']
+    _, _, ref_logits = train_oracle.gradients(opt.w, image, labels, wmap, filters, 'concat', ndim)
+    np.testing.assert_allclose(logits, ref_logits, rtol=0, atol=2e-4)
     tr.close()
 
 
@@ -127,10 +163,6 @@ def test_trainer_argument_errors(sq):
     bf.load_weights(w)
     with pytest.raises(ValueError):
         bf.trainer()
-    aff = synth.unet_weights((4, 8), 1, 2, ndim=2, bridge='concat', seed=1, affine=True)
-    net = _net(2, (4, 8), 1, 2, 'concat', (8, 8), aff, 0.0)
-    with pytest.raises(Exception, match='affine'):
-        net.trainer()
     net = _net(2, (4, 8), 1, 2, 'concat', (8, 8), w, 0.0)
     tr = net.trainer()
     image, labels, wmap = _batch(2, 1, (8, 8), 1, 2, seed=0)
