@@ -622,25 +622,7 @@ class Trainer(object):
             raise ValueError('image has shape %s, expected (N,%s%d)' %
                              (tuple(x.shape), 'D,H,W,' if net.ndim == 3 else 'H,W,', net.n_inputs))
         sp = tuple(x.shape[:-1])
-        lab = to_dev(target, torch.uint8)
-        wgt = to_dev(weights, torch.float32)
-        if tuple(wgt.shape) not in (sp, sp + (1,)):
-            raise ValueError('weights have shape %s, expected %s' % (tuple(wgt.shape), sp))
-        wgt = wgt.reshape(sp)
-        if tuple(lab.shape) == sp + (net.n_outputs,):
-            # one-hot (tr_augment :396-398): a pixel whose class lies beyond the K outputs has an all-zero row and
-            # contributes nothing to a softmax cross-entropy -- its weight is cleared
-            none = lab.sum(-1) == 0
-            lab = lab.argmax(-1).to(torch.uint8).contiguous()
-            if bool(none.any()):
-                wgt = torch.where(none, torch.zeros_like(wgt), wgt)
-        elif tuple(lab.shape) == sp + (1,):
-            lab = lab.reshape(sp)
-        elif tuple(lab.shape) != sp:
-            raise ValueError('labels have shape %s, expected %s (class ids) or %s (one-hot)' %
-                             (tuple(lab.shape), sp, sp + (net.n_outputs,)))
-        if int(lab.max()) >= net.n_outputs:
-            raise ValueError('class id %d >= num_outputs %d' % (int(lab.max()), net.n_outputs))
+        lab, wgt = self._class_ids(to_dev(target, torch.uint8), to_dev(weights, torch.float32), sp, net.n_outputs)
         n = sp[0]
         d, h, w = ((1,) + sp[1:3]) if net.ndim == 2 else sp[1:4]
         lib = _lib.load()
@@ -659,6 +641,31 @@ class Trainer(object):
             if apply_update:
                 _lib.check(lib.sq_trainer_apply(self._trainer, _lib.stream_ptr(x.device)))
         return float(loss.item())
+
+    @staticmethod
+    def _class_ids(lab, wgt, sp, num_outputs):
+        """Labels and weights in the layout ``sq_trainer_step`` takes (any device): class ids uint8 ``sp`` and weights
+        float32 ``sp`` from class ids ``sp`` / ``sp + (1,)`` or the one-hot ``sp + (K,)`` that ``tr_augment`` yields
+        (reference networks/unet.py:396-398).  A one-hot row of zeros (a class beyond the K outputs) contributes
+        nothing to a softmax cross-entropy: its weight is cleared."""
+        import torch
+        sp = tuple(sp)
+        if tuple(wgt.shape) not in (sp, sp + (1,)):
+            raise ValueError('weights have shape %s, expected %s' % (tuple(wgt.shape), sp))
+        wgt = wgt.reshape(sp)
+        if tuple(lab.shape) == sp + (num_outputs,) and not (num_outputs == 1 and tuple(lab.shape) == sp + (1,)):
+            none = lab.sum(-1) == 0
+            lab = lab.argmax(-1).to(torch.uint8).contiguous()
+            if bool(none.any()):
+                wgt = torch.where(none, torch.zeros_like(wgt), wgt)
+        elif tuple(lab.shape) == sp + (1,):
+            lab = lab.reshape(sp)
+        elif tuple(lab.shape) != sp:
+            raise ValueError('labels have shape %s, expected %s (class ids) or %s (one-hot)' %
+                             (tuple(lab.shape), sp, sp + (num_outputs,)))
+        if lab.numel() and int(lab.max()) >= num_outputs:
+            raise ValueError('class id %d >= num_outputs %d' % (int(lab.max()), num_outputs))
+        return lab.contiguous(), wgt.contiguous()
 
     def _read(self, what):
         self._check_alive()

@@ -395,3 +395,34 @@ def test_segment_stack_and_digest_with_a_stub_network():
     over = shard.segment_stack(s2, stack, frame0=0, frames_per_call=4, overlap=True)
     assert shard.tables_digest(over) == shard.tables_digest(whole)
     assert [c[1] for c in s2.calls] == [0, 8, 16] and [c[1] for c in s3.calls] == [4, 12, 20]
+
+
+def test_trainer_label_layouts():
+    """`Trainer._class_ids`: what tr_augment yields (one-hot uint8, weights with a trailing axis) and plain class ids
+    reach the C ABI as (class ids uint8, weights float32); an all-zero one-hot row clears its weight."""
+    import numpy as np
+    import pytest
+    import torch
+    from sequitr_b200.networks.unet import Trainer
+    sp = (2, 4, 6)
+    rng = np.random.default_rng(0)
+    ids = rng.integers(0, 3, sp).astype(np.uint8)
+    wgt = (1 + rng.random(sp)).astype(np.float32)
+    onehot = np.eye(3, dtype=np.uint8)[ids]
+    for lab_in, w_in in ((ids, wgt), (ids[..., None], wgt[..., None]), (onehot, wgt[..., None])):
+        lab, w = Trainer._class_ids(torch.from_numpy(lab_in.copy()), torch.from_numpy(w_in.copy()), sp, 3)
+        assert lab.dtype == torch.uint8 and tuple(lab.shape) == sp and lab.is_contiguous()
+        assert w.dtype == torch.float32 and tuple(w.shape) == sp
+        assert np.array_equal(lab.numpy(), ids) and np.array_equal(w.numpy(), wgt)
+    # a pixel of a class beyond the K outputs: tr_augment's one-hot row is all zero (networks/unet.py:396-398)
+    onehot2 = onehot[..., :2].copy()
+    lab, w = Trainer._class_ids(torch.from_numpy(onehot2), torch.from_numpy(wgt.copy()), sp, 2)
+    beyond = ids == 2
+    assert beyond.any() and (w.numpy()[beyond] == 0).all() and np.array_equal(w.numpy()[~beyond], wgt[~beyond])
+    assert (lab.numpy()[~beyond] == ids[~beyond]).all() and int(lab.max()) < 2
+    with pytest.raises(ValueError):
+        Trainer._class_ids(torch.from_numpy(ids), torch.from_numpy(wgt), sp, 2)          # class id 2 >= 2 outputs
+    with pytest.raises(ValueError):
+        Trainer._class_ids(torch.from_numpy(ids[:, :3]), torch.from_numpy(wgt), sp, 3)   # label shape
+    with pytest.raises(ValueError):
+        Trainer._class_ids(torch.from_numpy(ids), torch.from_numpy(wgt[:, :3]), sp, 3)   # weight shape
