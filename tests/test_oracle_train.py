@@ -58,6 +58,28 @@ def test_autograd_against_finite_differences(ndim, bridge):
             assert abs(fd - grads[name][idx]) <= 1e-6 + 1e-5 * abs(fd), (name, idx, fd, grads[name][idx])
 
 
+def test_frozen_affine_layers_against_finite_differences():
+    """conv + bias + frozen per-channel affine + ReLU: gradients only for kernels and biases, checked by finite
+    differences; scale / shift get none."""
+    filters = (3, 4)
+    w = synth.unet_weights(filters, 2, 3, ndim=2, bridge='concat', seed=5, affine=True)
+    image, labels, wmap = _batch(2, 2, 4, 2, 3, seed=7)
+    loss, grads, _ = train_oracle.gradients(w, image, labels, wmap, filters, 'concat', 2, rate=0.3, seed=1, step=0)
+    assert any(n.endswith('/scale') for n in w) and all(n.endswith(('/kernel', '/bias')) for n in grads)
+    rng = np.random.default_rng(1)
+    for name in ('UNet/down0/conv1/bias', 'UNet/up0/conv1/kernel', 'UNet/down1/conv2/kernel'):
+        idx = tuple(int(rng.integers(0, s)) for s in w[name].shape)
+        h = 1e-5
+        vals = []
+        for sgn in (+1, -1):
+            w2 = {k: v.astype(np.float64).copy() for k, v in w.items()}
+            w2[name][idx] += sgn * h
+            vals.append(train_oracle.gradients(w2, image, labels, wmap, filters, 'concat', 2, rate=0.3, seed=1,
+                                               step=0)[0])
+        fd = (vals[0] - vals[1]) / (2 * h)
+        assert abs(fd - grads[name][idx]) <= 1e-6 + 1e-5 * abs(fd), (name, idx, fd, grads[name][idx])
+
+
 def test_adam_rule_by_hand():
     opt = train_oracle.Adam({'a': np.array([1.0, -2.0])}, learning_rate=0.1, beta1=0.9, beta2=0.999, epsilon=1e-8)
     g = np.array([0.5, -0.25])
